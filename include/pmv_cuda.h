@@ -1,0 +1,118 @@
+/*
+ * pmv_cuda.h -- C ABI of libpmv_cuda.so: the B200 (sm_100a) replacement for the
+ * visual-odometry hot path of JeanElsner/practical-multi-view.
+ *
+ * Every entry point below replaces one call the reference's plugin layer makes into
+ * OpenCV / Ceres (reference file:line cited per function; paths relative to the
+ * reference checkout).  The header is plain C: POD arguments, caller-owned buffers,
+ * an opaque context that owns device memory and one CUDA stream.  No exception crosses
+ * the ABI; every function returns PMV_OK (0) or a negative pmv_status, and
+ * pmv_last_error() gives the text.  There is NO CPU fallback: without a CUDA device
+ * pmv_create() returns NULL and every other call fails.
+ *
+ * Threading (OdometryPipeline.cpp:210-245): the matcher and extractor run on the
+ * producer thread, the optimizer on the consumer thread -> contexts are independent
+ * and re-entrant across handles; one context must not be used from two threads at once.
+ *
+ * "host" entry points take host pointers (pageable or pinned) and include the H2D/D2H
+ * copies; "_dev" entry points take device pointers resident in HBM and enqueue on the
+ * context's stream without synchronising.
+ */
+#ifndef PMV_CUDA_H
+#define PMV_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PMV_API __attribute__((visibility("default")))
+#else
+#define PMV_API
+#endif
+
+typedef struct pmv_ctx pmv_ctx;
+
+typedef enum pmv_status {
+    PMV_OK = 0,
+    PMV_ERR_INVALID = -1,     /* bad argument (null pointer, non-positive size, ...) */
+    PMV_ERR_UNSUPPORTED = -2, /* valid for the reference but outside what the kernels cover */
+    PMV_ERR_CUDA = -3,        /* CUDA runtime / launch failure, see pmv_last_error */
+    PMV_ERR_NOMEM = -4,
+    PMV_ERR_NCCL = -5,
+    PMV_ERR_NUMERIC = -6      /* e.g. reduced camera system not positive definite */
+} pmv_status;
+
+#define PMV_MAX_PYR_LEVELS 8 /* level 0 + up to 7 reduced levels */
+
+/* flags of pmv_lk_track == cv::OPTFLOW_* (video/tracking.hpp) */
+#define PMV_LK_USE_INITIAL_FLOW 4
+#define PMV_LK_GET_MIN_EIGENVALS 8
+
+/* ------------------------------------------------------------------ context ---------- */
+/* One per adapter object (GpuLucasKanadeFM / Gpu*FeatureExtractor / GpuBundleAdjustment own
+ * one each; replaces nothing in the reference -- it has no device state).  NULL on failure. */
+PMV_API pmv_ctx *pmv_create(int device);
+PMV_API void pmv_destroy(pmv_ctx *ctx);
+/* Adopt a caller-owned cudaStream_t (e.g. torch's current stream); NULL = context's own. */
+PMV_API int pmv_set_stream(pmv_ctx *ctx, void *cuda_stream);
+PMV_API int pmv_sync(pmv_ctx *ctx);
+PMV_API const char *pmv_last_error(pmv_ctx *ctx);
+/* Number of kernel launches this context has issued since creation (bench "gpu_launches"). */
+PMV_API uint64_t pmv_launch_count(pmv_ctx *ctx);
+PMV_API const char *pmv_version(void);
+
+/* ------------------------------------------------------------------ pyramid ---------- */
+/* Effective top level of cv::buildOpticalFlowPyramid(img, Size(win_w,win_h), max_level):
+ * max_level is clipped when the next level would be <= the window (SURVEY Appx A.1).
+ * Pure host arithmetic.  Reached from OpenCVLucasKanadeFM.cpp:15. */
+PMV_API int pmv_pyr_levels(int rows, int cols, int win_w, int win_h, int max_level);
+
+/* Gaussian 5x5 pyramid (cv::pyrDown chain inside calcOpticalFlowPyrLK,
+ * OpenCVLucasKanadeFM.cpp:15).  Host image in, levels 1..L out, packed back to back
+ * (level l is rows_l x cols_l, no padding).  *out_levels = L. Bit-exact vs cv::pyrDown. */
+PMV_API int pmv_pyramid_build(pmv_ctx *ctx, const uint8_t *img, int rows, int cols, int step,
+                              int win_w, int win_h, int max_level,
+                              uint8_t *out_packed, size_t out_capacity, int *out_levels);
+
+/* Scharr derivative image, int16 x2 interleaved [Ix,Iy] (cv::calcSharrDeriv inside
+ * calcOpticalFlowPyrLK).  The LK kernel fuses this; the entry point exists for
+ * stage-by-stage parity.  out = rows*cols*2 int16. */
+PMV_API int pmv_scharr(pmv_ctx *ctx, const uint8_t *img, int rows, int cols, int step, int16_t *out);
+
+/* ------------------------------------------------------------------ Lucas-Kanade ------ */
+/* == cv::calcOpticalFlowPyrLK(prev, next, prevPts, nextPts, status, err, Size(win_w,win_h),
+ *    max_level, TermCriteria(COUNT+EPS, max_count, eps), flags, min_eig_thr)
+ * as called at OpenCVLucasKanadeFM.cpp:15 (win 32x32, max_level 4, defaults 30 / 0.01 / 0 / 1e-4).
+ * prev_xy/next_xy: n x (x,y) float; status: n bytes; err: n floats.  With
+ * PMV_LK_USE_INITIAL_FLOW next_xy is also an input.  Windows up to 32x32 (w*h <= 1024). */
+PMV_API int pmv_lk_track(pmv_ctx *ctx, const uint8_t *prev, const uint8_t *next,
+                         int rows, int cols, int step, const float *prev_xy, int n,
+                         int win_w, int win_h, int max_level, int max_count, double eps,
+                         int flags, double min_eig_thr,
+                         float *next_xy, uint8_t *status, float *err);
+
+/* B independent frame pairs in one call (BASELINE config 2).  Image b of prev/next starts at
+ * b*img_stride bytes; points of pair b at prev_xy + b*n*2.  Host buffers; uploads are chunked
+ * and overlapped with the kernels. */
+PMV_API int pmv_lk_track_batched(pmv_ctx *ctx, const uint8_t *prev, const uint8_t *next, int batch,
+                                 size_t img_stride, int rows, int cols, int step,
+                                 const float *prev_xy, int n, int win_w, int win_h, int max_level,
+                                 int max_count, double eps, int flags, double min_eig_thr,
+                                 float *next_xy, uint8_t *status, float *err);
+
+/* Same, everything resident in HBM (device pointers); asynchronous on the context stream. */
+PMV_API int pmv_lk_track_batched_dev(pmv_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next,
+                                     int batch, size_t img_stride, int rows, int cols, int step,
+                                     const float *d_prev_xy, int n, int win_w, int win_h,
+                                     int max_level, int max_count, double eps, int flags,
+                                     double min_eig_thr,
+                                     float *d_next_xy, uint8_t *d_status, float *d_err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMV_CUDA_H */

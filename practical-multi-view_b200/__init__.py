@@ -1,0 +1,188 @@
+"""practical-multi-view_b200 -- B200 (sm_100a) VO hot path behind the reference's plugin API.
+
+This Python module is only the *test/bench binding* of the product: ``libpmv_cuda.so``
+(hand-written CUDA behind the C ABI in ``include/pmv_cuda.h``) plus the C++ adapters in
+``host/`` that subclass the reference's ``Base*`` plugin interfaces.  Import as::
+
+    import pmv_b200            # via the repo-root shim (the directory name has a hyphen)
+
+There is NO CPU fallback: if the shared library is missing or no CUDA device is present the
+calls raise ``PmvError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libpmv_cuda.so"
+HEADER_PATH = _HERE.parent / "include" / "pmv_cuda.h"
+
+PMV_OK = 0
+LK_USE_INITIAL_FLOW = 4
+LK_GET_MIN_EIGENVALS = 8
+
+
+class PmvError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"pmv error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+_u8p, _i16p, _i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int16), C.POINTER(C.c_int32)
+_f32p, _f64p = C.POINTER(C.c_float), C.POINTER(C.c_double)
+_vp, _int, _sz, _dbl = C.c_void_p, C.c_int, C.c_size_t, C.c_double
+
+# name -> (restype, argtypes); mirrors include/pmv_cuda.h one to one
+_SIGS = {
+    "pmv_version": (C.c_char_p, []),
+    "pmv_create": (_vp, [_int]),
+    "pmv_destroy": (None, [_vp]),
+    "pmv_set_stream": (_int, [_vp, _vp]),
+    "pmv_sync": (_int, [_vp]),
+    "pmv_last_error": (C.c_char_p, [_vp]),
+    "pmv_launch_count": (C.c_uint64, [_vp]),
+    "pmv_pyr_levels": (_int, [_int] * 5),
+    "pmv_pyramid_build": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _vp, _sz, _i32p]),
+    "pmv_scharr": (_int, [_vp, _vp, _int, _int, _int, _vp]),
+    "pmv_lk_track": (_int, [_vp, _vp, _vp, _int, _int, _int, _vp, _int, _int, _int, _int, _int, _dbl,
+                            _int, _dbl, _vp, _vp, _vp]),
+    "pmv_lk_track_batched": (_int, [_vp, _vp, _vp, _int, _sz, _int, _int, _int, _vp, _int, _int, _int,
+                                    _int, _int, _dbl, _int, _dbl, _vp, _vp, _vp]),
+    "pmv_lk_track_batched_dev": (_int, [_vp, _vp, _vp, _int, _sz, _int, _int, _int, _vp, _int, _int, _int,
+                                        _int, _int, _dbl, _int, _dbl, _vp, _vp, _vp]),
+}
+
+
+def load_library() -> C.CDLL:
+    """dlopen libpmv_cuda.so and bind every symbol of the header.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise PmvError(-100, f"{LIB_PATH} is not built -- run __graft_entry__.build(); "
+                             "there is no CPU fallback")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """Owns one ``pmv_ctx`` (device buffers + a CUDA stream)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = load_library()
+        self.h = self.lib.pmv_create(device)
+        if not self.h:
+            raise PmvError(-101, "pmv_create failed: no usable CUDA device (no CPU fallback)")
+        if stream:
+            self.lib.pmv_set_stream(self.h, C.c_void_p(stream))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pmv_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc: int):
+        if rc != PMV_OK:
+            raise PmvError(rc, self.lib.pmv_last_error(self.h).decode())
+
+    def set_stream(self, stream: int | None):
+        self._chk(self.lib.pmv_set_stream(self.h, C.c_void_p(stream or 0)))
+
+    def sync(self):
+        self._chk(self.lib.pmv_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.pmv_launch_count(self.h))
+
+    # ------------------------------------------------------------------ pyramid
+    def pyramid_build(self, img: np.ndarray, win=(21, 21), max_level=3):
+        assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+        rows, cols = img.shape
+        L = self.lib.pmv_pyr_levels(rows, cols, win[0], win[1], max_level)
+        shapes, r, c = [], rows, cols
+        for _ in range(L):
+            r, c = (r + 1) // 2, (c + 1) // 2
+            shapes.append((r, c))
+        out = np.empty(max(1, sum(a * b for a, b in shapes)), np.uint8)
+        nl = C.c_int(0)
+        self._chk(self.lib.pmv_pyramid_build(self.h, _ptr(img), rows, cols, img.strides[0], win[0], win[1],
+                                             max_level, _ptr(out), out.size, C.byref(nl)))
+        levels, o = [], 0
+        for (r, c) in shapes[:nl.value]:
+            levels.append(out[o:o + r * c].reshape(r, c).copy())
+            o += r * c
+        return levels
+
+    def scharr(self, img: np.ndarray) -> np.ndarray:
+        assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+        rows, cols = img.shape
+        out = np.empty((rows, cols, 2), np.int16)
+        self._chk(self.lib.pmv_scharr(self.h, _ptr(img), rows, cols, img.strides[0], _ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ Lucas-Kanade
+    def lk_track(self, prev, nxt, pts, win=(21, 21), max_level=3, max_count=30, eps=0.01, flags=0,
+                 min_eig=1e-4, init=None):
+        assert prev.dtype == np.uint8 and nxt.dtype == np.uint8 and prev.shape == nxt.shape
+        assert prev.strides == nxt.strides and prev.strides[1] == 1
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        n = len(pts)
+        out = np.zeros((n, 2), np.float32) if init is None else np.ascontiguousarray(init, np.float32).reshape(-1, 2).copy()
+        st = np.zeros(n, np.uint8)
+        err = np.zeros(n, np.float32)
+        rows, cols = prev.shape
+        self._chk(self.lib.pmv_lk_track(self.h, _ptr(prev), _ptr(nxt), rows, cols, prev.strides[0], _ptr(pts), n,
+                                        win[0], win[1], max_level, max_count, eps, flags, min_eig,
+                                        _ptr(out), _ptr(st), _ptr(err)))
+        return out, st, err
+
+    def lk_track_batched(self, prev, nxt, pts, win=(21, 21), max_level=3, max_count=30, eps=0.01, flags=0,
+                         min_eig=1e-4, out=None):
+        """prev/nxt: (B, H, W) u8 C-contiguous host arrays; pts: (B, n, 2) float32."""
+        B, rows, cols = prev.shape
+        assert prev.flags.c_contiguous and nxt.flags.c_contiguous and pts.dtype == np.float32
+        n = pts.shape[1]
+        if out is None:
+            out = (np.zeros((B, n, 2), np.float32), np.zeros((B, n), np.uint8), np.zeros((B, n), np.float32))
+        nx, st, err = out
+        self._chk(self.lib.pmv_lk_track_batched(self.h, _ptr(prev), _ptr(nxt), B, rows * cols, rows, cols, cols,
+                                                _ptr(pts), n, win[0], win[1], max_level, max_count, eps, flags,
+                                                min_eig, _ptr(nx), _ptr(st), _ptr(err)))
+        return nx, st, err
+
+    def lk_track_batched_dev(self, d_prev: int, d_nxt: int, B, img_stride, rows, cols, step, d_pts: int, n,
+                             d_next: int, d_status: int, d_err: int, win=(21, 21), max_level=3, max_count=30,
+                             eps=0.01, flags=0, min_eig=1e-4):
+        """Device pointers (ints, e.g. torch.Tensor.data_ptr()); asynchronous on the context stream."""
+        self._chk(self.lib.pmv_lk_track_batched_dev(self.h, _ptr(d_prev), _ptr(d_nxt), B, img_stride, rows, cols,
+                                                    step, _ptr(d_pts), n, win[0], win[1], max_level, max_count,
+                                                    eps, flags, min_eig, _ptr(d_next), _ptr(d_status), _ptr(d_err)))

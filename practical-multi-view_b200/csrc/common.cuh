@@ -1,0 +1,132 @@
+// common.cuh -- shared plumbing for libpmv_cuda.so (context, error handling, device helpers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/pmv_cuda.h"
+
+// ------------------------------------------------------------------ device buffers -----
+// Grow-only device buffer owned by a context (no per-call cudaMalloc on the hot path).
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PinBuf {  // grow-only pinned host staging buffer
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes + 256);
+        if (e == cudaSuccess) cap = bytes + 256;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// ------------------------------------------------------------------ pyramid layout ------
+// Level l of a batch of B images lives at  base + b*img_stride + y*pitch + x  (u8).
+// Pitches of context-owned levels are multiples of 128 B so rows are 16 B aligned for
+// vector loads / TMA boxes.
+struct PyrLevel {
+    const uint8_t *ptr;
+    int rows, cols, pitch;
+    size_t img_stride;
+};
+
+struct PyrSet {  // levels of one image batch; level 0 may alias caller memory
+    PyrLevel lv[PMV_MAX_PYR_LEVELS];
+    int top = 0;  // effective max level
+};
+
+static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ context -------------
+struct pmv_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;      // stream work is enqueued on
+    cudaStream_t own_stream = nullptr;  // created by pmv_create
+    cudaStream_t copy_stream = nullptr; // second stream for chunked upload overlap
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    uint64_t launches = 0;
+
+    // workspaces
+    DevBuf img[2];    // uploaded level-0 images (prev / next)
+    DevBuf pyr[2];    // reduced levels (prev / next)
+    DevBuf pts[4];    // prev_xy, next_xy, status, err
+    DevBuf scratch[8];
+    PinBuf pin[4];
+
+    int fail(int code, const char *what, cudaError_t e = cudaSuccess)
+    {
+        char b[512];
+        if (e != cudaSuccess)
+            snprintf(b, sizeof b, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+        else
+            snprintf(b, sizeof b, "%s", what);
+        err = b;
+        return code;
+    }
+};
+
+#define PMV_CUDA_TRY(ctx, expr)                                                     \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) return (ctx)->fail(PMV_ERR_CUDA, #expr, _e);         \
+    } while (0)
+
+#define PMV_LAUNCH_CHECK(ctx, name)                                                 \
+    do {                                                                            \
+        (ctx)->launches++;                                                          \
+        cudaError_t _e = cudaGetLastError();                                        \
+        if (_e != cudaSuccess) return (ctx)->fail(PMV_ERR_CUDA, "launch " name, _e);\
+    } while (0)
+
+// ------------------------------------------------------------------ device helpers ------
+__host__ __device__ __forceinline__ int reflect101(int p, int len)
+{
+    // BORDER_REFLECT_101  gfedcb|abcdefgh|gfedcba ; loop form is safe for any overshoot
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+    return p;
+}
+
+// internal cross-file entry points (defined in pyramid.cu / lk.cu)
+int pmv_internal_pyr_plan(pmv_ctx *ctx, int which, int batch, int rows, int cols,
+                          const uint8_t *d_lvl0, int pitch0, size_t stride0,
+                          int win_w, int win_h, int max_level, PyrSet *out);
+int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, cudaStream_t s);

@@ -1,0 +1,457 @@
+// lk.cu -- K3: per-feature pyramidal Lucas-Kanade solve, one warp per feature.
+//
+// Replaces cv::calcOpticalFlowPyrLK as called at reference OpenCVLucasKanadeFM.cpp:15
+// (LKTrackerInvoker, SURVEY Appx A.3), with calcSharrDeriv (Appx A.2) fused in.
+//
+// Design (B200): a warp owns one feature for ALL pyramid levels (one launch per batch, no
+// inter-level round trip through HBM).  Per level the warp
+//   1. stages the (w+3)x(h+3) u8 patch of the previous image in shared memory (reflect-101),
+//   2. computes the Scharr derivative at the (w+1)x(h+1) bilinear support on the fly
+//      (zero outside the image, exactly like OpenCV's zero-bordered derivative image),
+//   3. builds the template: 14-bit fixed-point bilinear samples of I, dI/dx, dI/dy kept in
+//      REGISTERS (pixel p = lane + 32k), structure tensor by exact per-lane int32 sums +
+//      REDUX warp reductions,
+//   4. stages a (w+1+2M)x(h+1+2M) window of the next image and runs <= max_count Newton
+//      iterations entirely out of shared memory; the mismatch vector is again an exact integer
+//      sum reduced with REDUX.  The window is re-staged only if the point drifts > M px.
+// All floating point that decides status / termination is fp32 with explicit round-to-nearest
+// intrinsics (no FMA contraction) in OpenCV's operation order, so status flags match and
+// positions agree to ~1e-4 px (gate: 0.01 px).
+//
+// Roofline: NOT HBM bound (1.28 MB compulsory bytes per 2 000-feature pair vs ~6e8 integer
+// ops); the limiter is the integer/LSU issue rate -- see DESIGN.md.
+#include "common.cuh"
+
+namespace {
+
+constexpr int LK_WARPS = 8;   // features per CTA
+constexpr int LK_M = 4;       // drift margin (px) of the staged next-image window
+
+struct LKParams {
+    PyrLevel prev[PMV_MAX_PYR_LEVELS];
+    PyrLevel next[PMV_MAX_PYR_LEVELS];
+    int top;
+    const float *prev_xy;
+    float *next_xy;
+    uint8_t *status;
+    float *err;
+    int n;
+    int win_w, win_h;
+    int max_count;
+    double eps2;
+    int flags;
+    float min_eig;
+    int smem_per_warp;
+    int pp;  // pitch of the staged prev patch
+    int jp;  // pitch of the staged next window
+};
+
+__device__ __forceinline__ long long warp_sum_i64(int v)
+{
+    // exact sum of 32 int32 values: REDUX on the two 16-bit halves
+    int hi = __reduce_add_sync(0xffffffffu, v >> 16);
+    int lo = __reduce_add_sync(0xffffffffu, v & 0xffff);
+    return ((long long)hi << 16) + (long long)lo;
+}
+
+__device__ __forceinline__ void bilinear_weights(float a, float b, int &iw00, int &iw01, int &iw10, int &iw11)
+{
+    const float s = 16384.f;
+    float na = __fsub_rn(1.f, a), nb = __fsub_rn(1.f, b);
+    iw00 = __float2int_rn(__fmul_rn(__fmul_rn(na, nb), s));
+    iw01 = __float2int_rn(__fmul_rn(__fmul_rn(a, nb), s));
+    iw10 = __float2int_rn(__fmul_rn(__fmul_rn(na, b), s));
+    iw11 = 16384 - iw00 - iw01 - iw10;
+}
+
+__device__ __forceinline__ void stage_next(uint8_t *js, const PyrLevel &J, const uint8_t *img,
+                                           int jx0, int jy0, int jw, int jh, int jp, int lane)
+{
+    for (int r = 0; r < jh; r++) {
+        const uint8_t *row = img + (size_t)reflect101(jy0 + r, J.rows) * J.pitch;
+        for (int c = lane; c < jw; c += 32) js[r * jp + c] = __ldg(row + reflect101(jx0 + c, J.cols));
+    }
+    __syncwarp();
+}
+
+template <int KPIX>
+__global__ void __launch_bounds__(LK_WARPS * 32)
+lk_track_kernel(const LKParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint16_t s_tab[32 * KPIX];  // pixel p -> (y << 8) | x
+
+    const int w = P.win_w, h = P.win_h, npx = w * h;
+    for (int p = threadIdx.x; p < 32 * KPIX; p += LK_WARPS * 32) {
+        int y = p / w, x = p - y * w;
+        s_tab[p] = (uint16_t)(p < npx ? ((y << 8) | x) : 0);
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.x * LK_WARPS + warp;
+    const int b = blockIdx.y;
+    if (f >= P.n) return;  // warp-uniform; only __syncwarp below
+
+    uint8_t *ws = smem + (size_t)warp * P.smem_per_warp;
+    const int kmax = (npx + 31) >> 5;
+    const int pp = P.pp, jp = P.jp, dp = w + 1;
+    uint8_t *ps = ws;                                            // prev patch (h+3) x pp
+    int *ds = reinterpret_cast<int *>(ws + ((h + 3) * pp + 15) / 16 * 16);  // derivs (h+1) x (w+1), short2 packed
+    uint8_t *js = ws;                                            // next window, aliases ps/ds
+    const int jw = w + 1 + 2 * LK_M, jh = h + 1 + 2 * LK_M;
+
+    const size_t pt = (size_t)b * P.n + f;
+    const float pt_x = P.prev_xy[2 * pt], pt_y = P.prev_xy[2 * pt + 1];
+    float cur_x = 0.f, cur_y = 0.f;  // nextPts[i]
+    if (P.flags & PMV_LK_USE_INITIAL_FLOW) { cur_x = P.next_xy[2 * pt]; cur_y = P.next_xy[2 * pt + 1]; }
+    int status = 1;
+    float errv = 0.f;
+
+    const float halfx = (w - 1) * 0.5f, halfy = (h - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+
+    int Iw[KPIX], dxw[KPIX], dyw[KPIX], joff[KPIX];
+    int pyx[KPIX];
+#pragma unroll
+    for (int k = 0; k < KPIX; k++) {
+        pyx[k] = s_tab[lane + 32 * k];
+        joff[k] = (pyx[k] >> 8) * jp + (pyx[k] & 255);
+    }
+
+    for (int level = P.top; level >= 0; level--) {
+        const PyrLevel &I = P.prev[level];
+        const PyrLevel &J = P.next[level];
+        const uint8_t *Iimg = I.ptr + (size_t)b * I.img_stride;
+        const uint8_t *Jimg = J.ptr + (size_t)b * J.img_stride;
+        const float sc = 1.f / (float)(1 << level);
+        float px = __fmul_rn(pt_x, sc), py = __fmul_rn(pt_y, sc);
+        float nx, ny;
+        if (level == P.top) {
+            if (P.flags & PMV_LK_USE_INITIAL_FLOW) { nx = __fmul_rn(cur_x, sc); ny = __fmul_rn(cur_y, sc); }
+            else { nx = px; ny = py; }
+        } else {
+            nx = __fmul_rn(cur_x, 2.f); ny = __fmul_rn(cur_y, 2.f);
+        }
+        cur_x = nx; cur_y = ny;
+
+        px = __fsub_rn(px, halfx); py = __fsub_rn(py, halfy);
+        const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
+        if (ipx < -w || ipx >= I.cols || ipy < -h || ipy >= I.rows) {
+            if (level == 0) { status = 0; errv = 0.f; }
+            continue;
+        }
+        int iw00, iw01, iw10, iw11;
+        bilinear_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), iw00, iw01, iw10, iw11);
+
+        // ---- 1. stage prev patch: image (ipy-1+r, ipx-1+c), reflect-101 -----------------
+        __syncwarp();
+        for (int r = 0; r < h + 3; r++) {
+            const uint8_t *row = Iimg + (size_t)reflect101(ipy - 1 + r, I.rows) * I.pitch;
+            for (int c = lane; c < w + 3; c += 32) ps[r * pp + c] = __ldg(row + reflect101(ipx - 1 + c, I.cols));
+        }
+        __syncwarp();
+        // ---- 2. Scharr derivative on the bilinear support (zero outside the image) ------
+        for (int r = 0; r < h + 1; r++) {
+            const int yy = ipy + r;
+            const bool yin = (yy >= 0) && (yy < I.rows);
+            for (int c = lane; c < w + 1; c += 32) {
+                const int xx = ipx + c;
+                int packed = 0;
+                if (yin && xx >= 0 && xx < I.cols) {
+                    const uint8_t *q = ps + r * pp + c;  // top-left of the 3x3 support
+                    int a0 = q[0], a1 = q[1], a2 = q[2];
+                    int b0 = q[pp], b2 = q[pp + 2];
+                    int c0 = q[2 * pp], c1 = q[2 * pp + 1], c2 = q[2 * pp + 2];
+                    int gx = (3 * (a2 + c2) + 10 * b2) - (3 * (a0 + c0) + 10 * b0);
+                    int gy = 3 * ((c0 - a0) + (c2 - a2)) + 10 * (c1 - a1);
+                    packed = (gx & 0xffff) | (gy << 16);
+                }
+                ds[r * dp + c] = packed;
+            }
+        }
+        __syncwarp();
+        // ---- 3. template + structure tensor --------------------------------------------
+        int sA11 = 0, sA12 = 0, sA22 = 0;
+#pragma unroll
+        for (int k = 0; k < KPIX; k++) {
+            if (k < kmax) {
+                const int y = pyx[k] >> 8, x = pyx[k] & 255;
+                const bool valid = (lane + 32 * k) < npx;
+                const uint8_t *q = ps + (y + 1) * pp + (x + 1);
+                int ival = (q[0] * iw00 + q[1] * iw01 + q[pp] * iw10 + q[pp + 1] * iw11 + (1 << 8)) >> 9;
+                const int *d = ds + y * dp + x;
+                int d00 = d[0], d01 = d[1], d10 = d[dp], d11 = d[dp + 1];
+                int ix = ((int)(short)d00 * iw00 + (int)(short)d01 * iw01 + (int)(short)d10 * iw10 +
+                          (int)(short)d11 * iw11 + (1 << 13)) >> 14;
+                int iy = ((d00 >> 16) * iw00 + (d01 >> 16) * iw01 + (d10 >> 16) * iw10 +
+                          (d11 >> 16) * iw11 + (1 << 13)) >> 14;
+                if (!valid) { ival = 0; ix = 0; iy = 0; }
+                Iw[k] = ival; dxw[k] = ix; dyw[k] = iy;
+                sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
+            }
+        }
+        const float A11 = __fmul_rn((float)warp_sum_i64(sA11), FLT_SCALE);
+        const float A12 = __fmul_rn((float)warp_sum_i64(sA12), FLT_SCALE);
+        const float A22 = __fmul_rn((float)warp_sum_i64(sA22), FLT_SCALE);
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dA = __fsub_rn(A11, A22);
+        const float minEig = __fdiv_rn(
+            __fsub_rn(__fadd_rn(A22, A11),
+                      __fsqrt_rn(__fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12)))),
+            (float)(2 * w * h));
+        if (P.flags & PMV_LK_GET_MIN_EIGENVALS) errv = minEig;
+        if (minEig < P.min_eig || D < 1.1920928955078125e-07f) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+        nx = __fsub_rn(nx, halfx); ny = __fsub_rn(ny, halfy);
+
+        // ---- 4. Newton iterations out of the staged next-image window --------------------
+        __syncwarp();  // template reads of ps/ds are done before js overwrites them
+        int jx0 = 0, jy0 = 0;
+        bool staged = false;
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < P.max_count; j++) {
+            const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
+            if (inx < -w || inx >= J.cols || iny < -h || iny >= J.rows) {
+                if (level == 0) status = 0;
+                break;
+            }
+            int ox = inx - jx0, oy = iny - jy0;
+            if (!staged || ox < 0 || ox > 2 * LK_M || oy < 0 || oy > 2 * LK_M) {
+                __syncwarp();
+                jx0 = inx - LK_M; jy0 = iny - LK_M;
+                stage_next(js, J, Jimg, jx0, jy0, jw, jh, jp, lane);
+                staged = true;
+                ox = LK_M; oy = LK_M;
+            }
+            bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), iw00, iw01, iw10, iw11);
+            const uint8_t *jb = js + oy * jp + ox;
+            int ib1 = 0, ib2 = 0;
+#pragma unroll
+            for (int k = 0; k < KPIX; k++) {
+                if (k < kmax) {
+                    const uint8_t *q = jb + joff[k];
+                    int v = q[0] * iw00 + q[1] * iw01 + q[jp] * iw10 + q[jp + 1] * iw11;
+                    int diff = ((v + (1 << 8)) >> 9) - Iw[k];
+                    ib1 += diff * dxw[k];
+                    ib2 += diff * dyw[k];
+                }
+            }
+            const float b1 = __fmul_rn((float)warp_sum_i64(ib1), FLT_SCALE);
+            const float b2 = __fmul_rn((float)warp_sum_i64(ib2), FLT_SCALE);
+            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+            nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
+            cur_x = __fadd_rn(nx, halfx); cur_y = __fadd_rn(ny, halfy);
+            if ((double)dx * (double)dx + (double)dy * (double)dy <= P.eps2) break;
+            if (j > 0 && fabsf(__fadd_rn(dx, pdx)) < 0.01f && fabsf(__fadd_rn(dy, pdy)) < 0.01f) {
+                cur_x = __fsub_rn(cur_x, __fmul_rn(dx, 0.5f));
+                cur_y = __fsub_rn(cur_y, __fmul_rn(dy, 0.5f));
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+
+        // ---- 5. level-0 residual error ----------------------------------------------------
+        if (status && level == 0 && !(P.flags & PMV_LK_GET_MIN_EIGENVALS)) {
+            const float fx = __fsub_rn(cur_x, halfx), fy = __fsub_rn(cur_y, halfy);
+            const int inx = __float2int_rd(fx), iny = __float2int_rd(fy);
+            if (inx < -w || inx >= J.cols || iny < -h || iny >= J.rows) {
+                status = 0;
+                continue;
+            }
+            int ox = inx - jx0, oy = iny - jy0;
+            if (!staged || ox < 0 || ox > 2 * LK_M || oy < 0 || oy > 2 * LK_M) {
+                __syncwarp();
+                jx0 = inx - LK_M; jy0 = iny - LK_M;
+                stage_next(js, J, Jimg, jx0, jy0, jw, jh, jp, lane);
+                staged = true;
+                ox = LK_M; oy = LK_M;
+            }
+            bilinear_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), iw00, iw01, iw10, iw11);
+            const uint8_t *jb = js + oy * jp + ox;
+            int e = 0;
+#pragma unroll
+            for (int k = 0; k < KPIX; k++) {
+                if (k < kmax) {
+                    const uint8_t *q = jb + joff[k];
+                    int v = q[0] * iw00 + q[1] * iw01 + q[jp] * iw10 + q[jp + 1] * iw11;
+                    int diff = ((v + (1 << 8)) >> 9) - Iw[k];
+                    if ((lane + 32 * k) < npx) e += abs(diff);
+                }
+            }
+            e = __reduce_add_sync(0xffffffffu, e);
+            errv = __fdiv_rn(__fmul_rn((float)e, 1.f), (float)(32 * w * h));
+        }
+    }
+
+    if (lane == 0) {
+        P.next_xy[2 * pt] = cur_x;
+        P.next_xy[2 * pt + 1] = cur_y;
+        P.status[pt] = (uint8_t)status;
+        P.err[pt] = errv;
+    }
+}
+
+template <int KPIX>
+int launch_lk(pmv_ctx *ctx, LKParams &P, int batch, cudaStream_t s)
+{
+    size_t smem = (size_t)P.smem_per_warp * LK_WARPS;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(lk_track_kernel<KPIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    dim3 grid((P.n + LK_WARPS - 1) / LK_WARPS, batch);
+    lk_track_kernel<KPIX><<<grid, LK_WARPS * 32, smem, s>>>(P);
+    PMV_LAUNCH_CHECK(ctx, "lk_track_kernel");
+    return PMV_OK;
+}
+
+int check_lk_args(pmv_ctx *ctx, int rows, int cols, int step, int n, int win_w, int win_h, int max_level)
+{
+    if (rows <= 0 || cols <= 0 || step < cols || n < 0 || max_level < 0)
+        return ctx->fail(PMV_ERR_INVALID, "lk: bad argument");
+    if (win_w <= 2 || win_h <= 2)  // OpenCV asserts winSize > 2
+        return ctx->fail(PMV_ERR_INVALID, "lk: window must be larger than 2x2");
+    if (win_w > 255 || win_h > 255 || win_w * win_h > 1024)
+        return ctx->fail(PMV_ERR_UNSUPPORTED, "lk: window area above 1024 pixels is not supported");
+    if (max_level >= PMV_MAX_PYR_LEVELS)
+        return ctx->fail(PMV_ERR_UNSUPPORTED, "lk: max_level above 7 is not supported");
+    return PMV_OK;
+}
+
+// Enqueue pyramids + tracking for `batch` pairs resident on the device.
+int lk_enqueue(pmv_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, int batch, size_t img_stride,
+               int rows, int cols, int pitch, const float *d_prev_xy, int n, int win_w, int win_h,
+               int max_level, int max_count, double eps, int flags, double min_eig_thr,
+               float *d_next_xy, uint8_t *d_status, float *d_err, cudaStream_t s,
+               int pyr_slot_base = 0, size_t pyr_reuse_batch = 0)
+{
+    (void)pyr_slot_base; (void)pyr_reuse_batch;
+    LKParams P;
+    memset(&P, 0, sizeof P);
+    PyrSet sp, sn;
+    int rc = pmv_internal_pyr_plan(ctx, 0, batch, rows, cols, d_prev, pitch, img_stride, win_w, win_h, max_level, &sp);
+    if (rc) return rc;
+    rc = pmv_internal_pyr_plan(ctx, 1, batch, rows, cols, d_next, pitch, img_stride, win_w, win_h, max_level, &sn);
+    if (rc) return rc;
+    rc = pmv_internal_pyr_run(ctx, sp, batch, s);
+    if (rc) return rc;
+    rc = pmv_internal_pyr_run(ctx, sn, batch, s);
+    if (rc) return rc;
+    if (n == 0) return PMV_OK;
+    for (int l = 0; l <= sp.top; l++) { P.prev[l] = sp.lv[l]; P.next[l] = sn.lv[l]; }
+    P.top = sp.top;
+    P.prev_xy = d_prev_xy; P.next_xy = d_next_xy; P.status = d_status; P.err = d_err;
+    P.n = n; P.win_w = win_w; P.win_h = win_h;
+    if (max_count < 0) max_count = 0;
+    if (max_count > 100) max_count = 100;
+    if (eps < 0) eps = 0;
+    if (eps > 10) eps = 10;
+    P.max_count = max_count; P.eps2 = eps * eps; P.flags = flags; P.min_eig = (float)min_eig_thr;
+    P.pp = align_up(win_w + 3, 4);
+    P.jp = align_up(win_w + 1 + 2 * LK_M, 4);
+    int tmpl = align_up((win_h + 3) * P.pp, 16) + (win_h + 1) * (win_w + 1) * 4;
+    int jwin = (win_h + 1 + 2 * LK_M) * P.jp;
+    P.smem_per_warp = align_up(tmpl > jwin ? tmpl : jwin, 16);
+    int npx = win_w * win_h;
+    if (npx <= 32 * 8) return launch_lk<8>(ctx, P, batch, s);
+    if (npx <= 32 * 14) return launch_lk<14>(ctx, P, batch, s);
+    if (npx <= 32 * 20) return launch_lk<20>(ctx, P, batch, s);
+    return launch_lk<32>(ctx, P, batch, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+PMV_API int pmv_lk_track_batched_dev(pmv_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next,
+                                     int batch, size_t img_stride, int rows, int cols, int step,
+                                     const float *d_prev_xy, int n, int win_w, int win_h,
+                                     int max_level, int max_count, double eps, int flags,
+                                     double min_eig_thr, float *d_next_xy, uint8_t *d_status, float *d_err)
+{
+    if (!ctx) return PMV_ERR_INVALID;
+    if (!d_prev || !d_next || batch <= 0 || (n > 0 && (!d_prev_xy || !d_next_xy || !d_status || !d_err)))
+        return ctx->fail(PMV_ERR_INVALID, "pmv_lk_track_batched_dev: null pointer / empty batch");
+    int rc = check_lk_args(ctx, rows, cols, step, n, win_w, win_h, max_level);
+    if (rc) return rc;
+    if (img_stride < (size_t)rows * step) return ctx->fail(PMV_ERR_INVALID, "lk: img_stride < rows*step");
+    cudaSetDevice(ctx->device);
+    return lk_enqueue(ctx, d_prev, d_next, batch, img_stride, rows, cols, step, d_prev_xy, n, win_w, win_h,
+                      max_level, max_count, eps, flags, min_eig_thr, d_next_xy, d_status, d_err, ctx->stream);
+}
+
+PMV_API int pmv_lk_track_batched(pmv_ctx *ctx, const uint8_t *prev, const uint8_t *next, int batch,
+                                 size_t img_stride, int rows, int cols, int step,
+                                 const float *prev_xy, int n, int win_w, int win_h, int max_level,
+                                 int max_count, double eps, int flags, double min_eig_thr,
+                                 float *next_xy, uint8_t *status, float *err)
+{
+    if (!ctx) return PMV_ERR_INVALID;
+    if (!prev || !next || batch <= 0 || (n > 0 && (!prev_xy || !next_xy || !status || !err)))
+        return ctx->fail(PMV_ERR_INVALID, "pmv_lk_track_batched: null pointer / empty batch");
+    int rc = check_lk_args(ctx, rows, cols, step, n, win_w, win_h, max_level);
+    if (rc) return rc;
+    if (img_stride < (size_t)rows * step) return ctx->fail(PMV_ERR_INVALID, "lk: img_stride < rows*step");
+    cudaSetDevice(ctx->device);
+
+    const int pitch = align_up(cols, 128);
+    const size_t dstride = (size_t)pitch * rows;
+    cudaError_t e = ctx->img[0].reserve(dstride * batch);
+    if (e == cudaSuccess) e = ctx->img[1].reserve(dstride * batch);
+    if (e == cudaSuccess) e = ctx->pts[0].reserve((size_t)batch * n * 8 + 8);
+    if (e == cudaSuccess) e = ctx->pts[1].reserve((size_t)batch * n * 8 + 8);
+    if (e == cudaSuccess) e = ctx->pts[2].reserve((size_t)batch * n + 8);
+    if (e == cudaSuccess) e = ctx->pts[3].reserve((size_t)batch * n * 4 + 8);
+    if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "lk batch buffers", e);
+    uint8_t *dP = ctx->img[0].as<uint8_t>(), *dN = ctx->img[1].as<uint8_t>();
+    float *dpx = ctx->pts[0].as<float>(), *dnx = ctx->pts[1].as<float>();
+    uint8_t *dst = ctx->pts[2].as<uint8_t>();
+    float *der = ctx->pts[3].as<float>();
+    cudaStream_t s = ctx->stream;
+
+    if (n > 0) {
+        PMV_CUDA_TRY(ctx, cudaMemcpyAsync(dpx, prev_xy, (size_t)batch * n * 8, cudaMemcpyHostToDevice, s));
+        if (flags & PMV_LK_USE_INITIAL_FLOW)
+            PMV_CUDA_TRY(ctx, cudaMemcpyAsync(dnx, next_xy, (size_t)batch * n * 8, cudaMemcpyHostToDevice, s));
+    }
+    // Upload all images with two strided copies (rows of all images form one 2-D copy when the
+    // batch is contiguous), then one pyramid pass + one tracking launch for the whole batch.
+    const bool contiguous = (img_stride == (size_t)rows * step);
+    if (contiguous) {
+        PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(dP, pitch, prev, step, cols, (size_t)rows * batch, cudaMemcpyHostToDevice, s));
+        PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(dN, pitch, next, step, cols, (size_t)rows * batch, cudaMemcpyHostToDevice, s));
+    } else {
+        for (int b = 0; b < batch; b++) {
+            PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(dP + b * dstride, pitch, prev + b * img_stride, step, cols, rows, cudaMemcpyHostToDevice, s));
+            PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(dN + b * dstride, pitch, next + b * img_stride, step, cols, rows, cudaMemcpyHostToDevice, s));
+        }
+    }
+    rc = lk_enqueue(ctx, dP, dN, batch, dstride, rows, cols, pitch, dpx, n, win_w, win_h, max_level,
+                    max_count, eps, flags, min_eig_thr, dnx, dst, der, s);
+    if (rc) return rc;
+    if (n > 0) {
+        PMV_CUDA_TRY(ctx, cudaMemcpyAsync(next_xy, dnx, (size_t)batch * n * 8, cudaMemcpyDeviceToHost, s));
+        PMV_CUDA_TRY(ctx, cudaMemcpyAsync(status, dst, (size_t)batch * n, cudaMemcpyDeviceToHost, s));
+        PMV_CUDA_TRY(ctx, cudaMemcpyAsync(err, der, (size_t)batch * n * 4, cudaMemcpyDeviceToHost, s));
+    }
+    PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return PMV_OK;
+}
+
+PMV_API int pmv_lk_track(pmv_ctx *ctx, const uint8_t *prev, const uint8_t *next,
+                         int rows, int cols, int step, const float *prev_xy, int n,
+                         int win_w, int win_h, int max_level, int max_count, double eps,
+                         int flags, double min_eig_thr, float *next_xy, uint8_t *status, float *err)
+{
+    return pmv_lk_track_batched(ctx, prev, next, 1, (size_t)rows * step, rows, cols, step, prev_xy, n,
+                                win_w, win_h, max_level, max_count, eps, flags, min_eig_thr,
+                                next_xy, status, err);
+}
+
+}  // extern "C"
