@@ -65,6 +65,20 @@ PMV_API const char *pmv_last_error(pmv_ctx *ctx);
 PMV_API uint64_t pmv_launch_count(pmv_ctx *ctx);
 PMV_API const char *pmv_version(void);
 
+/* Per-phase device timing for bench.py's roofline: when enabled every API call brackets its
+ * kernel groups with CUDA events on the context stream.  pmv_profile_collect synchronises,
+ * returns the summed milliseconds and the number of bracketed groups per phase since the last
+ * collect, and resets. */
+#define PMV_PHASE_PYRAMID 0
+#define PMV_PHASE_LK 1
+#define PMV_PHASE_RESPONSE 2
+#define PMV_PHASE_SELECT 3
+#define PMV_PHASE_FAST 4
+#define PMV_PHASE_BA 5
+#define PMV_PHASE_COUNT 8
+PMV_API int pmv_profile_enable(pmv_ctx *ctx, int on);
+PMV_API int pmv_profile_collect(pmv_ctx *ctx, int n_phases, double *ms_sum, int *count);
+
 /* ------------------------------------------------------------------ pyramid ---------- */
 /* Effective top level of cv::buildOpticalFlowPyramid(img, Size(win_w,win_h), max_level):
  * max_level is clipped when the next level would be <= the window (SURVEY Appx A.1).

@@ -46,6 +46,8 @@ _SIGS = {
     "pmv_sync": (_int, [_vp]),
     "pmv_last_error": (C.c_char_p, [_vp]),
     "pmv_launch_count": (C.c_uint64, [_vp]),
+    "pmv_profile_enable": (_int, [_vp, _int]),
+    "pmv_profile_collect": (_int, [_vp, _int, _f64p, _i32p]),
     "pmv_pyr_levels": (_int, [_int] * 5),
     "pmv_pyramid_build": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _vp, _sz, _i32p]),
     "pmv_scharr": (_int, [_vp, _vp, _int, _int, _int, _vp]),
@@ -122,6 +124,18 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self.lib.pmv_launch_count(self.h))
+
+    PHASES = ("pyramid", "lk", "response", "select", "fast", "ba", "p6", "p7")
+
+    def profile(self, on: bool):
+        self._chk(self.lib.pmv_profile_enable(self.h, int(on)))
+
+    def profile_collect(self):
+        """{phase: (ms_sum, groups)} of CUDA-event time since the last collect."""
+        ms = (C.c_double * 8)()
+        cnt = (C.c_int32 * 8)()
+        self._chk(self.lib.pmv_profile_collect(self.h, 8, ms, cnt))
+        return {p: (ms[i], cnt[i]) for i, p in enumerate(self.PHASES) if cnt[i]}
 
     # ------------------------------------------------------------------ pyramid
     def pyramid_build(self, img: np.ndarray, win=(21, 21), max_level=3):

@@ -84,6 +84,19 @@ struct pmv_ctx {
     std::string err;
     uint64_t launches = 0;
 
+    // optional per-phase CUDA-event timing (bench roofline); see pmv_profile_*
+    bool prof_on = false;
+    struct ProfRec { int phase; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    cudaEvent_t prof_event()
+    {
+        cudaEvent_t e = nullptr;
+        if (!prof_pool.empty()) { e = prof_pool.back(); prof_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    }
+
     // workspaces
     DevBuf img[2];    // uploaded level-0 images (prev / next)
     DevBuf pyr[2];    // reduced levels (prev / next)
@@ -115,6 +128,19 @@ struct pmv_ctx {
         cudaError_t _e = cudaGetLastError();                                        \
         if (_e != cudaSuccess) return (ctx)->fail(PMV_ERR_CUDA, "launch " name, _e);\
     } while (0)
+
+// RAII phase timer: records an event pair on `s` around a group of launches when profiling is on.
+struct ProfScope {
+    pmv_ctx *c; cudaStream_t s; int phase; cudaEvent_t a = nullptr;
+    ProfScope(pmv_ctx *c_, int phase_, cudaStream_t s_) : c(c_), s(s_), phase(phase_)
+    {
+        if (c->prof_on) { a = c->prof_event(); cudaEventRecord(a, s); }
+    }
+    ~ProfScope()
+    {
+        if (a) { cudaEvent_t b = c->prof_event(); cudaEventRecord(b, s); c->prof_recs.push_back({phase, a, b}); }
+    }
+};
 
 // ------------------------------------------------------------------ device helpers ------
 __host__ __device__ __forceinline__ int reflect101(int p, int len)

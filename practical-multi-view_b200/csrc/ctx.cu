@@ -38,6 +38,8 @@ PMV_API void pmv_destroy(pmv_ctx *c)
     for (auto &b : c->scratch) b.release();
     for (auto &b : c->pin) b.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto &e : c->prof_pool) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -58,6 +60,32 @@ PMV_API int pmv_sync(pmv_ctx *c)
 }
 
 PMV_API const char *pmv_last_error(pmv_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+PMV_API int pmv_profile_enable(pmv_ctx *c, int on)
+{
+    if (!c) return PMV_ERR_INVALID;
+    c->prof_on = on != 0;
+    return PMV_OK;
+}
+
+PMV_API int pmv_profile_collect(pmv_ctx *c, int n_phases, double *ms_sum, int *count)
+{
+    if (!c || n_phases <= 0 || !ms_sum || !count) return PMV_ERR_INVALID;
+    for (int i = 0; i < n_phases; i++) { ms_sum[i] = 0; count[i] = 0; }
+    PMV_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (auto &r : c->prof_recs) {
+        float ms = 0.f;
+        cudaEventSynchronize(r.b);
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.phase < n_phases) {
+            ms_sum[r.phase] += ms;
+            count[r.phase]++;
+        }
+        c->prof_pool.push_back(r.a);
+        c->prof_pool.push_back(r.b);
+    }
+    c->prof_recs.clear();
+    return PMV_OK;
+}
 
 PMV_API uint64_t pmv_launch_count(pmv_ctx *c) { return c ? c->launches : 0; }
 

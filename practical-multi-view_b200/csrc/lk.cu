@@ -339,11 +339,15 @@ int lk_enqueue(pmv_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, int b
     if (rc) return rc;
     rc = pmv_internal_pyr_plan(ctx, 1, batch, rows, cols, d_next, pitch, img_stride, win_w, win_h, max_level, &sn);
     if (rc) return rc;
-    rc = pmv_internal_pyr_run(ctx, sp, batch, s);
-    if (rc) return rc;
-    rc = pmv_internal_pyr_run(ctx, sn, batch, s);
-    if (rc) return rc;
+    {
+        ProfScope ps(ctx, PMV_PHASE_PYRAMID, s);
+        rc = pmv_internal_pyr_run(ctx, sp, batch, s);
+        if (rc) return rc;
+        rc = pmv_internal_pyr_run(ctx, sn, batch, s);
+        if (rc) return rc;
+    }
     if (n == 0) return PMV_OK;
+    ProfScope pl(ctx, PMV_PHASE_LK, s);
     for (int l = 0; l <= sp.top; l++) { P.prev[l] = sp.lv[l]; P.next[l] = sn.lv[l]; }
     P.top = sp.top;
     P.prev_xy = d_prev_xy; P.next_xy = d_next_xy; P.status = d_status; P.err = d_err;
