@@ -180,7 +180,8 @@ def main():
 
     prev, nxt, pts = make_workload(rank, batch)
     ctx = pmv_b200.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-legacy) stream: events and kernels share it
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     # ---- resident inputs: pitched rows (128 B multiple) so image kernels use 16 B vector loads

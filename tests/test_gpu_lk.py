@@ -148,7 +148,9 @@ def test_lk_batched_dev_full_size_properties(ctx, synth):
     d_nx = torch.zeros(B, n, 2, device="cuda")
     d_st = torch.zeros(B, n, dtype=torch.uint8, device="cuda")
     d_err = torch.zeros(B, n, device="cuda")
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    ctx.set_stream(stream.cuda_stream)
     ctx.lk_track_batched_dev(d_img.data_ptr(), d_img.data_ptr(), B, 376 * 1241, 376, 1241, 1241, d_pts.data_ptr(), n,
                              d_nx.data_ptr(), d_st.data_ptr(), d_err.data_ptr(), (21, 21), 3)
     torch.cuda.synchronize()
