@@ -57,16 +57,20 @@ struct PinBuf {  // grow-only pinned host staging buffer
 };
 
 // ------------------------------------------------------------------ pyramid layout ------
-// Level l of a batch of B images lives at  base + b*img_stride + y*pitch + x  (u8).
-// Pitches of context-owned levels are multiples of 128 B so rows are 16 B aligned for
-// vector loads / TMA boxes.
+// Level l of a batch of B images lives at  ptr + b*img_stride + y*pitch + x  (u8), where ptr
+// addresses pixel (0,0) of the INTERIOR.  Every context-owned level (level 0 included: caller
+// images are imported) carries a BORDER_REFLECT_101 border of at least `border` pixels on all
+// four sides, so the LK kernel never reflects coordinates: reads at x in [-border, cols+border)
+// are plain loads.  ptr is 16 B aligned and pitch is a multiple of 128 B (vector loads / TMA).
 struct PyrLevel {
     const uint8_t *ptr;
     int rows, cols, pitch;
     size_t img_stride;
+    int border;  // reflect-101 border filled on all four sides (pixels)
+    int bxl;     // allocated bytes left of interior column 0 (>= border + 4, multiple of 16)
 };
 
-struct PyrSet {  // levels of one image batch; level 0 may alias caller memory
+struct PyrSet {  // all levels of one image batch
     PyrLevel lv[PMV_MAX_PYR_LEVELS];
     int top = 0;  // effective max level
 };
@@ -151,8 +155,11 @@ __host__ __device__ __forceinline__ int reflect101(int p, int len)
     return p;
 }
 
-// internal cross-file entry points (defined in pyramid.cu / lk.cu)
-int pmv_internal_pyr_plan(pmv_ctx *ctx, int which, int batch, int rows, int cols,
-                          const uint8_t *d_lvl0, int pitch0, size_t stride0,
+// internal cross-file entry points (defined in pyramid.cu)
+// Plan bordered storage for levels 0..L of `batch` images in ctx->pyr[which].
+int pmv_internal_pyr_plan(pmv_ctx *ctx, int which, int batch, int rows, int cols, int border,
                           int win_w, int win_h, int max_level, PyrSet *out);
-int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, cudaStream_t s);
+// Import level 0 from device memory (any pitch) / expect it already copied into the interior
+// (src == nullptr), fill its border, then build levels 1..top with their borders.
+int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, const uint8_t *d_src, int src_pitch,
+                         size_t src_stride, cudaStream_t s);

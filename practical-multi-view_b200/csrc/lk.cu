@@ -42,8 +42,8 @@ struct LKParams {
     int flags;
     float min_eig;
     int smem_per_warp;
-    int pp;  // pitch of the staged prev patch
-    int jp;  // pitch of the staged next window
+    int pp;  // byte pitch of the staged prev patch (multiple of 4)
+    int jp;  // byte pitch of the staged next window (multiple of 4)
 };
 
 __device__ __forceinline__ long long warp_sum_i64(int v)
@@ -64,14 +64,26 @@ __device__ __forceinline__ void bilinear_weights(float a, float b, int &iw00, in
     iw11 = 16384 - iw00 - iw01 - iw10;
 }
 
-__device__ __forceinline__ void stage_next(uint8_t *js, const PyrLevel &J, const uint8_t *img,
-                                           int jx0, int jy0, int jw, int jh, int jp, int lane)
+// Copy the rows [y0, y0+nrows) x bytes [x0, x0+nbytes) of a bordered level into shared memory with
+// aligned 4-byte loads.  The smem copy keeps the global misalignment: pixel (r, c) of the region is
+// at dst[r*spitch + mis + c] with mis = x0 & 3 (returned).  Level interiors are 16 B aligned and
+// pitched to 128 B, so the misalignment is the same for every row.
+__device__ __forceinline__ int stage_region(uint32_t *dst, int spitch_words, const uint8_t *img, int pitch,
+                                            int x0, int y0, int nbytes, int nrows, int lane)
 {
-    for (int r = 0; r < jh; r++) {
-        const uint8_t *row = img + (size_t)reflect101(jy0 + r, J.rows) * J.pitch;
-        for (int c = lane; c < jw; c += 32) js[r * jp + c] = __ldg(row + reflect101(jx0 + c, J.cols));
+    const int mis = x0 & 3;
+    const int nw = (mis + nbytes + 3) >> 2;
+    const uint32_t *g = reinterpret_cast<const uint32_t *>(img + (ptrdiff_t)y0 * pitch + (x0 - mis));
+    const int gp = pitch >> 2;
+    const int total = nw * nrows;
+    const int qd = 32 / nw, rm = 32 - qd * nw;
+    int r = lane / nw, cw = lane - r * nw;
+    for (int i = lane; i < total; i += 32) {
+        dst[r * spitch_words + cw] = __ldg(g + r * gp + cw);
+        cw += rm; r += qd;
+        if (cw >= nw) { cw -= nw; r++; }
     }
-    __syncwarp();
+    return mis;
 }
 
 template <int KPIX>
@@ -79,7 +91,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32)
 lk_track_kernel(const LKParams P)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ uint16_t s_tab[32 * KPIX];  // pixel p -> (y << 8) | x
+    __shared__ uint16_t s_tab[32 * KPIX];  // pixel p -> (y << 8) | x ; padding -> (0,0), masked by `valid`
 
     const int w = P.win_w, h = P.win_h, npx = w * h;
     for (int p = threadIdx.x; p < 32 * KPIX; p += LK_WARPS * 32) {
@@ -94,10 +106,9 @@ lk_track_kernel(const LKParams P)
     if (f >= P.n) return;  // warp-uniform; only __syncwarp below
 
     uint8_t *ws = smem + (size_t)warp * P.smem_per_warp;
-    const int kmax = (npx + 31) >> 5;
     const int pp = P.pp, jp = P.jp, dp = w + 1;
-    uint8_t *ps = ws;                                            // prev patch (h+3) x pp
-    int *ds = reinterpret_cast<int *>(ws + ((h + 3) * pp + 15) / 16 * 16);  // derivs (h+1) x (w+1), short2 packed
+    uint8_t *ps = ws;                                            // prev patch (h+3) rows x pp bytes
+    int *ds = reinterpret_cast<int *>(ws + (h + 3) * pp);        // derivs (h+1) x (w+1), short2 packed
     uint8_t *js = ws;                                            // next window, aliases ps/ds
     const int jw = w + 1 + 2 * LK_M, jh = h + 1 + 2 * LK_M;
 
@@ -112,11 +123,12 @@ lk_track_kernel(const LKParams P)
     const float FLT_SCALE = 1.f / (1 << 20);
 
     int Iw[KPIX], dxw[KPIX], dyw[KPIX], joff[KPIX];
-    int pyx[KPIX];
+    unsigned valid = 0;
 #pragma unroll
     for (int k = 0; k < KPIX; k++) {
-        pyx[k] = s_tab[lane + 32 * k];
-        joff[k] = (pyx[k] >> 8) * jp + (pyx[k] & 255);
+        const int t = s_tab[lane + 32 * k];
+        if (lane + 32 * k < npx) valid |= 1u << k;
+        joff[k] = (t >> 8) * jp + (t & 255);
     }
 
     for (int level = P.top; level >= 0; level--) {
@@ -144,30 +156,31 @@ lk_track_kernel(const LKParams P)
         int iw00, iw01, iw10, iw11;
         bilinear_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), iw00, iw01, iw10, iw11);
 
-        // ---- 1. stage prev patch: image (ipy-1+r, ipx-1+c), reflect-101 -----------------
+        // ---- 1. stage prev patch: image rows ipy-1.., cols ipx-1.. ((h+3) x (w+3)) -----------
         __syncwarp();
-        for (int r = 0; r < h + 3; r++) {
-            const uint8_t *row = Iimg + (size_t)reflect101(ipy - 1 + r, I.rows) * I.pitch;
-            for (int c = lane; c < w + 3; c += 32) ps[r * pp + c] = __ldg(row + reflect101(ipx - 1 + c, I.cols));
-        }
+        const int pmis = stage_region(reinterpret_cast<uint32_t *>(ps), pp >> 2, Iimg, I.pitch,
+                                      ipx - 1, ipy - 1, w + 3, h + 3, lane);
         __syncwarp();
         // ---- 2. Scharr derivative on the bilinear support (zero outside the image) ------
-        for (int r = 0; r < h + 1; r++) {
-            const int yy = ipy + r;
-            const bool yin = (yy >= 0) && (yy < I.rows);
-            for (int c = lane; c < w + 1; c += 32) {
-                const int xx = ipx + c;
+        {
+            const int total = (h + 1) * dp;
+            const int qd = 32 / dp, rm = 32 - qd * dp;
+            int r = lane / dp, c = lane - r * dp;
+            for (int i = lane; i < total; i += 32) {
+                const int yy = ipy + r, xx = ipx + c;
                 int packed = 0;
-                if (yin && xx >= 0 && xx < I.cols) {
-                    const uint8_t *q = ps + r * pp + c;  // top-left of the 3x3 support
+                if (yy >= 0 && yy < I.rows && xx >= 0 && xx < I.cols) {
+                    const uint8_t *q = ps + r * pp + pmis + c;  // top-left of the 3x3 support
                     int a0 = q[0], a1 = q[1], a2 = q[2];
                     int b0 = q[pp], b2 = q[pp + 2];
                     int c0 = q[2 * pp], c1 = q[2 * pp + 1], c2 = q[2 * pp + 2];
                     int gx = (3 * (a2 + c2) + 10 * b2) - (3 * (a0 + c0) + 10 * b0);
                     int gy = 3 * ((c0 - a0) + (c2 - a2)) + 10 * (c1 - a1);
-                    packed = (gx & 0xffff) | (gy << 16);
+                    packed = (gx & 0xffff) | (int)((unsigned)gy << 16);
                 }
-                ds[r * dp + c] = packed;
+                ds[i] = packed;
+                c += rm; r += qd;
+                if (c >= dp) { c -= dp; r++; }
             }
         }
         __syncwarp();
@@ -175,21 +188,19 @@ lk_track_kernel(const LKParams P)
         int sA11 = 0, sA12 = 0, sA22 = 0;
 #pragma unroll
         for (int k = 0; k < KPIX; k++) {
-            if (k < kmax) {
-                const int y = pyx[k] >> 8, x = pyx[k] & 255;
-                const bool valid = (lane + 32 * k) < npx;
-                const uint8_t *q = ps + (y + 1) * pp + (x + 1);
-                int ival = (q[0] * iw00 + q[1] * iw01 + q[pp] * iw10 + q[pp + 1] * iw11 + (1 << 8)) >> 9;
-                const int *d = ds + y * dp + x;
-                int d00 = d[0], d01 = d[1], d10 = d[dp], d11 = d[dp + 1];
-                int ix = ((int)(short)d00 * iw00 + (int)(short)d01 * iw01 + (int)(short)d10 * iw10 +
-                          (int)(short)d11 * iw11 + (1 << 13)) >> 14;
-                int iy = ((d00 >> 16) * iw00 + (d01 >> 16) * iw01 + (d10 >> 16) * iw10 +
-                          (d11 >> 16) * iw11 + (1 << 13)) >> 14;
-                if (!valid) { ival = 0; ix = 0; iy = 0; }
-                Iw[k] = ival; dxw[k] = ix; dyw[k] = iy;
-                sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
-            }
+            const int t = s_tab[lane + 32 * k];
+            const int y = t >> 8, x = t & 255;
+            const uint8_t *q = ps + (y + 1) * pp + pmis + (x + 1);
+            int ival = (q[0] * iw00 + q[1] * iw01 + q[pp] * iw10 + q[pp + 1] * iw11 + (1 << 8)) >> 9;
+            const int *d = ds + y * dp + x;
+            int d00 = d[0], d01 = d[1], d10 = d[dp], d11 = d[dp + 1];
+            int ix = ((int)(short)d00 * iw00 + (int)(short)d01 * iw01 + (int)(short)d10 * iw10 +
+                      (int)(short)d11 * iw11 + (1 << 13)) >> 14;
+            int iy = ((d00 >> 16) * iw00 + (d01 >> 16) * iw01 + (d10 >> 16) * iw10 +
+                      (d11 >> 16) * iw11 + (1 << 13)) >> 14;
+            if (!((valid >> k) & 1)) { ival = 0; ix = 0; iy = 0; }
+            Iw[k] = ival; dxw[k] = ix; dyw[k] = iy;
+            sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
         }
         const float A11 = __fmul_rn((float)warp_sum_i64(sA11), FLT_SCALE);
         const float A12 = __fmul_rn((float)warp_sum_i64(sA12), FLT_SCALE);
@@ -210,7 +221,7 @@ lk_track_kernel(const LKParams P)
 
         // ---- 4. Newton iterations out of the staged next-image window --------------------
         __syncwarp();  // template reads of ps/ds are done before js overwrites them
-        int jx0 = 0, jy0 = 0;
+        int jx0 = 0, jy0 = 0, jmis = 0;
         bool staged = false;
         float pdx = 0.f, pdy = 0.f;
         for (int j = 0; j < P.max_count; j++) {
@@ -223,22 +234,21 @@ lk_track_kernel(const LKParams P)
             if (!staged || ox < 0 || ox > 2 * LK_M || oy < 0 || oy > 2 * LK_M) {
                 __syncwarp();
                 jx0 = inx - LK_M; jy0 = iny - LK_M;
-                stage_next(js, J, Jimg, jx0, jy0, jw, jh, jp, lane);
+                jmis = stage_region(reinterpret_cast<uint32_t *>(js), jp >> 2, Jimg, J.pitch, jx0, jy0, jw, jh, lane);
+                __syncwarp();
                 staged = true;
                 ox = LK_M; oy = LK_M;
             }
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), iw00, iw01, iw10, iw11);
-            const uint8_t *jb = js + oy * jp + ox;
+            const uint8_t *jb = js + oy * jp + ox + jmis;
             int ib1 = 0, ib2 = 0;
 #pragma unroll
             for (int k = 0; k < KPIX; k++) {
-                if (k < kmax) {
-                    const uint8_t *q = jb + joff[k];
-                    int v = q[0] * iw00 + q[1] * iw01 + q[jp] * iw10 + q[jp + 1] * iw11;
-                    int diff = ((v + (1 << 8)) >> 9) - Iw[k];
-                    ib1 += diff * dxw[k];
-                    ib2 += diff * dyw[k];
-                }
+                const uint8_t *q = jb + joff[k];
+                int v = q[0] * iw00 + q[1] * iw01 + q[jp] * iw10 + q[jp + 1] * iw11;
+                int diff = ((v + (1 << 8)) >> 9) - Iw[k];
+                ib1 += diff * dxw[k];
+                ib2 += diff * dyw[k];
             }
             const float b1 = __fmul_rn((float)warp_sum_i64(ib1), FLT_SCALE);
             const float b2 = __fmul_rn((float)warp_sum_i64(ib2), FLT_SCALE);
@@ -267,24 +277,23 @@ lk_track_kernel(const LKParams P)
             if (!staged || ox < 0 || ox > 2 * LK_M || oy < 0 || oy > 2 * LK_M) {
                 __syncwarp();
                 jx0 = inx - LK_M; jy0 = iny - LK_M;
-                stage_next(js, J, Jimg, jx0, jy0, jw, jh, jp, lane);
+                jmis = stage_region(reinterpret_cast<uint32_t *>(js), jp >> 2, Jimg, J.pitch, jx0, jy0, jw, jh, lane);
+                __syncwarp();
                 staged = true;
                 ox = LK_M; oy = LK_M;
             }
             bilinear_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), iw00, iw01, iw10, iw11);
-            const uint8_t *jb = js + oy * jp + ox;
+            const uint8_t *jb = js + oy * jp + ox + jmis;
             int e = 0;
 #pragma unroll
             for (int k = 0; k < KPIX; k++) {
-                if (k < kmax) {
-                    const uint8_t *q = jb + joff[k];
-                    int v = q[0] * iw00 + q[1] * iw01 + q[jp] * iw10 + q[jp + 1] * iw11;
-                    int diff = ((v + (1 << 8)) >> 9) - Iw[k];
-                    if ((lane + 32 * k) < npx) e += abs(diff);
-                }
+                const uint8_t *q = jb + joff[k];
+                int v = q[0] * iw00 + q[1] * iw01 + q[jp] * iw10 + q[jp + 1] * iw11;
+                int diff = ((v + (1 << 8)) >> 9) - Iw[k];
+                if ((valid >> k) & 1) e += abs(diff);
             }
             e = __reduce_add_sync(0xffffffffu, e);
-            errv = __fdiv_rn(__fmul_rn((float)e, 1.f), (float)(32 * w * h));
+            errv = __fdiv_rn((float)e, (float)(32 * w * h));
         }
     }
 
@@ -324,30 +333,34 @@ int check_lk_args(pmv_ctx *ctx, int rows, int cols, int step, int n, int win_w, 
     return PMV_OK;
 }
 
-// Enqueue pyramids + tracking for `batch` pairs resident on the device.
-int lk_enqueue(pmv_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, int batch, size_t img_stride,
-               int rows, int cols, int pitch, const float *d_prev_xy, int n, int win_w, int win_h,
-               int max_level, int max_count, double eps, int flags, double min_eig_thr,
-               float *d_next_xy, uint8_t *d_status, float *d_err, cudaStream_t s,
-               int pyr_slot_base = 0, size_t pyr_reuse_batch = 0)
+// Enqueue import + pyramids + tracking for `batch` pairs.  d_prev/d_next: device images (any pitch) or
+// nullptr when the caller already copied level 0 into the planned interior (host upload path).
+int lk_plan(pmv_ctx *ctx, int batch, int rows, int cols, int win_w, int win_h, int max_level,
+            PyrSet *sp, PyrSet *sn)
 {
-    (void)pyr_slot_base; (void)pyr_reuse_batch;
-    LKParams P;
-    memset(&P, 0, sizeof P);
-    PyrSet sp, sn;
-    int rc = pmv_internal_pyr_plan(ctx, 0, batch, rows, cols, d_prev, pitch, img_stride, win_w, win_h, max_level, &sp);
+    const int border = (win_w > win_h ? win_w : win_h) + LK_M + 2;
+    int rc = pmv_internal_pyr_plan(ctx, 0, batch, rows, cols, border, win_w, win_h, max_level, sp);
     if (rc) return rc;
-    rc = pmv_internal_pyr_plan(ctx, 1, batch, rows, cols, d_next, pitch, img_stride, win_w, win_h, max_level, &sn);
-    if (rc) return rc;
+    return pmv_internal_pyr_plan(ctx, 1, batch, rows, cols, border, win_w, win_h, max_level, sn);
+}
+
+int lk_enqueue(pmv_ctx *ctx, const PyrSet &sp, const PyrSet &sn, const uint8_t *d_prev, const uint8_t *d_next,
+               int batch, size_t img_stride, int pitch, const float *d_prev_xy, int n, int win_w, int win_h,
+               int max_count, double eps, int flags, double min_eig_thr,
+               float *d_next_xy, uint8_t *d_status, float *d_err, cudaStream_t s)
+{
+    int rc;
     {
         ProfScope ps(ctx, PMV_PHASE_PYRAMID, s);
-        rc = pmv_internal_pyr_run(ctx, sp, batch, s);
+        rc = pmv_internal_pyr_run(ctx, sp, batch, d_prev, pitch, img_stride, s);
         if (rc) return rc;
-        rc = pmv_internal_pyr_run(ctx, sn, batch, s);
+        rc = pmv_internal_pyr_run(ctx, sn, batch, d_next, pitch, img_stride, s);
         if (rc) return rc;
     }
     if (n == 0) return PMV_OK;
     ProfScope pl(ctx, PMV_PHASE_LK, s);
+    LKParams P;
+    memset(&P, 0, sizeof P);
     for (int l = 0; l <= sp.top; l++) { P.prev[l] = sp.lv[l]; P.next[l] = sn.lv[l]; }
     P.top = sp.top;
     P.prev_xy = d_prev_xy; P.next_xy = d_next_xy; P.status = d_status; P.err = d_err;
@@ -357,15 +370,20 @@ int lk_enqueue(pmv_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, int b
     if (eps < 0) eps = 0;
     if (eps > 10) eps = 10;
     P.max_count = max_count; P.eps2 = eps * eps; P.flags = flags; P.min_eig = (float)min_eig_thr;
-    P.pp = align_up(win_w + 3, 4);
-    P.jp = align_up(win_w + 1 + 2 * LK_M, 4);
-    int tmpl = align_up((win_h + 3) * P.pp, 16) + (win_h + 1) * (win_w + 1) * 4;
+    P.pp = align_up(3 + win_w + 3 + 3, 4);
+    P.jp = align_up(3 + win_w + 1 + 2 * LK_M + 3, 4);
+    int tmpl = (win_h + 3) * P.pp + (win_h + 1) * (win_w + 1) * 4;
     int jwin = (win_h + 1 + 2 * LK_M) * P.jp;
     P.smem_per_warp = align_up(tmpl > jwin ? tmpl : jwin, 16);
-    int npx = win_w * win_h;
-    if (npx <= 32 * 8) return launch_lk<8>(ctx, P, batch, s);
-    if (npx <= 32 * 14) return launch_lk<14>(ctx, P, batch, s);
-    if (npx <= 32 * 20) return launch_lk<20>(ctx, P, batch, s);
+    const int kmax = (win_w * win_h + 31) / 32;
+    if (kmax <= 4) return launch_lk<4>(ctx, P, batch, s);
+    if (kmax <= 8) return launch_lk<8>(ctx, P, batch, s);
+    if (kmax <= 11) return launch_lk<11>(ctx, P, batch, s);
+    if (kmax <= 14) return launch_lk<14>(ctx, P, batch, s);
+    if (kmax <= 17) return launch_lk<17>(ctx, P, batch, s);
+    if (kmax <= 20) return launch_lk<20>(ctx, P, batch, s);
+    if (kmax <= 24) return launch_lk<24>(ctx, P, batch, s);
+    if (kmax <= 28) return launch_lk<28>(ctx, P, batch, s);
     return launch_lk<32>(ctx, P, batch, s);
 }
 
@@ -386,8 +404,11 @@ PMV_API int pmv_lk_track_batched_dev(pmv_ctx *ctx, const uint8_t *d_prev, const 
     if (rc) return rc;
     if (img_stride < (size_t)rows * step) return ctx->fail(PMV_ERR_INVALID, "lk: img_stride < rows*step");
     cudaSetDevice(ctx->device);
-    return lk_enqueue(ctx, d_prev, d_next, batch, img_stride, rows, cols, step, d_prev_xy, n, win_w, win_h,
-                      max_level, max_count, eps, flags, min_eig_thr, d_next_xy, d_status, d_err, ctx->stream);
+    PyrSet sp, sn;
+    rc = lk_plan(ctx, batch, rows, cols, win_w, win_h, max_level, &sp, &sn);
+    if (rc) return rc;
+    return lk_enqueue(ctx, sp, sn, d_prev, d_next, batch, img_stride, step, d_prev_xy, n, win_w, win_h,
+                      max_count, eps, flags, min_eig_thr, d_next_xy, d_status, d_err, ctx->stream);
 }
 
 PMV_API int pmv_lk_track_batched(pmv_ctx *ctx, const uint8_t *prev, const uint8_t *next, int batch,
@@ -404,16 +425,14 @@ PMV_API int pmv_lk_track_batched(pmv_ctx *ctx, const uint8_t *prev, const uint8_
     if (img_stride < (size_t)rows * step) return ctx->fail(PMV_ERR_INVALID, "lk: img_stride < rows*step");
     cudaSetDevice(ctx->device);
 
-    const int pitch = align_up(cols, 128);
-    const size_t dstride = (size_t)pitch * rows;
-    cudaError_t e = ctx->img[0].reserve(dstride * batch);
-    if (e == cudaSuccess) e = ctx->img[1].reserve(dstride * batch);
-    if (e == cudaSuccess) e = ctx->pts[0].reserve((size_t)batch * n * 8 + 8);
+    PyrSet sp, sn;
+    rc = lk_plan(ctx, batch, rows, cols, win_w, win_h, max_level, &sp, &sn);
+    if (rc) return rc;
+    cudaError_t e = ctx->pts[0].reserve((size_t)batch * n * 8 + 8);
     if (e == cudaSuccess) e = ctx->pts[1].reserve((size_t)batch * n * 8 + 8);
     if (e == cudaSuccess) e = ctx->pts[2].reserve((size_t)batch * n + 8);
     if (e == cudaSuccess) e = ctx->pts[3].reserve((size_t)batch * n * 4 + 8);
     if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "lk batch buffers", e);
-    uint8_t *dP = ctx->img[0].as<uint8_t>(), *dN = ctx->img[1].as<uint8_t>();
     float *dpx = ctx->pts[0].as<float>(), *dnx = ctx->pts[1].as<float>();
     uint8_t *dst = ctx->pts[2].as<uint8_t>();
     float *der = ctx->pts[3].as<float>();
@@ -424,19 +443,15 @@ PMV_API int pmv_lk_track_batched(pmv_ctx *ctx, const uint8_t *prev, const uint8_
         if (flags & PMV_LK_USE_INITIAL_FLOW)
             PMV_CUDA_TRY(ctx, cudaMemcpyAsync(dnx, next_xy, (size_t)batch * n * 8, cudaMemcpyHostToDevice, s));
     }
-    // Upload all images with two strided copies (rows of all images form one 2-D copy when the
-    // batch is contiguous), then one pyramid pass + one tracking launch for the whole batch.
-    const bool contiguous = (img_stride == (size_t)rows * step);
-    if (contiguous) {
-        PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(dP, pitch, prev, step, cols, (size_t)rows * batch, cudaMemcpyHostToDevice, s));
-        PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(dN, pitch, next, step, cols, (size_t)rows * batch, cudaMemcpyHostToDevice, s));
-    } else {
-        for (int b = 0; b < batch; b++) {
-            PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(dP + b * dstride, pitch, prev + b * img_stride, step, cols, rows, cudaMemcpyHostToDevice, s));
-            PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(dN + b * dstride, pitch, next + b * img_stride, step, cols, rows, cudaMemcpyHostToDevice, s));
-        }
+    // Upload straight into the interiors of the bordered level-0 buffers (one strided copy per image).
+    const PyrLevel &p0 = sp.lv[0], &n0 = sn.lv[0];
+    for (int b = 0; b < batch; b++) {
+        PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(const_cast<uint8_t *>(p0.ptr) + b * p0.img_stride, p0.pitch,
+                                            prev + b * img_stride, step, cols, rows, cudaMemcpyHostToDevice, s));
+        PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(const_cast<uint8_t *>(n0.ptr) + b * n0.img_stride, n0.pitch,
+                                            next + b * img_stride, step, cols, rows, cudaMemcpyHostToDevice, s));
     }
-    rc = lk_enqueue(ctx, dP, dN, batch, dstride, rows, cols, pitch, dpx, n, win_w, win_h, max_level,
+    rc = lk_enqueue(ctx, sp, sn, nullptr, nullptr, batch, 0, 0, dpx, n, win_w, win_h,
                     max_count, eps, flags, min_eig_thr, dnx, dst, der, s);
     if (rc) return rc;
     if (n > 0) {

@@ -5,10 +5,16 @@
 // Integer arithmetic, bit-exact: separable [1 4 6 4 1] taps centred on even source pixels,
 // BORDER_REFLECT_101, (sum + 128) >> 8.
 //
-// HBM-bound streaming kernel: one CTA produces a 128x16 output tile from a 259x35 input tile
-// staged in shared memory with 16-byte vector loads (rows of context-owned levels are pitched
-// to 128 B), horizontal pass into a uint16 tile, vertical pass + packed 4-byte stores.
-// Algorithmic bytes per image: W*H read + sum_l W_l*H_l written.
+// Storage: like OpenCV's optical-flow pyramid every level (level 0 included) is kept with a
+// reflect-101 border, in rows pitched to 128 B.  The border makes both the pyrDown taps and all
+// LK patch reads plain, aligned loads (no coordinate reflection in the hot loops).
+//
+// Kernels (all HBM-bound streaming kernels, DESIGN.md has the byte counts):
+//   import_kernel      caller image (any pitch) -> interior of the bordered level 0
+//   border_fill_kernel reflect-101 border of one level, all images of the batch
+//   pyr_down_kernel    one CTA = 128x16 output tile from a 288x35 staged input tile
+//                      (16 B vector loads), horizontal pass -> uint16 tile, vertical pass,
+//                      packed 4-byte stores
 #include "common.cuh"
 
 namespace {
@@ -17,12 +23,14 @@ constexpr int PT_W = 128;               // output tile width
 constexpr int PT_H = 16;                // output tile height
 constexpr int PIN_H = 2 * PT_H + 3;     // 35 input rows
 constexpr int PIN_W = 2 * PT_W + 32;    // 288 staged input bytes per row (16 B aligned superset)
-constexpr int PIN_X0 = 16;              // staged column c <-> global column 2*tx0 - 16 + c
+constexpr int PIN_X0 = 16;              // staged column c <-> interior column 2*tx0 - 16 + c
 
+// src: bordered level (interior pointer, border >= 16 left, >= 2 elsewhere; rows above/below the
+// allocation are clamped).  lo_row/hi_row: first/last addressable row relative to the interior.
 __global__ void __launch_bounds__(256)
-pyr_down_kernel(const uint8_t *__restrict__ src, int srows, int scols, int spitch, size_t sstride,
-                uint8_t *__restrict__ dst, int drows, int dcols, int dpitch, size_t dstride,
-                int vec_ok)
+pyr_down_kernel(const uint8_t *__restrict__ src, int spitch, size_t sstride, int lo_row, int hi_row,
+                int row_bytes_right,  // bytes addressable to the right of interior column 0
+                uint8_t *__restrict__ dst, int drows, int dcols, int dpitch, size_t dstride)
 {
     __shared__ __align__(16) uint8_t s_in[PIN_H][PIN_W];
     __shared__ __align__(16) uint16_t s_h[PIN_H][PT_W];
@@ -31,46 +39,22 @@ pyr_down_kernel(const uint8_t *__restrict__ src, int srows, int scols, int spitc
     src += (size_t)b * sstride;
     dst += (size_t)b * dstride;
     const int tx0 = blockIdx.x * PT_W, ty0 = blockIdx.y * PT_H;
-    const int gx0 = 2 * tx0 - PIN_X0;  // global column of staged column 0
-    const int gy0 = 2 * ty0 - 2;       // global row of staged row 0
+    const int gx0 = 2 * tx0 - PIN_X0;  // interior column of staged column 0 (multiple of 16)
+    const int gy0 = 2 * ty0 - 2;       // interior row of staged row 0
     const int tid = threadIdx.x;
 
-    // ---- stage input tile ------------------------------------------------------------
-    if (vec_ok) {
-        // 18 x uint4 per row; chunks fully inside [0, spitch) come straight from memory
-        for (int i = tid; i < PIN_H * (PIN_W / 16); i += 256) {
-            int r = i / (PIN_W / 16), ch = i % (PIN_W / 16);
-            int gy = reflect101(gy0 + r, srows);
-            int gx = gx0 + ch * 16;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (gx >= 0 && gx + 16 <= spitch)
-                v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)gy * spitch + gx));
-            *reinterpret_cast<uint4 *>(&s_in[r][ch * 16]) = v;
-        }
-        __syncthreads();
-        // fix-up: columns outside [0, scols) that the taps can touch (reflect-101)
-        const bool edge = (gx0 + PIN_X0 - 2 < 0) || (gx0 + PIN_X0 + 2 * PT_W + 2 > scols);
-        if (edge) {
-            for (int i = tid; i < PIN_H * (2 * PT_W + 3); i += 256) {
-                int r = i / (2 * PT_W + 3), c = PIN_X0 - 2 + i % (2 * PT_W + 3);
-                int gx = gx0 + c;
-                if (gx < 0 || gx >= scols) {
-                    int gy = reflect101(gy0 + r, srows);
-                    s_in[r][c] = src[(size_t)gy * spitch + reflect101(gx, scols)];
-                }
-            }
-        }
-    } else {
-        for (int i = tid; i < PIN_H * (2 * PT_W + 3); i += 256) {
-            int r = i / (2 * PT_W + 3), c = PIN_X0 - 2 + i % (2 * PT_W + 3);
-            int gy = reflect101(gy0 + r, srows);
-            int gx = reflect101(gx0 + c, scols);
-            s_in[r][c] = src[(size_t)gy * spitch + gx];
-        }
+    for (int i = tid; i < PIN_H * (PIN_W / 16); i += 256) {
+        int r = i / (PIN_W / 16), ch = i % (PIN_W / 16);
+        int gy = min(max(gy0 + r, lo_row), hi_row);
+        int gx = gx0 + ch * 16;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (gx + 16 <= row_bytes_right)
+            v = __ldg(reinterpret_cast<const uint4 *>(src + (ptrdiff_t)gy * spitch + gx));
+        *reinterpret_cast<uint4 *>(&s_in[r][ch * 16]) = v;
     }
     __syncthreads();
 
-    // ---- horizontal pass: s_h[r][x] = taps over s_in[r][2x-2 .. 2x+2] -------------------
+    // horizontal pass: s_h[r][x] = taps over s_in[r][2x-2 .. 2x+2]
     for (int i = tid; i < PIN_H * PT_W; i += 256) {
         int r = i / PT_W, x = i % PT_W;
         const uint8_t *p = &s_in[r][PIN_X0 + 2 * x - 2];
@@ -78,7 +62,7 @@ pyr_down_kernel(const uint8_t *__restrict__ src, int srows, int scols, int spitc
     }
     __syncthreads();
 
-    // ---- vertical pass + store: a warp owns a row, a lane 4 consecutive outputs ---------
+    // vertical pass + store: a warp owns a row, a lane 4 consecutive outputs
     const int lane = tid & 31, warp = tid >> 5;
     for (int yy = warp; yy < PT_H; yy += 8) {
         int oy = ty0 + yy;
@@ -92,16 +76,55 @@ pyr_down_kernel(const uint8_t *__restrict__ src, int srows, int scols, int spitc
                     6 * s_h[2 * yy + 2][x];
             packed |= (uint32_t)((v + 128) >> 8) << (8 * k);
         }
-        uint8_t *o = dst + (size_t)oy * dpitch + ox;
-        if (ox + 4 <= dpitch && (dpitch & 3) == 0) {
-            // pitch padding absorbs the partial word at the right edge
-            if (ox < dcols) *reinterpret_cast<uint32_t *>(o) = packed;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (ox + k < dcols) o[k] = (uint8_t)(packed >> (8 * k));
-        }
+        // the right border of the destination absorbs the partial word (filled afterwards)
+        if (ox < dcols) *reinterpret_cast<uint32_t *>(dst + (size_t)oy * dpitch + ox) = packed;
     }
+}
+
+// Reflect-101 border of one level: bands top / bottom (full bordered width) and left / right.
+__global__ void __launch_bounds__(256)
+border_fill_kernel(uint8_t *__restrict__ img, int rows, int cols, int pitch, size_t stride,
+                   int by, int bxl, int bxr)
+{
+    uint8_t *base = img + (size_t)blockIdx.y * stride;
+    const int fullw = bxl + cols + bxr;
+    const int n_tb = 2 * by * fullw;          // top + bottom bands
+    const int n_lr = rows * (bxl + bxr);      // left + right bands
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n_tb + n_lr; i += gridDim.x * 256) {
+        int y, x;
+        if (i < n_tb) {
+            int r = i / fullw;
+            x = i - r * fullw - bxl;
+            y = r < by ? r - by : rows + (r - by);
+        } else {
+            int j = i - n_tb;
+            y = j / (bxl + bxr);
+            int c = j - y * (bxl + bxr);
+            x = c < bxl ? c - bxl : cols + (c - bxl);
+        }
+        base[(ptrdiff_t)y * pitch + x] = base[(ptrdiff_t)reflect101(y, rows) * pitch + reflect101(x, cols)];
+    }
+}
+
+// Caller image (device memory, any pitch / alignment) -> interior of bordered level 0.
+__global__ void __launch_bounds__(256)
+import_kernel(const uint8_t *__restrict__ src, int spitch, size_t sstride, int rows, int cols,
+              uint8_t *__restrict__ dst, int dpitch, size_t dstride, int src_aligned4)
+{
+    const int x4 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (y >= rows || x4 >= cols) return;
+    const uint8_t *s = src + (size_t)blockIdx.z * sstride + (size_t)y * spitch + x4;
+    uint32_t v;
+    if (src_aligned4 && x4 + 4 <= spitch) {
+        v = __ldg(reinterpret_cast<const uint32_t *>(s));
+    } else {
+        v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (x4 + k < cols) v |= (uint32_t)__ldg(s + k) << (8 * k);
+    }
+    *reinterpret_cast<uint32_t *>(dst + (size_t)blockIdx.z * dstride + (size_t)y * dpitch + x4) = v;
 }
 
 // K2: int16 x2 Scharr derivative, reflect-101 (stage-by-stage parity entry point; the LK
@@ -124,45 +147,65 @@ scharr_kernel(const uint8_t *__restrict__ src, int rows, int cols, int pitch, sh
 }  // namespace
 
 // ------------------------------------------------------------------ internal planning ---
-// Lay out reduced levels 1..L of a batch in ctx->pyr[which]; level 0 aliases d_lvl0.
-int pmv_internal_pyr_plan(pmv_ctx *ctx, int which, int batch, int rows, int cols,
-                          const uint8_t *d_lvl0, int pitch0, size_t stride0,
+int pmv_internal_pyr_plan(pmv_ctx *ctx, int which, int batch, int rows, int cols, int border,
                           int win_w, int win_h, int max_level, PyrSet *out)
 {
     int L = pmv_pyr_levels(rows, cols, win_w, win_h, max_level);
     if (L < 0 || L >= PMV_MAX_PYR_LEVELS) return ctx->fail(PMV_ERR_UNSUPPORTED, "max_level too large");
+    if (border < 2) border = 2;
     out->top = L;
-    out->lv[0] = PyrLevel{d_lvl0, rows, cols, pitch0, stride0};
+    const int bxl = align_up(border + 4, 16);  // left border: keeps the interior 16 B aligned
     size_t total = 0;
-    size_t off[PMV_MAX_PYR_LEVELS] = {0};
+    size_t off[PMV_MAX_PYR_LEVELS];
     int r = rows, c = cols;
-    for (int l = 1; l <= L; l++) {
-        r = (r + 1) / 2;
-        c = (c + 1) / 2;
-        int pitch = align_up(c, 128);
-        size_t stride = (size_t)pitch * r;
-        off[l] = total;
+    for (int l = 0; l <= L; l++) {
+        if (l > 0) { r = (r + 1) / 2; c = (c + 1) / 2; }
+        int pitch = align_up(bxl + c + border + 3, 128);
+        size_t stride = (size_t)pitch * (r + 2 * border);
+        off[l] = total + (size_t)border * pitch + bxl;  // interior origin of image 0
         total += stride * batch;
-        out->lv[l] = PyrLevel{nullptr, r, c, pitch, stride};
+        out->lv[l] = PyrLevel{nullptr, r, c, pitch, stride, border, bxl};
     }
-    if (total) {
-        cudaError_t e = ctx->pyr[which].reserve(total);
-        if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "pyramid workspace", e);
-    }
-    for (int l = 1; l <= L; l++) out->lv[l].ptr = ctx->pyr[which].as<uint8_t>() + off[l];
+    cudaError_t e = ctx->pyr[which].reserve(total + 256);
+    if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "pyramid workspace", e);
+    for (int l = 0; l <= L; l++) out->lv[l].ptr = ctx->pyr[which].as<uint8_t>() + off[l];
     return PMV_OK;
 }
 
-int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, cudaStream_t s)
+static int fill_border(pmv_ctx *ctx, const PyrLevel &d, int batch, cudaStream_t s)
 {
+    const int bxl = d.bxl;
+    const int n = 2 * d.border * (bxl + d.cols + d.border) + d.rows * (bxl + d.border);
+    dim3 grid(min((n + 255) / 256, 64), batch);
+    border_fill_kernel<<<grid, 256, 0, s>>>(const_cast<uint8_t *>(d.ptr), d.rows, d.cols, d.pitch, d.img_stride,
+                                            d.border, bxl, d.border);
+    PMV_LAUNCH_CHECK(ctx, "border_fill_kernel");
+    return PMV_OK;
+}
+
+int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, const uint8_t *d_src, int src_pitch,
+                         size_t src_stride, cudaStream_t s)
+{
+    const PyrLevel &l0 = set.lv[0];
+    if (d_src) {
+        int al = (((uintptr_t)d_src) % 4 == 0) && (src_pitch % 4 == 0) && (src_stride % 4 == 0);
+        dim3 grid((l0.cols + 127) / 128, (l0.rows + 7) / 8, batch);
+        import_kernel<<<grid, 256, 0, s>>>(d_src, src_pitch, src_stride, l0.rows, l0.cols,
+                                           const_cast<uint8_t *>(l0.ptr), l0.pitch, l0.img_stride, al);
+        PMV_LAUNCH_CHECK(ctx, "import_kernel");
+    }
+    int rc = fill_border(ctx, l0, batch, s);
+    if (rc) return rc;
     for (int l = 1; l <= set.top; l++) {
         const PyrLevel &a = set.lv[l - 1], &d = set.lv[l];
-        int vec_ok = (a.pitch % 16 == 0) && (((uintptr_t)a.ptr) % 16 == 0) && (a.img_stride % 16 == 0);
+        const int bxl = a.bxl;
         dim3 grid((d.cols + PT_W - 1) / PT_W, (d.rows + PT_H - 1) / PT_H, batch);
-        pyr_down_kernel<<<grid, 256, 0, s>>>(a.ptr, a.rows, a.cols, a.pitch, a.img_stride,
-                                             const_cast<uint8_t *>(d.ptr), d.rows, d.cols, d.pitch,
-                                             d.img_stride, vec_ok);
+        pyr_down_kernel<<<grid, 256, 0, s>>>(a.ptr, a.pitch, a.img_stride, -a.border, a.rows + a.border - 1,
+                                             a.pitch - bxl, const_cast<uint8_t *>(d.ptr), d.rows, d.cols,
+                                             d.pitch, d.img_stride);
         PMV_LAUNCH_CHECK(ctx, "pyr_down_kernel");
+        rc = fill_border(ctx, d, batch, s);
+        if (rc) return rc;
     }
     return PMV_OK;
 }
@@ -191,16 +234,13 @@ PMV_API int pmv_pyramid_build(pmv_ctx *ctx, const uint8_t *img, int rows, int co
     if (!img || rows <= 0 || cols <= 0 || step < cols || max_level < 0 || !out_levels)
         return ctx->fail(PMV_ERR_INVALID, "pmv_pyramid_build: bad argument");
     cudaSetDevice(ctx->device);
-    int pitch0 = align_up(cols, 128);
-    cudaError_t e = ctx->img[0].reserve((size_t)pitch0 * rows);
-    if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "image upload buffer", e);
-    PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->img[0].p, pitch0, img, step, cols, rows,
-                                        cudaMemcpyHostToDevice, ctx->stream));
     PyrSet set;
-    int rc = pmv_internal_pyr_plan(ctx, 0, 1, rows, cols, ctx->img[0].as<uint8_t>(), pitch0,
-                                   (size_t)pitch0 * rows, win_w, win_h, max_level, &set);
+    int rc = pmv_internal_pyr_plan(ctx, 0, 1, rows, cols, 2, win_w, win_h, max_level, &set);
     if (rc) return rc;
-    rc = pmv_internal_pyr_run(ctx, set, 1, ctx->stream);
+    const PyrLevel &l0 = set.lv[0];
+    PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(const_cast<uint8_t *>(l0.ptr), l0.pitch, img, step, cols, rows,
+                                        cudaMemcpyHostToDevice, ctx->stream));
+    rc = pmv_internal_pyr_run(ctx, set, 1, nullptr, 0, 0, ctx->stream);
     if (rc) return rc;
     size_t need = 0;
     for (int l = 1; l <= set.top; l++) need += (size_t)set.lv[l].rows * set.lv[l].cols;
@@ -240,4 +280,4 @@ PMV_API int pmv_scharr(pmv_ctx *ctx, const uint8_t *img, int rows, int cols, int
     return PMV_OK;
 }
 
-}  // extern "C"
+}  // namespace
