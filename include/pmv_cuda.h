@@ -126,6 +126,47 @@ PMV_API int pmv_lk_track_batched_dev(pmv_ctx *ctx, const uint8_t *d_prev, const 
                                      double min_eig_thr,
                                      float *d_next_xy, uint8_t *d_status, float *d_err);
 
+/* ------------------------------------------------------------------ corner detectors -- */
+/* Image arguments of the extractors: `base` is the PARENT image (full_rows x full_cols, row step
+ * `step` bytes) and (roi_x, roi_y, roi_w, roi_h) the view the pipeline passes
+ * (Frame::regionOfInterest, Frame.cpp:95-117; OdometryPipeline.cpp:674-692 makes 255x255 tiles).
+ * Like cv::Sobel on a cv::Mat sub-view, derivative taps read parent pixels beyond the ROI edge
+ * and reflect (BORDER_REFLECT_101) only at the parent's edges.  Coordinates returned are
+ * ROI-local, as the reference extractors return them. */
+
+/* cv::cornerMinEigenVal(view, eig, 3, 3) -- response stage of goodFeaturesToTrack
+ * (OpenCVGoodFeatureExtractor.cpp:7).  eig: roi_h x roi_w floats.  Stage-by-stage parity. */
+PMV_API int pmv_min_eigen_val(pmv_ctx *ctx, const uint8_t *base, int full_rows, int full_cols, int step,
+                              int roi_x, int roi_y, int roi_w, int roi_h, float *eig);
+
+/* == cv::goodFeaturesToTrack(view, corners, max_corners, quality, min_dist, Mat(), block_size,
+ *    ksize, false, 0.04) as called at OpenCVGoodFeatureExtractor.cpp:7 (max, 0.01, 5, 3, 3).
+ * xy: max_corners x (x,y) floats (integer valued), strongest first; score: the response
+ * (the reference adapter leaves Feature::score 0); *n_out corners written.
+ * max_corners <= 0 means "all" (size xy for roi_w*roi_h/4).  Only block_size 3 / ksize 3. */
+PMV_API int pmv_gftt(pmv_ctx *ctx, const uint8_t *base, int full_rows, int full_cols, int step,
+                     int roi_x, int roi_y, int roi_w, int roi_h, int max_corners, double quality,
+                     double min_dist, int block_size, int ksize, float *xy, float *score, int *n_out);
+
+/* ShiTomasiFeatureExtractor::computeShiTomasiResponse (ShiTomasiFeatureExtractor.cpp:49-75) on
+ * Frame::getHarrisMatrix() (Frame.cpp:58-86, 119-138): fp64 response map, rows x cols doubles.
+ * The view is isolated exactly as in the reference (fresh gradient / harris Mats).
+ * signed_quirk = 1 reproduces the reference's u8-read-as-schar gradient (Frame.cpp:65-67). */
+PMV_API int pmv_shitomasi_response(pmv_ctx *ctx, const uint8_t *img, int rows, int cols, int step,
+                                   int signed_quirk, double *R);
+
+/* == ShiTomasiFeatureExtractor::extractFeatures(frame, max) (ShiTomasiFeatureExtractor.cpp:5-47):
+ * pixels with R > quality * max(R) (quality 0.4, .h:10), sorted by score descending, first `max`.
+ * col/row/score: max entries.  No NMS, like the reference. */
+PMV_API int pmv_shitomasi(pmv_ctx *ctx, const uint8_t *img, int rows, int cols, int step, int max_feats,
+                          double quality, int signed_quirk, int *col, int *row, double *score, int *n_out);
+
+/* == cv::FAST(view, kp, threshold, nonmax) TYPE_9_16 + "first max in raster order"
+ * (OpenCVFASTFeatureExtractor.cpp:8-20; threshold 10, nonmax true).  score = KeyPoint::response.
+ * *n_total (optional) = number of keypoints cv::FAST would return. */
+PMV_API int pmv_fast(pmv_ctx *ctx, const uint8_t *img, int rows, int cols, int step, int threshold, int nonmax,
+                     int max_feats, int *col, int *row, float *score, int *n_out, int *n_total);
+
 #ifdef __cplusplus
 }
 #endif

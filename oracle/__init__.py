@@ -99,3 +99,65 @@ def lk_track(prev, nxt, pts, win=(21, 21), max_level=3, max_count=30, eps=0.01, 
     fn(_p(prev, _u8), _p(nxt, _u8), r, c, c, _p(pts, _f32), n, win[0], win[1], max_level, max_count,
        eps, flags, min_eig, _p(out, _f32), _p(st, _u8), _p(err, _f32))
     return out, st, err
+
+
+# ----------------------------------------------------------------------------- corner detectors
+def min_eigen_val(img: np.ndarray, roi=None) -> np.ndarray:
+    """cornerMinEigenVal(src,3,3) of an ROI (x, y, w, h) of `img` with C++ sub-Mat border semantics."""
+    img = np.ascontiguousarray(img, np.uint8)
+    R, Cc = img.shape
+    x, y, w, h = roi if roi is not None else (0, 0, Cc, R)
+    out = np.empty((h, w), np.float32)
+    lib().orc_min_eigen_val(_p(img, _u8), R, Cc, Cc, x, y, w, h, _p(out, _f32))
+    return out
+
+
+def gftt_select(eig: np.ndarray, max_corners: int, quality=0.01, min_dist=5.0):
+    eig = np.ascontiguousarray(eig, np.float32)
+    r, c = eig.shape
+    cap = r * c if max_corners <= 0 else max_corners
+    xy = np.zeros((cap, 2), np.float32)
+    sc = np.zeros(cap, np.float32)
+    fn = lib().orc_gftt_select
+    fn.argtypes = [C.POINTER(_f32), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(_f32),
+                   C.POINTER(_f32), C.c_int]
+    n = fn(_p(eig, _f32), r, c, max_corners, quality, min_dist, _p(xy, _f32), _p(sc, _f32), cap)
+    return xy[:n], sc[:n]
+
+
+def gftt(img: np.ndarray, max_corners: int, quality=0.01, min_dist=5.0, roi=None):
+    """== cv::goodFeaturesToTrack(view, corners, max, quality, min_dist, Mat(), 3, 3, false, .04)."""
+    return gftt_select(min_eigen_val(img, roi), max_corners, quality, min_dist)
+
+
+def shitomasi_response(img: np.ndarray, signed_quirk=True) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    r, c = img.shape
+    out = np.empty((r, c), np.float64)
+    lib().orc_shitomasi_response(_p(img, _u8), r, c, c, int(signed_quirk), _p(out, _f64))
+    return out
+
+
+def shitomasi(img: np.ndarray, max_feats: int, quality=0.4, signed_quirk=True):
+    """== ShiTomasiFeatureExtractor::extractFeatures(frame, max): (col, row, score) by score desc."""
+    img = np.ascontiguousarray(img, np.uint8)
+    r, c = img.shape
+    cap = max(max_feats, 1)
+    col = np.zeros(cap, np.int32); row = np.zeros(cap, np.int32); sc = np.zeros(cap, np.float64)
+    fn = lib().orc_shitomasi
+    fn.argtypes = [C.POINTER(_u8), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                   C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_f64)]
+    n = fn(_p(img, _u8), r, c, c, max_feats, quality, int(signed_quirk), _p(col, _i32), _p(row, _i32), _p(sc, _f64))
+    return col[:n], row[:n], sc[:n]
+
+
+def fast(img: np.ndarray, threshold=10, nonmax=True, max_feats=None):
+    """== cv::FAST(img, kp, threshold, nonmax) TYPE_9_16; raster order; first `max_feats`."""
+    img = np.ascontiguousarray(img, np.uint8)
+    r, c = img.shape
+    cap = r * c
+    col = np.zeros(cap, np.int32); row = np.zeros(cap, np.int32); sc = np.zeros(cap, np.float32)
+    n = lib().orc_fast(_p(img, _u8), r, c, c, threshold, int(nonmax), _p(col, _i32), _p(row, _i32), _p(sc, _f32), cap)
+    if max_feats is not None:
+        n = min(n, max_feats)
+    return col[:n], row[:n], sc[:n]

@@ -57,6 +57,12 @@ _SIGS = {
                                     _int, _int, _dbl, _int, _dbl, _vp, _vp, _vp]),
     "pmv_lk_track_batched_dev": (_int, [_vp, _vp, _vp, _int, _sz, _int, _int, _int, _vp, _int, _int, _int,
                                         _int, _int, _dbl, _int, _dbl, _vp, _vp, _vp]),
+    "pmv_min_eigen_val": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp]),
+    "pmv_gftt": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _dbl, _dbl, _int, _int,
+                        _vp, _vp, _i32p]),
+    "pmv_shitomasi_response": (_int, [_vp, _vp, _int, _int, _int, _int, _vp]),
+    "pmv_shitomasi": (_int, [_vp, _vp, _int, _int, _int, _int, _dbl, _int, _vp, _vp, _vp, _i32p]),
+    "pmv_fast": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _i32p, _i32p]),
 }
 
 
@@ -200,3 +206,52 @@ class Context:
         self._chk(self.lib.pmv_lk_track_batched_dev(self.h, _ptr(d_prev), _ptr(d_nxt), B, img_stride, rows, cols,
                                                     step, _ptr(d_pts), n, win[0], win[1], max_level, max_count,
                                                     eps, flags, min_eig, _ptr(d_next), _ptr(d_status), _ptr(d_err)))
+
+    # ------------------------------------------------------------------ corner detectors
+    @staticmethod
+    def _roi(img, roi):
+        assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+        R, Cc = img.shape
+        return roi if roi is not None else (0, 0, Cc, R)
+
+    def min_eigen_val(self, img, roi=None):
+        x, y, w, h = self._roi(img, roi)
+        out = np.empty((h, w), np.float32)
+        self._chk(self.lib.pmv_min_eigen_val(self.h, _ptr(img), img.shape[0], img.shape[1], img.strides[0],
+                                             x, y, w, h, _ptr(out)))
+        return out
+
+    def gftt(self, img, max_corners, quality=0.01, min_dist=5.0, roi=None, block_size=3, ksize=3):
+        x, y, w, h = self._roi(img, roi)
+        cap = max_corners if max_corners > 0 else w * h
+        xy = np.zeros((max(cap, 1), 2), np.float32)
+        sc = np.zeros(max(cap, 1), np.float32)
+        n = C.c_int(0)
+        self._chk(self.lib.pmv_gftt(self.h, _ptr(img), img.shape[0], img.shape[1], img.strides[0], x, y, w, h,
+                                    max_corners, quality, min_dist, block_size, ksize, _ptr(xy), _ptr(sc), C.byref(n)))
+        return xy[:n.value], sc[:n.value]
+
+    def shitomasi_response(self, img, signed_quirk=True):
+        assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+        out = np.empty(img.shape, np.float64)
+        self._chk(self.lib.pmv_shitomasi_response(self.h, _ptr(img), img.shape[0], img.shape[1], img.strides[0],
+                                                  int(signed_quirk), _ptr(out)))
+        return out
+
+    def shitomasi(self, img, max_feats, quality=0.4, signed_quirk=True):
+        assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+        cap = max(max_feats, 1)
+        col = np.zeros(cap, np.int32); row = np.zeros(cap, np.int32); sc = np.zeros(cap, np.float64)
+        n = C.c_int(0)
+        self._chk(self.lib.pmv_shitomasi(self.h, _ptr(img), img.shape[0], img.shape[1], img.strides[0], max_feats,
+                                         quality, int(signed_quirk), _ptr(col), _ptr(row), _ptr(sc), C.byref(n)))
+        return col[:n.value], row[:n.value], sc[:n.value]
+
+    def fast(self, img, threshold=10, nonmax=True, max_feats=None):
+        assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+        cap = img.size if max_feats is None else max_feats
+        col = np.zeros(max(cap, 1), np.int32); row = np.zeros(max(cap, 1), np.int32); sc = np.zeros(max(cap, 1), np.float32)
+        n, tot = C.c_int(0), C.c_int(0)
+        self._chk(self.lib.pmv_fast(self.h, _ptr(img), img.shape[0], img.shape[1], img.strides[0], threshold,
+                                    int(nonmax), cap, _ptr(col), _ptr(row), _ptr(sc), C.byref(n), C.byref(tot)))
+        return col[:n.value], row[:n.value], sc[:n.value], tot.value

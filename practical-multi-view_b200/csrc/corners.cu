@@ -1,0 +1,563 @@
+// corners.cu -- K4 min-eigenvalue response (GFTT flavour), K5 the reference's own Shi-Tomasi
+// response (fp64), K6 corner selection (threshold, 3x3 NMS, sort, greedy min-distance, top-N).
+//
+// Replaces
+//   cv::goodFeaturesToTrack(bw, corners, max, 0.01, 5, Mat(), 3, 3, false, 0.04)
+//       reference OpenCVGoodFeatureExtractor.cpp:7           (SURVEY Appx B.1, B.2)
+//   ShiTomasiFeatureExtractor::extractFeatures / computeShiTomasiResponse
+//       reference ShiTomasiFeatureExtractor.cpp:5-75 + Frame.cpp:58-86,119-138   (Appx B.3)
+//
+// K4 arithmetic: the Sobel responses are small integers (|s| <= 1020), so the 3x3 box sums of
+// their products are EXACT in int32; one fp32 scaling + OpenCV's closed form follows.  This is
+// the same quantity OpenCV computes through rounded fp32 products (agreement ~1e-6 of the map
+// maximum, inside the 1e-5 tie tolerance) at a third of the instruction count -- the kernel is
+// meant to be HBM bound (1 B/px in, 4 B/px out).
+// K5 arithmetic: gradients are half-integers, products quarter-integers -> box sums exact in
+// int32, then the reference's fp64 expression order with explicit round-to-nearest intrinsics.
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ image tile staging ---
+constexpr int CT_W = 64;   // output tile width  (one thread column each)
+constexpr int CT_H = 32;   // output tile height (4 thread rows x 8 outputs)
+constexpr int CT_R = 8;
+constexpr int CS_W = CT_W + 4, CS_H = CT_H + 4;   // staged u8 tile (halo 2)
+constexpr int CS_P = 72;                           // staged pitch (bytes)
+constexpr int CD_W = CT_W + 2, CD_H = CT_H + 2;   // derivative tile (halo 1)
+
+struct ImgView {            // uploaded patch of the parent image
+    const uint8_t *ptr;     // device pointer to patch pixel (0,0)
+    int pitch;
+    int ox, oy;             // parent coordinates of patch pixel (0,0)
+    int full_rows, full_cols;  // parent size (reflect-101 happens at the PARENT's edges)
+    int rx, ry, rw, rh;     // ROI in parent coordinates
+};
+
+// stage ROI-coordinates [ty0-2, ty0+CT_H+2) x [tx0-2, tx0+CT_W+2) into s (u8, pitch CS_P)
+__device__ __forceinline__ void stage_tile(uint8_t (*s)[CS_P], const ImgView &v, int tx0, int ty0, int tid)
+{
+    for (int i = tid; i < CS_H * CS_W; i += 256) {
+        int r = i / CS_W, c = i - r * CS_W;
+        int gy = reflect101(v.ry + ty0 - 2 + r, v.full_rows) - v.oy;
+        int gx = reflect101(v.rx + tx0 - 2 + c, v.full_cols) - v.ox;
+        s[r][c] = __ldg(v.ptr + (size_t)gy * v.pitch + gx);
+    }
+}
+
+__device__ __forceinline__ float block_max_f(float v, float *s_red)
+{
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = threadIdx.x < 8 ? s_red[threadIdx.x] : 0.f;
+        for (int o = 4; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    }
+    return v;  // valid in thread 0
+}
+
+// K4: eig(y,x) over the ROI + global max (atomicMax on the bits of a non-negative float)
+__global__ void __launch_bounds__(256)
+mineig_kernel(const ImgView v, float *__restrict__ eig, int *__restrict__ max_bits)
+{
+    __shared__ __align__(16) uint8_t s_px[CS_H][CS_P];
+    __shared__ int s_d[CD_H][CD_W];   // Sobel (sx | sy << 16) at ROI coords (ty0-1+r, tx0-1+c)
+    __shared__ float s_red[8];
+    const int tid = threadIdx.x;
+    const int tx0 = blockIdx.x * CT_W, ty0 = blockIdx.y * CT_H;
+    stage_tile(s_px, v, tx0, ty0, tid);
+    __syncthreads();
+    // Sobel at halo-1 positions; positions outside the ROI take the value of their reflect-101
+    // image INSIDE the ROI (the covariance image is isolated, B.1)
+    for (int i = tid; i < CD_H * CD_W; i += 256) {
+        int r = i / CD_W, c = i - r * CD_W;
+        int y = reflect101(ty0 - 1 + r, v.rh), x = reflect101(tx0 - 1 + c, v.rw);
+        int sr = y - (ty0 - 2), sc = x - (tx0 - 2);   // staged indices of the centre
+        int packed = 0;
+        if (sr >= 1 && sr < CS_H - 1 && sc >= 1 && sc < CS_W - 1) {
+            const uint8_t *p = &s_px[sr][sc];
+            int a0 = p[-CS_P - 1], a1 = p[-CS_P], a2 = p[-CS_P + 1];
+            int b0 = p[-1], b2 = p[1];
+            int c0 = p[CS_P - 1], c1 = p[CS_P], c2 = p[CS_P + 1];
+            int sx = (a2 - a0) + 2 * (b2 - b0) + (c2 - c0);
+            int sy = (c0 - a0) + 2 * (c1 - a1) + (c2 - a2);
+            packed = (sx & 0xffff) | (int)((unsigned)sy << 16);
+        }
+        s_d[r][c] = packed;
+    }
+    __syncthreads();
+    const int tx = tid & 63, tyb = (tid >> 6) * CT_R;
+    const int x = tx0 + tx;
+    // sliding 3-row window of horizontal 3-sums of products
+    int hxx[3], hxy[3], hyy[3];
+    auto hsum = [&](int dr, int &oxx, int &oxy, int &oyy) {
+        oxx = oxy = oyy = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            int d = s_d[dr][tx + k];
+            int sx = (int)(short)d, sy = d >> 16;
+            oxx += sx * sx; oxy += sx * sy; oyy += sy * sy;
+        }
+    };
+    hsum(tyb + 0, hxx[0], hxy[0], hyy[0]);
+    hsum(tyb + 1, hxx[1], hxy[1], hyy[1]);
+    const float kf = (float)((1.0 / 3060.0) * (1.0 / 3060.0));
+    float vmax = 0.f;
+#pragma unroll
+    for (int r = 0; r < CT_R; r++) {
+        hsum(tyb + r + 2, hxx[(r + 2) % 3], hxy[(r + 2) % 3], hyy[(r + 2) % 3]);
+        const int y = ty0 + tyb + r;
+        if (x < v.rw && y < v.rh) {
+            float a = __fmul_rn(__fmul_rn((float)(hxx[0] + hxx[1] + hxx[2]), kf), 0.5f);
+            float b = __fmul_rn((float)(hxy[0] + hxy[1] + hxy[2]), kf);
+            float c = __fmul_rn(__fmul_rn((float)(hyy[0] + hyy[1] + hyy[2]), kf), 0.5f);
+            float amc = __fsub_rn(a, c);
+            float e = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(amc, amc), __fmul_rn(b, b))));
+            eig[(size_t)y * v.rw + x] = e;
+            vmax = fmaxf(vmax, e);
+        }
+    }
+    vmax = block_max_f(vmax, s_red);
+    if (tid == 0 && vmax > 0.f) atomicMax(max_bits, __float_as_int(vmax));
+}
+
+// K6a: threshold + 3x3 NMS + unordered compaction of (response bits, index) records
+__global__ void __launch_bounds__(256)
+gftt_candidates_kernel(const float *__restrict__ eig, int rows, int cols, const int *__restrict__ max_bits,
+                       double quality, Rec128 *__restrict__ out, int *__restrict__ count, int cap)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x < 1 || y < 1 || x >= cols - 1 || y >= rows - 1) return;
+    const float thr = (float)((double)__int_as_float(*max_bits) * quality);
+    const float *p = eig + (size_t)y * cols + x;
+    const float val = p[0];
+    if (!(val > thr)) return;
+    float m = fmaxf(fmaxf(p[-cols - 1], p[-cols]), fmaxf(p[-cols + 1], p[-1]));
+    m = fmaxf(m, fmaxf(fmaxf(p[1], p[cols - 1]), fmaxf(p[cols], p[cols + 1])));
+    if (val < m) return;  // val == dilate(thresholded) <=> val >= every neighbour
+    int slot = atomicAdd(count, 1);
+    if (slot < cap) out[slot] = Rec128{(unsigned long long)__float_as_uint(val), (unsigned long long)(y * cols + x)};
+}
+
+__global__ void __launch_bounds__(256)
+rank_scatter_kernel(const Rec128 *__restrict__ recs, int n, int *__restrict__ rankmap)
+{
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) rankmap[(int)recs[i].lo] = i;
+}
+
+// K6b: greedy min-distance selection == the sequential loop of goodFeaturesToTrack, evaluated in
+// rank-ordered chunks of 1024 by ONE CTA: candidate i is accepted iff no ACCEPTED candidate of
+// smaller rank lies within min_dist; inside a chunk the decision is iterated to its fixed point.
+__global__ void __launch_bounds__(1024)
+gftt_select_kernel(const Rec128 *__restrict__ recs, int n, int rows, int cols, const int *__restrict__ rankmap,
+                   unsigned char *status /* n, zeroed */, float min_dist, int max_corners,
+                   float *__restrict__ out_xy, float *__restrict__ out_score, int *__restrict__ out_n)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_total, s_chunk;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    const float md2 = min_dist * min_dist;
+    int R = (int)min_dist;
+    if ((float)R >= min_dist) R -= 1;  // largest integer offset with d*d < min_dist^2
+    if (R < 0) R = 0;
+    volatile unsigned char *vst = status;
+    const int limit = max_corners > 0 ? max_corners : n;
+    for (int base = 0; base < n; base += 1024) {
+        if (s_total >= limit) break;
+        const int i = base + tid;
+        const bool active = i < n;
+        int x = 0, y = 0;
+        float val = 0.f;
+        if (active) {
+            Rec128 r = recs[i];
+            int idx = (int)r.lo;
+            y = idx / cols; x = idx - y * cols;
+            val = __uint_as_float((unsigned)r.hi);
+        }
+        int st = 0;
+        while (true) {
+            if (active && st == 0) {
+                bool pending = false, rejected = false;
+                if (min_dist >= 1.f) {
+                    for (int dy = -R; dy <= R && !rejected; dy++) {
+                        int yy = y + dy;
+                        if (yy < 0 || yy >= rows) continue;
+                        for (int dx = -R; dx <= R; dx++) {
+                            int xx = x + dx;
+                            if (xx < 0 || xx >= cols) continue;
+                            if ((float)(dx * dx + dy * dy) >= md2) continue;
+                            int rk = rankmap[yy * cols + xx];
+                            if (rk < 0 || rk >= i) continue;
+                            unsigned char s = vst[rk];
+                            if (s == 1) { rejected = true; break; }
+                            if (s == 0) pending = true;
+                        }
+                    }
+                }
+                if (rejected) st = 2; else if (!pending) st = 1;
+                if (st) vst[i] = (unsigned char)st;
+            }
+            __threadfence_block();
+            if (!__syncthreads_or(active && st == 0)) break;
+        }
+        // ordered output of the accepted candidates of this chunk
+        const int acc = (active && st == 1) ? 1 : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, acc);
+        const int lane = tid & 31, warp = tid >> 5;
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        if (warp == 0) {
+            int v = s_warp[lane], incl = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            s_warp[lane] = incl - v;  // exclusive prefix per warp
+            if (lane == 31) s_chunk = incl;
+        }
+        __syncthreads();
+        const int before = s_total;
+        const int pos = before + s_warp[warp] + __popc(bal & ((1u << lane) - 1));
+        if (acc && pos < limit) {
+            out_xy[2 * pos] = (float)x;
+            out_xy[2 * pos + 1] = (float)y;
+            out_score[pos] = val;
+        }
+        __syncthreads();
+        if (tid == 0) s_total = before + s_chunk;
+        __syncthreads();
+    }
+    if (tid == 0) *out_n = s_total < limit ? s_total : limit;
+}
+
+// ------------------------------------------------------------------ K5 reference ShiTomasi
+// R(y,x) in fp64 + global max (bits of a non-negative double).  The view is isolated (fresh Mats in
+// the reference): gradient zero on the rim, blur reflects at the view's own edges, last column 0.
+__global__ void __launch_bounds__(256)
+shitomasi_response_kernel(const ImgView v, int signed_quirk, double *__restrict__ R,
+                          unsigned long long *__restrict__ max_bits)
+{
+    __shared__ __align__(16) uint8_t s_px[CS_H][CS_P];
+    __shared__ int s_d[CD_H][CD_W];   // (2*gx) | (2*gy) << 16 at view coords (ty0-1+r, tx0-1+c)
+    __shared__ double s_redd[8];
+    const int tid = threadIdx.x;
+    const int tx0 = blockIdx.x * CT_W, ty0 = blockIdx.y * CT_H;
+    stage_tile(s_px, v, tx0, ty0, tid);
+    __syncthreads();
+    for (int i = tid; i < CD_H * CD_W; i += 256) {
+        int r = i / CD_W, c = i - r * CD_W;
+        int y = reflect101(ty0 - 1 + r, v.rh), x = reflect101(tx0 - 1 + c, v.rw);
+        int sr = y - (ty0 - 2), sc = x - (tx0 - 2);
+        int packed = 0;
+        // Frame.cpp:63-84: interior pixels only, rim gradients stay zero
+        if (y >= 1 && y < v.rh - 1 && x >= 1 && x < v.rw - 1 && sr >= 1 && sr < CS_H - 1 && sc >= 1 && sc < CS_W - 1) {
+            const uint8_t *p = &s_px[sr][sc];
+            int l = p[-1], rr = p[1], u = p[-CS_P], d = p[CS_P];
+            if (signed_quirk) { l = (signed char)l; rr = (signed char)rr; u = (signed char)u; d = (signed char)d; }
+            int gx2 = rr - l, gy2 = d - u;   // 2*gx, 2*gy (exact)
+            packed = (gx2 & 0xffff) | (int)((unsigned)gy2 << 16);
+        }
+        s_d[r][c] = packed;
+    }
+    __syncthreads();
+    const int tx = tid & 63, tyb = (tid >> 6) * CT_R;
+    const int x = tx0 + tx;
+    int hxx[3], hxy[3], hyy[3];
+    auto hsum = [&](int dr, int &oxx, int &oxy, int &oyy) {
+        oxx = oxy = oyy = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            int d = s_d[dr][tx + k];
+            int gx = (int)(short)d, gy = d >> 16;
+            oxx += gx * gx; oxy += gx * gy; oyy += gy * gy;
+        }
+    };
+    hsum(tyb + 0, hxx[0], hxy[0], hyy[0]);
+    hsum(tyb + 1, hxx[1], hxy[1], hyy[1]);
+    double vmax = 0.0;
+    const double ninth = 1.0 / 9;
+#pragma unroll
+    for (int r = 0; r < CT_R; r++) {
+        hsum(tyb + r + 2, hxx[(r + 2) % 3], hxy[(r + 2) % 3], hyy[(r + 2) % 3]);
+        const int y = ty0 + tyb + r;
+        if (x < v.rw && y < v.rh) {
+            double out = 0.0;
+            if (x < v.rw - 1) {  // ShiTomasiFeatureExtractor.cpp:58 skips the last column
+                // sums of (2g)^2 are exact integers; /4 is exact; then the reference's fp64 order
+                double Ixx = __dmul_rn((double)(hxx[0] + hxx[1] + hxx[2]) * 0.25, ninth);
+                double Iyy = __dmul_rn((double)(hyy[0] + hyy[1] + hyy[2]) * 0.25, ninth);
+                double Ixy = __dmul_rn((double)(hxy[0] + hxy[1] + hxy[2]) * 0.25, ninth);
+                double B = __dsub_rn(-Ixx, Iyy);
+                double C = __dsub_rn(__dmul_rn(Ixx, Iyy), __dmul_rn(Ixy, Ixy));
+                double disc = __dsub_rn(__dmul_rn(B, B), __dmul_rn(4.0, C));
+                double sq = __dsqrt_rn(disc);
+                double l1 = __dmul_rn(__dadd_rn(-B, sq), 0.5);
+                double l2 = __dmul_rn(__dsub_rn(-B, sq), 0.5);
+                out = (l2 < l1) ? l2 : l1;  // std::min(l1, l2)
+            }
+            R[(size_t)y * v.rw + x] = out;
+            if (out > vmax) vmax = out;
+        }
+    }
+    for (int o = 16; o; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if ((tid & 31) == 0) s_redd[tid >> 5] = vmax;
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 1; k < 8; k++) vmax = fmax(vmax, s_redd[k]);
+        if (vmax > 0.0) atomicMax(max_bits, (unsigned long long)__double_as_longlong(vmax));
+    }
+}
+
+// K6 (reference flavour): every pixel with R > rmax*quality, no NMS
+__global__ void __launch_bounds__(256)
+shitomasi_candidates_kernel(const double *__restrict__ R, int n, const unsigned long long *__restrict__ max_bits,
+                            double quality, Rec128 *__restrict__ out, int *__restrict__ count, int cap)
+{
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const double thr = __dmul_rn(__longlong_as_double((long long)*max_bits), quality);
+    const double v = R[i];
+    if (!(v > thr)) return;
+    int slot = atomicAdd(count, 1);
+    // ties (std::sort is unstable in the reference): lower raster index first
+    if (slot < cap) out[slot] = Rec128{(unsigned long long)__double_as_longlong(v), ~(unsigned long long)i};
+}
+
+__global__ void __launch_bounds__(256)
+shitomasi_emit_kernel(const Rec128 *__restrict__ recs, int n, int cols, int *__restrict__ col, int *__restrict__ row,
+                      double *__restrict__ score)
+{
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    int idx = (int)(~recs[i].lo);
+    row[i] = idx / cols; col[i] = idx - (idx / cols) * cols;
+    score[i] = __longlong_as_double((long long)recs[i].hi);
+}
+
+// ------------------------------------------------------------------ host-side helpers -----
+// Upload the ROI plus a 2 px halo (clipped to the parent) of a host image into ctx->img[0].
+int upload_roi(pmv_ctx *ctx, const uint8_t *base, int full_rows, int full_cols, int step,
+               int rx, int ry, int rw, int rh, ImgView *v)
+{
+    int x0 = rx - 2 < 0 ? 0 : rx - 2, y0 = ry - 2 < 0 ? 0 : ry - 2;
+    int x1 = rx + rw + 2 > full_cols ? full_cols : rx + rw + 2;
+    int y1 = ry + rh + 2 > full_rows ? full_rows : ry + rh + 2;
+    int pw = x1 - x0, ph = y1 - y0;
+    int pitch = align_up(pw, 128);
+    cudaError_t e = ctx->img[0].reserve((size_t)pitch * ph);
+    if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "roi upload buffer", e);
+    PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->img[0].p, pitch, base + (size_t)y0 * step + x0, step, pw, ph,
+                                        cudaMemcpyHostToDevice, ctx->stream));
+    *v = ImgView{ctx->img[0].as<uint8_t>(), pitch, x0, y0, full_rows, full_cols, rx, ry, rw, rh};
+    return PMV_OK;
+}
+
+int check_roi(pmv_ctx *ctx, const void *base, int full_rows, int full_cols, int step, int rx, int ry, int rw, int rh)
+{
+    if (!base || full_rows <= 0 || full_cols <= 0 || step < full_cols)
+        return ctx->fail(PMV_ERR_INVALID, "corner detector: bad image argument");
+    if (rw <= 0 || rh <= 0 || rx < 0 || ry < 0 || rx + rw > full_cols || ry + rh > full_rows)
+        return ctx->fail(PMV_ERR_INVALID, "corner detector: ROI outside the image");
+    return PMV_OK;
+}
+
+int run_mineig(pmv_ctx *ctx, const ImgView &v, float *d_eig, int *d_max, cudaStream_t s)
+{
+    ProfScope ps(ctx, PMV_PHASE_RESPONSE, s);
+    PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_max, 0, sizeof(int), s));
+    dim3 grid((v.rw + CT_W - 1) / CT_W, (v.rh + CT_H - 1) / CT_H);
+    mineig_kernel<<<grid, 256, 0, s>>>(v, d_eig, d_max);
+    PMV_LAUNCH_CHECK(ctx, "mineig_kernel");
+    return PMV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+PMV_API int pmv_min_eigen_val(pmv_ctx *ctx, const uint8_t *base, int full_rows, int full_cols, int step,
+                              int roi_x, int roi_y, int roi_w, int roi_h, float *eig)
+{
+    if (!ctx) return PMV_ERR_INVALID;
+    int rc = check_roi(ctx, base, full_rows, full_cols, step, roi_x, roi_y, roi_w, roi_h);
+    if (rc) return rc;
+    if (!eig) return ctx->fail(PMV_ERR_INVALID, "pmv_min_eigen_val: null output");
+    cudaSetDevice(ctx->device);
+    ImgView v;
+    rc = upload_roi(ctx, base, full_rows, full_cols, step, roi_x, roi_y, roi_w, roi_h, &v);
+    if (rc) return rc;
+    size_t n = (size_t)roi_w * roi_h;
+    cudaError_t e = ctx->scratch[0].reserve(n * 4);
+    if (e == cudaSuccess) e = ctx->scratch[1].reserve(64);
+    if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "eig map", e);
+    rc = run_mineig(ctx, v, ctx->scratch[0].as<float>(), ctx->scratch[1].as<int>(), ctx->stream);
+    if (rc) return rc;
+    PMV_CUDA_TRY(ctx, cudaMemcpyAsync(eig, ctx->scratch[0].p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PMV_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMV_OK;
+}
+
+PMV_API int pmv_gftt(pmv_ctx *ctx, const uint8_t *base, int full_rows, int full_cols, int step,
+                     int roi_x, int roi_y, int roi_w, int roi_h, int max_corners, double quality,
+                     double min_dist, int block_size, int ksize, float *xy, float *score, int *n_out)
+{
+    if (!ctx) return PMV_ERR_INVALID;
+    int rc = check_roi(ctx, base, full_rows, full_cols, step, roi_x, roi_y, roi_w, roi_h);
+    if (rc) return rc;
+    if (!n_out || quality <= 0 || min_dist < 0) return ctx->fail(PMV_ERR_INVALID, "pmv_gftt: bad argument");
+    if (block_size != 3 || ksize != 3)
+        return ctx->fail(PMV_ERR_UNSUPPORTED, "pmv_gftt: only blockSize 3 / ksize 3 (the reference's call)");
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    ImgView v;
+    rc = upload_roi(ctx, base, full_rows, full_cols, step, roi_x, roi_y, roi_w, roi_h, &v);
+    if (rc) return rc;
+    const size_t npx = (size_t)roi_w * roi_h;
+    const int cap = (int)npx;  // plateaus of equal responses can make every pixel a candidate
+    const int cap2 = sort_capacity(cap);
+    cudaError_t e = ctx->scratch[0].reserve(npx * 4);                 // eig map
+    if (e == cudaSuccess) e = ctx->scratch[1].reserve(256);          // max bits, count, n_out
+    if (e == cudaSuccess) e = ctx->scratch[2].reserve((size_t)cap2 * sizeof(Rec128));
+    if (e == cudaSuccess) e = ctx->scratch[3].reserve(npx * 4);      // rank map
+    if (e == cudaSuccess) e = ctx->scratch[4].reserve(cap);          // status
+    if (e == cudaSuccess) e = ctx->pin[0].reserve(64);
+    if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "gftt workspace", e);
+    float *d_eig = ctx->scratch[0].as<float>();
+    int *d_misc = ctx->scratch[1].as<int>();   // [0] max bits, [1] count, [2] n_out
+    Rec128 *d_rec = ctx->scratch[2].as<Rec128>();
+    int *d_rank = ctx->scratch[3].as<int>();
+    unsigned char *d_status = ctx->scratch[4].as<unsigned char>();
+    int *h_misc = ctx->pin[0].as<int>();
+
+    PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_misc, 0, 16, s));
+    rc = run_mineig(ctx, v, d_eig, d_misc, s);
+    if (rc) return rc;
+    int n_cand = 0;
+    {
+        ProfScope ps(ctx, PMV_PHASE_SELECT, s);
+        dim3 grid((roi_w + 31) / 32, (roi_h + 7) / 8);
+        gftt_candidates_kernel<<<grid, 256, 0, s>>>(d_eig, roi_h, roi_w, d_misc, quality, d_rec, d_misc + 1, cap);
+        PMV_LAUNCH_CHECK(ctx, "gftt_candidates_kernel");
+        PMV_CUDA_TRY(ctx, cudaMemcpyAsync(h_misc, d_misc, 16, cudaMemcpyDeviceToHost, s));
+        PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+        n_cand = h_misc[1] < cap ? h_misc[1] : cap;
+        const int want = max_corners > 0 ? max_corners : n_cand;
+        if (n_cand > 0) {
+            rc = sort_desc_128(ctx, d_rec, n_cand, s);
+            if (rc) return rc;
+            PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_rank, 0xff, npx * 4, s));
+            PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_status, 0, n_cand, s));
+            rank_scatter_kernel<<<(n_cand + 255) / 256, 256, 0, s>>>(d_rec, n_cand, d_rank);
+            PMV_LAUNCH_CHECK(ctx, "rank_scatter_kernel");
+            e = ctx->scratch[5].reserve((size_t)want * 12 + 16);
+            if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "gftt output", e);
+            float *d_xy = ctx->scratch[5].as<float>();
+            float *d_sc = d_xy + 2 * (size_t)want;
+            gftt_select_kernel<<<1, 1024, 0, s>>>(d_rec, n_cand, roi_h, roi_w, d_rank, d_status, (float)min_dist,
+                                                  max_corners, d_xy, d_sc, d_misc + 2);
+            PMV_LAUNCH_CHECK(ctx, "gftt_select_kernel");
+            PMV_CUDA_TRY(ctx, cudaMemcpyAsync(h_misc, d_misc, 16, cudaMemcpyDeviceToHost, s));
+            PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+            int n = h_misc[2];
+            if (n > 0) {
+                if (xy) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(xy, d_xy, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+                if (score) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(score, d_sc, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+                PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+            }
+            *n_out = n;
+            return PMV_OK;
+        }
+    }
+    *n_out = 0;
+    return PMV_OK;
+}
+
+PMV_API int pmv_shitomasi_response(pmv_ctx *ctx, const uint8_t *img, int rows, int cols, int step,
+                                   int signed_quirk, double *R)
+{
+    if (!ctx) return PMV_ERR_INVALID;
+    int rc = check_roi(ctx, img, rows, cols, step, 0, 0, cols, rows);
+    if (rc) return rc;
+    if (!R) return ctx->fail(PMV_ERR_INVALID, "pmv_shitomasi_response: null output");
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    ImgView v;
+    rc = upload_roi(ctx, img, rows, cols, step, 0, 0, cols, rows, &v);
+    if (rc) return rc;
+    size_t n = (size_t)rows * cols;
+    cudaError_t e = ctx->scratch[0].reserve(n * 8);
+    if (e == cudaSuccess) e = ctx->scratch[1].reserve(256);
+    if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "shitomasi map", e);
+    PMV_CUDA_TRY(ctx, cudaMemsetAsync(ctx->scratch[1].p, 0, 16, s));
+    dim3 grid((cols + CT_W - 1) / CT_W, (rows + CT_H - 1) / CT_H);
+    shitomasi_response_kernel<<<grid, 256, 0, s>>>(v, signed_quirk, ctx->scratch[0].as<double>(),
+                                                   ctx->scratch[1].as<unsigned long long>());
+    PMV_LAUNCH_CHECK(ctx, "shitomasi_response_kernel");
+    PMV_CUDA_TRY(ctx, cudaMemcpyAsync(R, ctx->scratch[0].p, n * 8, cudaMemcpyDeviceToHost, s));
+    PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return PMV_OK;
+}
+
+PMV_API int pmv_shitomasi(pmv_ctx *ctx, const uint8_t *img, int rows, int cols, int step, int max_feats,
+                          double quality, int signed_quirk, int *col, int *row, double *score, int *n_out)
+{
+    if (!ctx) return PMV_ERR_INVALID;
+    int rc = check_roi(ctx, img, rows, cols, step, 0, 0, cols, rows);
+    if (rc) return rc;
+    if (!n_out || max_feats < 0) return ctx->fail(PMV_ERR_INVALID, "pmv_shitomasi: bad argument");
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    ImgView v;
+    rc = upload_roi(ctx, img, rows, cols, step, 0, 0, cols, rows, &v);
+    if (rc) return rc;
+    const size_t npx = (size_t)rows * cols;
+    const int cap2 = sort_capacity((int)npx);
+    cudaError_t e = ctx->scratch[0].reserve(npx * 8);
+    if (e == cudaSuccess) e = ctx->scratch[1].reserve(256);
+    if (e == cudaSuccess) e = ctx->scratch[2].reserve((size_t)cap2 * sizeof(Rec128));
+    if (e == cudaSuccess) e = ctx->pin[0].reserve(64);
+    if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "shitomasi workspace", e);
+    double *d_R = ctx->scratch[0].as<double>();
+    unsigned long long *d_max = ctx->scratch[1].as<unsigned long long>();
+    int *d_count = reinterpret_cast<int *>(d_max + 1);
+    Rec128 *d_rec = ctx->scratch[2].as<Rec128>();
+    int *h_misc = ctx->pin[0].as<int>();
+    PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_max, 0, 16, s));
+    {
+        ProfScope ps(ctx, PMV_PHASE_RESPONSE, s);
+        dim3 grid((cols + CT_W - 1) / CT_W, (rows + CT_H - 1) / CT_H);
+        shitomasi_response_kernel<<<grid, 256, 0, s>>>(v, signed_quirk, d_R, d_max);
+        PMV_LAUNCH_CHECK(ctx, "shitomasi_response_kernel");
+    }
+    ProfScope ps(ctx, PMV_PHASE_SELECT, s);
+    shitomasi_candidates_kernel<<<(int)((npx + 255) / 256), 256, 0, s>>>(d_R, (int)npx, d_max, quality, d_rec, d_count, (int)npx);
+    PMV_LAUNCH_CHECK(ctx, "shitomasi_candidates_kernel");
+    PMV_CUDA_TRY(ctx, cudaMemcpyAsync(h_misc, d_count, 4, cudaMemcpyDeviceToHost, s));
+    PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    int n_cand = h_misc[0];
+    int n = n_cand < max_feats ? n_cand : max_feats;
+    if (n > 0) {
+        rc = sort_desc_128(ctx, d_rec, n_cand, s);
+        if (rc) return rc;
+        e = ctx->scratch[5].reserve((size_t)n * 16 + 16);
+        if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "shitomasi output", e);
+        double *d_sc = ctx->scratch[5].as<double>();
+        int *d_col = reinterpret_cast<int *>(d_sc + n), *d_row = d_col + n;
+        shitomasi_emit_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_rec, n, cols, d_col, d_row, d_sc);
+        PMV_LAUNCH_CHECK(ctx, "shitomasi_emit_kernel");
+        if (col) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(col, d_col, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        if (row) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(row, d_row, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        if (score) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(score, d_sc, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    }
+    *n_out = n;
+    return PMV_OK;
+}
+
+}  // extern "C"

@@ -27,6 +27,27 @@ def lk_small():
                         next_xy=nx.reshape(-1, 2), status=st.ravel(), err=err.ravel(), pyr1=p1, pyr2=p2)
 
 
+def corners_small():
+    """cv2 outputs for GFTT / FAST / cornerMinEigenVal; the reference-flavour ShiTomasi list comes from the
+    numpy + cv2.blur restatement in tests/test_oracle_corners.py (the reference source is its own spec)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from test_oracle_corners import shitomasi_numpy
+    img = synth.base_frame(21, 128, 160)
+    xy = cv2.goodFeaturesToTrack(img, 60, 0.01, 5).reshape(-1, 2)
+    kp = cv2.FastFeatureDetector_create(10, True).detect(img)
+    k = np.array([[p.pt[0], p.pt[1], p.response] for p in kp])
+    R = shitomasi_numpy(img, True)
+    sel = R > R.max() * 0.4
+    cand = np.argwhere(sel)
+    order = np.argsort(-R[sel], kind="stable")[:50]
+    np.savez_compressed(OUT / "corners_small.npz", img=img, gftt_xy=xy, eig=cv2.cornerMinEigenVal(img, 3, 3),
+                        fast_col=k[:, 0].astype(np.int32), fast_row=k[:, 1].astype(np.int32),
+                        fast_score=k[:, 2].astype(np.float32),
+                        shi_row=cand[order][:, 0].astype(np.int32), shi_col=cand[order][:, 1].astype(np.int32),
+                        shi_score=R[sel][order])
+
+
 if __name__ == "__main__":
     lk_small()
+    corners_small()
     print("wrote", sorted(p.name for p in OUT.glob("*.npz")))
