@@ -167,6 +167,69 @@ PMV_API int pmv_shitomasi(pmv_ctx *ctx, const uint8_t *img, int rows, int cols, 
 PMV_API int pmv_fast(pmv_ctx *ctx, const uint8_t *img, int rows, int cols, int step, int threshold, int nonmax,
                      int max_feats, int *col, int *row, float *score, int *n_out, int *n_total);
 
+/* ------------------------------------------------------------------ bundle adjustment -- */
+/* Parameterisation of CeresBundleAdjustment::apply (CeresBundleAdjustment.cpp:26-52):
+ *   pose block  [a(3), c(3)]  a = Rodrigues(R_i^T), c = -t_i                       (fp64)
+ *   point block X(3) world coordinates
+ *   observation (column, row) of the Feature, integer valued; cam_idx / pt_idx name its blocks
+ *   K row-major 3x3 (fx = K[0], cx = K[2], fy = K[4], cy = K[5], ProjectionResidual.h:51-52)
+ *   loss ceres::HuberLoss(huber_delta) (1.0 in the reference; <= 0 disables the loss). */
+typedef struct pmv_ba_summary {
+    double initial_cost, final_cost; /* 1/2 sum rho(|r|^2) at the first / last accepted iterate */
+    int iterations;                  /* LM iterations executed (accepted + rejected + invalid) */
+    int successful_steps;
+    int termination;                 /* 0 max iterations, 1 function tol, 2 parameter tol, 3 gradient tol,
+                                        4 failure (5 consecutive invalid steps), 5 min trust-region radius */
+    double final_radius;
+} pmv_ba_summary;
+
+typedef struct pmv_ba_problem pmv_ba_problem;
+
+/* ProjectionResidual::operator() + its AutoDiff Jacobians (include/ProjectionResidual.h:38-58,
+ * ProjectionResidual.cpp:3-8) for No observations: r (No x 2), J_pose (No x 2 x 6 row major),
+ * J_pt (No x 2 x 3) exactly as the CostFunction returns them (loss not applied), and
+ * *cost = 1/2 sum rho(|r|^2).  Any output pointer may be NULL. */
+PMV_API int pmv_ba_eval(pmv_ctx *ctx, const double *poses, const double *points, const double *obs,
+                        const int32_t *cam_idx, const int32_t *pt_idx, int Nc, int Np, int No, const double K[9],
+                        double huber_delta, double *r, double *J_pose, double *J_pt, double *cost);
+
+/* == ceres::Solve with SPARSE_SCHUR, max_num_iterations = max_iters, everything else default
+ * (CeresBundleAdjustment.cpp:54-61): Levenberg-Marquardt trust region, Jacobi scaling, points eliminated,
+ * reduced camera system solved by Cholesky.  poses (Nc x 6) and points (Np x 3) are updated in place,
+ * like tr_opt / p3d_opt are (:67-88).  Blocks without observations are left untouched. */
+PMV_API int pmv_ba_solve(pmv_ctx *ctx, double *poses, double *points, const double *obs, const int32_t *cam_idx,
+                         const int32_t *pt_idx, int Nc, int Np, int No, const double K[9], double huber_delta,
+                         int max_iters, pmv_ba_summary *summary);
+
+/* W independent windows in one call (BASELINE config 4): window w owns poses[w*Nc..], points[w*Np..]
+ * and the observation slice [obs_off[w], obs_off[w+1]) whose cam_idx / pt_idx are window-local. */
+PMV_API int pmv_ba_solve_batched(pmv_ctx *ctx, double *poses, double *points, const double *obs,
+                                 const int32_t *cam_idx, const int32_t *pt_idx, const int32_t *obs_off, int W,
+                                 int Nc, int Np, int No, const double K[9], double huber_delta, int max_iters,
+                                 pmv_ba_summary *sums);
+
+/* Resident form of the same solve: create uploads and indexes the problem once, solve enqueues
+ * max_iters LM iterations on the context stream WITHOUT host synchronisation, download fetches the
+ * result (synchronises), reset restores the initial parameters (NULL = the ones given at creation).
+ * sharded_nranks > 1: this rank holds all Nc poses but only its shard of the points / observations;
+ * every LM iteration sums the partial reduced camera system over ranks (pmv_comm_init first). */
+PMV_API pmv_ba_problem *pmv_ba_problem_create(pmv_ctx *ctx, const double *poses, const double *points,
+                                              const double *obs, const int32_t *cam_idx, const int32_t *pt_idx,
+                                              const int32_t *obs_off, int W, int Nc, int Np, int No,
+                                              const double K[9], double huber_delta, int sharded_rank,
+                                              int sharded_nranks);
+PMV_API int pmv_ba_problem_reset(pmv_ba_problem *p, const double *poses, const double *points);
+PMV_API int pmv_ba_problem_solve(pmv_ba_problem *p, int max_iters);
+PMV_API int pmv_ba_problem_download(pmv_ba_problem *p, double *poses, double *points, pmv_ba_summary *sums);
+PMV_API size_t pmv_ba_problem_device_bytes(pmv_ba_problem *p);
+PMV_API void pmv_ba_problem_destroy(pmv_ba_problem *p);
+
+/* NCCL communicator of the sharded bundle adjuster (one rank per GPU): rank 0 makes the id, the
+ * caller broadcasts its 128 bytes (e.g. torch.distributed), every rank calls pmv_comm_init. */
+PMV_API int pmv_comm_unique_id(char id[128]);
+PMV_API int pmv_comm_init(pmv_ctx *ctx, int nranks, int rank, const char id[128]);
+PMV_API int pmv_comm_destroy(pmv_ctx *ctx);
+
 #ifdef __cplusplus
 }
 #endif

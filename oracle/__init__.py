@@ -161,3 +161,63 @@ def fast(img: np.ndarray, threshold=10, nonmax=True, max_feats=None):
     if max_feats is not None:
         n = min(n, max_feats)
     return col[:n], row[:n], sc[:n]
+
+
+# ----------------------------------------------------------------------------- bundle adjustment
+class BASummary(C.Structure):
+    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double), ("iterations", C.c_int),
+                ("successful_steps", C.c_int), ("termination", C.c_int), ("final_radius", C.c_double),
+                ("cost_log", C.c_double * 128), ("radius_log", C.c_double * 128), ("accepted_log", C.c_int * 128)]
+
+    def as_dict(self):
+        n = min(self.iterations, 127) + 1
+        return {"initial_cost": self.initial_cost, "final_cost": self.final_cost, "iterations": self.iterations,
+                "successful_steps": self.successful_steps, "termination": self.termination,
+                "final_radius": self.final_radius, "cost_log": list(self.cost_log[:n]),
+                "radius_log": list(self.radius_log[:n]), "accepted_log": list(self.accepted_log[:n])}
+
+
+def ba_eval(poses, points, obs, cam_idx, pt_idx, K, huber_delta=1.0):
+    """Raw residuals / Jacobians of ProjectionResidual under Jets + the robustified cost."""
+    poses = np.ascontiguousarray(poses, np.float64); points = np.ascontiguousarray(points, np.float64)
+    obs = np.ascontiguousarray(obs, np.float64); K = np.ascontiguousarray(K, np.float64).ravel()
+    cam_idx = np.ascontiguousarray(cam_idx, np.int32); pt_idx = np.ascontiguousarray(pt_idx, np.int32)
+    n = len(cam_idx)
+    r = np.zeros((n, 2)); Jc = np.zeros((n, 2, 6)); Jp = np.zeros((n, 2, 3))
+    fn = lib().orc_ba_eval
+    fn.restype = C.c_double
+    fn.argtypes = [C.POINTER(_f64)] * 3 + [C.POINTER(_i32)] * 2 + [C.c_int, C.POINTER(_f64), C.c_double] + [C.POINTER(_f64)] * 3
+    cost = fn(_p(poses, _f64), _p(points, _f64), _p(obs, _f64), _p(cam_idx, _i32), _p(pt_idx, _i32), n,
+              _p(K, _f64), huber_delta, _p(r, _f64), _p(Jc, _f64), _p(Jp, _f64))
+    return r, Jc, Jp, cost
+
+
+def ba_solve(poses, points, obs, cam_idx, pt_idx, K, huber_delta=1.0, max_iters=5, dense=False):
+    """Ceres-equivalent LM + SPARSE_SCHUR (CeresBundleAdjustment.cpp:54-61).  Returns new poses, points, summary."""
+    poses = np.array(poses, np.float64, order="C"); points = np.array(points, np.float64, order="C")
+    obs = np.ascontiguousarray(obs, np.float64); K = np.ascontiguousarray(K, np.float64).ravel()
+    cam_idx = np.ascontiguousarray(cam_idx, np.int32); pt_idx = np.ascontiguousarray(pt_idx, np.int32)
+    s = BASummary()
+    fn = lib().orc_ba_solve
+    fn.argtypes = [C.POINTER(_f64)] * 3 + [C.POINTER(_i32)] * 2 + [C.c_int] * 3 + [C.POINTER(_f64), C.c_double, C.c_int,
+                                                                               C.c_int, C.POINTER(BASummary)]
+    fn(_p(poses, _f64), _p(points, _f64), _p(obs, _f64), _p(cam_idx, _i32), _p(pt_idx, _i32), len(poses), len(points),
+       len(cam_idx), _p(K, _f64), huber_delta, max_iters, int(dense), C.byref(s))
+    return poses, points, s.as_dict()
+
+
+def ba_solve_batched(poses, points, obs, cam_idx, pt_idx, obs_off, K, huber_delta=1.0, max_iters=5, nthreads=0):
+    """poses (W,Nc,6), points (W,Np,3); observation slices by obs_off (W+1).  OpenMP over windows."""
+    poses = np.array(poses, np.float64, order="C"); points = np.array(points, np.float64, order="C")
+    obs = np.ascontiguousarray(obs, np.float64); K = np.ascontiguousarray(K, np.float64).ravel()
+    cam_idx = np.ascontiguousarray(cam_idx, np.int32); pt_idx = np.ascontiguousarray(pt_idx, np.int32)
+    obs_off = np.ascontiguousarray(obs_off, np.int32)
+    W, Nc, _ = poses.shape
+    Np = points.shape[1]
+    sums = (BASummary * W)()
+    fn = lib().orc_ba_solve_batched
+    fn.argtypes = [C.POINTER(_f64)] * 3 + [C.POINTER(_i32)] * 3 + [C.c_int] * 3 + [C.POINTER(_f64), C.c_double, C.c_int,
+                                                                               C.c_int, C.POINTER(BASummary)]
+    fn(_p(poses, _f64), _p(points, _f64), _p(obs, _f64), _p(cam_idx, _i32), _p(pt_idx, _i32), _p(obs_off, _i32),
+       W, Nc, Np, _p(K, _f64), huber_delta, max_iters, nthreads, sums)
+    return poses, points, [s.as_dict() for s in sums]

@@ -63,7 +63,27 @@ _SIGS = {
     "pmv_shitomasi_response": (_int, [_vp, _vp, _int, _int, _int, _int, _vp]),
     "pmv_shitomasi": (_int, [_vp, _vp, _int, _int, _int, _int, _dbl, _int, _vp, _vp, _vp, _i32p]),
     "pmv_fast": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _i32p, _i32p]),
+    "pmv_ba_eval": (_int, [_vp] * 6 + [_int] * 3 + [_vp, _dbl] + [_vp] * 4),
+    "pmv_ba_solve": (_int, [_vp] * 6 + [_int] * 3 + [_vp, _dbl, _int, _vp]),
+    "pmv_ba_solve_batched": (_int, [_vp] * 7 + [_int] * 4 + [_vp, _dbl, _int, _vp]),
+    "pmv_ba_problem_create": (_vp, [_vp] * 7 + [_int] * 4 + [_vp, _dbl, _int, _int]),
+    "pmv_ba_problem_reset": (_int, [_vp, _vp, _vp]),
+    "pmv_ba_problem_solve": (_int, [_vp, _int]),
+    "pmv_ba_problem_download": (_int, [_vp, _vp, _vp, _vp]),
+    "pmv_ba_problem_device_bytes": (_sz, [_vp]),
+    "pmv_ba_problem_destroy": (None, [_vp]),
+    "pmv_comm_unique_id": (_int, [_vp]),
+    "pmv_comm_init": (_int, [_vp, _int, _int, _vp]),
+    "pmv_comm_destroy": (_int, [_vp]),
 }
+
+
+class BASummary(C.Structure):
+    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double), ("iterations", C.c_int),
+                ("successful_steps", C.c_int), ("termination", C.c_int), ("final_radius", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 def load_library() -> C.CDLL:
@@ -255,3 +275,99 @@ class Context:
         self._chk(self.lib.pmv_fast(self.h, _ptr(img), img.shape[0], img.shape[1], img.strides[0], threshold,
                                     int(nonmax), cap, _ptr(col), _ptr(row), _ptr(sc), C.byref(n), C.byref(tot)))
         return col[:n.value], row[:n.value], sc[:n.value], tot.value
+
+    # ------------------------------------------------------------------ bundle adjustment
+    @staticmethod
+    def _ba_args(poses, points, obs, cam_idx, pt_idx, K):
+        return (np.array(poses, np.float64, order="C"), np.array(points, np.float64, order="C"),
+                np.ascontiguousarray(obs, np.float64), np.ascontiguousarray(cam_idx, np.int32),
+                np.ascontiguousarray(pt_idx, np.int32), np.ascontiguousarray(K, np.float64).ravel())
+
+    def ba_eval(self, poses, points, obs, cam_idx, pt_idx, K, huber_delta=1.0):
+        poses, points, obs, cam_idx, pt_idx, K = self._ba_args(poses, points, obs, cam_idx, pt_idx, K)
+        n = len(cam_idx)
+        r = np.zeros((n, 2)); Jc = np.zeros((n, 2, 6)); Jp = np.zeros((n, 2, 3)); cost = np.zeros(1)
+        self._chk(self.lib.pmv_ba_eval(self.h, _ptr(poses), _ptr(points), _ptr(obs), _ptr(cam_idx), _ptr(pt_idx),
+                                       len(poses), len(points), n, _ptr(K), huber_delta, _ptr(r), _ptr(Jc), _ptr(Jp),
+                                       _ptr(cost)))
+        return r, Jc, Jp, float(cost[0])
+
+    def ba_solve(self, poses, points, obs, cam_idx, pt_idx, K, huber_delta=1.0, max_iters=5):
+        poses, points, obs, cam_idx, pt_idx, K = self._ba_args(poses, points, obs, cam_idx, pt_idx, K)
+        s = BASummary()
+        self._chk(self.lib.pmv_ba_solve(self.h, _ptr(poses), _ptr(points), _ptr(obs), _ptr(cam_idx), _ptr(pt_idx),
+                                        len(poses), len(points), len(cam_idx), _ptr(K), huber_delta, max_iters,
+                                        C.byref(s)))
+        return poses, points, s.as_dict()
+
+    def ba_solve_batched(self, poses, points, obs, cam_idx, pt_idx, obs_off, K, huber_delta=1.0, max_iters=5):
+        poses, points, obs, cam_idx, pt_idx, K = self._ba_args(poses, points, obs, cam_idx, pt_idx, K)
+        obs_off = np.ascontiguousarray(obs_off, np.int32)
+        W, Nc, _ = poses.shape
+        sums = (BASummary * W)()
+        self._chk(self.lib.pmv_ba_solve_batched(self.h, _ptr(poses), _ptr(points), _ptr(obs), _ptr(cam_idx),
+                                                _ptr(pt_idx), _ptr(obs_off), W, Nc, points.shape[1], len(cam_idx),
+                                                _ptr(K), huber_delta, max_iters, sums))
+        return poses, points, [x.as_dict() for x in sums]
+
+    def ba_problem(self, poses, points, obs, cam_idx, pt_idx, K, huber_delta=1.0, obs_off=None, rank=0, nranks=1):
+        return BAProblem(self, poses, points, obs, cam_idx, pt_idx, K, huber_delta, obs_off, rank, nranks)
+
+    # ------------------------------------------------------------------ NCCL (sharded BA)
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = self.lib.pmv_comm_unique_id(buf)
+        if rc != PMV_OK:
+            raise PmvError(rc, "pmv_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes):
+        self._chk(self.lib.pmv_comm_init(self.h, nranks, rank, C.c_char_p(uid)))
+
+    def comm_destroy(self):
+        self._chk(self.lib.pmv_comm_destroy(self.h))
+
+
+class BAProblem:
+    """Device-resident bundle-adjustment problem (pmv_ba_problem_*)."""
+
+    def __init__(self, ctx, poses, points, obs, cam_idx, pt_idx, K, huber_delta, obs_off, rank, nranks):
+        self.ctx = ctx
+        poses, points, obs, cam_idx, pt_idx, K = Context._ba_args(poses, points, obs, cam_idx, pt_idx, K)
+        if poses.ndim == 2:
+            poses, points = poses[None], points[None]
+        self.W, self.Nc, _ = poses.shape
+        self.Np = points.shape[1]
+        off = None if obs_off is None else np.ascontiguousarray(obs_off, np.int32)
+        self.h = ctx.lib.pmv_ba_problem_create(ctx.h, _ptr(poses), _ptr(points), _ptr(obs), _ptr(cam_idx), _ptr(pt_idx),
+                                               _ptr(off), self.W, self.Nc, self.Np, len(cam_idx), _ptr(K), huber_delta,
+                                               rank, nranks)
+        if not self.h:
+            raise PmvError(-1, ctx.lib.pmv_last_error(ctx.h).decode())
+
+    def reset(self):
+        self.ctx._chk(self.ctx.lib.pmv_ba_problem_reset(self.h, None, None))
+
+    def solve(self, max_iters):
+        self.ctx._chk(self.ctx.lib.pmv_ba_problem_solve(self.h, max_iters))
+
+    def download(self):
+        poses = np.zeros((self.W, self.Nc, 6)); points = np.zeros((self.W, self.Np, 3))
+        sums = (BASummary * self.W)()
+        self.ctx._chk(self.ctx.lib.pmv_ba_problem_download(self.h, _ptr(poses), _ptr(points), sums))
+        return poses, points, [x.as_dict() for x in sums]
+
+    @property
+    def device_bytes(self):
+        return int(self.ctx.lib.pmv_ba_problem_device_bytes(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.pmv_ba_problem_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

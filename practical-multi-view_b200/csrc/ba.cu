@@ -1,0 +1,410 @@
+// ba.cu -- host side of the bundle adjuster: problem upload, the launch sequence of one
+// Levenberg-Marquardt iteration (no host synchronisation inside a solve) and the C ABI.
+//
+// Drop-in for CeresBundleAdjustment::apply (reference CeresBundleAdjustment.cpp:5-89): the adapter
+// marshals tracker->R/t -> pose blocks [rodrigues(R^T), -t] (:26-34), Feature3D -> point blocks (:47-48),
+// (column,row) -> observations (:45) and calls pmv_ba_solve with huber_delta 1.0 and
+// max_iters = tracker->ba_iterations (:54-61).
+#include <algorithm>
+#include <numeric>
+
+#include "ba.cuh"
+#include "ba_kernels.cuh"
+
+int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, cudaStream_t s);  // ba_chol.cu
+int pmv_internal_ba_allreduce(pmv_ctx *ctx, const double *send, double *recv, size_t count, int op_max,
+                              cudaStream_t s);                                      // ba_nccl.cu
+
+struct pmv_ba_problem {
+    pmv_ctx *ctx = nullptr;
+    BADev D{};
+    int sharded = 0;     // points sharded over ranks: reduce camera blocks / S / scalars with NCCL
+    int rank = 0;
+    std::vector<void *> allocs;
+    double *d_init_poses = nullptr, *d_init_points = nullptr;
+    double *d_Uraw = nullptr, *d_Uraw_red = nullptr;   // 27 doubles per camera (+ W cost slots at the end)
+    double *d_scal = nullptr, *d_scal_red = nullptr;   // per window: model_change, cand_cost, step_norm2, x_norm2
+    std::vector<int> perm;                               // caller observation order -> device order
+    size_t bytes = 0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(pmv_ba_problem *p, T **out, size_t count)
+{
+    void *q = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) return p->ctx->fail(PMV_ERR_NOMEM, "ba problem allocation", e);
+    p->allocs.push_back(q);
+    p->bytes += bytes;
+    *out = reinterpret_cast<T *>(q);
+    return PMV_OK;
+}
+
+__global__ void ba_state_init_kernel(BAState *st, int W)
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    BAState s;
+    memset(&s, 0, sizeof s);
+    s.radius = 1e4; s.decrease_factor = 2.0; s.need_linearize = 1; s.chol_ok = 0;
+    st[w] = s;
+}
+
+// pack / unpack the per-window scalars that a sharded solve must sum across ranks
+__global__ void ba_pack_cost_kernel(const BADev D, double *Uraw_tail)
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < D.W) Uraw_tail[w] = D.st[w].new_cost;
+}
+__global__ void ba_unpack_cost_kernel(const BADev D, const double *Uraw_tail)
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < D.W) D.st[w].new_cost = Uraw_tail[w];
+}
+__global__ void ba_pack_scalars_kernel(const BADev D, double *buf)
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= D.W) return;
+    const BAState *st = &D.st[w];
+    buf[4 * w] = st->model_change; buf[4 * w + 1] = st->cand_cost; buf[4 * w + 2] = st->step_norm2; buf[4 * w + 3] = st->x_norm2;
+}
+__global__ void ba_unpack_scalars_kernel(const BADev D, const double *buf)
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= D.W) return;
+    BAState *st = &D.st[w];
+    st->model_change = buf[4 * w]; st->cand_cost = buf[4 * w + 1]; st->step_norm2 = buf[4 * w + 2]; st->x_norm2 = buf[4 * w + 3];
+}
+__global__ void ba_pack_gmax_kernel(const BADev D, double *buf)
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < D.W) buf[w] = D.st[w].gmax;
+}
+__global__ void ba_unpack_gmax_kernel(const BADev D, const double *buf)
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < D.W) D.st[w].gmax = buf[w];
+}
+
+int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
+{
+    pmv_ctx *ctx = p->ctx;
+    const BADev &D = p->D;
+    const int W = D.W, n = D.n;
+    const int wc = W * D.Nc, wp = W * D.Np;
+    const int wblocks = (W + 127) / 128;
+    if (D.No > 0) {
+        ba_linearize_kernel<<<(D.No + 127) / 128, 128, 0, s>>>(D);
+        PMV_LAUNCH_CHECK(ctx, "ba_linearize_kernel");
+    }
+    ba_cam_accumulate_kernel<<<(wc + 3) / 4, 128, 0, s>>>(D, p->d_Uraw);
+    PMV_LAUNCH_CHECK(ctx, "ba_cam_accumulate_kernel");
+    const double *Uraw = p->d_Uraw;
+    if (p->sharded) {
+        ba_pack_cost_kernel<<<wblocks, 128, 0, s>>>(D, p->d_Uraw + 27 * (size_t)wc);
+        PMV_LAUNCH_CHECK(ctx, "ba_pack_cost_kernel");
+        int rc = pmv_internal_ba_allreduce(ctx, p->d_Uraw, p->d_Uraw_red, 27 * (size_t)wc + W, 0, s);
+        if (rc) return rc;
+        ba_unpack_cost_kernel<<<wblocks, 128, 0, s>>>(D, p->d_Uraw_red + 27 * (size_t)wc);
+        PMV_LAUNCH_CHECK(ctx, "ba_unpack_cost_kernel");
+        Uraw = p->d_Uraw_red;
+    }
+    ba_latch_cost_kernel<<<wblocks, 128, 0, s>>>(D);
+    PMV_LAUNCH_CHECK(ctx, "ba_latch_cost_kernel");
+    ba_cam_finalize_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D, Uraw);
+    PMV_LAUNCH_CHECK(ctx, "ba_cam_finalize_kernel");
+    {
+        size_t nn = (size_t)n * n;
+        dim3 grid((unsigned)std::min<size_t>((nn + 255) / 256, 1024), W);
+        ba_clear_system_kernel<<<grid, 256, 0, s>>>(D);
+        PMV_LAUNCH_CHECK(ctx, "ba_clear_system_kernel");
+    }
+    if (wp > 0) {
+        ba_point_schur_kernel<<<(wp + 3) / 4, 128, 0, s>>>(D);
+        PMV_LAUNCH_CHECK(ctx, "ba_point_schur_kernel");
+    }
+    if (p->sharded) {
+        // [S | rhs] are contiguous per problem (W == 1 in sharded mode): one in-place sum over ranks
+        int rc = pmv_internal_ba_allreduce(ctx, D.S, D.S, (size_t)n * n + n, 0, s);
+        if (rc) return rc;
+        ba_pack_gmax_kernel<<<wblocks, 128, 0, s>>>(D, p->d_scal);
+        PMV_LAUNCH_CHECK(ctx, "ba_pack_gmax_kernel");
+        rc = pmv_internal_ba_allreduce(ctx, p->d_scal, p->d_scal_red, W, 1, s);
+        if (rc) return rc;
+        ba_unpack_gmax_kernel<<<wblocks, 128, 0, s>>>(D, p->d_scal_red);
+        PMV_LAUNCH_CHECK(ctx, "ba_unpack_gmax_kernel");
+    }
+    ba_add_cam_blocks_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D);
+    PMV_LAUNCH_CHECK(ctx, "ba_add_cam_blocks_kernel");
+    if (n <= 160) {
+        size_t smem = ((size_t)n * (n + 1) + n) * sizeof(double);
+        ba_cholesky_small_kernel<<<W, 256, smem, s>>>(D);
+        PMV_LAUNCH_CHECK(ctx, "ba_cholesky_small_kernel");
+    } else {
+        int rc = pmv_internal_ba_cholesky_large(ctx, D, s);
+        if (rc) return rc;
+    }
+    ba_cam_candidate_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D, p->sharded ? (p->rank == 0) : 1);
+    PMV_LAUNCH_CHECK(ctx, "ba_cam_candidate_kernel");
+    if (wp > 0) {
+        ba_backsub_kernel<<<(wp + 3) / 4, 128, 0, s>>>(D);
+        PMV_LAUNCH_CHECK(ctx, "ba_backsub_kernel");
+    }
+    if (p->sharded) {
+        ba_pack_scalars_kernel<<<wblocks, 128, 0, s>>>(D, p->d_scal);
+        PMV_LAUNCH_CHECK(ctx, "ba_pack_scalars_kernel");
+        int rc = pmv_internal_ba_allreduce(ctx, p->d_scal, p->d_scal_red, 4 * (size_t)W, 0, s);
+        if (rc) return rc;
+        ba_unpack_scalars_kernel<<<wblocks, 128, 0, s>>>(D, p->d_scal_red);
+        PMV_LAUNCH_CHECK(ctx, "ba_unpack_scalars_kernel");
+    }
+    ba_lm_update_kernel<<<wblocks, 128, 0, s>>>(D);
+    PMV_LAUNCH_CHECK(ctx, "ba_lm_update_kernel");
+    {
+        size_t tot = (size_t)wc * 6 + (size_t)wp * 3;
+        ba_accept_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(D);
+        PMV_LAUNCH_CHECK(ctx, "ba_accept_kernel");
+    }
+    return PMV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+PMV_API pmv_ba_problem *pmv_ba_problem_create(pmv_ctx *ctx, const double *poses, const double *points,
+                                              const double *obs, const int32_t *cam_idx, const int32_t *pt_idx,
+                                              const int32_t *obs_off, int W, int Nc, int Np, int No,
+                                              const double K[9], double huber_delta, int sharded_rank,
+                                              int sharded_nranks)
+{
+    if (!ctx) return nullptr;
+    if (!poses || !points || (No > 0 && (!obs || !cam_idx || !pt_idx)) || !K || W <= 0 || Nc <= 0 || Np <= 0 || No < 0 ||
+        (W > 1 && !obs_off)) {
+        ctx->fail(PMV_ERR_INVALID, "pmv_ba_problem_create: bad argument");
+        return nullptr;
+    }
+    if (sharded_nranks > 1 && W != 1) {
+        ctx->fail(PMV_ERR_UNSUPPORTED, "sharded bundle adjustment takes one problem (W == 1)");
+        return nullptr;
+    }
+    cudaSetDevice(ctx->device);
+    // ---- host: order observations by (window, point), group them by (window, camera) ---------------
+    std::vector<int> win(No);
+    for (int w = 0; w < W; w++) {
+        int o0 = obs_off ? obs_off[w] : 0, o1 = obs_off ? obs_off[w + 1] : No;
+        if (o0 < 0 || o1 < o0 || o1 > No) { ctx->fail(PMV_ERR_INVALID, "pmv_ba_problem_create: bad obs_off"); return nullptr; }
+        for (int i = o0; i < o1; i++) win[i] = w;
+    }
+    for (int i = 0; i < No; i++)
+        if (cam_idx[i] < 0 || cam_idx[i] >= Nc || pt_idx[i] < 0 || pt_idx[i] >= Np) {
+            ctx->fail(PMV_ERR_INVALID, "pmv_ba_problem_create: observation index out of range");
+            return nullptr;
+        }
+    std::vector<int> pt_off((size_t)W * Np + 1, 0), cam_off((size_t)W * Nc + 1, 0);
+    for (int i = 0; i < No; i++) { pt_off[(size_t)win[i] * Np + pt_idx[i] + 1]++; cam_off[(size_t)win[i] * Nc + cam_idx[i] + 1]++; }
+    std::partial_sum(pt_off.begin(), pt_off.end(), pt_off.begin());
+    std::partial_sum(cam_off.begin(), cam_off.end(), cam_off.begin());
+    std::vector<int> perm(No), h_cam(No), h_pt(No), h_win(No), cam_obs(No);
+    std::vector<double> h_obs(2 * (size_t)No);
+    {
+        std::vector<int> pos(pt_off.begin(), pt_off.end() - 1);
+        for (int i = 0; i < No; i++) {
+            int d = pos[(size_t)win[i] * Np + pt_idx[i]]++;
+            perm[i] = d; h_cam[d] = cam_idx[i]; h_pt[d] = pt_idx[i]; h_win[d] = win[i];
+            h_obs[2 * (size_t)d] = obs[2 * (size_t)i]; h_obs[2 * (size_t)d + 1] = obs[2 * (size_t)i + 1];
+        }
+        std::vector<int> cpos(cam_off.begin(), cam_off.end() - 1);
+        for (int d = 0; d < No; d++) cam_obs[cpos[(size_t)h_win[d] * Nc + h_cam[d]]++] = d;
+    }
+    pmv_ba_problem *p = new pmv_ba_problem();
+    p->ctx = ctx;
+    p->sharded = sharded_nranks > 1;
+    p->rank = sharded_rank;
+    p->perm = perm;
+    BADev &D = p->D;
+    D.W = W; D.Nc = Nc; D.Np = Np; D.n = 6 * Nc; D.No = No;
+    D.fx = K[0]; D.cx = K[2]; D.fy = K[4]; D.cy = K[5]; D.delta = huber_delta;
+    const size_t wc = (size_t)W * Nc, wp = (size_t)W * Np, n = D.n;
+    int *d_cam, *d_pt, *d_win, *d_ptoff, *d_camoff, *d_camobs;
+    double *d_obs;
+    int rc = 0;
+    rc |= dev_alloc(p, &d_cam, No); rc |= dev_alloc(p, &d_pt, No); rc |= dev_alloc(p, &d_win, No);
+    rc |= dev_alloc(p, &d_obs, 2 * (size_t)No); rc |= dev_alloc(p, &d_ptoff, wp + 1); rc |= dev_alloc(p, &d_camoff, wc + 1);
+    rc |= dev_alloc(p, &d_camobs, No);
+    rc |= dev_alloc(p, &D.poses, wc * 6); rc |= dev_alloc(p, &D.points, wp * 3);
+    rc |= dev_alloc(p, &D.cand_poses, wc * 6); rc |= dev_alloc(p, &D.cand_points, wp * 3);
+    rc |= dev_alloc(p, &p->d_init_poses, wc * 6); rc |= dev_alloc(p, &p->d_init_points, wp * 3);
+    rc |= dev_alloc(p, &D.Lr, 2 * (size_t)No); rc |= dev_alloc(p, &D.Ljc, 12 * (size_t)No); rc |= dev_alloc(p, &D.Ljp, 6 * (size_t)No);
+    rc |= dev_alloc(p, &D.scale_c, wc * 6); rc |= dev_alloc(p, &D.scale_p, wp * 3);
+    rc |= dev_alloc(p, &D.diag_c, wc * 6); rc |= dev_alloc(p, &D.diag_p, wp * 3);
+    rc |= dev_alloc(p, &D.U, wc * 36); rc |= dev_alloc(p, &D.gc, wc * 6);
+    // S and rhs contiguous ([S | rhs]) so a sharded solve reduces them with one collective
+    double *d_sys = nullptr;
+    rc |= dev_alloc(p, &d_sys, (size_t)W * (n * n + n) + (n + 1) * 8);
+    rc |= dev_alloc(p, &D.yc, (size_t)W * n);
+    rc |= dev_alloc(p, &D.Vinv, wp * 6); rc |= dev_alloc(p, &D.gp, wp * 3);
+    rc |= dev_alloc(p, &D.st, W);
+    rc |= dev_alloc(p, &p->d_Uraw, 27 * wc + W); rc |= dev_alloc(p, &p->d_Uraw_red, 27 * wc + W);
+    rc |= dev_alloc(p, &p->d_scal, 4 * (size_t)W); rc |= dev_alloc(p, &p->d_scal_red, 4 * (size_t)W);
+    if (rc) { pmv_ba_problem_destroy(p); return nullptr; }
+    D.S = d_sys; D.rhs = d_sys + (size_t)W * n * n;
+    D.obs_cam = d_cam; D.obs_pt = d_pt; D.obs_win = d_win; D.obs_xy = d_obs;
+    D.pt_off = d_ptoff; D.cam_off = d_camoff; D.cam_obs = d_camobs;
+    cudaStream_t s = ctx->stream;
+    bool ok = true;
+    auto up = [&](void *dst, const void *src, size_t bytes) {
+        if (bytes && cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) ok = false;
+    };
+    up(d_cam, h_cam.data(), sizeof(int) * No); up(d_pt, h_pt.data(), sizeof(int) * No); up(d_win, h_win.data(), sizeof(int) * No);
+    up(d_obs, h_obs.data(), sizeof(double) * 2 * No); up(d_ptoff, pt_off.data(), sizeof(int) * (wp + 1));
+    up(d_camoff, cam_off.data(), sizeof(int) * (wc + 1)); up(d_camobs, cam_obs.data(), sizeof(int) * No);
+    up(p->d_init_poses, poses, sizeof(double) * wc * 6); up(p->d_init_points, points, sizeof(double) * wp * 3);
+    if (ok && cudaStreamSynchronize(s) != cudaSuccess) ok = false;  // host vectors die at return
+    if (!ok) { ctx->fail(PMV_ERR_CUDA, "pmv_ba_problem_create: upload failed", cudaGetLastError()); pmv_ba_problem_destroy(p); return nullptr; }
+    if (pmv_ba_problem_reset(p, nullptr, nullptr) != PMV_OK) { pmv_ba_problem_destroy(p); return nullptr; }
+    return p;
+}
+
+PMV_API void pmv_ba_problem_destroy(pmv_ba_problem *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    for (void *q : p->allocs) cudaFree(q);
+    delete p;
+}
+
+PMV_API int pmv_ba_problem_reset(pmv_ba_problem *p, const double *poses, const double *points)
+{
+    if (!p) return PMV_ERR_INVALID;
+    pmv_ctx *ctx = p->ctx;
+    cudaSetDevice(ctx->device);
+    const BADev &D = p->D;
+    cudaStream_t s = ctx->stream;
+    const size_t pc = (size_t)D.W * D.Nc * 6 * sizeof(double), pp = (size_t)D.W * D.Np * 3 * sizeof(double);
+    if (poses) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(p->d_init_poses, poses, pc, cudaMemcpyHostToDevice, s));
+    if (points) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(p->d_init_points, points, pp, cudaMemcpyHostToDevice, s));
+    PMV_CUDA_TRY(ctx, cudaMemcpyAsync(D.poses, p->d_init_poses, pc, cudaMemcpyDeviceToDevice, s));
+    PMV_CUDA_TRY(ctx, cudaMemcpyAsync(D.points, p->d_init_points, pp, cudaMemcpyDeviceToDevice, s));
+    ba_state_init_kernel<<<(D.W + 127) / 128, 128, 0, s>>>(D.st, D.W);
+    PMV_LAUNCH_CHECK(ctx, "ba_state_init_kernel");
+    if (poses || points) PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return PMV_OK;
+}
+
+PMV_API int pmv_ba_problem_solve(pmv_ba_problem *p, int max_iters)
+{
+    if (!p) return PMV_ERR_INVALID;
+    pmv_ctx *ctx = p->ctx;
+    if (max_iters < 0) return ctx->fail(PMV_ERR_INVALID, "pmv_ba_problem_solve: max_iters < 0");
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    p->D.max_iters = max_iters;
+    if (p->D.n <= 160) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(ba_cholesky_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
+    }
+    ProfScope ps(ctx, PMV_PHASE_BA, s);
+    // iteration 0 evaluates the cost even when max_iters == 0 (Ceres: IterationZero)
+    for (int it = 0; it < std::max(max_iters, 1); it++) {
+        int rc = ba_iteration(p, s);
+        if (rc) return rc;
+    }
+    return PMV_OK;
+}
+
+PMV_API int pmv_ba_problem_download(pmv_ba_problem *p, double *poses, double *points, pmv_ba_summary *sums)
+{
+    if (!p) return PMV_ERR_INVALID;
+    pmv_ctx *ctx = p->ctx;
+    cudaSetDevice(ctx->device);
+    const BADev &D = p->D;
+    cudaStream_t s = ctx->stream;
+    std::vector<BAState> st(D.W);
+    if (poses) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(poses, D.poses, (size_t)D.W * D.Nc * 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (points) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(points, D.points, (size_t)D.W * D.Np * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PMV_CUDA_TRY(ctx, cudaMemcpyAsync(st.data(), D.st, sizeof(BAState) * D.W, cudaMemcpyDeviceToHost, s));
+    PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    if (sums)
+        for (int w = 0; w < D.W; w++) {
+            sums[w].initial_cost = st[w].initial_cost; sums[w].final_cost = st[w].cost;
+            sums[w].iterations = st[w].iter; sums[w].successful_steps = st[w].successful_steps;
+            sums[w].termination = st[w].termination; sums[w].final_radius = st[w].radius;
+        }
+    return PMV_OK;
+}
+
+PMV_API size_t pmv_ba_problem_device_bytes(pmv_ba_problem *p) { return p ? p->bytes : 0; }
+
+PMV_API int pmv_ba_solve_batched(pmv_ctx *ctx, double *poses, double *points, const double *obs,
+                                 const int32_t *cam_idx, const int32_t *pt_idx, const int32_t *obs_off, int W,
+                                 int Nc, int Np, int No, const double K[9], double huber_delta, int max_iters,
+                                 pmv_ba_summary *sums)
+{
+    if (!ctx) return PMV_ERR_INVALID;
+    pmv_ba_problem *p = pmv_ba_problem_create(ctx, poses, points, obs, cam_idx, pt_idx, obs_off, W, Nc, Np, No, K,
+                                              huber_delta, 0, 1);
+    if (!p) return PMV_ERR_INVALID;
+    int rc = pmv_ba_problem_solve(p, max_iters);
+    if (rc == PMV_OK) rc = pmv_ba_problem_download(p, poses, points, sums);
+    pmv_ba_problem_destroy(p);
+    return rc;
+}
+
+PMV_API int pmv_ba_solve(pmv_ctx *ctx, double *poses, double *points, const double *obs, const int32_t *cam_idx,
+                         const int32_t *pt_idx, int Nc, int Np, int No, const double K[9], double huber_delta,
+                         int max_iters, pmv_ba_summary *summary)
+{
+    return pmv_ba_solve_batched(ctx, poses, points, obs, cam_idx, pt_idx, nullptr, 1, Nc, Np, No, K, huber_delta,
+                                max_iters, summary);
+}
+
+PMV_API int pmv_ba_eval(pmv_ctx *ctx, const double *poses, const double *points, const double *obs,
+                        const int32_t *cam_idx, const int32_t *pt_idx, int Nc, int Np, int No, const double K[9],
+                        double huber_delta, double *r, double *J_pose, double *J_pt, double *cost)
+{
+    if (!ctx) return PMV_ERR_INVALID;
+    if (!poses || !points || !obs || !cam_idx || !pt_idx || !K || Nc <= 0 || Np <= 0 || No <= 0)
+        return ctx->fail(PMV_ERR_INVALID, "pmv_ba_eval: bad argument");
+    for (int i = 0; i < No; i++)
+        if (cam_idx[i] < 0 || cam_idx[i] >= Nc || pt_idx[i] < 0 || pt_idx[i] >= Np)
+            return ctx->fail(PMV_ERR_INVALID, "pmv_ba_eval: observation index out of range");
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    size_t need = sizeof(double) * ((size_t)Nc * 6 + (size_t)Np * 3 + (size_t)No * 22 + 8) + sizeof(int) * 2 * (size_t)No;
+    cudaError_t e = ctx->scratch[6].reserve(need);
+    if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "ba_eval workspace", e);
+    double *d = ctx->scratch[6].as<double>();
+    double *d_poses = d; d += (size_t)Nc * 6;
+    double *d_pts = d; d += (size_t)Np * 3;
+    double *d_obs = d; d += (size_t)No * 2;
+    double *d_r = d; d += (size_t)No * 2;
+    double *d_jc = d; d += (size_t)No * 12;
+    double *d_jp = d; d += (size_t)No * 6;
+    double *d_cost = d; d += 8;
+    int *d_cam = reinterpret_cast<int *>(d), *d_pt = d_cam + No;
+    PMV_CUDA_TRY(ctx, cudaMemcpyAsync(d_poses, poses, sizeof(double) * Nc * 6, cudaMemcpyHostToDevice, s));
+    PMV_CUDA_TRY(ctx, cudaMemcpyAsync(d_pts, points, sizeof(double) * Np * 3, cudaMemcpyHostToDevice, s));
+    PMV_CUDA_TRY(ctx, cudaMemcpyAsync(d_obs, obs, sizeof(double) * No * 2, cudaMemcpyHostToDevice, s));
+    PMV_CUDA_TRY(ctx, cudaMemcpyAsync(d_cam, cam_idx, sizeof(int) * No, cudaMemcpyHostToDevice, s));
+    PMV_CUDA_TRY(ctx, cudaMemcpyAsync(d_pt, pt_idx, sizeof(int) * No, cudaMemcpyHostToDevice, s));
+    PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_cost, 0, 8, s));
+    {
+        ProfScope ps(ctx, PMV_PHASE_BA, s);
+        ba_eval_kernel<<<(No + 127) / 128, 128, 0, s>>>(d_poses, d_pts, d_obs, d_cam, d_pt, No, K[0], K[2], K[4], K[5],
+                                                       huber_delta, d_r, d_jc, d_jp, d_cost);
+        PMV_LAUNCH_CHECK(ctx, "ba_eval_kernel");
+    }
+    if (r) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(r, d_r, sizeof(double) * No * 2, cudaMemcpyDeviceToHost, s));
+    if (J_pose) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(J_pose, d_jc, sizeof(double) * No * 12, cudaMemcpyDeviceToHost, s));
+    if (J_pt) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(J_pt, d_jp, sizeof(double) * No * 6, cudaMemcpyDeviceToHost, s));
+    if (cost) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(cost, d_cost, 8, cudaMemcpyDeviceToHost, s));
+    PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return PMV_OK;
+}
+
+}  // extern "C"

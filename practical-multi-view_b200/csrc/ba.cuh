@@ -1,0 +1,52 @@
+// ba.cuh -- shared device structures of the bundle adjuster (K8-K11).
+#pragma once
+#include "common.cuh"
+
+// Per-problem (per-window) Levenberg-Marquardt state, resident on the device so the whole solve runs
+// without host synchronisation.  Mirrors Ceres' TrustRegionMinimizer + LevenbergMarquardtStrategy
+// members (SURVEY Appx C.3).
+struct BAState {
+    double cost;            // cost at the current iterate x
+    double new_cost;        // accumulator: cost of the latest linearisation
+    double cand_cost;       // accumulator: cost at the candidate point
+    double model_change;    // accumulator: -(J step)^T (r + J step / 2)
+    double step_norm2;      // accumulator: |delta|^2 over active parameters
+    double x_norm2;         // accumulator: |x|^2 over active parameters
+    double radius;
+    double decrease_factor;
+    double initial_cost;
+    double gmax;            // accumulator: max |gradient| (unscaled), as bits of a non-negative double
+    int iter;               // LM iterations executed
+    int done;               // termination reached (see termination)
+    int termination;        // 0 max iterations, 1 function tol, 2 parameter tol, 3 gradient tol, 4 failure, 5 min radius
+    int need_linearize;     // 1 -> x changed (or first iteration): re-evaluate r, J
+    int reuse_diagonal;
+    int invalid_run;
+    int chol_ok;            // reduced system factorised
+    int accepted;           // last step accepted (candidate must be copied into x)
+    int successful_steps;
+    int scale_ready;        // Jacobi scaling computed (first linearisation)
+    int pad0, pad1;
+};
+
+struct BADev {
+    int W, Nc, Np, n, No;
+    // topology, observations sorted by (window, point)
+    const int *obs_cam, *obs_pt, *obs_win;
+    const double *obs_xy;
+    const int *pt_off;    // W*Np + 1
+    const int *cam_off;   // W*Nc + 1
+    const int *cam_obs;   // No, observation indices grouped by (window, camera)
+    double fx, cx, fy, cy, delta;
+    // parameters
+    double *poses, *points, *cand_poses, *cand_points;
+    // linearisation (Corrector applied, columns NOT yet scaled): 2 + 12 + 6 doubles per observation
+    double *Lr, *Ljc, *Ljp;
+    double *scale_c, *scale_p;   // Jacobi scaling, fixed after the first linearisation
+    double *diag_c, *diag_p;     // clamp(|J_:j|^2) of the scaled Jacobian (LM diagonal before / radius)
+    double *U, *gc;              // per camera: scaled J_c^T J_c (36) and J_c^T r (6)
+    double *S, *rhs, *yc;        // reduced camera system per window (n x n, upper blocks valid), solution
+    double *Vinv, *gp;           // per point: (V + D^2)^-1 (6 unique) and J_p^T r (3)
+    BAState *st;
+    int max_iters;
+};

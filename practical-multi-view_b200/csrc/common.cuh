@@ -87,6 +87,8 @@ struct pmv_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     uint64_t launches = 0;
+    void *nccl_comm = nullptr;          // ncclComm_t of the sharded bundle adjuster (ba_nccl.cu)
+    int nranks = 1, rank = 0;
 
     // optional per-phase CUDA-event timing (bench roofline); see pmv_profile_*
     bool prof_on = false;

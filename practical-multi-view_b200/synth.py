@@ -45,3 +45,95 @@ def track_points(img: np.ndarray, n: int, seed: int, jitter: float = 0.25, min_d
         pts = np.concatenate([pts, extra.astype(np.float32)])
     pts = pts + rng.uniform(-jitter, jitter, pts.shape).astype(np.float32)
     return np.ascontiguousarray(pts, np.float32)
+
+
+# ----------------------------------------------------------------------------- bundle adjustment
+KITTI_K = np.array([[718.856, 0.0, 607.1928], [0.0, 718.856, 185.2157], [0.0, 0.0, 1.0]])
+
+
+def _rodrigues(a):
+    th = np.linalg.norm(a)
+    if th < 1e-12:
+        return np.eye(3)
+    w = a / th
+    Kx = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    return np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+
+
+def project(pose, X, K=KITTI_K):
+    """ProjectionResidual's camera model (ProjectionResidual.h:44-52): p = R(a)(X+c), z flipped."""
+    p = (_rodrigues(pose[:3]) @ (X + pose[3:]).T).T
+    z = -p[:, 2]
+    return np.stack([p[:, 0] / z * K[0, 0] + K[0, 2], p[:, 1] / z * K[1, 1] + K[1, 2]], -1), p[:, 2]
+
+
+def ba_window(seed: int, n_poses=20, n_points=2000, width=1241, height=376, outlier_frac=0.05, K=KITTI_K):
+    """BASELINE config 4 window: forward trajectory 1 m/frame along -z with yaw noise,
+    points in the frustum at depth 5-50 m, integer-rounded observations with N(0, .5 px) noise and
+    5 % gross outliers, initial parameters = truth + noise.  Returns a dict of numpy arrays."""
+    rng = np.random.default_rng(seed)
+    poses_t = np.zeros((n_poses, 6))
+    for i in range(n_poses):
+        poses_t[i, :3] = [0, rng.normal(0, 0.01), 0]
+        poses_t[i, 3:] = [0, 0, 1.0 * i] + rng.normal(0, 0.02, 3)          # c = -t ; camera moves along -z
+    depth = rng.uniform(5, 50, n_points) + n_poses * 0.5
+    u = rng.uniform(0, width, n_points); v = rng.uniform(0, height, n_points)
+    # back-project through the middle camera so most points are seen by most poses
+    mid = poses_t[n_poses // 2]
+    pc = np.stack([(u - K[0, 2]) / K[0, 0] * depth, (v - K[1, 2]) / K[1, 1] * depth, -depth], -1)
+    pts_t = (_rodrigues(mid[:3]).T @ pc.T).T - mid[3:]
+    cam_idx, pt_idx, obs = [], [], []
+    for i in range(n_poses):
+        uv, z = project(poses_t[i], pts_t, K)
+        vis = (z < -0.5) & (uv[:, 0] >= 0) & (uv[:, 0] < width) & (uv[:, 1] >= 0) & (uv[:, 1] < height)
+        ids = np.nonzero(vis)[0]
+        o = uv[ids] + rng.normal(0, 0.5, (len(ids), 2))
+        bad = rng.random(len(ids)) < outlier_frac
+        o[bad] += rng.uniform(5, 30, (bad.sum(), 2)) * rng.choice([-1, 1], (bad.sum(), 2))
+        cam_idx.append(np.full(len(ids), i)); pt_idx.append(ids); obs.append(np.round(o))
+    cam_idx = np.concatenate(cam_idx).astype(np.int32); pt_idx = np.concatenate(pt_idx).astype(np.int32)
+    obs = np.concatenate(obs).astype(np.float64)
+    poses0 = poses_t + np.concatenate([rng.normal(0, 0.005, (n_poses, 3)), rng.normal(0, 0.05, (n_poses, 3))], 1)
+    pts0 = (pts_t + rng.normal(0, 0.1, pts_t.shape)).astype(np.float32).astype(np.float64)  # Feature3D stores float
+    return {"poses": poses0, "points": pts0, "obs": obs, "cam_idx": cam_idx, "pt_idx": pt_idx, "K": K.copy(),
+            "poses_true": poses_t, "points_true": pts_t}
+
+
+def ba_large(seed: int, n_poses=1000, n_points=1_000_000, views=5, span=40, width=1241, height=376, K=KITTI_K):
+    """BASELINE config 5 (BAL scale): each point is seen by `views` poses chosen among the `span` poses
+    nearest to it along a straight trajectory; observations need not fall inside an image."""
+    rng = np.random.default_rng(seed)
+    poses_t = np.zeros((n_poses, 6))
+    poses_t[:, 1] = rng.normal(0, 0.01, n_poses)
+    poses_t[:, 5] = np.arange(n_poses) * 1.0
+    poses_t[:, 3:] += rng.normal(0, 0.02, (n_poses, 3))
+    anchor = rng.integers(0, n_poses, n_points)
+    depth = rng.uniform(8, 50, n_points)
+    u = rng.uniform(0.2 * width, 0.8 * width, n_points); v = rng.uniform(0.2 * height, 0.8 * height, n_points)
+    pc = np.stack([(u - K[0, 2]) / K[0, 0] * depth, (v - K[1, 2]) / K[1, 1] * depth, -depth], -1)
+    # anchor rotation is a tiny yaw: back-project with the exact model point by point in blocks
+    pts_t = np.empty_like(pc)
+    for a in np.unique(anchor):
+        m = anchor == a
+        pts_t[m] = (_rodrigues(poses_t[a, :3]).T @ pc[m].T).T - poses_t[a, 3:]
+    # `views` distinct poses within [anchor-span/2, anchor+span/2) that stay in front of the point (z < 0)
+    offs = np.stack([rng.permutation(span // 2)[:views] for _ in range(1)], 0)  # same pattern base, shifted per point
+    shift = rng.integers(0, span // 2, n_points)
+    cams = (anchor[:, None] - ((offs + shift[:, None]) % (span // 2))).clip(0, n_poses - 1)
+    cams = np.sort(cams, 1)
+    keep = np.ones_like(cams, bool)
+    keep[:, 1:] = cams[:, 1:] != cams[:, :-1]
+    pt_idx = np.repeat(np.arange(n_points), views).reshape(n_points, views)[keep].astype(np.int32)
+    cam_idx = cams[keep].astype(np.int32)
+    obs = np.empty((len(cam_idx), 2))
+    order = np.argsort(cam_idx, kind="stable")
+    bounds = np.searchsorted(cam_idx[order], np.arange(n_poses + 1))
+    for c in range(n_poses):
+        sel = order[bounds[c]:bounds[c + 1]]
+        if len(sel):
+            uv, _ = project(poses_t[c], pts_t[pt_idx[sel]], K)
+            obs[sel] = np.round(uv + rng.normal(0, 0.5, uv.shape))
+    poses0 = poses_t + np.concatenate([rng.normal(0, 0.002, (n_poses, 3)), rng.normal(0, 0.03, (n_poses, 3))], 1)
+    pts0 = (pts_t + rng.normal(0, 0.05, pts_t.shape)).astype(np.float32).astype(np.float64)
+    return {"poses": poses0, "points": pts0, "obs": obs, "cam_idx": cam_idx, "pt_idx": pt_idx, "K": K.copy(),
+            "poses_true": poses_t, "points_true": pts_t}

@@ -1,0 +1,127 @@
+"""GPU parity of the bundle adjuster (through the C ABI) against the fp64 oracle.  Bars (north_star):
+residuals / Jacobians within 1e-5 relative, final cost within 1e-6 relative for the same iteration
+count.  (The oracle itself is unpinned against Ceres -- see tests/test_oracle_ba.py.)"""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _args(w):
+    return (w["poses"], w["points"], w["obs"], w["cam_idx"], w["pt_idx"], w["K"])
+
+
+def test_residual_jacobian_vs_oracle(ctx, synth):
+    w = synth.ba_window(1, n_poses=8, n_points=300)
+    r, Jc, Jp, cost = ctx.ba_eval(*_args(w))
+    ro, Jco, Jpo, costo = oracle.ba_eval(*_args(w))
+    assert np.abs(r - ro).max() <= 1e-5 * np.abs(ro).max()
+    assert np.abs(Jc - Jco).max() <= 1e-5 * np.abs(Jco).max()
+    assert np.abs(Jp - Jpo).max() <= 1e-5 * np.abs(Jpo).max()
+    # per-entry relative check where entries are not tiny (analytic vs Jets agree to ~1e-12)
+    big = np.abs(Jco) > 1e-3 * np.abs(Jco).max()
+    assert np.abs(Jc[big] / Jco[big] - 1).max() < 1e-9
+    assert abs(cost - costo) <= 1e-10 * costo
+
+
+def test_small_angle_and_no_loss(ctx):
+    K = np.array([[700., 0, 300], [0, 700, 200], [0, 0, 1]])
+    poses = np.array([[0, 0, 0, .1, -.2, .3], [1e-9, -2e-9, 5e-10, 0, 0, 0], [.3, -.2, .1, .2, .1, 0]])
+    pts = np.array([[1.0, -0.5, -12.0], [-2, 1, -30.]])
+    cam = np.array([0, 1, 2, 0, 1, 2], np.int32); pt = np.array([0, 0, 0, 1, 1, 1], np.int32)
+    obs = np.array([[320., 190.]] * 6)
+    for delta in (1.0, 0.0):
+        got = ctx.ba_eval(poses, pts, obs, cam, pt, K, delta)
+        want = oracle.ba_eval(poses, pts, obs, cam, pt, K, delta)
+        for g, wv in zip(got[:3], want[:3]):
+            assert np.allclose(g, wv, rtol=1e-10, atol=1e-9)
+        assert np.isclose(got[3], want[3], rtol=1e-12)
+
+
+@pytest.mark.parametrize("npose,npts,iters", [(5, 150, 5), (6, 80, 10), (3, 600, 5), (20, 400, 5)])
+def test_solve_vs_oracle(ctx, synth, npose, npts, iters):
+    w = synth.ba_window(2 + npose, n_poses=npose, n_points=npts)
+    p, x, s = ctx.ba_solve(*_args(w), 1.0, iters)
+    po, xo, so = oracle.ba_solve(*_args(w), 1.0, iters)
+    assert s["iterations"] == so["iterations"] and s["successful_steps"] == so["successful_steps"]
+    assert s["termination"] == so["termination"]
+    assert abs(s["initial_cost"] - so["initial_cost"]) <= 1e-10 * so["initial_cost"]
+    assert abs(s["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]        # north_star bar
+    assert np.abs(p - po).max() < 1e-5 and np.abs(x - xo).max() < 1e-4
+
+
+def test_solve_pipeline_shape_sparse_visibility(ctx, synth):
+    """Reference shape: <=5 poses, a few hundred points each seen in 2-5 frames, 5 iterations."""
+    rng = np.random.default_rng(0)
+    w = synth.ba_window(77, n_poses=5, n_points=400)
+    keep = rng.random(len(w["obs"])) < 0.6
+    a = (w["poses"], w["points"], w["obs"][keep], w["cam_idx"][keep], w["pt_idx"][keep], w["K"])
+    p, x, s = ctx.ba_solve(*a, 1.0, 5)
+    po, xo, so = oracle.ba_solve(*a, 1.0, 5)
+    assert abs(s["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]
+    assert s["iterations"] == so["iterations"]
+    unseen = np.setdiff1d(np.arange(400), w["pt_idx"][keep])
+    assert np.array_equal(x[unseen], w["points"][unseen])          # blocks without residuals untouched
+
+
+def test_rejected_steps_follow_oracle(ctx, synth):
+    """Start far from the optimum so the LM loop rejects steps and shrinks the radius."""
+    w = synth.ba_window(5, n_poses=4, n_points=60)
+    rng = np.random.default_rng(1)
+    poses = w["poses"] + rng.normal(0, 0.05, w["poses"].shape)
+    pts = w["points"] + rng.normal(0, 2.0, w["points"].shape)
+    a = (poses, pts, w["obs"], w["cam_idx"], w["pt_idx"], w["K"])
+    p, x, s = ctx.ba_solve(*a, 1.0, 12)
+    po, xo, so = oracle.ba_solve(*a, 1.0, 12)
+    assert s["iterations"] == so["iterations"] and s["successful_steps"] == so["successful_steps"]
+    assert abs(s["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]
+
+
+def test_converged_problem_terminates_like_oracle(ctx, synth):
+    w = synth.ba_window(3, n_poses=5, n_points=60, outlier_frac=0.0)
+    obs = np.concatenate([synth.project(w["poses_true"][c], w["points_true"][[p]], w["K"])[0]
+                          for c, p in zip(w["cam_idx"], w["pt_idx"])])
+    a = (w["poses"], w["points"], obs, w["cam_idx"], w["pt_idx"], w["K"])
+    p, x, s = ctx.ba_solve(*a, 1.0, 50)
+    po, xo, so = oracle.ba_solve(*a, 1.0, 50)
+    assert s["termination"] in (1, 2, 3) and s["final_cost"] < 1e-9
+    assert abs(s["iterations"] - so["iterations"]) <= 1        # at the 1e-16 cost floor the last test may flip
+
+
+def test_batched_windows(ctx, synth):
+    ws = [synth.ba_window(10 + i, n_poses=6, n_points=120) for i in range(5)]
+    off = np.cumsum([0] + [len(w["obs"]) for w in ws])
+    P, X, S = ctx.ba_solve_batched(np.stack([w["poses"] for w in ws]), np.stack([w["points"] for w in ws]),
+                                   np.concatenate([w["obs"] for w in ws]), np.concatenate([w["cam_idx"] for w in ws]),
+                                   np.concatenate([w["pt_idx"] for w in ws]), off, ws[0]["K"], 1.0, 5)
+    for i, w in enumerate(ws):
+        po, xo, so = oracle.ba_solve(*_args(w), 1.0, 5)
+        assert abs(S[i]["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]
+        assert S[i]["iterations"] == so["iterations"]
+        assert np.abs(P[i] - po).max() < 1e-5
+
+
+def test_large_reduced_system_uses_blocked_cholesky(ctx, synth):
+    """n = 6*40 = 240 > 160: the blocked HBM Cholesky (DMMA trailing update) instead of the smem one."""
+    w = synth.ba_large(3, n_poses=40, n_points=3000, views=5, span=20)
+    p, x, s = ctx.ba_solve(*_args(w), 1.0, 4)
+    po, xo, so = oracle.ba_solve(*_args(w), 1.0, 4)
+    assert s["iterations"] == so["iterations"]
+    assert abs(s["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]
+    assert np.abs(p - po).max() < 1e-5
+
+
+def test_resident_problem_reset_and_errors(ctx, pmv, synth):
+    w = synth.ba_window(9, n_poses=5, n_points=100)
+    prob = ctx.ba_problem(*_args(w))
+    prob.solve(5)
+    p1, x1, s1 = prob.download()
+    prob.reset(); prob.solve(5)
+    p2, x2, s2 = prob.download()
+    assert np.allclose(p1, p2, atol=1e-9) and abs(s1[0]["final_cost"] - s2[0]["final_cost"]) <= 1e-9 * s1[0]["final_cost"]
+    assert prob.device_bytes > 0
+    prob.close()
+    with pytest.raises(pmv.PmvError):
+        ctx.ba_solve(w["poses"], w["points"], w["obs"], w["cam_idx"] + 100, w["pt_idx"], w["K"])
