@@ -85,6 +85,7 @@ struct pmv_ctx {
     cudaStream_t own_stream = nullptr;  // created by pmv_create
     cudaStream_t copy_stream = nullptr; // second stream for chunked upload overlap
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> chunk_ev;  // upload/compute hand-off events of the chunked host paths
     std::string err;
     uint64_t launches = 0;
     void *nccl_comm = nullptr;          // ncclComm_t of the sharded bundle adjuster (ba_nccl.cu)
@@ -163,5 +164,5 @@ int pmv_internal_pyr_plan(pmv_ctx *ctx, int which, int batch, int rows, int cols
                           int win_w, int win_h, int max_level, PyrSet *out);
 // Import level 0 from device memory (any pitch) / expect it already copied into the interior
 // (src == nullptr), fill its border, then build levels 1..top with their borders.
-int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, const uint8_t *d_src, int src_pitch,
-                         size_t src_stride, cudaStream_t s);
+int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, const uint8_t *d_src, const uint8_t *d_src2,
+                         int src_pitch, size_t src_stride, cudaStream_t s);

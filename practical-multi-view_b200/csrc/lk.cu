@@ -335,13 +335,17 @@ int check_lk_args(pmv_ctx *ctx, int rows, int cols, int step, int n, int win_w, 
 
 // Enqueue import + pyramids + tracking for `batch` pairs.  d_prev/d_next: device images (any pitch) or
 // nullptr when the caller already copied level 0 into the planned interior (host upload path).
+// prev and next image sets share ONE bordered allocation of 2*batch images (prev = [0, batch),
+// next = [batch, 2*batch)), so import / pyrDown / border fill run once per step for both.
 int lk_plan(pmv_ctx *ctx, int batch, int rows, int cols, int win_w, int win_h, int max_level,
             PyrSet *sp, PyrSet *sn)
 {
     const int border = (win_w > win_h ? win_w : win_h) + LK_M + 2;
-    int rc = pmv_internal_pyr_plan(ctx, 0, batch, rows, cols, border, win_w, win_h, max_level, sp);
+    int rc = pmv_internal_pyr_plan(ctx, 0, 2 * batch, rows, cols, border, win_w, win_h, max_level, sp);
     if (rc) return rc;
-    return pmv_internal_pyr_plan(ctx, 1, batch, rows, cols, border, win_w, win_h, max_level, sn);
+    *sn = *sp;
+    for (int l = 0; l <= sp->top; l++) sn->lv[l].ptr = sp->lv[l].ptr + (size_t)batch * sp->lv[l].img_stride;
+    return PMV_OK;
 }
 
 int lk_enqueue(pmv_ctx *ctx, const PyrSet &sp, const PyrSet &sn, const uint8_t *d_prev, const uint8_t *d_next,
@@ -352,10 +356,15 @@ int lk_enqueue(pmv_ctx *ctx, const PyrSet &sp, const PyrSet &sn, const uint8_t *
     int rc;
     {
         ProfScope ps(ctx, PMV_PHASE_PYRAMID, s);
-        rc = pmv_internal_pyr_run(ctx, sp, batch, d_prev, pitch, img_stride, s);
-        if (rc) return rc;
-        rc = pmv_internal_pyr_run(ctx, sn, batch, d_next, pitch, img_stride, s);
-        if (rc) return rc;
+        if (sn.lv[0].ptr == sp.lv[0].ptr + (size_t)batch * sp.lv[0].img_stride) {
+            rc = pmv_internal_pyr_run(ctx, sp, 2 * batch, d_prev, d_next, pitch, img_stride, s);
+            if (rc) return rc;
+        } else {  // chunk smaller than the planned batch: the two sets are not adjacent -> two passes
+            rc = pmv_internal_pyr_run(ctx, sp, batch, d_prev, nullptr, pitch, img_stride, s);
+            if (rc) return rc;
+            rc = pmv_internal_pyr_run(ctx, sn, batch, d_next, nullptr, pitch, img_stride, s);
+            if (rc) return rc;
+        }
     }
     if (n == 0) return PMV_OK;
     ProfScope pl(ctx, PMV_PHASE_LK, s);
@@ -425,35 +434,52 @@ PMV_API int pmv_lk_track_batched(pmv_ctx *ctx, const uint8_t *prev, const uint8_
     if (img_stride < (size_t)rows * step) return ctx->fail(PMV_ERR_INVALID, "lk: img_stride < rows*step");
     cudaSetDevice(ctx->device);
 
+    // Chunked pipeline: raw image bytes go up on the copy stream (one contiguous transfer per chunk and
+    // image set), the compute stream imports / builds pyramids / tracks chunk c while chunk c+1 is in flight.
+    const int CH = batch <= 8 ? batch : 32;
+    const int nchunks = (batch + CH - 1) / CH;
     PyrSet sp, sn;
-    rc = lk_plan(ctx, batch, rows, cols, win_w, win_h, max_level, &sp, &sn);
+    rc = lk_plan(ctx, CH, rows, cols, win_w, win_h, max_level, &sp, &sn);
     if (rc) return rc;
+    const size_t raw_bytes = (size_t)batch * img_stride;
     cudaError_t e = ctx->pts[0].reserve((size_t)batch * n * 8 + 8);
     if (e == cudaSuccess) e = ctx->pts[1].reserve((size_t)batch * n * 8 + 8);
     if (e == cudaSuccess) e = ctx->pts[2].reserve((size_t)batch * n + 8);
     if (e == cudaSuccess) e = ctx->pts[3].reserve((size_t)batch * n * 4 + 8);
+    if (e == cudaSuccess) e = ctx->img[0].reserve(raw_bytes + 16);
+    if (e == cudaSuccess) e = ctx->img[1].reserve(raw_bytes + 16);
     if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "lk batch buffers", e);
     float *dpx = ctx->pts[0].as<float>(), *dnx = ctx->pts[1].as<float>();
     uint8_t *dst = ctx->pts[2].as<uint8_t>();
     float *der = ctx->pts[3].as<float>();
-    cudaStream_t s = ctx->stream;
-
+    uint8_t *rawP = ctx->img[0].as<uint8_t>(), *rawN = ctx->img[1].as<uint8_t>();
+    cudaStream_t s = ctx->stream, cs = nchunks > 1 ? ctx->copy_stream : ctx->stream;
+    while ((int)ctx->chunk_ev.size() < nchunks) {
+        cudaEvent_t ev = nullptr;
+        PMV_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->chunk_ev.push_back(ev);
+    }
     if (n > 0) {
         PMV_CUDA_TRY(ctx, cudaMemcpyAsync(dpx, prev_xy, (size_t)batch * n * 8, cudaMemcpyHostToDevice, s));
         if (flags & PMV_LK_USE_INITIAL_FLOW)
             PMV_CUDA_TRY(ctx, cudaMemcpyAsync(dnx, next_xy, (size_t)batch * n * 8, cudaMemcpyHostToDevice, s));
     }
-    // Upload straight into the interiors of the bordered level-0 buffers (one strided copy per image).
-    const PyrLevel &p0 = sp.lv[0], &n0 = sn.lv[0];
-    for (int b = 0; b < batch; b++) {
-        PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(const_cast<uint8_t *>(p0.ptr) + b * p0.img_stride, p0.pitch,
-                                            prev + b * img_stride, step, cols, rows, cudaMemcpyHostToDevice, s));
-        PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(const_cast<uint8_t *>(n0.ptr) + b * n0.img_stride, n0.pitch,
-                                            next + b * img_stride, step, cols, rows, cudaMemcpyHostToDevice, s));
+    for (int c = 0; c < nchunks; c++) {
+        const int b0 = c * CH, nb = (batch - b0 < CH) ? batch - b0 : CH;
+        const size_t off = (size_t)b0 * img_stride;
+        // the last image of the batch may be shorter than img_stride in the caller's buffer
+        const size_t bytes = (size_t)(nb - 1) * img_stride + (size_t)(rows - 1) * step + cols;
+        PMV_CUDA_TRY(ctx, cudaMemcpyAsync(rawP + off, prev + off, bytes, cudaMemcpyHostToDevice, cs));
+        PMV_CUDA_TRY(ctx, cudaMemcpyAsync(rawN + off, next + off, bytes, cudaMemcpyHostToDevice, cs));
+        if (nchunks > 1) {
+            PMV_CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[c], cs));
+            PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->chunk_ev[c], 0));
+        }
+        rc = lk_enqueue(ctx, sp, sn, rawP + off, rawN + off, nb, img_stride, step, dpx + (size_t)b0 * n * 2, n, win_w,
+                        win_h, max_count, eps, flags, min_eig_thr, dnx + (size_t)b0 * n * 2, dst + (size_t)b0 * n,
+                        der + (size_t)b0 * n, s);
+        if (rc) return rc;
     }
-    rc = lk_enqueue(ctx, sp, sn, nullptr, nullptr, batch, 0, 0, dpx, n, win_w, win_h,
-                    max_count, eps, flags, min_eig_thr, dnx, dst, der, s);
-    if (rc) return rc;
     if (n > 0) {
         PMV_CUDA_TRY(ctx, cudaMemcpyAsync(next_xy, dnx, (size_t)batch * n * 8, cudaMemcpyDeviceToHost, s));
         PMV_CUDA_TRY(ctx, cudaMemcpyAsync(status, dst, (size_t)batch * n, cudaMemcpyDeviceToHost, s));

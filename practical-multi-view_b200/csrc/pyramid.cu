@@ -25,11 +25,12 @@ constexpr int PIN_H = 2 * PT_H + 3;     // 35 input rows
 constexpr int PIN_W = 2 * PT_W + 32;    // 288 staged input bytes per row (16 B aligned superset)
 constexpr int PIN_X0 = 16;              // staged column c <-> interior column 2*tx0 - 16 + c
 
-// src: bordered level (interior pointer, border >= 16 left, >= 2 elsewhere; rows above/below the
-// allocation are clamped).  lo_row/hi_row: first/last addressable row relative to the interior.
+// src: level interior pointer inside a bordered allocation (>= 16 addressable bytes left of column 0,
+// row_bytes_right addressable bytes from column 0).  Image edges are handled here (reflect-101), so the
+// kernel does not depend on the border having been filled.
 __global__ void __launch_bounds__(256)
-pyr_down_kernel(const uint8_t *__restrict__ src, int spitch, size_t sstride, int lo_row, int hi_row,
-                int row_bytes_right,  // bytes addressable to the right of interior column 0
+pyr_down_kernel(const uint8_t *__restrict__ src, int srows, int scols, int spitch, size_t sstride,
+                int row_bytes_right,
                 uint8_t *__restrict__ dst, int drows, int dcols, int dpitch, size_t dstride)
 {
     __shared__ __align__(16) uint8_t s_in[PIN_H][PIN_W];
@@ -45,12 +46,24 @@ pyr_down_kernel(const uint8_t *__restrict__ src, int spitch, size_t sstride, int
 
     for (int i = tid; i < PIN_H * (PIN_W / 16); i += 256) {
         int r = i / (PIN_W / 16), ch = i % (PIN_W / 16);
-        int gy = min(max(gy0 + r, lo_row), hi_row);
+        int gy = reflect101(gy0 + r, srows);
         int gx = gx0 + ch * 16;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (gx + 16 <= row_bytes_right)
             v = __ldg(reinterpret_cast<const uint4 *>(src + (ptrdiff_t)gy * spitch + gx));
         *reinterpret_cast<uint4 *>(&s_in[r][ch * 16]) = v;
+    }
+    // tiles touching the left / right image edge: columns outside [0, scols) come from their mirror
+    if (2 * tx0 - 2 < 0 || 2 * tx0 + 2 * PT_W + 2 > scols) {
+        __syncthreads();
+        for (int i = tid; i < PIN_H * (2 * PT_W + 3); i += 256) {
+            int r = i / (2 * PT_W + 3), c = PIN_X0 - 2 + i % (2 * PT_W + 3);
+            int gx = gx0 + c;
+            if (gx < 0 || gx >= scols) {
+                int gy = reflect101(gy0 + r, srows);
+                s_in[r][c] = src[(ptrdiff_t)gy * spitch + reflect101(gx, scols)];
+            }
+        }
     }
     __syncthreads();
 
@@ -81,12 +94,21 @@ pyr_down_kernel(const uint8_t *__restrict__ src, int spitch, size_t sstride, int
     }
 }
 
-// Reflect-101 border of one level: bands top / bottom (full bordered width) and left / right.
-__global__ void __launch_bounds__(256)
-border_fill_kernel(uint8_t *__restrict__ img, int rows, int cols, int pitch, size_t stride,
-                   int by, int bxl, int bxr)
+// Reflect-101 border of ALL levels of a batch in one launch (grid.y = image, grid.z = level):
+// bands top / bottom (full bordered width) and left / right.
+struct BorderArgs {
+    uint8_t *ptr[PMV_MAX_PYR_LEVELS];
+    int rows[PMV_MAX_PYR_LEVELS], cols[PMV_MAX_PYR_LEVELS], pitch[PMV_MAX_PYR_LEVELS];
+    size_t stride[PMV_MAX_PYR_LEVELS];
+    int by, bxl, bxr;
+};
+
+__global__ void __launch_bounds__(256) border_fill_kernel(const BorderArgs A)
 {
-    uint8_t *base = img + (size_t)blockIdx.y * stride;
+    const int l = blockIdx.z;
+    const int rows = A.rows[l], cols = A.cols[l], pitch = A.pitch[l];
+    uint8_t *base = A.ptr[l] + (size_t)blockIdx.y * A.stride[l];
+    const int by = A.by, bxl = A.bxl, bxr = A.bxr;
     const int fullw = bxl + cols + bxr;
     const int n_tb = 2 * by * fullw;          // top + bottom bands
     const int n_lr = rows * (bxl + bxr);      // left + right bands
@@ -172,42 +194,51 @@ int pmv_internal_pyr_plan(pmv_ctx *ctx, int which, int batch, int rows, int cols
     return PMV_OK;
 }
 
-static int fill_border(pmv_ctx *ctx, const PyrLevel &d, int batch, cudaStream_t s)
+static int fill_borders(pmv_ctx *ctx, const PyrSet &set, int batch, cudaStream_t s)
 {
-    const int bxl = d.bxl;
-    const int n = 2 * d.border * (bxl + d.cols + d.border) + d.rows * (bxl + d.border);
-    dim3 grid(min((n + 255) / 256, 64), batch);
-    border_fill_kernel<<<grid, 256, 0, s>>>(const_cast<uint8_t *>(d.ptr), d.rows, d.cols, d.pitch, d.img_stride,
-                                            d.border, bxl, d.border);
+    BorderArgs A;
+    memset(&A, 0, sizeof A);
+    int nmax = 0;
+    for (int l = 0; l <= set.top; l++) {
+        const PyrLevel &d = set.lv[l];
+        A.ptr[l] = const_cast<uint8_t *>(d.ptr); A.rows[l] = d.rows; A.cols[l] = d.cols; A.pitch[l] = d.pitch;
+        A.stride[l] = d.img_stride;
+        int n = 2 * d.border * (d.bxl + d.cols + d.border) + d.rows * (d.bxl + d.border);
+        nmax = n > nmax ? n : nmax;
+    }
+    A.by = set.lv[0].border; A.bxl = set.lv[0].bxl; A.bxr = set.lv[0].border;
+    dim3 grid(min((nmax + 255) / 256, 96), batch, set.top + 1);
+    border_fill_kernel<<<grid, 256, 0, s>>>(A);
     PMV_LAUNCH_CHECK(ctx, "border_fill_kernel");
     return PMV_OK;
 }
 
-int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, const uint8_t *d_src, int src_pitch,
-                         size_t src_stride, cudaStream_t s)
+// d_src / d_src2: caller images for the first / second half of the batch (prev / next image sets share one
+// bordered allocation so every pyramid kernel runs once per step); d_src2 == nullptr -> one source.
+int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, const uint8_t *d_src, const uint8_t *d_src2,
+                         int src_pitch, size_t src_stride, cudaStream_t s)
 {
     const PyrLevel &l0 = set.lv[0];
     if (d_src) {
-        int al = (((uintptr_t)d_src) % 4 == 0) && (src_pitch % 4 == 0) && (src_stride % 4 == 0);
-        dim3 grid((l0.cols + 127) / 128, (l0.rows + 7) / 8, batch);
-        import_kernel<<<grid, 256, 0, s>>>(d_src, src_pitch, src_stride, l0.rows, l0.cols,
-                                           const_cast<uint8_t *>(l0.ptr), l0.pitch, l0.img_stride, al);
-        PMV_LAUNCH_CHECK(ctx, "import_kernel");
+        const int half = d_src2 ? batch / 2 : batch;
+        const uint8_t *srcs[2] = {d_src, d_src2};
+        for (int k = 0; k < (d_src2 ? 2 : 1); k++) {
+            int al = (((uintptr_t)srcs[k]) % 4 == 0) && (src_pitch % 4 == 0) && (src_stride % 4 == 0);
+            dim3 grid((l0.cols + 127) / 128, (l0.rows + 7) / 8, half);
+            import_kernel<<<grid, 256, 0, s>>>(srcs[k], src_pitch, src_stride, l0.rows, l0.cols,
+                                               const_cast<uint8_t *>(l0.ptr) + (size_t)k * half * l0.img_stride,
+                                               l0.pitch, l0.img_stride, al);
+            PMV_LAUNCH_CHECK(ctx, "import_kernel");
+        }
     }
-    int rc = fill_border(ctx, l0, batch, s);
-    if (rc) return rc;
     for (int l = 1; l <= set.top; l++) {
         const PyrLevel &a = set.lv[l - 1], &d = set.lv[l];
-        const int bxl = a.bxl;
         dim3 grid((d.cols + PT_W - 1) / PT_W, (d.rows + PT_H - 1) / PT_H, batch);
-        pyr_down_kernel<<<grid, 256, 0, s>>>(a.ptr, a.pitch, a.img_stride, -a.border, a.rows + a.border - 1,
-                                             a.pitch - bxl, const_cast<uint8_t *>(d.ptr), d.rows, d.cols,
-                                             d.pitch, d.img_stride);
+        pyr_down_kernel<<<grid, 256, 0, s>>>(a.ptr, a.rows, a.cols, a.pitch, a.img_stride, a.pitch - a.bxl,
+                                             const_cast<uint8_t *>(d.ptr), d.rows, d.cols, d.pitch, d.img_stride);
         PMV_LAUNCH_CHECK(ctx, "pyr_down_kernel");
-        rc = fill_border(ctx, d, batch, s);
-        if (rc) return rc;
     }
-    return PMV_OK;
+    return fill_borders(ctx, set, batch, s);
 }
 
 // ------------------------------------------------------------------ C ABI ---------------
@@ -240,7 +271,7 @@ PMV_API int pmv_pyramid_build(pmv_ctx *ctx, const uint8_t *img, int rows, int co
     const PyrLevel &l0 = set.lv[0];
     PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(const_cast<uint8_t *>(l0.ptr), l0.pitch, img, step, cols, rows,
                                         cudaMemcpyHostToDevice, ctx->stream));
-    rc = pmv_internal_pyr_run(ctx, set, 1, nullptr, 0, 0, ctx->stream);
+    rc = pmv_internal_pyr_run(ctx, set, 1, nullptr, nullptr, 0, 0, ctx->stream);
     if (rc) return rc;
     size_t need = 0;
     for (int l = 1; l <= set.top; l++) need += (size_t)set.lv[l].rows * set.lv[l].cols;
