@@ -162,25 +162,31 @@ lk_track_kernel(const LKParams P)
                                       ipx - 1, ipy - 1, w + 3, h + 3, lane);
         __syncwarp();
         // ---- 2. Scharr derivative on the bilinear support (zero outside the image) ------
-        {
-            const int total = (h + 1) * dp;
-            const int qd = 32 / dp, rm = 32 - qd * dp;
-            int r = lane / dp, c = lane - r * dp;
-            for (int i = lane; i < total; i += 32) {
-                const int yy = ipy + r, xx = ipx + c;
-                int packed = 0;
-                if (yy >= 0 && yy < I.rows && xx >= 0 && xx < I.cols) {
-                    const uint8_t *q = ps + r * pp + pmis + c;  // top-left of the 3x3 support
-                    int a0 = q[0], a1 = q[1], a2 = q[2];
-                    int b0 = q[pp], b2 = q[pp + 2];
-                    int c0 = q[2 * pp], c1 = q[2 * pp + 1], c2 = q[2 * pp + 2];
-                    int gx = (3 * (a2 + c2) + 10 * b2) - (3 * (a0 + c0) + 10 * b0);
-                    int gy = 3 * ((c0 - a0) + (c2 - a2)) + 10 * (c1 - a1);
-                    packed = (gx & 0xffff) | (int)((unsigned)gy << 16);
+        // Lane = column of the staged patch, rows stream through a 3-deep register window; the
+        // horizontal neighbours come from shuffles (separable: t0 = 3(a+c)+10b, t1 = c-a per column).
+        for (int c0 = 0; c0 < w + 1; c0 += 30) {
+            const int pc = c0 + lane;                         // patch column held by this lane
+            const bool cin = pc < w + 3;
+            const uint8_t *col = ps + pmis + (cin ? pc : 0);
+            int v0 = col[0], v1 = col[pp];
+            const int xx = ipx + pc;                           // image x of the derivative this lane OUTPUTS
+            const bool xin = lane < 30 && pc < w + 1 && xx >= 0 && xx < I.cols;
+            for (int r = 0; r < h + 1; r++) {
+                const int v2 = col[(r + 2) * pp];
+                const int t0 = 3 * (v0 + v2) + 10 * v1, t1 = v2 - v0;
+                const int t0r = __shfl_down_sync(0xffffffffu, t0, 2);
+                const int t1m = __shfl_down_sync(0xffffffffu, t1, 1);
+                const int t1r = __shfl_down_sync(0xffffffffu, t1, 2);
+                const int yy = ipy + r;
+                if (lane < 30 && pc < w + 1) {
+                    int packed = 0;
+                    if (xin && yy >= 0 && yy < I.rows) {
+                        const int gx = t0r - t0, gy = 3 * (t1 + t1r) + 10 * t1m;
+                        packed = (gx & 0xffff) | (int)((unsigned)gy << 16);
+                    }
+                    ds[r * dp + pc] = packed;
                 }
-                ds[i] = packed;
-                c += rm; r += qd;
-                if (c >= dp) { c -= dp; r++; }
+                v0 = v1; v1 = v2;
             }
         }
         __syncwarp();
