@@ -6,6 +6,7 @@
 // (column,row) -> observations (:45) and calls pmv_ba_solve with huber_delta 1.0 and
 // max_iters = tracker->ba_iterations (:54-61).
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 
 #include "ba.cuh"
@@ -14,6 +15,9 @@
 int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, cudaStream_t s);  // ba_chol.cu
 int pmv_internal_ba_allreduce(pmv_ctx *ctx, const double *send, double *recv, size_t count, int op_max,
                               cudaStream_t s);                                      // ba_nccl.cu
+bool pmv_internal_ba_window_eligible(int Nc, int Np);                               // ba_window.cu
+int pmv_internal_ba_window_iteration(pmv_ctx *ctx, const BADev &D, const unsigned *d_vis, double *d_camR,
+                                     double *d_candR, cudaStream_t s);
 
 struct pmv_ba_problem {
     pmv_ctx *ctx = nullptr;
@@ -26,6 +30,10 @@ struct pmv_ba_problem {
     double *d_scal = nullptr, *d_scal_red = nullptr;   // per window: model_change, cand_cost, step_norm2, x_norm2
     std::vector<int> perm;                               // caller observation order -> device order
     size_t bytes = 0;
+    // window-batched path (ba_window.cu): Nc <= 22, every (point, camera) pair observed at most once
+    int use_window = 0;
+    unsigned *d_vis = nullptr;
+    double *d_camR = nullptr, *d_candR = nullptr;
 };
 
 namespace {
@@ -217,8 +225,37 @@ PMV_API pmv_ba_problem *pmv_ba_problem_create(pmv_ctx *ctx, const double *poses,
             perm[i] = d; h_cam[d] = cam_idx[i]; h_pt[d] = pt_idx[i]; h_win[d] = win[i];
             h_obs[2 * (size_t)d] = obs[2 * (size_t)i]; h_obs[2 * (size_t)d + 1] = obs[2 * (size_t)i + 1];
         }
+        // inside each point: observations ordered by camera (the window path indexes them by popcount)
+        std::vector<std::pair<int, int>> tmp;
+        std::vector<int> inv(No);
+        for (int i = 0; i < No; i++) inv[perm[i]] = i;
+        for (size_t q = 0; q + 1 < pt_off.size(); q++) {
+            const int a = pt_off[q], b = pt_off[q + 1];
+            if (b - a < 2) continue;
+            tmp.clear();
+            for (int d = a; d < b; d++) tmp.push_back({h_cam[d], inv[d]});
+            std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) { return x.first < y.first; });
+            for (int d = a; d < b; d++) {
+                const int src = tmp[d - a].second;
+                perm[src] = d; h_cam[d] = cam_idx[src];
+                h_obs[2 * (size_t)d] = obs[2 * (size_t)src]; h_obs[2 * (size_t)d + 1] = obs[2 * (size_t)src + 1];
+            }
+        }
         std::vector<int> cpos(cam_off.begin(), cam_off.end() - 1);
         for (int d = 0; d < No; d++) cam_obs[cpos[(size_t)h_win[d] * Nc + h_cam[d]]++] = d;
+    }
+    // PMV_BA_FORCE_GENERAL=1 (tests) keeps small problems on the general path so both are exercised
+    const char *force_general = getenv("PMV_BA_FORCE_GENERAL");
+    bool window_ok = pmv_internal_ba_window_eligible(Nc, Np) && sharded_nranks <= 1 &&
+                     !(force_general && force_general[0] == '1');
+    std::vector<unsigned> h_vis;
+    if (window_ok) {
+        h_vis.assign((size_t)W * Np, 0u);
+        for (int d = 0; d < No && window_ok; d++) {
+            unsigned &m = h_vis[(size_t)h_win[d] * Np + h_pt[d]];
+            if (m & (1u << h_cam[d])) window_ok = false;   // the same camera sees the point twice -> general path
+            m |= 1u << h_cam[d];
+        }
     }
     pmv_ba_problem *p = new pmv_ba_problem();
     p->ctx = ctx;
@@ -238,13 +275,18 @@ PMV_API pmv_ba_problem *pmv_ba_problem_create(pmv_ctx *ctx, const double *poses,
     rc |= dev_alloc(p, &D.poses, wc * 6); rc |= dev_alloc(p, &D.points, wp * 3);
     rc |= dev_alloc(p, &D.cand_poses, wc * 6); rc |= dev_alloc(p, &D.cand_points, wp * 3);
     rc |= dev_alloc(p, &p->d_init_poses, wc * 6); rc |= dev_alloc(p, &p->d_init_points, wp * 3);
-    rc |= dev_alloc(p, &D.Lr, 2 * (size_t)No); rc |= dev_alloc(p, &D.Ljc, 12 * (size_t)No); rc |= dev_alloc(p, &D.Ljp, 6 * (size_t)No);
+    p->use_window = window_ok ? 1 : 0;
+    if (!window_ok) {   // the window path never materialises the linearisation
+        rc |= dev_alloc(p, &D.Lr, 2 * (size_t)No); rc |= dev_alloc(p, &D.Ljc, 12 * (size_t)No); rc |= dev_alloc(p, &D.Ljp, 6 * (size_t)No);
+    } else {
+        rc |= dev_alloc(p, &p->d_vis, wp); rc |= dev_alloc(p, &p->d_camR, wc * 36); rc |= dev_alloc(p, &p->d_candR, wc * 9);
+    }
     rc |= dev_alloc(p, &D.scale_c, wc * 6); rc |= dev_alloc(p, &D.scale_p, wp * 3);
     rc |= dev_alloc(p, &D.diag_c, wc * 6); rc |= dev_alloc(p, &D.diag_p, wp * 3);
     rc |= dev_alloc(p, &D.U, wc * 36); rc |= dev_alloc(p, &D.gc, wc * 6);
     // S and rhs contiguous ([S | rhs]) so a sharded solve reduces them with one collective
     double *d_sys = nullptr;
-    rc |= dev_alloc(p, &d_sys, (size_t)W * (n * n + n) + (n + 1) * 8);
+    rc |= dev_alloc(p, &d_sys, window_ok ? 8 : (size_t)W * (n * n + n) + (n + 1) * 8);   // the window path keeps S on chip
     rc |= dev_alloc(p, &D.yc, (size_t)W * n);
     rc |= dev_alloc(p, &D.Vinv, wp * 6); rc |= dev_alloc(p, &D.gp, wp * 3);
     rc |= dev_alloc(p, &D.st, W);
@@ -263,6 +305,7 @@ PMV_API pmv_ba_problem *pmv_ba_problem_create(pmv_ctx *ctx, const double *poses,
     up(d_obs, h_obs.data(), sizeof(double) * 2 * No); up(d_ptoff, pt_off.data(), sizeof(int) * (wp + 1));
     up(d_camoff, cam_off.data(), sizeof(int) * (wc + 1)); up(d_camobs, cam_obs.data(), sizeof(int) * No);
     up(p->d_init_poses, poses, sizeof(double) * wc * 6); up(p->d_init_points, points, sizeof(double) * wp * 3);
+    if (window_ok) up(p->d_vis, h_vis.data(), sizeof(unsigned) * wp);
     if (ok && cudaStreamSynchronize(s) != cudaSuccess) ok = false;  // host vectors die at return
     if (!ok) { ctx->fail(PMV_ERR_CUDA, "pmv_ba_problem_create: upload failed", cudaGetLastError()); pmv_ba_problem_destroy(p); return nullptr; }
     if (pmv_ba_problem_reset(p, nullptr, nullptr) != PMV_OK) { pmv_ba_problem_destroy(p); return nullptr; }
@@ -311,7 +354,8 @@ PMV_API int pmv_ba_problem_solve(pmv_ba_problem *p, int max_iters)
     ProfScope ps(ctx, PMV_PHASE_BA, s);
     // iteration 0 evaluates the cost even when max_iters == 0 (Ceres: IterationZero)
     for (int it = 0; it < std::max(max_iters, 1); it++) {
-        int rc = ba_iteration(p, s);
+        int rc = p->use_window ? pmv_internal_ba_window_iteration(ctx, p->D, p->d_vis, p->d_camR, p->d_candR, s)
+                               : ba_iteration(p, s);
         if (rc) return rc;
     }
     return PMV_OK;

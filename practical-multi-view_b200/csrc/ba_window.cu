@@ -1,0 +1,548 @@
+// ba_window.cu -- window-batched bundle adjustment (BASELINE config 4: thousands of independent
+// windows of <= 22 poses): K8 + K9 + K10 fused per window, no Jacobian ever written to HBM.
+//
+// One CTA owns one window for a whole LM iteration:
+//   win_prepare_kernel   per camera: rotation R(a) and dR/da_k (so an observation costs ~100 flops, no
+//                        trig), Jacobi column norms on the first linearisation
+//   win_schur_kernel     per chunk of P points: thread (point slot, camera) evaluates residual + Jacobians
+//                        (Huber-corrected, Jacobi-scaled), per-point V^-1 in shared memory, Y = W V^-1 and
+//                        W blocks staged in shared memory; then thread (ci <= cj) accumulates its 6x6 block
+//                        of S -= Y_ci W_cj^T in REGISTERS over all points (the K = 3 Np contraction that
+//                        dominates: Nc(Nc+1)/2 * 108 FMA per point).  Afterwards S (+ U_c + D_c^2) is laid
+//                        out in shared memory, factorised (Cholesky) and solved in place -> y_c.
+//   win_backsub_kernel   per point: y_p, candidate point, model cost change, candidate cost.
+// LM bookkeeping reuses ba_lm_update_kernel / ba_accept_kernel.  Same arithmetic as the general path
+// (ba_kernels.cuh) up to fp64 summation order; replaces ceres::Solve at CeresBundleAdjustment.cpp:61.
+#include <algorithm>
+
+#include "ba.cuh"
+#include "ba_kernels.cuh"
+
+namespace {
+
+constexpr int WIN_MAXC = 22;          // Nc(Nc+1)/2 <= 253 tile threads
+constexpr int WIN_THREADS = 256;
+
+struct WinDev {
+    const unsigned *vis;   // per (window, point): bit c set <=> camera c observes it (observations sorted by camera)
+    double *camR;          // per (window, camera): R (9) | dR/da_0 (9) | dR/da_1 (9) | dR/da_2 (9)
+    double *candR;         // per (window, camera): R of the candidate pose (9)
+    int P;                 // points per chunk
+};
+
+// rotation matrix and its derivatives w.r.t. the angle-axis vector, via the same code as the residual
+__device__ void cam_matrices(const double *pose, double *out36)
+{
+    const double a[6] = {pose[0], pose[1], pose[2], 0.0, 0.0, 0.0};
+    for (int j = 0; j < 3; j++) {
+        double e[3] = {0, 0, 0};
+        e[j] = 1.0;
+        double p[3], R[9], dpa[9];
+        ba_project(a, e, p, R, dpa, true);
+        for (int i = 0; i < 3; i++) {
+            out36[3 * i + j] = p[i];                                  // column j of R
+            for (int k = 0; k < 3; k++) out36[9 + 9 * k + 3 * i + j] = dpa[3 * k + i];   // column j of dR/da_k
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) win_prepare_kernel(const BADev D, const WinDev Wd, int candidate)
+{
+    const int wc = blockIdx.x * 128 + threadIdx.x;
+    if (wc >= D.W * D.Nc) return;
+    const BAState *st = &D.st[wc / D.Nc];
+    if (st->done) return;
+    if (candidate) {
+        if (!st->chol_ok) return;
+        double m[36];
+        cam_matrices(D.cand_poses + 6 * (size_t)wc, m);
+        for (int k = 0; k < 9; k++) Wd.candR[9 * (size_t)wc + k] = m[k];
+    } else {
+        if (!st->need_linearize) return;
+        double m[36];
+        cam_matrices(D.poses + 6 * (size_t)wc, m);
+        for (int k = 0; k < 36; k++) Wd.camR[36 * (size_t)wc + k] = m[k];
+    }
+}
+
+// residual + Jacobians of one observation from the per-camera matrices (q = X + c)
+__device__ __forceinline__ void win_residual_jac(const double *M /* 36, shared */, const double *c3, const double *X,
+                                                 double ox, double oy, double fx, double cx, double fy, double cy,
+                                                 double r[2], double Jc[12], double Jp[6])
+{
+    const double q0 = X[0] + c3[0], q1 = X[1] + c3[1], q2 = X[2] + c3[2];
+    double p[3], dp[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++) p[i] = M[3 * i] * q0 + M[3 * i + 1] * q1 + M[3 * i + 2] * q2;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            dp[3 * k + i] = M[9 + 9 * k + 3 * i] * q0 + M[9 + 9 * k + 3 * i + 1] * q1 + M[9 + 9 * k + 3 * i + 2] * q2;
+    const double pz = p[2] * -1.0;
+    r[0] = ox - (p[0] / pz * fx + cx);
+    r[1] = oy - (p[1] / pz * fy + cy);
+    const double iz = 1.0 / p[2];
+    const double a0 = fx * iz, a2 = -fx * p[0] * iz * iz, b1 = fy * iz, b2 = -fy * p[1] * iz * iz;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        Jc[k] = a0 * dp[3 * k] + a2 * dp[3 * k + 2];
+        Jc[6 + k] = b1 * dp[3 * k + 1] + b2 * dp[3 * k + 2];
+        const double j0 = a0 * M[k] + a2 * M[6 + k], j1 = b1 * M[3 + k] + b2 * M[6 + k];
+        Jc[3 + k] = j0; Jc[9 + k] = j1;
+        Jp[k] = j0; Jp[3 + k] = j1;
+    }
+}
+
+// Jacobi column norms of the first linearisation (unscaled, Huber-corrected): scale = 1 / (1 + |J_:j|)
+__global__ void __launch_bounds__(WIN_THREADS) win_colnorm_kernel(const BADev D, const WinDev Wd)
+{
+    extern __shared__ double sm[];
+    const int w = blockIdx.x, tid = threadIdx.x, Nc = D.Nc;
+    const BAState *st = &D.st[w];
+    if (st->done || st->scale_ready || !st->need_linearize) return;
+    double *sM = sm;                    // Nc*36
+    double *sC = sM + Nc * 36;          // Nc*3
+    double *sAcc = sC + Nc * 3;         // Nc*6 camera column sums
+    for (int i = tid; i < Nc * 36; i += WIN_THREADS) sM[i] = Wd.camR[36 * (size_t)w * Nc + i];
+    for (int i = tid; i < Nc * 3; i += WIN_THREADS) sC[i] = D.poses[6 * ((size_t)w * Nc + i / 3) + 3 + i % 3];
+    for (int i = tid; i < Nc * 6; i += WIN_THREADS) sAcc[i] = 0.0;
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    double cacc[6] = {0, 0, 0, 0, 0, 0};   // lane = camera
+    for (int p = warp; p < D.Np; p += WIN_THREADS / 32) {
+        const size_t wp = (size_t)w * D.Np + p;
+        const unsigned mask = Wd.vis[wp];
+        double ps[3] = {0, 0, 0};
+        if (lane < Nc && (mask >> lane & 1)) {
+            const int i = D.pt_off[wp] + __popc(mask & ((1u << lane) - 1));
+            double r[2], jc[12], jp[6];
+            win_residual_jac(sM + 36 * lane, sC + 3 * lane, D.points + 3 * wp, D.obs_xy[2 * (size_t)i], D.obs_xy[2 * (size_t)i + 1],
+                             D.fx, D.cx, D.fy, D.cy, r, jc, jp);
+            double rho0, rho1;
+            ba_huber(D.delta, r[0] * r[0] + r[1] * r[1], rho0, rho1);
+#pragma unroll
+            for (int a = 0; a < 6; a++) cacc[a] += rho1 * (jc[a] * jc[a] + jc[6 + a] * jc[6 + a]);
+#pragma unroll
+            for (int a = 0; a < 3; a++) ps[a] = rho1 * (jp[a] * jp[a] + jp[3 + a] * jp[3 + a]);
+        }
+#pragma unroll
+        for (int a = 0; a < 3; a++) ps[a] = warp_sum_d(ps[a]);
+        if (lane < 3) D.scale_p[3 * wp + lane] = 1.0 / (1.0 + sqrt(ps[lane]));
+    }
+    if (lane < Nc)
+        for (int a = 0; a < 6; a++) atomicAdd(&sAcc[6 * lane + a], cacc[a]);
+    __syncthreads();
+    for (int i = tid; i < Nc * 6; i += WIN_THREADS) D.scale_c[6 * (size_t)w * Nc + i] = 1.0 / (1.0 + sqrt(sAcc[i]));
+}
+
+__global__ void __launch_bounds__(WIN_THREADS, 1) win_schur_kernel(const BADev D, const WinDev Wd)
+{
+    extern __shared__ double sm[];
+    const int w = blockIdx.x, tid = threadIdx.x, Nc = D.Nc, n = D.n, P = Wd.P;
+    BAState *st = &D.st[w];
+    if (st->done) return;
+    const bool lin = st->need_linearize != 0;
+    // ---- shared memory carve-up -----------------------------------------------------------------------
+    double *sM = sm;                         // Nc*36 camera matrices
+    double *sC = sM + Nc * 36;               // Nc*3  camera centres c
+    double *sSc = sC + Nc * 3;               // Nc*6  Jacobi scale of the camera columns
+    double *sRed = sSc + Nc * 6;             // Nc*33 reduced camera sums (U 21 | g 6 | rhs 6)
+    double *sScal = sRed + Nc * 33;          // 8 scalars
+    double *sUnion = sScal + 8;
+    // phase A (points loop)
+    double *sItem = sUnion;                  // P*Nc*8 : Jp (6) | r (2) per item
+    double *sPt = sItem + P * Nc * 8;        // P*12   : Vinv (6) | g (3) | pad
+    double *sY = sPt + P * 12;               // P*Nc*18
+    double *sW = sY + P * Nc * 18;           // P*Nc*18
+    unsigned *sMask = reinterpret_cast<unsigned *>(sW + P * Nc * 18);   // P
+    // phase B (factorisation) aliases the union region
+    double *A = sUnion;                      // n x (n+1)
+    double *bvec = A + (size_t)n * (n + 1);  // n
+
+    for (int i = tid; i < Nc * 36; i += WIN_THREADS) sM[i] = Wd.camR[36 * (size_t)w * Nc + i];
+    for (int i = tid; i < Nc * 3; i += WIN_THREADS) sC[i] = D.poses[6 * ((size_t)w * Nc + i / 3) + 3 + i % 3];
+    for (int i = tid; i < Nc * 6; i += WIN_THREADS) sSc[i] = D.scale_c[6 * (size_t)w * Nc + i];
+    for (int i = tid; i < Nc * 33; i += WIN_THREADS) sRed[i] = 0.0;
+    if (tid < 8) sScal[tid] = 0.0;
+    __syncthreads();
+    const double radius = st->radius;
+
+    // producer role: thread (pslot, cam)
+    const int pslot = tid / Nc, pcam = tid - pslot * Nc;
+    const bool producer = pslot < P;
+    // consumer role: thread <-> tile (ci <= cj)
+    int ci = 0, cj = 0;
+    const int ntiles = Nc * (Nc + 1) / 2;
+    const bool consumer = tid < ntiles;
+    if (consumer) { int rem = tid; while (rem >= Nc - ci) { rem -= Nc - ci; ci++; } cj = ci + rem; }
+    double T[36];
+#pragma unroll
+    for (int k = 0; k < 36; k++) T[k] = 0.0;
+    double accU[21], accG[6], accR[6];
+#pragma unroll
+    for (int k = 0; k < 21; k++) accU[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) accG[k] = accR[k] = 0.0;
+    double cost = 0.0, gmax = 0.0;
+
+    for (int p0 = 0; p0 < D.Np; p0 += P) {
+        // ---- A1: residual + Jacobians of item (point p0+pslot, camera pcam) -------------------------------
+        double jc[12], jp[6], r[2];
+        bool vis = false;
+        size_t wp = 0;
+        if (producer && p0 + pslot < D.Np) {
+            wp = (size_t)w * D.Np + p0 + pslot;
+            const unsigned mask = Wd.vis[wp];
+            if (pcam == 0) sMask[pslot] = mask;
+            vis = (mask >> pcam) & 1;
+            if (vis) {
+                const int i = D.pt_off[wp] + __popc(mask & ((1u << pcam) - 1));
+                win_residual_jac(sM + 36 * pcam, sC + 3 * pcam, D.points + 3 * wp, D.obs_xy[2 * (size_t)i],
+                                 D.obs_xy[2 * (size_t)i + 1], D.fx, D.cx, D.fy, D.cy, r, jc, jp);
+                double rho0, rho1;
+                ba_huber(D.delta, r[0] * r[0] + r[1] * r[1], rho0, rho1);
+                cost += 0.5 * rho0;
+                const double sr = sqrt(rho1);
+                const double *sp = D.scale_p + 3 * wp;
+                r[0] *= sr; r[1] *= sr;
+#pragma unroll
+                for (int k = 0; k < 6; k++) { const double s = sr * sSc[6 * pcam + k]; jc[k] *= s; jc[6 + k] *= s; }
+#pragma unroll
+                for (int k = 0; k < 3; k++) { const double s = sr * sp[k]; jp[k] *= s; jp[3 + k] *= s; }
+            }
+            double *it = sItem + (size_t)(pslot * Nc + pcam) * 8;
+#pragma unroll
+            for (int k = 0; k < 6; k++) it[k] = vis ? jp[k] : 0.0;
+            it[6] = vis ? r[0] : 0.0; it[7] = vis ? r[1] : 0.0;
+        } else if (producer && pcam == 0) {
+            sMask[pslot] = 0u;
+        }
+        __syncthreads();
+        // ---- A2: per point V + D^2, g, V^-1 (one thread per point slot) --------------------------------------
+        if (tid < P && p0 + tid < D.Np) {
+            const size_t wpp = (size_t)w * D.Np + p0 + tid;
+            double V[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+            for (int c = 0; c < Nc; c++) {
+                const double *it = sItem + (size_t)(tid * Nc + c) * 8;
+                V[0] += it[0] * it[0] + it[3] * it[3]; V[1] += it[0] * it[1] + it[3] * it[4]; V[2] += it[0] * it[2] + it[3] * it[5];
+                V[3] += it[1] * it[1] + it[4] * it[4]; V[4] += it[1] * it[2] + it[4] * it[5]; V[5] += it[2] * it[2] + it[5] * it[5];
+                g[0] += it[0] * it[6] + it[3] * it[7]; g[1] += it[1] * it[6] + it[4] * it[7]; g[2] += it[2] * it[6] + it[5] * it[7];
+            }
+            double *pt = sPt + tid * 12;
+            if (sMask[tid] == 0u) {
+                for (int k = 0; k < 9; k++) pt[k] = 0.0;   // unobserved point: contributes nothing
+            } else {
+                if (lin) {
+                    D.diag_p[3 * wpp] = fmin(fmax(V[0], 1e-6), 1e32);
+                    D.diag_p[3 * wpp + 1] = fmin(fmax(V[3], 1e-6), 1e32);
+                    D.diag_p[3 * wpp + 2] = fmin(fmax(V[5], 1e-6), 1e32);
+                    const double *sp = D.scale_p + 3 * wpp;
+                    gmax = fmax(gmax, fmax(fabs(g[0] / sp[0]), fmax(fabs(g[1] / sp[1]), fabs(g[2] / sp[2]))));
+                }
+                const double d0 = sqrt(D.diag_p[3 * wpp] / radius), d1 = sqrt(D.diag_p[3 * wpp + 1] / radius),
+                             d2 = sqrt(D.diag_p[3 * wpp + 2] / radius);
+                V[0] += d0 * d0; V[3] += d1 * d1; V[5] += d2 * d2;
+                const double l00 = sqrt(V[0]), l10 = V[1] / l00, l20 = V[2] / l00;
+                const double l11 = sqrt(V[3] - l10 * l10), l21 = (V[4] - l20 * l10) / l11;
+                const double l22 = sqrt(V[5] - l20 * l20 - l21 * l21);
+                const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
+                const double i10 = -l10 * i00 * i11, i21 = -l21 * i11 * i22, i20 = -(l20 * i00 + l21 * i10) * i22;
+                pt[0] = i00 * i00 + i10 * i10 + i20 * i20; pt[1] = i10 * i11 + i20 * i21; pt[2] = i20 * i22;
+                pt[3] = i11 * i11 + i21 * i21; pt[4] = i21 * i22; pt[5] = i22 * i22;
+                pt[6] = g[0]; pt[7] = g[1]; pt[8] = g[2];
+                for (int k = 0; k < 6; k++) D.Vinv[6 * wpp + k] = pt[k];
+                for (int k = 0; k < 3; k++) D.gp[3 * wpp + k] = g[k];
+            }
+        }
+        __syncthreads();
+        // ---- A3: W = Jc^T Jp, Y = W V^-1 into shared memory; camera sums in registers ---------------------
+        if (producer && p0 + pslot < D.Np) {
+            double *Yo = sY + (size_t)(pslot * Nc + pcam) * 18, *Wo = sW + (size_t)(pslot * Nc + pcam) * 18;
+            if (vis) {
+                const double *pt = sPt + pslot * 12;
+                const double vg0 = pt[0] * pt[6] + pt[1] * pt[7] + pt[2] * pt[8], vg1 = pt[1] * pt[6] + pt[3] * pt[7] + pt[4] * pt[8],
+                             vg2 = pt[2] * pt[6] + pt[4] * pt[7] + pt[5] * pt[8];
+                int t = 0;
+#pragma unroll
+                for (int a = 0; a < 6; a++) {
+                    const double w0 = jc[a] * jp[0] + jc[6 + a] * jp[3], w1 = jc[a] * jp[1] + jc[6 + a] * jp[4],
+                                 w2 = jc[a] * jp[2] + jc[6 + a] * jp[5];
+                    Wo[3 * a] = w0; Wo[3 * a + 1] = w1; Wo[3 * a + 2] = w2;
+                    Yo[3 * a] = w0 * pt[0] + w1 * pt[1] + w2 * pt[2];
+                    Yo[3 * a + 1] = w0 * pt[1] + w1 * pt[3] + w2 * pt[4];
+                    Yo[3 * a + 2] = w0 * pt[2] + w1 * pt[4] + w2 * pt[5];
+                    accR[a] -= w0 * vg0 + w1 * vg1 + w2 * vg2;
+                    accG[a] += jc[a] * r[0] + jc[6 + a] * r[1];
+#pragma unroll
+                    for (int b = a; b < 6; b++) accU[t++] += jc[a] * jc[b] + jc[6 + a] * jc[6 + b];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 18; k++) { Yo[k] = 0.0; Wo[k] = 0.0; }
+            }
+        }
+        __syncthreads();
+        // ---- A4: S(ci, cj) -= sum_p Y_ci W_cj^T ---------------------------------------------------------------
+        if (consumer) {
+            const int np = min(P, D.Np - p0);
+            for (int q = 0; q < np; q++) {
+                const unsigned m = sMask[q];
+                if (!((m >> ci) & 1) || !((m >> cj) & 1)) continue;
+                const double *Y = sY + (size_t)(q * Nc + ci) * 18, *Wv = sW + (size_t)(q * Nc + cj) * 18;
+                double y[18];
+#pragma unroll
+                for (int k = 0; k < 18; k++) y[k] = Y[k];
+#pragma unroll
+                for (int b = 0; b < 6; b++) {
+                    const double w0 = Wv[3 * b], w1 = Wv[3 * b + 1], w2 = Wv[3 * b + 2];
+#pragma unroll
+                    for (int a = 0; a < 6; a++) T[6 * a + b] -= y[3 * a] * w0 + y[3 * a + 1] * w1 + y[3 * a + 2] * w2;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- reduce camera sums over the point slots -----------------------------------------------------------
+    if (producer) {
+        for (int k = 0; k < 21; k++) atomicAdd(&sRed[33 * pcam + k], accU[k]);
+        for (int k = 0; k < 6; k++) { atomicAdd(&sRed[33 * pcam + 21 + k], accG[k]); atomicAdd(&sRed[33 * pcam + 27 + k], accR[k]); }
+    }
+    cost = warp_sum_d(cost);
+    if ((tid & 31) == 0) atomicAdd(&sScal[0], cost);
+    if (lin) {
+        for (int o = 16; o; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+        if ((tid & 31) == 0 && gmax > 0) atomicMax(reinterpret_cast<unsigned long long *>(&sScal[1]), (unsigned long long)__double_as_longlong(gmax));
+    }
+    __syncthreads();   // also: phase A shared memory is dead from here on
+    // ---- camera diagonal: LM diagonal, gradient max; latch cost ---------------------------------------------
+    if (tid < Nc && lin) {
+        const int dg[6] = {0, 6, 11, 15, 18, 20};
+        double gm = 0;
+        for (int a = 0; a < 6; a++) {
+            D.diag_c[6 * ((size_t)w * Nc + tid) + a] = fmin(fmax(sRed[33 * tid + dg[a]], 1e-6), 1e32);
+            gm = fmax(gm, fabs(sRed[33 * tid + 21 + a] / sSc[6 * tid + a]));
+        }
+        atomicMax(reinterpret_cast<unsigned long long *>(&sScal[1]), (unsigned long long)__double_as_longlong(gm));
+    }
+    __syncthreads();
+    if (tid == 0 && lin) {
+        st->cost = sScal[0];
+        if (st->iter == 0) st->initial_cost = sScal[0];
+        st->gmax = sScal[1];
+    }
+    // ---- lay S out in shared memory (lower triangle of A), rhs ----------------------------------------------
+    const int ld = n + 1;
+    if (consumer) {
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = 0; b < 6; b++) {
+                double v = T[6 * a + b];
+                if (ci == cj) {
+                    const int lo = a < b ? a : b, hi = a < b ? b : a;
+                    const int t = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);      // index of (lo,hi) in the 21-entry upper triangle
+                    v += sRed[33 * ci + t];
+                    if (a == b) { const double d = sqrt(D.diag_c[6 * ((size_t)w * Nc + ci) + a] / radius); v += d * d; }
+                }
+                // S[6ci+a][6cj+b] -> lower triangle entry A[6cj+b][6ci+a]
+                if (6 * cj + b >= 6 * ci + a) A[(size_t)(6 * cj + b) * ld + 6 * ci + a] = v;
+            }
+    }
+    for (int i = tid; i < n; i += WIN_THREADS) bvec[i] = sRed[33 * (i / 6) + 21 + i % 6] + sRed[33 * (i / 6) + 27 + i % 6];
+    __shared__ int s_ok;
+    if (tid == 0) {
+        s_ok = 1;
+        if (st->need_linearize && !(sScal[1] > 1e-10)) { st->done = 1; st->termination = 3; s_ok = -1; }
+    }
+    __syncthreads();
+    if (s_ok < 0) return;
+    // ---- K10: Cholesky + two triangular solves in shared memory ----------------------------------------------
+    for (int j = 0; j < n; j++) {
+        if (tid == 0) {
+            const double d = A[(size_t)j * ld + j];
+            if (!(d > 0) || !isfinite(d)) s_ok = 0; else A[(size_t)j * ld + j] = sqrt(d);
+        }
+        __syncthreads();
+        if (!s_ok) break;
+        const double dj = A[(size_t)j * ld + j];
+        for (int i = j + 1 + tid; i < n; i += WIN_THREADS) A[(size_t)i * ld + j] /= dj;
+        __syncthreads();
+        const int m = n - j - 1;
+        for (int t = tid; t < m * m; t += WIN_THREADS) {
+            const int ii = t / m, kk = t - ii * m;
+            if (kk <= ii) { const int i = j + 1 + ii, k = j + 1 + kk; A[(size_t)i * ld + k] -= A[(size_t)i * ld + j] * A[(size_t)k * ld + j]; }
+        }
+        __syncthreads();
+    }
+    if (!s_ok) { if (tid == 0) st->chol_ok = 0; return; }
+    for (int j = 0; j < n; j++) {
+        if (tid == 0) bvec[j] /= A[(size_t)j * ld + j];
+        __syncthreads();
+        const double bj = bvec[j];
+        for (int i = j + 1 + tid; i < n; i += WIN_THREADS) bvec[i] -= A[(size_t)i * ld + j] * bj;
+        __syncthreads();
+    }
+    for (int j = n - 1; j >= 0; j--) {
+        if (tid == 0) bvec[j] /= A[(size_t)j * ld + j];
+        __syncthreads();
+        const double bj = bvec[j];
+        for (int i = tid; i < j; i += WIN_THREADS) bvec[i] -= A[(size_t)j * ld + i] * bj;
+        __syncthreads();
+    }
+    bool fin = true;
+    for (int i = tid; i < n; i += WIN_THREADS) { D.yc[(size_t)w * n + i] = bvec[i]; fin = fin && isfinite(bvec[i]); }
+    const int allfin = __syncthreads_and(fin);
+    if (tid == 0) st->chol_ok = allfin ? 1 : 0;
+}
+
+// K11 for windows: blockIdx.y = window, each CTA walks a slice of the points; warp per point, lane = camera
+__global__ void __launch_bounds__(WIN_THREADS) win_backsub_kernel(const BADev D, const WinDev Wd, int slices)
+{
+    extern __shared__ double sm[];
+    const int w = blockIdx.y, tid = threadIdx.x, Nc = D.Nc;
+    BAState *st = &D.st[w];
+    if (st->done || !st->chol_ok) return;
+    double *sM = sm;                     // Nc*36
+    double *sC = sM + Nc * 36;           // Nc*3
+    double *sSc = sC + Nc * 3;           // Nc*6
+    double *sY = sSc + Nc * 6;           // Nc*6  y_c .* scale_c
+    double *sRc = sY + Nc * 6;           // Nc*9  candidate rotation
+    double *sCc = sRc + Nc * 9;          // Nc*3  candidate centre
+    for (int i = tid; i < Nc * 36; i += WIN_THREADS) sM[i] = Wd.camR[36 * (size_t)w * Nc + i];
+    for (int i = tid; i < Nc * 3; i += WIN_THREADS) {
+        sC[i] = D.poses[6 * ((size_t)w * Nc + i / 3) + 3 + i % 3];
+        sCc[i] = D.cand_poses[6 * ((size_t)w * Nc + i / 3) + 3 + i % 3];
+    }
+    for (int i = tid; i < Nc * 6; i += WIN_THREADS) {
+        sSc[i] = D.scale_c[6 * (size_t)w * Nc + i];
+        sY[i] = D.yc[(size_t)w * D.n + i] * sSc[i];
+    }
+    for (int i = tid; i < Nc * 9; i += WIN_THREADS) sRc[i] = Wd.candR[9 * (size_t)w * Nc + i];
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    const int per = (D.Np + slices - 1) / slices;
+    const int pbeg = blockIdx.x * per, pend = min(D.Np, pbeg + per);
+    double mc_acc = 0, cc_acc = 0, sn_acc = 0, xn_acc = 0;
+    for (int p = pbeg + warp; p < pend; p += WIN_THREADS / 32) {
+        const size_t wp = (size_t)w * D.Np + p;
+        const unsigned mask = Wd.vis[wp];
+        if (mask == 0u) {
+            if (lane < 3) D.cand_points[3 * wp + lane] = D.points[3 * wp + lane];
+            continue;
+        }
+        const double sp[3] = {D.scale_p[3 * wp], D.scale_p[3 * wp + 1], D.scale_p[3 * wp + 2]};
+        const double X[3] = {D.points[3 * wp], D.points[3 * wp + 1], D.points[3 * wp + 2]};
+        const bool vis = lane < Nc && ((mask >> lane) & 1);
+        double r[2] = {0, 0}, jc[12], jp[6], ox = 0, oy = 0;
+        double t0 = 0, t1 = 0, t2 = 0, jy0 = 0, jy1 = 0;
+        if (vis) {
+            const int i = D.pt_off[wp] + __popc(mask & ((1u << lane) - 1));
+            ox = D.obs_xy[2 * (size_t)i]; oy = D.obs_xy[2 * (size_t)i + 1];
+            win_residual_jac(sM + 36 * lane, sC + 3 * lane, X, ox, oy, D.fx, D.cx, D.fy, D.cy, r, jc, jp);
+            double rho0, rho1;
+            ba_huber(D.delta, r[0] * r[0] + r[1] * r[1], rho0, rho1);
+            const double sr = sqrt(rho1);
+            r[0] *= sr; r[1] *= sr;
+#pragma unroll
+            for (int k = 0; k < 6; k++) { jc[k] *= sr; jc[6 + k] *= sr; jy0 += jc[k] * sY[6 * lane + k]; jy1 += jc[6 + k] * sY[6 * lane + k]; }
+#pragma unroll
+            for (int k = 0; k < 3; k++) { jp[k] *= sr * sp[k]; jp[3 + k] *= sr * sp[k]; }
+            t0 = -(jp[0] * jy0 + jp[3] * jy1); t1 = -(jp[1] * jy0 + jp[4] * jy1); t2 = -(jp[2] * jy0 + jp[5] * jy1);
+        }
+        t0 = warp_sum_d(t0) + D.gp[3 * wp]; t1 = warp_sum_d(t1) + D.gp[3 * wp + 1]; t2 = warp_sum_d(t2) + D.gp[3 * wp + 2];
+        const double *Vi = D.Vinv + 6 * wp;
+        const double yp[3] = {Vi[0] * t0 + Vi[1] * t1 + Vi[2] * t2, Vi[1] * t0 + Vi[3] * t1 + Vi[4] * t2,
+                              Vi[2] * t0 + Vi[4] * t1 + Vi[5] * t2};
+        double cand[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) cand[k] = X[k] + (-yp[k] * sp[k]);
+        if (lane < 3) D.cand_points[3 * wp + lane] = cand[lane];
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { const double d = X[k] - cand[k]; sn_acc += d * d; xn_acc += X[k] * X[k]; }
+        }
+        if (vis) {
+            double m0 = -jy0, m1 = -jy1;
+#pragma unroll
+            for (int k = 0; k < 3; k++) { m0 -= jp[k] * yp[k]; m1 -= jp[3 + k] * yp[k]; }
+            mc_acc -= m0 * (r[0] + m0 / 2.0) + m1 * (r[1] + m1 / 2.0);
+            // candidate residual with the candidate rotation matrix
+            const double *Rc = sRc + 9 * lane;
+            const double q0 = cand[0] + sCc[3 * lane], q1 = cand[1] + sCc[3 * lane + 1], q2 = cand[2] + sCc[3 * lane + 2];
+            const double px = Rc[0] * q0 + Rc[1] * q1 + Rc[2] * q2, py = Rc[3] * q0 + Rc[4] * q1 + Rc[5] * q2,
+                         pz = (Rc[6] * q0 + Rc[7] * q1 + Rc[8] * q2) * -1.0;
+            const double e0 = ox - (px / pz * D.fx + D.cx), e1 = oy - (py / pz * D.fy + D.cy);
+            double rho0, rho1;
+            ba_huber(D.delta, e0 * e0 + e1 * e1, rho0, rho1);
+            cc_acc += 0.5 * rho0;
+        }
+    }
+    mc_acc = warp_sum_d(mc_acc); cc_acc = warp_sum_d(cc_acc);
+    if (lane == 0) {
+        atomicAdd(&st->model_change, mc_acc);
+        atomicAdd(&st->cand_cost, cc_acc);
+        atomicAdd(&st->step_norm2, sn_acc);
+        atomicAdd(&st->x_norm2, xn_acc);
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ host side -------------------------
+struct pmv_ba_window_ws {
+    unsigned *vis = nullptr;
+    double *camR = nullptr, *candR = nullptr;
+};
+
+bool pmv_internal_ba_window_eligible(int Nc, int Np) { return Nc <= WIN_MAXC && Nc >= 1 && Np >= 1; }
+
+size_t pmv_internal_ba_window_bytes(int W, int Nc, int Np)
+{
+    return sizeof(unsigned) * (size_t)W * Np + sizeof(double) * (size_t)W * Nc * 45;
+}
+
+int pmv_internal_ba_window_iteration(pmv_ctx *ctx, const BADev &D, const unsigned *d_vis, double *d_camR, double *d_candR,
+                                     cudaStream_t s)
+{
+    WinDev Wd;
+    Wd.vis = d_vis; Wd.camR = d_camR; Wd.candR = d_candR;
+    const int Nc = D.Nc, n = D.n;
+    Wd.P = std::max(1, std::min(WIN_THREADS / Nc, 12));
+    const int wc = D.W * Nc;
+    const size_t smem_col = sizeof(double) * (size_t)Nc * 45;
+    const size_t unionA = (size_t)Wd.P * Nc * 8 + (size_t)Wd.P * 12 + 2 * (size_t)Wd.P * Nc * 18 + Wd.P;
+    const size_t unionB = (size_t)n * (n + 1) + n;
+    const size_t smem_schur = sizeof(double) * ((size_t)Nc * 78 + 8 + std::max(unionA, unionB) + 2);
+    const size_t smem_back = sizeof(double) * (size_t)Nc * 63;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(win_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr = true;
+    }
+    win_prepare_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D, Wd, 0);
+    PMV_LAUNCH_CHECK(ctx, "win_prepare_kernel");
+    win_colnorm_kernel<<<D.W, WIN_THREADS, smem_col, s>>>(D, Wd);
+    PMV_LAUNCH_CHECK(ctx, "win_colnorm_kernel");
+    win_schur_kernel<<<D.W, WIN_THREADS, smem_schur, s>>>(D, Wd);
+    PMV_LAUNCH_CHECK(ctx, "win_schur_kernel");
+    ba_cam_candidate_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D, 1);
+    PMV_LAUNCH_CHECK(ctx, "ba_cam_candidate_kernel");
+    win_prepare_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D, Wd, 1);
+    PMV_LAUNCH_CHECK(ctx, "win_prepare_kernel");
+    {
+        // enough CTAs to fill the machine: slices per window so that W * slices >= ~4 waves of 148 SMs
+        int slices = std::max(1, std::min((148 * 8 + D.W - 1) / D.W, (D.Np + 63) / 64));
+        dim3 grid(slices, D.W);
+        win_backsub_kernel<<<grid, WIN_THREADS, smem_back, s>>>(D, Wd, slices);
+        PMV_LAUNCH_CHECK(ctx, "win_backsub_kernel");
+    }
+    ba_lm_update_kernel<<<(D.W + 127) / 128, 128, 0, s>>>(D);
+    PMV_LAUNCH_CHECK(ctx, "ba_lm_update_kernel");
+    {
+        size_t tot = (size_t)wc * 6 + (size_t)D.W * D.Np * 3;
+        ba_accept_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(D);
+        PMV_LAUNCH_CHECK(ctx, "ba_accept_kernel");
+    }
+    return PMV_OK;
+}

@@ -9,6 +9,16 @@ import oracle
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["window", "general"], autouse=True)
+def ba_path(request, monkeypatch):
+    """Run every solve twice: the window-batched kernels (Nc <= 22) and the general multi-kernel path."""
+    if request.param == "general":
+        monkeypatch.setenv("PMV_BA_FORCE_GENERAL", "1")
+    else:
+        monkeypatch.delenv("PMV_BA_FORCE_GENERAL", raising=False)
+    return request.param
+
+
 def _args(w):
     return (w["poses"], w["points"], w["obs"], w["cam_idx"], w["pt_idx"], w["K"])
 
@@ -88,6 +98,18 @@ def test_converged_problem_terminates_like_oracle(ctx, synth):
     po, xo, so = oracle.ba_solve(*a, 1.0, 50)
     assert s["termination"] in (1, 2, 3) and s["final_cost"] < 1e-9
     assert abs(s["iterations"] - so["iterations"]) <= 1        # at the 1e-16 cost floor the last test may flip
+
+
+def test_full_size_window_config4_shape(ctx, synth, ba_path):
+    """One BASELINE config-4 window (20 poses, 2 000 points, ~35 k observations), 5 iterations."""
+    if ba_path == "general":
+        pytest.skip("covered by the smaller shapes; the general path is atomics-bound at this density")
+    w = synth.ba_window(2)
+    p, x, s = ctx.ba_solve(*_args(w), 1.0, 5)
+    po, xo, so = oracle.ba_solve(*_args(w), 1.0, 5)
+    assert s["iterations"] == so["iterations"] and s["successful_steps"] == so["successful_steps"]
+    assert abs(s["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]
+    assert np.abs(p - po).max() < 1e-5
 
 
 def test_batched_windows(ctx, synth):
