@@ -136,7 +136,18 @@ __global__ void __launch_bounds__(WIN_THREADS) win_colnorm_kernel(const BADev D,
     for (int i = tid; i < Nc * 6; i += WIN_THREADS) D.scale_c[6 * (size_t)w * Nc + i] = 1.0 / (1.0 + sqrt(sAcc[i]));
 }
 
-__global__ void __launch_bounds__(WIN_THREADS, 1) win_schur_kernel(const BADev D, const WinDev Wd)
+constexpr int WS_THREADS = 384;       // 8 consumer warps (tiles) + 4 producer warps (observations)
+constexpr int WS_PRODUCERS = WS_THREADS - 256;
+constexpr int WS_STRIDE = 19;         // doubles per 6x3 block in shared memory (18 + 1: conflict-free 64-bit reads)
+
+__device__ __forceinline__ void producer_barrier()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(WS_PRODUCERS) : "memory");
+}
+
+// Warp-specialised: producers (threads 256..383) evaluate chunk k into buffer k&1 while consumers
+// (threads 0..255, one 6x6 tile of S each) contract chunk k-1; one CTA-wide barrier per chunk.
+__global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D, const WinDev Wd)
 {
     extern __shared__ double sm[];
     const int w = blockIdx.x, tid = threadIdx.x, Nc = D.Nc, n = D.n, P = Wd.P;
@@ -151,179 +162,235 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) win_schur_kernel(const BADev D
     double *sScal = sRed + Nc * 33;          // 8 scalars
     double *sUnion = sScal + 8;
     // phase A (points loop)
-    double *sItem = sUnion;                  // P*Nc*8 : Jp (6) | r (2) per item
-    double *sPt = sItem + P * Nc * 8;        // P*12   : Vinv (6) | g (3) | pad
-    double *sY = sPt + P * 12;               // P*Nc*18
-    double *sW = sY + P * Nc * 18;           // P*Nc*18
-    unsigned *sMask = reinterpret_cast<unsigned *>(sW + P * Nc * 18);   // P
+    double *sItem = sUnion;                  // P*Nc*20 : Jp (6) | r (2) | Jc (12) per item
+    double *sPt = sItem + P * Nc * 20;       // P*12   : Vinv (6) | g (3) | pad
+    double *sVg = sPt + P * 12;              // P*9    : raw V (6) | g (3) sums
+    double *sYW = sVg + P * 9;               // 2 buffers x (Y | W) x P*Nc*WS_STRIDE
+    const size_t bufsz = (size_t)P * Nc * WS_STRIDE;
+    unsigned *sMask = reinterpret_cast<unsigned *>(sYW + 4 * bufsz);   // 2 x P
     // phase B (factorisation) aliases the union region
     double *A = sUnion;                      // n x (n+1)
     double *bvec = A + (size_t)n * (n + 1);  // n
 
-    for (int i = tid; i < Nc * 36; i += WIN_THREADS) sM[i] = Wd.camR[36 * (size_t)w * Nc + i];
-    for (int i = tid; i < Nc * 3; i += WIN_THREADS) sC[i] = D.poses[6 * ((size_t)w * Nc + i / 3) + 3 + i % 3];
-    for (int i = tid; i < Nc * 6; i += WIN_THREADS) sSc[i] = D.scale_c[6 * (size_t)w * Nc + i];
-    for (int i = tid; i < Nc * 33; i += WIN_THREADS) sRed[i] = 0.0;
+    for (int i = tid; i < Nc * 36; i += WS_THREADS) sM[i] = Wd.camR[36 * (size_t)w * Nc + i];
+    for (int i = tid; i < Nc * 3; i += WS_THREADS) sC[i] = D.poses[6 * ((size_t)w * Nc + i / 3) + 3 + i % 3];
+    for (int i = tid; i < Nc * 6; i += WS_THREADS) sSc[i] = D.scale_c[6 * (size_t)w * Nc + i];
+    for (int i = tid; i < Nc * 33; i += WS_THREADS) sRed[i] = 0.0;
     if (tid < 8) sScal[tid] = 0.0;
     __syncthreads();
     const double radius = st->radius;
+    const int nchunks = (D.Np + P - 1) / P;
+    const bool is_producer = tid >= 256;
 
-    // producer role: thread (pslot, cam)
-    const int pslot = tid / Nc, pcam = tid - pslot * Nc;
-    const bool producer = pslot < P;
-    // consumer role: thread <-> tile (ci <= cj)
-    int ci = 0, cj = 0;
     const int ntiles = Nc * (Nc + 1) / 2;
-    const bool consumer = tid < ntiles;
-    if (consumer) { int rem = tid; while (rem >= Nc - ci) { rem -= Nc - ci; ci++; } cj = ci + rem; }
-    double T[36];
-#pragma unroll
-    for (int k = 0; k < 36; k++) T[k] = 0.0;
-    double accU[21], accG[6], accR[6];
-#pragma unroll
-    for (int k = 0; k < 21; k++) accU[k] = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; k++) accG[k] = accR[k] = 0.0;
-    double cost = 0.0, gmax = 0.0;
+    const int ld = n + 1;
+    // The two roles keep their accumulators in DISJOINT code paths so the register allocation is the
+    // maximum of the two, not the sum.  cta_barrier() = one hand-off per chunk.
+    auto cta_barrier = []() { asm volatile("bar.sync 2, %0;" ::"n"(WS_THREADS) : "memory"); };
 
-    for (int p0 = 0; p0 < D.Np; p0 += P) {
-        // ---- A1: residual + Jacobians of item (point p0+pslot, camera pcam) -------------------------------
-        double jc[12], jp[6], r[2];
-        bool vis = false;
-        size_t wp = 0;
-        if (producer && p0 + pslot < D.Np) {
-            wp = (size_t)w * D.Np + p0 + pslot;
-            const unsigned mask = Wd.vis[wp];
-            if (pcam == 0) sMask[pslot] = mask;
-            vis = (mask >> pcam) & 1;
-            if (vis) {
-                const int i = D.pt_off[wp] + __popc(mask & ((1u << pcam) - 1));
-                win_residual_jac(sM + 36 * pcam, sC + 3 * pcam, D.points + 3 * wp, D.obs_xy[2 * (size_t)i],
-                                 D.obs_xy[2 * (size_t)i + 1], D.fx, D.cx, D.fy, D.cy, r, jc, jp);
-                double rho0, rho1;
-                ba_huber(D.delta, r[0] * r[0] + r[1] * r[1], rho0, rho1);
-                cost += 0.5 * rho0;
-                const double sr = sqrt(rho1);
-                const double *sp = D.scale_p + 3 * wp;
-                r[0] *= sr; r[1] *= sr;
+    if (is_producer) {
+        // producer thread (slot s, camera c) evaluates points s and s + P/2 of every chunk for camera c,
+        // so its camera sums (U 21 | g 6 | rhs 6) stay in registers for the whole window
+        const int ptid = tid - 256;
+        const int H = P >> 1;                    // point slots per pass
+        const int pslot = ptid / Nc, pcam = ptid - pslot * Nc;
+        const bool producer = pslot < H;
+        double accU[21], accG[6], accR[6];
 #pragma unroll
-                for (int k = 0; k < 6; k++) { const double s = sr * sSc[6 * pcam + k]; jc[k] *= s; jc[6 + k] *= s; }
+        for (int k = 0; k < 21; k++) accU[k] = 0.0;
 #pragma unroll
-                for (int k = 0; k < 3; k++) { const double s = sr * sp[k]; jp[k] *= s; jp[3 + k] *= s; }
-            }
-            double *it = sItem + (size_t)(pslot * Nc + pcam) * 8;
+        for (int k = 0; k < 6; k++) accG[k] = accR[k] = 0.0;
+        double cost = 0.0, gmax = 0.0;
+        for (int step = 0; step <= nchunks; step++) {
+            if (step < nchunks) {
+                const int p0 = step * P, buf = step & 1;
+                double *sY = sYW + (size_t)buf * 2 * bufsz, *sW = sY + bufsz;
+                unsigned *mk = sMask + buf * P;
+                // ---- A1: residual + Jacobians of items (point p0+slot, camera pcam) -> shared memory ---------------
+                for (int pass = 0; pass < 2; pass++) {
+                    const int slot = pslot + pass * H;
+                    if (!producer) break;
+                    double *it = sItem + (size_t)(slot * Nc + pcam) * 20;
+                    if (p0 + slot < D.Np) {
+                        const size_t wp = (size_t)w * D.Np + p0 + slot;
+                        const unsigned mask = Wd.vis[wp];
+                        if (pcam == 0) mk[slot] = mask;
+                        if ((mask >> pcam) & 1) {
+                            double jc[12], jp[6], r[2];
+                            const int i = D.pt_off[wp] + __popc(mask & ((1u << pcam) - 1));
+                            win_residual_jac(sM + 36 * pcam, sC + 3 * pcam, D.points + 3 * wp, D.obs_xy[2 * (size_t)i],
+                                             D.obs_xy[2 * (size_t)i + 1], D.fx, D.cx, D.fy, D.cy, r, jc, jp);
+                            double rho0, rho1;
+                            ba_huber(D.delta, r[0] * r[0] + r[1] * r[1], rho0, rho1);
+                            cost += 0.5 * rho0;
+                            const double sr = sqrt(rho1);
+                            const double *sp = D.scale_p + 3 * wp;
 #pragma unroll
-            for (int k = 0; k < 6; k++) it[k] = vis ? jp[k] : 0.0;
-            it[6] = vis ? r[0] : 0.0; it[7] = vis ? r[1] : 0.0;
-        } else if (producer && pcam == 0) {
-            sMask[pslot] = 0u;
-        }
-        __syncthreads();
-        // ---- A2: per point V + D^2, g, V^-1 (one thread per point slot) --------------------------------------
-        if (tid < P && p0 + tid < D.Np) {
-            const size_t wpp = (size_t)w * D.Np + p0 + tid;
-            double V[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
-            for (int c = 0; c < Nc; c++) {
-                const double *it = sItem + (size_t)(tid * Nc + c) * 8;
-                V[0] += it[0] * it[0] + it[3] * it[3]; V[1] += it[0] * it[1] + it[3] * it[4]; V[2] += it[0] * it[2] + it[3] * it[5];
-                V[3] += it[1] * it[1] + it[4] * it[4]; V[4] += it[1] * it[2] + it[4] * it[5]; V[5] += it[2] * it[2] + it[5] * it[5];
-                g[0] += it[0] * it[6] + it[3] * it[7]; g[1] += it[1] * it[6] + it[4] * it[7]; g[2] += it[2] * it[6] + it[5] * it[7];
-            }
-            double *pt = sPt + tid * 12;
-            if (sMask[tid] == 0u) {
-                for (int k = 0; k < 9; k++) pt[k] = 0.0;   // unobserved point: contributes nothing
-            } else {
-                if (lin) {
-                    D.diag_p[3 * wpp] = fmin(fmax(V[0], 1e-6), 1e32);
-                    D.diag_p[3 * wpp + 1] = fmin(fmax(V[3], 1e-6), 1e32);
-                    D.diag_p[3 * wpp + 2] = fmin(fmax(V[5], 1e-6), 1e32);
-                    const double *sp = D.scale_p + 3 * wpp;
-                    gmax = fmax(gmax, fmax(fabs(g[0] / sp[0]), fmax(fabs(g[1] / sp[1]), fabs(g[2] / sp[2]))));
+                            for (int k = 0; k < 3; k++) { const double sc = sr * sp[k]; it[k] = jp[k] * sc; it[3 + k] = jp[3 + k] * sc; }
+                            it[6] = r[0] * sr; it[7] = r[1] * sr;
+#pragma unroll
+                            for (int k = 0; k < 6; k++) { const double sc = sr * sSc[6 * pcam + k]; it[8 + k] = jc[k] * sc; it[14 + k] = jc[6 + k] * sc; }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; k++) it[k] = 0.0;
+                        }
+                    } else {
+                        if (pcam == 0) mk[slot] = 0u;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) it[k] = 0.0;
+                    }
                 }
-                const double d0 = sqrt(D.diag_p[3 * wpp] / radius), d1 = sqrt(D.diag_p[3 * wpp + 1] / radius),
-                             d2 = sqrt(D.diag_p[3 * wpp + 2] / radius);
-                V[0] += d0 * d0; V[3] += d1 * d1; V[5] += d2 * d2;
-                const double l00 = sqrt(V[0]), l10 = V[1] / l00, l20 = V[2] / l00;
-                const double l11 = sqrt(V[3] - l10 * l10), l21 = (V[4] - l20 * l10) / l11;
-                const double l22 = sqrt(V[5] - l20 * l20 - l21 * l21);
-                const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
-                const double i10 = -l10 * i00 * i11, i21 = -l21 * i11 * i22, i20 = -(l20 * i00 + l21 * i10) * i22;
-                pt[0] = i00 * i00 + i10 * i10 + i20 * i20; pt[1] = i10 * i11 + i20 * i21; pt[2] = i20 * i22;
-                pt[3] = i11 * i11 + i21 * i21; pt[4] = i21 * i22; pt[5] = i22 * i22;
-                pt[6] = g[0]; pt[7] = g[1]; pt[8] = g[2];
-                for (int k = 0; k < 6; k++) D.Vinv[6 * wpp + k] = pt[k];
-                for (int k = 0; k < 3; k++) D.gp[3 * wpp + k] = g[k];
-            }
-        }
-        __syncthreads();
-        // ---- A3: W = Jc^T Jp, Y = W V^-1 into shared memory; camera sums in registers ---------------------
-        if (producer && p0 + pslot < D.Np) {
-            double *Yo = sY + (size_t)(pslot * Nc + pcam) * 18, *Wo = sW + (size_t)(pslot * Nc + pcam) * 18;
-            if (vis) {
-                const double *pt = sPt + pslot * 12;
-                const double vg0 = pt[0] * pt[6] + pt[1] * pt[7] + pt[2] * pt[8], vg1 = pt[1] * pt[6] + pt[3] * pt[7] + pt[4] * pt[8],
-                             vg2 = pt[2] * pt[6] + pt[4] * pt[7] + pt[5] * pt[8];
-                int t = 0;
-#pragma unroll
-                for (int a = 0; a < 6; a++) {
-                    const double w0 = jc[a] * jp[0] + jc[6 + a] * jp[3], w1 = jc[a] * jp[1] + jc[6 + a] * jp[4],
-                                 w2 = jc[a] * jp[2] + jc[6 + a] * jp[5];
-                    Wo[3 * a] = w0; Wo[3 * a + 1] = w1; Wo[3 * a + 2] = w2;
-                    Yo[3 * a] = w0 * pt[0] + w1 * pt[1] + w2 * pt[2];
-                    Yo[3 * a + 1] = w0 * pt[1] + w1 * pt[3] + w2 * pt[4];
-                    Yo[3 * a + 2] = w0 * pt[2] + w1 * pt[4] + w2 * pt[5];
-                    accR[a] -= w0 * vg0 + w1 * vg1 + w2 * vg2;
-                    accG[a] += jc[a] * r[0] + jc[6 + a] * r[1];
-#pragma unroll
-                    for (int b = a; b < 6; b++) accU[t++] += jc[a] * jc[b] + jc[6 + a] * jc[6 + b];
+                producer_barrier();
+                // ---- A2a: raw V (6) and g (3) sums, thread (point slot, component) --------------------------------
+                for (int idx = ptid; idx < P * 9; idx += WS_PRODUCERS) {
+                    const int q = idx / 9, comp = idx - q * 9;
+                    const int ia[9] = {0, 0, 0, 1, 1, 2, 0, 1, 2}, ib[9] = {0, 1, 2, 1, 2, 2, 6, 6, 6};
+                    const int a = ia[comp], b2 = ib[comp];
+                    double sacc = 0;
+                    for (int c = 0; c < Nc; c++) {
+                        const double *it = sItem + (size_t)(q * Nc + c) * 20;
+                        sacc += (b2 == 6) ? (it[a] * it[6] + it[3 + a] * it[7]) : (it[a] * it[b2] + it[3 + a] * it[3 + b2]);
+                    }
+                    sVg[q * 9 + comp] = sacc;
                 }
-            } else {
+                producer_barrier();
+                // ---- A2b: (V + D^2)^-1 by adjugate / determinant (one thread per point slot) ---------------------
+                if (ptid < P && p0 + ptid < D.Np) {
+                    const size_t wpp = (size_t)w * D.Np + p0 + ptid;
+                    double V[6], g[3];
+                    for (int k = 0; k < 6; k++) V[k] = sVg[ptid * 9 + k];
+                    for (int k = 0; k < 3; k++) g[k] = sVg[ptid * 9 + 6 + k];
+                    double *pt = sPt + ptid * 12;
+                    if (mk[ptid] == 0u) {
+                        for (int k = 0; k < 9; k++) pt[k] = 0.0;   // unobserved point: contributes nothing
+                    } else {
+                        if (lin) {
+                            D.diag_p[3 * wpp] = fmin(fmax(V[0], 1e-6), 1e32);
+                            D.diag_p[3 * wpp + 1] = fmin(fmax(V[3], 1e-6), 1e32);
+                            D.diag_p[3 * wpp + 2] = fmin(fmax(V[5], 1e-6), 1e32);
+                            const double *sp = D.scale_p + 3 * wpp;
+                            gmax = fmax(gmax, fmax(fabs(g[0] / sp[0]), fmax(fabs(g[1] / sp[1]), fabs(g[2] / sp[2]))));
+                        }
+                        // D^2 = (sqrt(diag / radius))^2, like the LM strategy
+                        const double d0 = sqrt(D.diag_p[3 * wpp] / radius), d1 = sqrt(D.diag_p[3 * wpp + 1] / radius),
+                                     d2 = sqrt(D.diag_p[3 * wpp + 2] / radius);
+                        const double a = V[0] + d0 * d0, b2 = V[1], c = V[2], d = V[3] + d1 * d1, e = V[4], f = V[5] + d2 * d2;
+                        const double A0 = d * f - e * e, A1 = c * e - b2 * f, A2 = b2 * e - c * d;
+                        const double idet = 1.0 / (a * A0 + b2 * A1 + c * A2);
+                        pt[0] = A0 * idet; pt[1] = A1 * idet; pt[2] = A2 * idet;
+                        pt[3] = (a * f - c * c) * idet; pt[4] = (b2 * c - a * e) * idet; pt[5] = (a * d - b2 * b2) * idet;
+                        pt[6] = g[0]; pt[7] = g[1]; pt[8] = g[2];
+                        for (int k = 0; k < 6; k++) D.Vinv[6 * wpp + k] = pt[k];
+                        for (int k = 0; k < 3; k++) D.gp[3 * wpp + k] = g[k];
+                    }
+                }
+                producer_barrier();
+                // ---- A3: W = Jc^T Jp, Y = W V^-1 into the chunk buffer; camera sums in registers -----------------------
+                for (int pass = 0; pass < 2; pass++) {
+                    const int slot = pslot + pass * H;
+                    if (!producer || p0 + slot >= D.Np || !((mk[slot] >> pcam) & 1)) continue;
+                    const double *it = sItem + (size_t)(slot * Nc + pcam) * 20;
+                    double *Yo = sY + (size_t)(slot * Nc + pcam) * WS_STRIDE, *Wo = sW + (size_t)(slot * Nc + pcam) * WS_STRIDE;
+                    const double *pt = sPt + slot * 12;
+                    const double vg0 = pt[0] * pt[6] + pt[1] * pt[7] + pt[2] * pt[8], vg1 = pt[1] * pt[6] + pt[3] * pt[7] + pt[4] * pt[8],
+                                 vg2 = pt[2] * pt[6] + pt[4] * pt[7] + pt[5] * pt[8];
+                    double jp[6], jc[12];
 #pragma unroll
-                for (int k = 0; k < 18; k++) { Yo[k] = 0.0; Wo[k] = 0.0; }
+                    for (int k = 0; k < 6; k++) jp[k] = it[k];
+#pragma unroll
+                    for (int k = 0; k < 12; k++) jc[k] = it[8 + k];
+                    const double r0 = it[6], r1 = it[7];
+                    int t = 0;
+#pragma unroll
+                    for (int a = 0; a < 6; a++) {
+                        const double w0 = jc[a] * jp[0] + jc[6 + a] * jp[3], w1 = jc[a] * jp[1] + jc[6 + a] * jp[4],
+                                     w2 = jc[a] * jp[2] + jc[6 + a] * jp[5];
+                        Wo[3 * a] = w0; Wo[3 * a + 1] = w1; Wo[3 * a + 2] = w2;
+                        Yo[3 * a] = w0 * pt[0] + w1 * pt[1] + w2 * pt[2];
+                        Yo[3 * a + 1] = w0 * pt[1] + w1 * pt[3] + w2 * pt[4];
+                        Yo[3 * a + 2] = w0 * pt[2] + w1 * pt[4] + w2 * pt[5];
+                        accR[a] -= w0 * vg0 + w1 * vg1 + w2 * vg2;
+                        accG[a] += jc[a] * r0 + jc[6 + a] * r1;
+#pragma unroll
+                        for (int b2 = a; b2 < 6; b2++) accU[t++] += jc[a] * jc[b2] + jc[6 + a] * jc[6 + b2];
+                    }
+                }
             }
+            cta_barrier();
         }
-        __syncthreads();
-        // ---- A4: S(ci, cj) -= sum_p Y_ci W_cj^T ---------------------------------------------------------------
+        // reduce camera sums over the point slots
+        if (producer) {
+            for (int k = 0; k < 21; k++) atomicAdd(&sRed[33 * pcam + k], accU[k]);
+            for (int k = 0; k < 6; k++) { atomicAdd(&sRed[33 * pcam + 21 + k], accG[k]); atomicAdd(&sRed[33 * pcam + 27 + k], accR[k]); }
+        }
+        cost = warp_sum_d(cost);
+        if ((tid & 31) == 0 && cost != 0) atomicAdd(&sScal[0], cost);
+        if (lin) {
+            for (int o = 16; o; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+            if ((tid & 31) == 0 && gmax > 0) atomicMax(reinterpret_cast<unsigned long long *>(&sScal[1]), (unsigned long long)__double_as_longlong(gmax));
+        }
+        cta_barrier();   // B1: sRed complete, chunk buffers dead
+        cta_barrier();   // B2: camera diagonal written
+    } else {
+        int ci = 0, cj = 0;
+        const bool consumer = tid < ntiles;
+        if (consumer) { int rem = tid; while (rem >= Nc - ci) { rem -= Nc - ci; ci++; } cj = ci + rem; }
+        double T[36];
+#pragma unroll
+        for (int k = 0; k < 36; k++) T[k] = 0.0;
+        for (int step = 0; step <= nchunks; step++) {
+            if (step > 0 && consumer) {
+                // ---- A4: S(ci, cj) -= sum_p Y_ci W_cj^T over chunk step-1 ----------------------------------------------
+                const int p0 = (step - 1) * P, buf = (step - 1) & 1;
+                const double *sY = sYW + (size_t)buf * 2 * bufsz, *sW = sY + bufsz;
+                const unsigned *mk = sMask + buf * P;
+                const int np = min(P, D.Np - p0);
+                for (int q = 0; q < np; q++) {
+                    const unsigned m = mk[q];
+                    if (!((m >> ci) & 1) || !((m >> cj) & 1)) continue;
+                    const double *Y = sY + (size_t)(q * Nc + ci) * WS_STRIDE, *Wv = sW + (size_t)(q * Nc + cj) * WS_STRIDE;
+                    double y[18];
+#pragma unroll
+                    for (int k = 0; k < 18; k++) y[k] = Y[k];
+#pragma unroll
+                    for (int b2 = 0; b2 < 6; b2++) {
+                        const double w0 = Wv[3 * b2], w1 = Wv[3 * b2 + 1], w2 = Wv[3 * b2 + 2];
+#pragma unroll
+                        for (int a = 0; a < 6; a++) T[6 * a + b2] -= y[3 * a] * w0 + y[3 * a + 1] * w1 + y[3 * a + 2] * w2;
+                    }
+                }
+            }
+            cta_barrier();
+        }
+        cta_barrier();   // B1
+        // camera diagonal: LM diagonal, gradient max
+        if (tid < Nc && lin) {
+            const int dg[6] = {0, 6, 11, 15, 18, 20};
+            double gm = 0;
+            for (int a = 0; a < 6; a++) {
+                D.diag_c[6 * ((size_t)w * Nc + tid) + a] = fmin(fmax(sRed[33 * tid + dg[a]], 1e-6), 1e32);
+                gm = fmax(gm, fabs(sRed[33 * tid + 21 + a] / sSc[6 * tid + a]));
+            }
+            atomicMax(reinterpret_cast<unsigned long long *>(&sScal[1]), (unsigned long long)__double_as_longlong(gm));
+        }
+        cta_barrier();   // B2
+        // lay S out in shared memory (lower triangle of A)
         if (consumer) {
-            const int np = min(P, D.Np - p0);
-            for (int q = 0; q < np; q++) {
-                const unsigned m = sMask[q];
-                if (!((m >> ci) & 1) || !((m >> cj) & 1)) continue;
-                const double *Y = sY + (size_t)(q * Nc + ci) * 18, *Wv = sW + (size_t)(q * Nc + cj) * 18;
-                double y[18];
 #pragma unroll
-                for (int k = 0; k < 18; k++) y[k] = Y[k];
+            for (int a = 0; a < 6; a++)
 #pragma unroll
-                for (int b = 0; b < 6; b++) {
-                    const double w0 = Wv[3 * b], w1 = Wv[3 * b + 1], w2 = Wv[3 * b + 2];
-#pragma unroll
-                    for (int a = 0; a < 6; a++) T[6 * a + b] -= y[3 * a] * w0 + y[3 * a + 1] * w1 + y[3 * a + 2] * w2;
+                for (int b2 = 0; b2 < 6; b2++) {
+                    double v = T[6 * a + b2];
+                    if (ci == cj) {
+                        const int lo = a < b2 ? a : b2, hi = a < b2 ? b2 : a;
+                        const int t = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);      // index of (lo,hi) in the 21-entry upper triangle
+                        v += sRed[33 * ci + t];
+                        if (a == b2) { const double d = sqrt(D.diag_c[6 * ((size_t)w * Nc + ci) + a] / radius); v += d * d; }
+                    }
+                    // S[6ci+a][6cj+b] -> lower triangle entry A[6cj+b][6ci+a]
+                    if (6 * cj + b2 >= 6 * ci + a) A[(size_t)(6 * cj + b2) * ld + 6 * ci + a] = v;
                 }
-            }
         }
-        __syncthreads();
-    }
-    // ---- reduce camera sums over the point slots -----------------------------------------------------------
-    if (producer) {
-        for (int k = 0; k < 21; k++) atomicAdd(&sRed[33 * pcam + k], accU[k]);
-        for (int k = 0; k < 6; k++) { atomicAdd(&sRed[33 * pcam + 21 + k], accG[k]); atomicAdd(&sRed[33 * pcam + 27 + k], accR[k]); }
-    }
-    cost = warp_sum_d(cost);
-    if ((tid & 31) == 0) atomicAdd(&sScal[0], cost);
-    if (lin) {
-        for (int o = 16; o; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-        if ((tid & 31) == 0 && gmax > 0) atomicMax(reinterpret_cast<unsigned long long *>(&sScal[1]), (unsigned long long)__double_as_longlong(gmax));
-    }
-    __syncthreads();   // also: phase A shared memory is dead from here on
-    // ---- camera diagonal: LM diagonal, gradient max; latch cost ---------------------------------------------
-    if (tid < Nc && lin) {
-        const int dg[6] = {0, 6, 11, 15, 18, 20};
-        double gm = 0;
-        for (int a = 0; a < 6; a++) {
-            D.diag_c[6 * ((size_t)w * Nc + tid) + a] = fmin(fmax(sRed[33 * tid + dg[a]], 1e-6), 1e32);
-            gm = fmax(gm, fabs(sRed[33 * tid + 21 + a] / sSc[6 * tid + a]));
-        }
-        atomicMax(reinterpret_cast<unsigned long long *>(&sScal[1]), (unsigned long long)__double_as_longlong(gm));
     }
     __syncthreads();
     if (tid == 0 && lin) {
@@ -331,25 +398,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) win_schur_kernel(const BADev D
         if (st->iter == 0) st->initial_cost = sScal[0];
         st->gmax = sScal[1];
     }
-    // ---- lay S out in shared memory (lower triangle of A), rhs ----------------------------------------------
-    const int ld = n + 1;
-    if (consumer) {
-#pragma unroll
-        for (int a = 0; a < 6; a++)
-#pragma unroll
-            for (int b = 0; b < 6; b++) {
-                double v = T[6 * a + b];
-                if (ci == cj) {
-                    const int lo = a < b ? a : b, hi = a < b ? b : a;
-                    const int t = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);      // index of (lo,hi) in the 21-entry upper triangle
-                    v += sRed[33 * ci + t];
-                    if (a == b) { const double d = sqrt(D.diag_c[6 * ((size_t)w * Nc + ci) + a] / radius); v += d * d; }
-                }
-                // S[6ci+a][6cj+b] -> lower triangle entry A[6cj+b][6ci+a]
-                if (6 * cj + b >= 6 * ci + a) A[(size_t)(6 * cj + b) * ld + 6 * ci + a] = v;
-            }
-    }
-    for (int i = tid; i < n; i += WIN_THREADS) bvec[i] = sRed[33 * (i / 6) + 21 + i % 6] + sRed[33 * (i / 6) + 27 + i % 6];
+    __shared__ double s_rhs[6 * WIN_MAXC];
+    if (tid < n) s_rhs[tid] = sRed[33 * (tid / 6) + 21 + tid % 6] + sRed[33 * (tid / 6) + 27 + tid % 6];
     __shared__ int s_ok;
     if (tid == 0) {
         s_ok = 1;
@@ -357,6 +407,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) win_schur_kernel(const BADev D
     }
     __syncthreads();
     if (s_ok < 0) return;
+    if (tid < n) bvec[tid] = s_rhs[tid];
+    __syncthreads();
     // ---- K10: Cholesky + two triangular solves in shared memory ----------------------------------------------
     for (int j = 0; j < n; j++) {
         if (tid == 0) {
@@ -366,10 +418,10 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) win_schur_kernel(const BADev D
         __syncthreads();
         if (!s_ok) break;
         const double dj = A[(size_t)j * ld + j];
-        for (int i = j + 1 + tid; i < n; i += WIN_THREADS) A[(size_t)i * ld + j] /= dj;
+        for (int i = j + 1 + tid; i < n; i += WS_THREADS) A[(size_t)i * ld + j] /= dj;
         __syncthreads();
         const int m = n - j - 1;
-        for (int t = tid; t < m * m; t += WIN_THREADS) {
+        for (int t = tid; t < m * m; t += WS_THREADS) {
             const int ii = t / m, kk = t - ii * m;
             if (kk <= ii) { const int i = j + 1 + ii, k = j + 1 + kk; A[(size_t)i * ld + k] -= A[(size_t)i * ld + j] * A[(size_t)k * ld + j]; }
         }
@@ -380,18 +432,18 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) win_schur_kernel(const BADev D
         if (tid == 0) bvec[j] /= A[(size_t)j * ld + j];
         __syncthreads();
         const double bj = bvec[j];
-        for (int i = j + 1 + tid; i < n; i += WIN_THREADS) bvec[i] -= A[(size_t)i * ld + j] * bj;
+        for (int i = j + 1 + tid; i < n; i += WS_THREADS) bvec[i] -= A[(size_t)i * ld + j] * bj;
         __syncthreads();
     }
     for (int j = n - 1; j >= 0; j--) {
         if (tid == 0) bvec[j] /= A[(size_t)j * ld + j];
         __syncthreads();
         const double bj = bvec[j];
-        for (int i = tid; i < j; i += WIN_THREADS) bvec[i] -= A[(size_t)j * ld + i] * bj;
+        for (int i = tid; i < j; i += WS_THREADS) bvec[i] -= A[(size_t)j * ld + i] * bj;
         __syncthreads();
     }
     bool fin = true;
-    for (int i = tid; i < n; i += WIN_THREADS) { D.yc[(size_t)w * n + i] = bvec[i]; fin = fin && isfinite(bvec[i]); }
+    for (int i = tid; i < n; i += WS_THREADS) { D.yc[(size_t)w * n + i] = bvec[i]; fin = fin && isfinite(bvec[i]); }
     const int allfin = __syncthreads_and(fin);
     if (tid == 0) st->chol_ok = allfin ? 1 : 0;
 }
@@ -508,10 +560,10 @@ int pmv_internal_ba_window_iteration(pmv_ctx *ctx, const BADev &D, const unsigne
     WinDev Wd;
     Wd.vis = d_vis; Wd.camR = d_camR; Wd.candR = d_candR;
     const int Nc = D.Nc, n = D.n;
-    Wd.P = std::max(1, std::min(WIN_THREADS / Nc, 12));
+    Wd.P = 2 * std::max(1, std::min(WS_PRODUCERS / Nc, 8));   // two passes of P/2 point slots per chunk
     const int wc = D.W * Nc;
     const size_t smem_col = sizeof(double) * (size_t)Nc * 45;
-    const size_t unionA = (size_t)Wd.P * Nc * 8 + (size_t)Wd.P * 12 + 2 * (size_t)Wd.P * Nc * 18 + Wd.P;
+    const size_t unionA = (size_t)Wd.P * Nc * 20 + (size_t)Wd.P * 21 + 4 * (size_t)Wd.P * Nc * WS_STRIDE + Wd.P + 2;
     const size_t unionB = (size_t)n * (n + 1) + n;
     const size_t smem_schur = sizeof(double) * ((size_t)Nc * 78 + 8 + std::max(unionA, unionB) + 2);
     const size_t smem_back = sizeof(double) * (size_t)Nc * 63;
@@ -524,7 +576,7 @@ int pmv_internal_ba_window_iteration(pmv_ctx *ctx, const BADev &D, const unsigne
     PMV_LAUNCH_CHECK(ctx, "win_prepare_kernel");
     win_colnorm_kernel<<<D.W, WIN_THREADS, smem_col, s>>>(D, Wd);
     PMV_LAUNCH_CHECK(ctx, "win_colnorm_kernel");
-    win_schur_kernel<<<D.W, WIN_THREADS, smem_schur, s>>>(D, Wd);
+    win_schur_kernel<<<D.W, WS_THREADS, smem_schur, s>>>(D, Wd);
     PMV_LAUNCH_CHECK(ctx, "win_schur_kernel");
     ba_cam_candidate_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D, 1);
     PMV_LAUNCH_CHECK(ctx, "ba_cam_candidate_kernel");
