@@ -28,6 +28,8 @@ struct WinDev {
     double *camR;          // per (window, camera): R (9) | dR/da_0 (9) | dR/da_1 (9) | dR/da_2 (9)
     double *candR;         // per (window, camera): R of the candidate pose (9)
     int P;                 // points per chunk
+    int LD;                // row stride (doubles) of the chunk matrices, == 4 (mod 16)
+    int passes;            // producer passes per chunk (1 or 2)
 };
 
 // rotation matrix and its derivatives w.r.t. the angle-axis vector, via the same code as the residual
@@ -136,9 +138,14 @@ __global__ void __launch_bounds__(WIN_THREADS) win_colnorm_kernel(const BADev D,
     for (int i = tid; i < Nc * 6; i += WIN_THREADS) D.scale_c[6 * (size_t)w * Nc + i] = 1.0 / (1.0 + sqrt(sAcc[i]));
 }
 
-constexpr int WS_THREADS = 384;       // 8 consumer warps (tiles) + 4 producer warps (observations)
+constexpr int WS_THREADS = 512;       // 8 consumer warps (tiles) + 8 producer warps (observations)
 constexpr int WS_PRODUCERS = WS_THREADS - 256;
-constexpr int WS_STRIDE = 19;         // doubles per 6x3 block in shared memory (18 + 1: conflict-free 64-bit reads)
+
+__device__ __forceinline__ void win_dmma(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 
 __device__ __forceinline__ void producer_barrier()
 {
@@ -147,6 +154,8 @@ __device__ __forceinline__ void producer_barrier()
 
 // Warp-specialised: producers (threads 256..383) evaluate chunk k into buffer k&1 while consumers
 // (threads 0..255, one 6x6 tile of S each) contract chunk k-1; one CTA-wide barrier per chunk.
+// WS_MAXST: 16x16 super-tiles of S per consumer warp (NS(NS+1)/2 super-tiles over 8 warps: 5 up to n = 128, else 6)
+template <int WS_MAXST>
 __global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D, const WinDev Wd)
 {
     extern __shared__ double sm[];
@@ -165,8 +174,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D,
     double *sItem = sUnion;                  // P*Nc*20 : Jp (6) | r (2) | Jc (12) per item
     double *sPt = sItem + P * Nc * 20;       // P*12   : Vinv (6) | g (3) | pad
     double *sVg = sPt + P * 12;              // P*9    : raw V (6) | g (3) sums
-    double *sYW = sVg + P * 9;               // 2 buffers x (Y | W) x P*Nc*WS_STRIDE
-    const size_t bufsz = (size_t)P * Nc * WS_STRIDE;
+    // chunk buffers: Y and W as row-major [rows = 16*NS >= n][LD] matrices (row = 6*cam + a, column =
+    // 3*slot + b), two buffers; LD == 4 (mod 16) makes the fp64 mma fragment loads conflict-free
+    const int NS = (n + 15) >> 4, LD = Wd.LD, KS = (3 * P + 3) >> 2;
+    double *sYW = sVg + P * 9;
+    const size_t bufsz = (size_t)16 * NS * LD;
     unsigned *sMask = reinterpret_cast<unsigned *>(sYW + 4 * bufsz);   // 2 x P
     // phase B (factorisation) aliases the union region
     double *A = sUnion;                      // n x (n+1)
@@ -177,6 +189,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D,
     for (int i = tid; i < Nc * 6; i += WS_THREADS) sSc[i] = D.scale_c[6 * (size_t)w * Nc + i];
     for (int i = tid; i < Nc * 33; i += WS_THREADS) sRed[i] = 0.0;
     if (tid < 8) sScal[tid] = 0.0;
+    for (size_t i = tid; i < 4 * bufsz; i += WS_THREADS) sYW[i] = 0.0;   // padding rows / columns stay zero
     __syncthreads();
     const double radius = st->radius;
     const int nchunks = (D.Np + P - 1) / P;
@@ -192,7 +205,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D,
         // producer thread (slot s, camera c) evaluates points s and s + P/2 of every chunk for camera c,
         // so its camera sums (U 21 | g 6 | rhs 6) stay in registers for the whole window
         const int ptid = tid - 256;
-        const int H = P >> 1;                    // point slots per pass
+        const int passes = Wd.passes;            // 1 when every (point slot, camera) item has its own thread, else 2
+        const int H = P / passes;                // point slots per pass
         const int pslot = ptid / Nc, pcam = ptid - pslot * Nc;
         const bool producer = pslot < H;
         double accU[21], accG[6], accR[6];
@@ -207,7 +221,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D,
                 double *sY = sYW + (size_t)buf * 2 * bufsz, *sW = sY + bufsz;
                 unsigned *mk = sMask + buf * P;
                 // ---- A1: residual + Jacobians of items (point p0+slot, camera pcam) -> shared memory ---------------
-                for (int pass = 0; pass < 2; pass++) {
+                for (int pass = 0; pass < passes; pass++) {
                     const int slot = pslot + pass * H;
                     if (!producer) break;
                     double *it = sItem + (size_t)(slot * Nc + pcam) * 20;
@@ -285,12 +299,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D,
                     }
                 }
                 producer_barrier();
-                // ---- A3: W = Jc^T Jp, Y = W V^-1 into the chunk buffer; camera sums in registers -----------------------
-                for (int pass = 0; pass < 2; pass++) {
+                // ---- A3: W = Jc^T Jp, Y = W V^-1 into the chunk matrices; camera sums in registers -----------------
+                for (int pass = 0; pass < passes; pass++) {
                     const int slot = pslot + pass * H;
-                    if (!producer || p0 + slot >= D.Np || !((mk[slot] >> pcam) & 1)) continue;
+                    if (!producer) break;
+                    double *Yo = sY + (size_t)(6 * pcam) * LD + 3 * slot, *Wo = sW + (size_t)(6 * pcam) * LD + 3 * slot;
+                    if (p0 + slot >= D.Np || !((mk[slot] >> pcam) & 1)) {
+#pragma unroll
+                        for (int a = 0; a < 6; a++) {
+                            Yo[a * LD] = 0.0; Yo[a * LD + 1] = 0.0; Yo[a * LD + 2] = 0.0;
+                            Wo[a * LD] = 0.0; Wo[a * LD + 1] = 0.0; Wo[a * LD + 2] = 0.0;
+                        }
+                        continue;
+                    }
                     const double *it = sItem + (size_t)(slot * Nc + pcam) * 20;
-                    double *Yo = sY + (size_t)(slot * Nc + pcam) * WS_STRIDE, *Wo = sW + (size_t)(slot * Nc + pcam) * WS_STRIDE;
                     const double *pt = sPt + slot * 12;
                     const double vg0 = pt[0] * pt[6] + pt[1] * pt[7] + pt[2] * pt[8], vg1 = pt[1] * pt[6] + pt[3] * pt[7] + pt[4] * pt[8],
                                  vg2 = pt[2] * pt[6] + pt[4] * pt[7] + pt[5] * pt[8];
@@ -305,10 +327,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D,
                     for (int a = 0; a < 6; a++) {
                         const double w0 = jc[a] * jp[0] + jc[6 + a] * jp[3], w1 = jc[a] * jp[1] + jc[6 + a] * jp[4],
                                      w2 = jc[a] * jp[2] + jc[6 + a] * jp[5];
-                        Wo[3 * a] = w0; Wo[3 * a + 1] = w1; Wo[3 * a + 2] = w2;
-                        Yo[3 * a] = w0 * pt[0] + w1 * pt[1] + w2 * pt[2];
-                        Yo[3 * a + 1] = w0 * pt[1] + w1 * pt[3] + w2 * pt[4];
-                        Yo[3 * a + 2] = w0 * pt[2] + w1 * pt[4] + w2 * pt[5];
+                        Wo[a * LD] = w0; Wo[a * LD + 1] = w1; Wo[a * LD + 2] = w2;
+                        Yo[a * LD] = w0 * pt[0] + w1 * pt[1] + w2 * pt[2];
+                        Yo[a * LD + 1] = w0 * pt[1] + w1 * pt[3] + w2 * pt[4];
+                        Yo[a * LD + 2] = w0 * pt[2] + w1 * pt[4] + w2 * pt[5];
                         accR[a] -= w0 * vg0 + w1 * vg1 + w2 * vg2;
                         accG[a] += jc[a] * r0 + jc[6 + a] * r1;
 #pragma unroll
@@ -332,31 +354,39 @@ __global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D,
         cta_barrier();   // B1: sRed complete, chunk buffers dead
         cta_barrier();   // B2: camera diagonal written
     } else {
-        int ci = 0, cj = 0;
-        const bool consumer = tid < ntiles;
-        if (consumer) { int rem = tid; while (rem >= Nc - ci) { rem -= Nc - ci; ci++; } cj = ci + rem; }
-        double T[36];
+        // ---- consumers: 8 warps, each owns up to WS_MAXST 16x16 super-tiles (2x2 fp64 mma tiles) of the upper
+        // triangle of S = sum_p Y W^T; accumulators in registers, operands straight from the chunk matrices
+        const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+        const int NST = NS * (NS + 1) / 2;
+        int stI[WS_MAXST], stJ[WS_MAXST];
 #pragma unroll
-        for (int k = 0; k < 36; k++) T[k] = 0.0;
+        for (int j = 0; j < WS_MAXST; j++) {
+            int idx = warp + 8 * j, I = 0;
+            if (idx < NST) { while (idx >= NS - I) { idx -= NS - I; I++; } stI[j] = I; stJ[j] = I + idx; }
+            else { stI[j] = -1; stJ[j] = -1; }
+        }
+        double C[WS_MAXST][2][2][2];
+#pragma unroll
+        for (int j = 0; j < WS_MAXST; j++)
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int b2 = 0; b2 < 2; b2++) C[j][a][b2][0] = C[j][a][b2][1] = 0.0;
         for (int step = 0; step <= nchunks; step++) {
-            if (step > 0 && consumer) {
-                // ---- A4: S(ci, cj) -= sum_p Y_ci W_cj^T over chunk step-1 ----------------------------------------------
-                const int p0 = (step - 1) * P, buf = (step - 1) & 1;
+            if (step > 0) {
+                const int buf = (step - 1) & 1;
                 const double *sY = sYW + (size_t)buf * 2 * bufsz, *sW = sY + bufsz;
-                const unsigned *mk = sMask + buf * P;
-                const int np = min(P, D.Np - p0);
-                for (int q = 0; q < np; q++) {
-                    const unsigned m = mk[q];
-                    if (!((m >> ci) & 1) || !((m >> cj) & 1)) continue;
-                    const double *Y = sY + (size_t)(q * Nc + ci) * WS_STRIDE, *Wv = sW + (size_t)(q * Nc + cj) * WS_STRIDE;
-                    double y[18];
+                for (int ks = 0; ks < KS; ks++) {
+                    const int kc = 4 * ks + q;
 #pragma unroll
-                    for (int k = 0; k < 18; k++) y[k] = Y[k];
-#pragma unroll
-                    for (int b2 = 0; b2 < 6; b2++) {
-                        const double w0 = Wv[3 * b2], w1 = Wv[3 * b2 + 1], w2 = Wv[3 * b2 + 2];
-#pragma unroll
-                        for (int a = 0; a < 6; a++) T[6 * a + b2] -= y[3 * a] * w0 + y[3 * a + 1] * w1 + y[3 * a + 2] * w2;
+                    for (int j = 0; j < WS_MAXST; j++) {
+                        if (stI[j] < 0) continue;
+                        const double a0 = sY[(size_t)(16 * stI[j] + g) * LD + kc], a1 = sY[(size_t)(16 * stI[j] + 8 + g) * LD + kc];
+                        const double b0 = sW[(size_t)(16 * stJ[j] + g) * LD + kc], b1 = sW[(size_t)(16 * stJ[j] + 8 + g) * LD + kc];
+                        win_dmma(C[j][0][0][0], C[j][0][0][1], a0, b0);
+                        win_dmma(C[j][0][1][0], C[j][0][1][1], a0, b1);
+                        win_dmma(C[j][1][0][0], C[j][1][0][1], a1, b0);
+                        win_dmma(C[j][1][1][0], C[j][1][1][1], a1, b1);
                     }
                 }
             }
@@ -374,23 +404,31 @@ __global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D,
             atomicMax(reinterpret_cast<unsigned long long *>(&sScal[1]), (unsigned long long)__double_as_longlong(gm));
         }
         cta_barrier();   // B2
-        // lay S out in shared memory (lower triangle of A)
-        if (consumer) {
+        // S = -sum Y W^T into the lower triangle of A (A[c][r] = S[r][c], r <= c)
 #pragma unroll
-            for (int a = 0; a < 6; a++)
+        for (int j = 0; j < WS_MAXST; j++) {
+            if (stI[j] < 0) continue;
 #pragma unroll
-                for (int b2 = 0; b2 < 6; b2++) {
-                    double v = T[6 * a + b2];
-                    if (ci == cj) {
-                        const int lo = a < b2 ? a : b2, hi = a < b2 ? b2 : a;
-                        const int t = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);      // index of (lo,hi) in the 21-entry upper triangle
-                        v += sRed[33 * ci + t];
-                        if (a == b2) { const double d = sqrt(D.diag_c[6 * ((size_t)w * Nc + ci) + a] / radius); v += d * d; }
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int b2 = 0; b2 < 2; b2++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int r = 16 * stI[j] + 8 * a + g, c = 16 * stJ[j] + 8 * b2 + 2 * q + e;
+                        if (r <= c && c < n) A[(size_t)c * ld + r] = -C[j][a][b2][e];
                     }
-                    // S[6ci+a][6cj+b] -> lower triangle entry A[6cj+b][6ci+a]
-                    if (6 * cj + b2 >= 6 * ci + a) A[(size_t)(6 * cj + b2) * ld + 6 * ci + a] = v;
-                }
         }
+    }
+    __syncthreads();
+    // camera diagonal blocks: += U_c + D_c^2
+    for (int i = tid; i < Nc * 21; i += WS_THREADS) {
+        const int c = i / 21, t = i - c * 21;
+        int lo = 0, rem = t;
+        while (rem >= 6 - lo) { rem -= 6 - lo; lo++; }
+        const int hi = lo + rem;
+        double v = sRed[33 * c + t];
+        if (lo == hi) { const double d = sqrt(D.diag_c[6 * ((size_t)w * Nc + c) + lo] / radius); v += d * d; }
+        A[(size_t)(6 * c + hi) * ld + 6 * c + lo] += v;
     }
     __syncthreads();
     if (tid == 0 && lin) {
@@ -560,23 +598,29 @@ int pmv_internal_ba_window_iteration(pmv_ctx *ctx, const BADev &D, const unsigne
     WinDev Wd;
     Wd.vis = d_vis; Wd.camR = d_camR; Wd.candR = d_candR;
     const int Nc = D.Nc, n = D.n;
-    Wd.P = 2 * std::max(1, std::min(WS_PRODUCERS / Nc, 8));   // two passes of P/2 point slots per chunk
+    Wd.P = 12;                                  // 3 P = 36 columns = 9 mma k-steps, LD = 36
+    Wd.passes = (Wd.P * Nc > WS_PRODUCERS) ? 2 : 1;
     const int wc = D.W * Nc;
     const size_t smem_col = sizeof(double) * (size_t)Nc * 45;
-    const size_t unionA = (size_t)Wd.P * Nc * 20 + (size_t)Wd.P * 21 + 4 * (size_t)Wd.P * Nc * WS_STRIDE + Wd.P + 2;
+    Wd.LD = 3 * Wd.P;
+    while (Wd.LD % 16 != 4) Wd.LD++;
+    const int NS = (n + 15) / 16;
+    const size_t unionA = (size_t)Wd.P * Nc * 20 + (size_t)Wd.P * 21 + 4 * (size_t)16 * NS * Wd.LD + Wd.P + 2;
     const size_t unionB = (size_t)n * (n + 1) + n;
     const size_t smem_schur = sizeof(double) * ((size_t)Nc * 78 + 8 + std::max(unionA, unionB) + 2);
     const size_t smem_back = sizeof(double) * (size_t)Nc * 63;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(win_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(win_schur_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(win_schur_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         attr = true;
     }
     win_prepare_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D, Wd, 0);
     PMV_LAUNCH_CHECK(ctx, "win_prepare_kernel");
     win_colnorm_kernel<<<D.W, WIN_THREADS, smem_col, s>>>(D, Wd);
     PMV_LAUNCH_CHECK(ctx, "win_colnorm_kernel");
-    win_schur_kernel<<<D.W, WS_THREADS, smem_schur, s>>>(D, Wd);
+    if (NS * (NS + 1) / 2 <= 40) win_schur_kernel<5><<<D.W, WS_THREADS, smem_schur, s>>>(D, Wd);
+    else win_schur_kernel<6><<<D.W, WS_THREADS, smem_schur, s>>>(D, Wd);
     PMV_LAUNCH_CHECK(ctx, "win_schur_kernel");
     ba_cam_candidate_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D, 1);
     PMV_LAUNCH_CHECK(ctx, "ba_cam_candidate_kernel");
