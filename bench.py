@@ -254,9 +254,99 @@ def run_ba_windows(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_ba_large(args, rank, world, local_rank):
+    """BASELINE config 5: BAL-scale synthetic BA (1k cameras, 1M points, ~5M observations); points sharded
+    contiguous-by-index over the ranks, poses replicated, NCCL all-reduce of the reduced camera system every
+    LM iteration.  Unit = one LM iteration of the whole problem -> STRONG scaling (total work fixed)."""
+    import torch
+    import torch.distributed as dist
+    import pmv_b200
+    from pmv_b200 import sharding, synth
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    iters = args.ba_iters
+    w = synth.ba_large(7, n_poses=args.cams, n_points=args.points, views=5, span=40)
+    ctx = pmv_b200.Context(local_rank)
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.from_numpy(np.frombuffer(ctx.comm_unique_id(), np.uint8).copy()).cuda()
+        dist.broadcast(uid, 0)
+        ctx.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+    pl, ol, cl, ptl, (lo, hi), sel = sharding.shard_points(w["points"], w["obs"], w["cam_idx"], w["pt_idx"], rank, world)
+    prob = ctx.ba_problem(w["poses"], pl, ol, cl, ptl, w["K"], 1.0, rank=rank, nranks=world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
+        prob.reset(); prob.solve(iters)
+    barrier()
+    sampler = ClockSampler(local_rank); l0 = ctx.launches
+    barrier(); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        prob.reset(); prob.solve(iters)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop(); launches = ctx.launches - l0
+    ms = e0.elapsed_time(e1)
+    P, X, S = prob.download()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    done_iters = S[0]["iterations"]
+    value = done_iters * args.steps / (float(t.item()) * 1e-3)
+    # e2e: host arrays in -> create (index + upload) + solve + download
+    barrier(); te = time.perf_counter()
+    prob2 = ctx.ba_problem(w["poses"], pl, ol, cl, ptl, w["K"], 1.0, rank=rank, nranks=world)
+    prob2.solve(iters); P2, X2, S2 = prob2.download()
+    barrier(); t_e2e = time.perf_counter() - te
+    prob2.close()
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            import oracle
+            tc = time.perf_counter()
+            po, xo, so = oracle.ba_solve(w["poses"], w["points"], w["obs"], w["cam_idx"], w["pt_idx"], w["K"], 1.0, 2)
+            tcpu = time.perf_counter() - tc
+            cpu = {"value": so["iterations"] / tcpu, "unit": "LM iterations/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"2 LM iterations of the full problem, oracle LM + Schur + envelope Cholesky ({tcpu:.1f} s; OpenMP linearisation)"}
+        n_obs = len(w["obs"])
+        n = 6 * args.cams
+        out = {"metric": "ba_large_lm_iterations_per_s", "value": value, "unit": "LM iterations/s", "n_gpus": world,
+               "steps": args.steps, "warmup": warmup, "ms_per_step": float(t.item()) / args.steps, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": f"BASELINE config 5: BAL-scale BA, {args.cams} cameras, {args.points} points, {n_obs} observations, "
+                                      f"points sharded over {world} GPU(s), NCCL all-reduce of [S|rhs] ({(n * n + n) * 8 / 1e6:.0f} MB) per iteration, "
+                                      f"{iters} LM iterations", "l2_policy": f"linearisation ({n_obs * 160 / 1e6:.0f} MB) + S ({n * n * 8 / 1e6:.0f} MB) larger than the 126 MB L2",
+                          "parallelism": f"points sharded x{world}, poses replicated"},
+               "e2e": {"value": S2[0]["iterations"] / t_e2e, "unit": "LM iterations/s",
+                       "h2d_bytes_per_step": int(len(ol) * 28 + w["poses"].nbytes + pl.nbytes), "d2h_bytes_per_step": int(w["poses"].nbytes + pl.nbytes),
+                       "api": "pmv_ba_problem_create + solve + download (host buffers; includes indexing)"},
+               "gpu_launches": int(launches), "roofline": None, "cpu_baseline": cpu, "clocks": clocks,
+               "final_cost": S[0]["final_cost"], "initial_cost": S[0]["initial_cost"], "iterations": done_iters}
+        print(json.dumps(out))
+    prob.close()
+    if world > 1:
+        ctx.comm_destroy()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="lk", choices=["lk", "ba_windows"])
+    ap.add_argument("--workload", default="lk", choices=["lk", "ba_windows", "ba_large"])
+    ap.add_argument("--cams", type=int, default=1000)
+    ap.add_argument("--points", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--windows", type=int, default=4096)
     ap.add_argument("--ba-iters", type=int, default=5)
     ap.add_argument("--gpus", type=int, default=1)
@@ -275,6 +365,9 @@ def main():
         return
     if args.workload == "ba_windows":
         run_ba_windows(args, rank, world, local_rank)
+        return
+    if args.workload == "ba_large":
+        run_ba_large(args, rank, world, local_rank)
         return
 
     import torch

@@ -12,7 +12,7 @@
 #include "ba.cuh"
 #include "ba_kernels.cuh"
 
-int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, cudaStream_t s);  // ba_chol.cu
+int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_host, cudaStream_t s);  // ba_chol.cu
 int pmv_internal_ba_allreduce(pmv_ctx *ctx, const double *send, double *recv, size_t count, int op_max,
                               cudaStream_t s);                                      // ba_nccl.cu
 bool pmv_internal_ba_window_eligible(int Nc, int Np);                               // ba_window.cu
@@ -29,6 +29,7 @@ struct pmv_ba_problem {
     double *d_Uraw = nullptr, *d_Uraw_red = nullptr;   // 27 doubles per camera (+ W cost slots at the end)
     double *d_scal = nullptr, *d_scal_red = nullptr;   // per window: model_change, cand_cost, step_norm2, x_norm2
     std::vector<int> perm;                               // caller observation order -> device order
+    std::vector<int> chol_lim;                           // envelope of S per 64-row block (host copy)
     size_t bytes = 0;
     // window-batched path (ba_window.cu): Nc <= 22, every (point, camera) pair observed at most once
     int use_window = 0;
@@ -152,7 +153,7 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
         ba_cholesky_small_kernel<<<W, 256, smem, s>>>(D);
         PMV_LAUNCH_CHECK(ctx, "ba_cholesky_small_kernel");
     } else {
-        int rc = pmv_internal_ba_cholesky_large(ctx, D, s);
+        int rc = pmv_internal_ba_cholesky_large(ctx, D, p->chol_lim.empty() ? nullptr : p->chol_lim.data(), s);
         if (rc) return rc;
     }
     ba_cam_candidate_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D, p->sharded ? (p->rank == 0) : 1);
@@ -257,6 +258,18 @@ PMV_API pmv_ba_problem *pmv_ba_problem_create(pmv_ctx *ctx, const double *poses,
             m |= 1u << h_cam[d];
         }
     }
+    // structural envelope of the reduced camera system: camera c couples with cameras up to emax[c]
+    std::vector<double> emax(Nc);
+    for (int c = 0; c < Nc; c++) emax[c] = c;
+    if (W == 1) {
+        for (size_t q = 0; q + 1 < pt_off.size(); q++) {
+            int cm = -1;
+            for (int d = pt_off[q]; d < pt_off[q + 1]; d++) cm = std::max(cm, h_cam[d]);
+            for (int d = pt_off[q]; d < pt_off[q + 1]; d++) emax[h_cam[d]] = std::max(emax[h_cam[d]], (double)cm);
+        }
+    } else {
+        for (int c = 0; c < Nc; c++) emax[c] = Nc - 1;   // batched windows use the small-n kernels anyway
+    }
     pmv_ba_problem *p = new pmv_ba_problem();
     p->ctx = ctx;
     p->sharded = sharded_nranks > 1;
@@ -308,6 +321,30 @@ PMV_API pmv_ba_problem *pmv_ba_problem_create(pmv_ctx *ctx, const double *poses,
     if (window_ok) up(p->d_vis, h_vis.data(), sizeof(unsigned) * wp);
     if (ok && cudaStreamSynchronize(s) != cudaSuccess) ok = false;  // host vectors die at return
     if (!ok) { ctx->fail(PMV_ERR_CUDA, "pmv_ba_problem_create: upload failed", cudaGetLastError()); pmv_ba_problem_destroy(p); return nullptr; }
+    {
+        // envelope per 64-row block (global over ranks when the points are sharded)
+        if (p->sharded) {
+            double *d_e = nullptr;
+            if (dev_alloc(p, &d_e, 2 * (size_t)Nc) != PMV_OK) { pmv_ba_problem_destroy(p); return nullptr; }
+            cudaMemcpyAsync(d_e, emax.data(), sizeof(double) * Nc, cudaMemcpyHostToDevice, s);
+            if (pmv_internal_ba_allreduce(ctx, d_e, d_e + Nc, Nc, 1, s) != PMV_OK) { pmv_ba_problem_destroy(p); return nullptr; }
+            cudaMemcpyAsync(emax.data(), d_e + Nc, sizeof(double) * Nc, cudaMemcpyDeviceToHost, s);
+            if (cudaStreamSynchronize(s) != cudaSuccess) { ctx->fail(PMV_ERR_CUDA, "envelope exchange failed"); pmv_ba_problem_destroy(p); return nullptr; }
+        }
+        const int nblk = ((int)n + 63) / 64;
+        p->chol_lim.assign(nblk, (int)n);
+        int run = 0;
+        for (int kb = 0; kb < nblk; kb++) {
+            const int c0 = (kb * 64) / 6, c1 = std::min(Nc - 1, (kb * 64 + 63) / 6);
+            for (int c = c0; c <= c1; c++) run = std::max(run, (int)emax[c]);
+            p->chol_lim[kb] = std::min((int)n, 6 * (run + 1));
+        }
+        int *d_lim = nullptr;
+        if (dev_alloc(p, &d_lim, nblk) != PMV_OK) { pmv_ba_problem_destroy(p); return nullptr; }
+        cudaMemcpyAsync(d_lim, p->chol_lim.data(), sizeof(int) * nblk, cudaMemcpyHostToDevice, s);
+        cudaStreamSynchronize(s);
+        D.chol_lim = d_lim;
+    }
     if (pmv_ba_problem_reset(p, nullptr, nullptr) != PMV_OK) { pmv_ba_problem_destroy(p); return nullptr; }
     return p;
 }

@@ -48,5 +48,6 @@ struct BADev {
     double *S, *rhs, *yc;        // reduced camera system per window (n x n, upper blocks valid), solution
     double *Vinv, *gp;           // per point: (V + D^2)^-1 (6 unique) and J_p^T r (3)
     BAState *st;
+    const int *chol_lim;         // per 64-row block of S: end column of its envelope (blocked Cholesky)
     int max_iters;
 };

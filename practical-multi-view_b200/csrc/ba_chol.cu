@@ -11,6 +11,8 @@
 //                       b_j -= U_kj^T z_k (forward substitution fused as an extra column)
 //   chol_backsub_kernel U y = z, one CTA walking the block rows from the bottom
 // The trailing update is the n^3/3 term and the only place the tensor pipe is used in this library.
+#include <algorithm>
+
 #include "ba.cuh"
 
 namespace {
@@ -70,7 +72,7 @@ chol_diag_kernel(double *S, double *b, int n, int k0, BAState *st)
 
 // U_kj = U_kk^-T S_kj : one thread per column of the block row (columns k0+NB .. n-1)
 __global__ void __launch_bounds__(128)
-chol_panel_kernel(double *S, int n, int k0, const BAState *st)
+chol_panel_kernel(double *S, int n, int k0, int nlim, const BAState *st)
 {
     __shared__ double Ukk[NB][NB + 1];
     if (st->done || !st->chol_ok) return;
@@ -81,7 +83,7 @@ chol_panel_kernel(double *S, int n, int k0, const BAState *st)
     }
     __syncthreads();
     const int col = k0 + nb + blockIdx.x * 128 + threadIdx.x;
-    if (col >= n) return;
+    if (col >= nlim) return;   // columns beyond the envelope of this block row are structurally zero
     double x[NB];
 #pragma unroll 8
     for (int r = 0; r < NB; r++) x[r] = r < nb ? S[(size_t)(k0 + r) * n + col] : 0.0;
@@ -103,14 +105,14 @@ __device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, dou
 // trailing update: tile (bi, bj), bi <= bj, of the upper triangle right/below block row k.
 // S[i0+r][j0+c] -= sum_t P[t][i0+r] * P[t][j0+c],  P = block row k (nb x n).
 __global__ void __launch_bounds__(256)
-chol_update_kernel(double *S, double *b, int n, int k0, int t0 /* first trailing column */, const BAState *st)
+chol_update_kernel(double *S, double *b, int n, int k0, int t0 /* first trailing column */, int nlim, const BAState *st)
 {
     constexpr int KH = 32;   // the 64-row block row is staged in two halves (48 KB static smem limit)
     __shared__ double Pi[KH * LDS_];
     __shared__ double Pj[KH * LDS_];
     if (st->done || !st->chol_ok) return;
     // linear tile index -> (bi, bj) with bi <= bj
-    const int nt = (n - t0 + NB - 1) / NB;
+    const int nt = (nlim - t0 + NB - 1) / NB;   // only tiles inside the envelope [t0, nlim) of block row k
     int bi = 0, rem = blockIdx.x;
     while (rem >= nt - bi) { rem -= nt - bi; bi++; }
     const int bj = bi + rem;
@@ -167,7 +169,7 @@ chol_update_kernel(double *S, double *b, int n, int k0, int t0 /* first trailing
 
 // U y = z from the bottom block row upwards; one CTA (1024 threads)
 __global__ void __launch_bounds__(1024)
-chol_backsub_kernel(const double *S, const double *z, double *y, int n, BAState *st)
+chol_backsub_kernel(const double *S, const double *z, double *y, int n, const int *__restrict__ lim, BAState *st)
 {
     __shared__ double part[32][NB + 1];
     __shared__ double yk[NB];
@@ -181,7 +183,8 @@ chol_backsub_kernel(const double *S, const double *z, double *y, int n, BAState 
         // dot products of the block row with the already-known tail of y: 32 warps x 2 rows each
         for (int r = warp; r < nb; r += 32) {
             double s = 0;
-            for (int c = k0 + nb + lane; c < n; c += 32) s += S[(size_t)(k0 + r) * n + c] * y[c];
+            const int cend = lim[kb];   // U_kj == 0 beyond the envelope
+            for (int c = k0 + nb + lane; c < cend; c += 32) s += S[(size_t)(k0 + r) * n + c] * y[c];
             for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0) yk[r] = z[k0 + r] - s;
         }
@@ -217,7 +220,10 @@ __global__ void chol_gradient_check_kernel(BAState *st)
 
 }  // namespace
 
-int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, cudaStream_t s)
+// lim_host[kb] / D.chol_lim[kb]: end column (exclusive, <= n) of the envelope of block row kb -- cumulative
+// maximum of the camera co-visibility reach, so fill-in stays inside it.  A banded reduced camera system
+// (BASELINE config 5: every point seen by 5 of the <= 40 nearest poses) is factorised in O(n * band^2).
+int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_host, cudaStream_t s)
 {
     const int n = D.n;
     for (int w = 0; w < D.W; w++) {
@@ -225,19 +231,20 @@ int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, cudaStream_t s)
         BAState *st = D.st + w;
         chol_gradient_check_kernel<<<1, 1, 0, s>>>(st);
         PMV_LAUNCH_CHECK(ctx, "chol_gradient_check_kernel");
-        for (int k0 = 0; k0 < n; k0 += NB) {
+        for (int k0 = 0, kb = 0; k0 < n; k0 += NB, kb++) {
             chol_diag_kernel<<<1, 256, 0, s>>>(S, b, n, k0, st);
             PMV_LAUNCH_CHECK(ctx, "chol_diag_kernel");
             const int t0 = k0 + NB;
-            if (t0 < n) {
-                chol_panel_kernel<<<(n - t0 + 127) / 128, 128, 0, s>>>(S, n, k0, st);
+            const int nlim = lim_host ? std::min(n, lim_host[kb]) : n;
+            if (t0 < nlim) {
+                chol_panel_kernel<<<(nlim - t0 + 127) / 128, 128, 0, s>>>(S, n, k0, nlim, st);
                 PMV_LAUNCH_CHECK(ctx, "chol_panel_kernel");
-                const int nt = (n - t0 + NB - 1) / NB;
-                chol_update_kernel<<<nt * (nt + 1) / 2, 256, 0, s>>>(S, b, n, k0, t0, st);
+                const int nt = (nlim - t0 + NB - 1) / NB;
+                chol_update_kernel<<<nt * (nt + 1) / 2, 256, 0, s>>>(S, b, n, k0, t0, nlim, st);
                 PMV_LAUNCH_CHECK(ctx, "chol_update_kernel");
             }
         }
-        chol_backsub_kernel<<<1, 1024, 0, s>>>(S, b, y, n, st);
+        chol_backsub_kernel<<<1, 1024, 0, s>>>(S, b, y, n, D.chol_lim, st);
         PMV_LAUNCH_CHECK(ctx, "chol_backsub_kernel");
     }
     return PMV_OK;
