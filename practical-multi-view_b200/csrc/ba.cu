@@ -29,7 +29,13 @@ struct pmv_ba_problem {
     double *d_Uraw = nullptr, *d_Uraw_red = nullptr;   // 27 doubles per camera (+ W cost slots at the end)
     double *d_scal = nullptr, *d_scal_red = nullptr;   // per window: model_change, cand_cost, step_norm2, x_norm2
     std::vector<int> perm;                               // caller observation order -> device order
-    std::vector<int> chol_lim;                           // envelope of S per 64-row block (host copy)
+    std::vector<int> chol_lim;                           // envelope of S per PMV_CHOL_NB-row block (host copy)
+    // one LM iteration is a fixed launch sequence (all decisions live in BAState on the device), so it is
+    // captured once into a CUDA graph and replayed: removes the launch gaps of the ~600 dependent launches
+    // of the blocked Cholesky
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_max_iters = -1;
+    uint64_t graph_launches = 0;                         // kernel launches inside one replay
     size_t bytes = 0;
     // window-batched path (ba_window.cu): Nc <= 22, every (point, camera) pair observed at most once
     int use_window = 0;
@@ -132,7 +138,7 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
         PMV_LAUNCH_CHECK(ctx, "ba_clear_system_kernel");
     }
     if (wp > 0) {
-        ba_point_schur_kernel<<<(wp + 3) / 4, 128, 0, s>>>(D);
+        ba_point_schur_kernel<<<std::min((wp + 3) / 4, 148 * 32), 128, 0, s>>>(D);
         PMV_LAUNCH_CHECK(ctx, "ba_point_schur_kernel");
     }
     if (p->sharded) {
@@ -159,7 +165,7 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
     ba_cam_candidate_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D, p->sharded ? (p->rank == 0) : 1);
     PMV_LAUNCH_CHECK(ctx, "ba_cam_candidate_kernel");
     if (wp > 0) {
-        ba_backsub_kernel<<<(wp + 3) / 4, 128, 0, s>>>(D);
+        ba_backsub_kernel<<<std::min((wp + 3) / 4, 148 * 32), 128, 0, s>>>(D);
         PMV_LAUNCH_CHECK(ctx, "ba_backsub_kernel");
     }
     if (p->sharded) {
@@ -331,11 +337,11 @@ PMV_API pmv_ba_problem *pmv_ba_problem_create(pmv_ctx *ctx, const double *poses,
             cudaMemcpyAsync(emax.data(), d_e + Nc, sizeof(double) * Nc, cudaMemcpyDeviceToHost, s);
             if (cudaStreamSynchronize(s) != cudaSuccess) { ctx->fail(PMV_ERR_CUDA, "envelope exchange failed"); pmv_ba_problem_destroy(p); return nullptr; }
         }
-        const int nblk = ((int)n + 63) / 64;
+        const int nblk = ((int)n + PMV_CHOL_NB - 1) / PMV_CHOL_NB;
         p->chol_lim.assign(nblk, (int)n);
         int run = 0;
         for (int kb = 0; kb < nblk; kb++) {
-            const int c0 = (kb * 64) / 6, c1 = std::min(Nc - 1, (kb * 64 + 63) / 6);
+            const int c0 = (kb * PMV_CHOL_NB) / 6, c1 = std::min(Nc - 1, (kb * PMV_CHOL_NB + PMV_CHOL_NB - 1) / 6);
             for (int c = c0; c <= c1; c++) run = std::max(run, (int)emax[c]);
             p->chol_lim[kb] = std::min((int)n, 6 * (run + 1));
         }
@@ -354,6 +360,7 @@ PMV_API void pmv_ba_problem_destroy(pmv_ba_problem *p)
     if (!p) return;
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
+    if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
     for (void *q : p->allocs) cudaFree(q);
     delete p;
 }
@@ -390,10 +397,53 @@ PMV_API int pmv_ba_problem_solve(pmv_ba_problem *p, int max_iters)
     }
     ProfScope ps(ctx, PMV_PHASE_BA, s);
     // iteration 0 evaluates the cost even when max_iters == 0 (Ceres: IterationZero)
-    for (int it = 0; it < std::max(max_iters, 1); it++) {
-        int rc = p->use_window ? pmv_internal_ba_window_iteration(ctx, p->D, p->d_vis, p->d_camR, p->d_candR, s)
-                               : ba_iteration(p, s);
+    auto one_iteration = [&]() {
+        return p->use_window ? pmv_internal_ba_window_iteration(ctx, p->D, p->d_vis, p->d_camR, p->d_candR, s)
+                             : ba_iteration(p, s);
+    };
+    const char *no_graph = getenv("PMV_BA_NO_GRAPH");
+    const bool want_graph = !(no_graph && no_graph[0] == '1');
+    if (want_graph && (!p->graph_exec || p->graph_max_iters != max_iters)) {
+        if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+        // first iteration runs eagerly (sets function attributes, validates the launches) ...
+        int rc = one_iteration();
         if (rc) return rc;
+        // ... then the same sequence is captured for replay
+        cudaGraph_t graph = nullptr;
+        const uint64_t l0 = ctx->launches;
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+            rc = one_iteration();
+            cudaError_t e = cudaStreamEndCapture(s, &graph);
+            if (rc == PMV_OK && e == cudaSuccess && graph &&
+                cudaGraphInstantiate(&p->graph_exec, graph, 0) == cudaSuccess) {
+                p->graph_max_iters = max_iters;
+                p->graph_launches = ctx->launches - l0;
+            } else {
+                p->graph_exec = nullptr;
+            }
+            if (graph) cudaGraphDestroy(graph);
+            ctx->launches = l0;   // capture enqueued nothing
+            cudaGetLastError();
+        }
+        for (int it = 1; it < std::max(max_iters, 1); it++) {
+            if (p->graph_exec) {
+                PMV_CUDA_TRY(ctx, cudaGraphLaunch(p->graph_exec, s));
+                ctx->launches += p->graph_launches;
+            } else {
+                rc = one_iteration();
+                if (rc) return rc;
+            }
+        }
+        return PMV_OK;
+    }
+    for (int it = 0; it < std::max(max_iters, 1); it++) {
+        if (want_graph && p->graph_exec) {
+            PMV_CUDA_TRY(ctx, cudaGraphLaunch(p->graph_exec, s));
+            ctx->launches += p->graph_launches;
+        } else {
+            int rc = one_iteration();
+            if (rc) return rc;
+        }
     }
     return PMV_OK;
 }

@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 
+constexpr int PMV_CHOL_NB = 32;   // block-row height of the blocked HBM Cholesky (ba_chol.cu)
+
 // Per-problem (per-window) Levenberg-Marquardt state, resident on the device so the whole solve runs
 // without host synchronisation.  Mirrors Ceres' TrustRegionMinimizer + LevenbergMarquardtStrategy
 // members (SURVEY Appx C.3).
@@ -48,6 +50,6 @@ struct BADev {
     double *S, *rhs, *yc;        // reduced camera system per window (n x n, upper blocks valid), solution
     double *Vinv, *gp;           // per point: (V + D^2)^-1 (6 unique) and J_p^T r (3)
     BAState *st;
-    const int *chol_lim;         // per 64-row block of S: end column of its envelope (blocked Cholesky)
+    const int *chol_lim;         // per PMV_CHOL_NB-row block of S: end column of its envelope (blocked Cholesky)
     int max_iters;
 };

@@ -275,14 +275,21 @@ __global__ void ba_latch_cost_kernel(const BADev D)
 // V = sum J_p^T J_p + D_p^2, g = sum J_p^T r; S(ci,ck) -= W_i V^-1 W_k^T (ci <= ck); rhs_ci -= W_i V^-1 g.
 __global__ void __launch_bounds__(128) ba_point_schur_kernel(const BADev D)
 {
-    const int wp = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (wp >= D.W * D.Np) return;
-    const int w = wp / D.Np, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * 4;
+    double gm_acc = 0.0;   // max |gradient| of this warp's points, flushed with ONE atomic per window
+    int gm_w = -1;
+    for (int wp = blockIdx.x * 4 + (threadIdx.x >> 5); wp < D.W * D.Np; wp += nwarps) {
+    const int w = wp / D.Np;
     BAState *st = &D.st[w];
-    if (st->done) return;
+    if (st->done) continue;
     const int o0 = D.pt_off[wp], o1 = D.pt_off[wp + 1];
-    if (o1 == o0) return;
+    if (o1 == o0) continue;
     const bool lin = st->need_linearize != 0;
+    if (w != gm_w) {
+        if (gm_w >= 0 && lane == 0) atomic_max_pos_double(&D.st[gm_w].gmax, gm_acc);
+        gm_w = w; gm_acc = 0.0;
+    }
     // pass 1: raw column sums of J_p (3x3 upper + gradient 3)
     double a[9];
 #pragma unroll
@@ -314,7 +321,7 @@ __global__ void __launch_bounds__(128) ba_point_schur_kernel(const BADev D)
         D.diag_p[3 * (size_t)wp] = fmin(fmax(V[0], 1e-6), 1e32);
         D.diag_p[3 * (size_t)wp + 1] = fmin(fmax(V[3], 1e-6), 1e32);
         D.diag_p[3 * (size_t)wp + 2] = fmin(fmax(V[5], 1e-6), 1e32);
-        atomic_max_pos_double(&st->gmax, fmax(fabs(a[6]), fmax(fabs(a[7]), fabs(a[8]))));
+        gm_acc = fmax(gm_acc, fmax(fabs(a[6]), fmax(fabs(a[7]), fabs(a[8]))));
     }
     __syncwarp();
     const double radius = st->radius;
@@ -385,6 +392,8 @@ __global__ void __launch_bounds__(128) ba_point_schur_kernel(const BADev D)
             }
         }
     }
+    }   // grid-stride loop over points
+    if (gm_w >= 0 && lane == 0) atomic_max_pos_double(&D.st[gm_w].gmax, gm_acc);
 }
 
 // after the optional cross-rank reduction of S / rhs: add the camera diagonal blocks U + D_c^2 and J_c^T r
@@ -496,16 +505,30 @@ __global__ void __launch_bounds__(128) ba_cam_candidate_kernel(const BADev D, in
 // ---- K11 back-substitution + model cost change + candidate cost: one warp per (window, point) ----------
 __global__ void __launch_bounds__(128) ba_backsub_kernel(const BADev D)
 {
-    const int wp = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (wp >= D.W * D.Np) return;
-    const int w = wp / D.Np, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * 4;
+    // per-warp partial sums, flushed with one set of atomics per window (a same-address atomic per point
+    // serialises in L2: 1M points -> milliseconds)
+    double a_mc = 0, a_cc = 0, a_sn = 0, a_xn = 0;
+    int a_w = -1;
+    auto flush = [&]() {
+        if (a_w >= 0 && lane == 0) {
+            BAState *fs = &D.st[a_w];
+            atomicAdd(&fs->model_change, a_mc); atomicAdd(&fs->cand_cost, a_cc);
+            atomicAdd(&fs->step_norm2, a_sn); atomicAdd(&fs->x_norm2, a_xn);
+        }
+        a_mc = a_cc = a_sn = a_xn = 0;
+    };
+    for (int wp = blockIdx.x * 4 + (threadIdx.x >> 5); wp < D.W * D.Np; wp += nwarps) {
+    const int w = wp / D.Np;
     BAState *st = &D.st[w];
-    if (st->done || !st->chol_ok) return;
+    if (st->done || !st->chol_ok) continue;
     const int o0 = D.pt_off[wp], o1 = D.pt_off[wp + 1];
     if (o1 == o0) {  // inactive point: candidate = x
         if (lane < 3) D.cand_points[3 * (size_t)wp + lane] = D.points[3 * (size_t)wp + lane];
-        return;
+        continue;
     }
+    if (w != a_w) { flush(); a_w = w; }
     const double sp[3] = {D.scale_p[3 * (size_t)wp], D.scale_p[3 * (size_t)wp + 1], D.scale_p[3 * (size_t)wp + 2]};
     const double *yc = D.yc + (size_t)w * D.n;
     // t = g_p - sum W_i^T y_c(i) = g_p - sum J_p^T (J_c y_c)
@@ -562,12 +585,9 @@ __global__ void __launch_bounds__(128) ba_backsub_kernel(const BADev D)
         cc += 0.5 * rho0;
     }
     mc = warp_sum_d(mc); cc = warp_sum_d(cc);
-    if (lane == 0) {
-        atomicAdd(&st->model_change, mc);
-        atomicAdd(&st->cand_cost, cc);
-        atomicAdd(&st->step_norm2, sn);
-        atomicAdd(&st->x_norm2, xn);
-    }
+    a_mc += mc; a_cc += cc; a_sn += sn; a_xn += xn;
+    }   // grid-stride loop over points
+    flush();
 }
 
 // ---- trust-region bookkeeping: one thread per window (Ceres TrustRegionMinimizer / LM strategy) --------
