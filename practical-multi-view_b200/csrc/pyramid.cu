@@ -103,50 +103,89 @@ struct BorderArgs {
     int by, bxl, bxr;
 };
 
+// Work item = one aligned 16-byte chunk of a destination row.  Border rows (above / below the image) copy
+// whole chunks from their mirror row with one uint4 load where the chunk lies inside [0, cols); everything
+// else (left / right margins, row ends) is assembled byte-wise with reflect-101.
 __global__ void __launch_bounds__(256) border_fill_kernel(const BorderArgs A)
 {
     const int l = blockIdx.z;
     const int rows = A.rows[l], cols = A.cols[l], pitch = A.pitch[l];
     uint8_t *base = A.ptr[l] + (size_t)blockIdx.y * A.stride[l];
     const int by = A.by, bxl = A.bxl, bxr = A.bxr;
-    const int fullw = bxl + cols + bxr;
-    const int n_tb = 2 * by * fullw;          // top + bottom bands
-    const int n_lr = rows * (bxl + bxr);      // left + right bands
+    const int row_chunks = (bxl + cols + bxr + 15) >> 4;          // chunks of a full bordered row
+    const int right0 = cols & ~15;                                // first chunk (interior x) touching the right margin
+    const int side_chunks = (bxl >> 4) + ((cols + bxr + 15 - right0) >> 4);
+    const int n_tb = 2 * by * row_chunks, n_lr = rows * side_chunks;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n_tb + n_lr; i += gridDim.x * 256) {
-        int y, x;
+        int y, x0;
         if (i < n_tb) {
-            int r = i / fullw;
-            x = i - r * fullw - bxl;
+            const int r = i / row_chunks;
+            x0 = (i - r * row_chunks) * 16 - bxl;
             y = r < by ? r - by : rows + (r - by);
         } else {
-            int j = i - n_tb;
-            y = j / (bxl + bxr);
-            int c = j - y * (bxl + bxr);
-            x = c < bxl ? c - bxl : cols + (c - bxl);
+            const int j = i - n_tb;
+            y = j / side_chunks;
+            const int c = j - y * side_chunks;
+            x0 = c < (bxl >> 4) ? c * 16 - bxl : right0 + (c - (bxl >> 4)) * 16;
         }
-        base[(ptrdiff_t)y * pitch + x] = base[(ptrdiff_t)reflect101(y, rows) * pitch + reflect101(x, cols)];
+        const uint8_t *srow = base + (ptrdiff_t)reflect101(y, rows) * pitch;
+        uint8_t *drow = base + (ptrdiff_t)y * pitch;
+        if (x0 >= 0 && x0 + 16 <= cols) {
+            if (y < 0 || y >= rows) *reinterpret_cast<uint4 *>(drow + x0) = *reinterpret_cast<const uint4 *>(srow + x0);
+        } else {
+            uint32_t wv[4];
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int x = x0 + 4 * k4 + k;
+                    v |= (uint32_t)srow[reflect101(x, cols)] << (8 * k);
+                }
+                wv[k4] = v;
+            }
+            if (y >= 0 && y < rows && (x0 + 16 <= 0 || (x0 >= cols && x0 + 16 <= cols + bxr))) {
+                *reinterpret_cast<uint4 *>(drow + x0) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            } else if (y >= 0 && y < rows) {
+                // interior row: keep the image bytes of a chunk that straddles the edge
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const int x = x0 + k;
+                    if ((x < 0 || x >= cols) && x < cols + bxr) drow[x] = (uint8_t)(wv[k >> 2] >> (8 * (k & 3)));
+                }
+            } else if (x0 + 16 <= cols + bxr) {
+                *reinterpret_cast<uint4 *>(drow + x0) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                    if (x0 + k < cols + bxr) drow[x0 + k] = (uint8_t)(wv[k >> 2] >> (8 * (k & 3)));
+            }
+        }
     }
 }
 
 // Caller image (device memory, any pitch / alignment) -> interior of bordered level 0.
+// 16 bytes per thread: one uint4 load when the source is 16 B aligned and pitched, else byte gathers.
 __global__ void __launch_bounds__(256)
 import_kernel(const uint8_t *__restrict__ src, int spitch, size_t sstride, int rows, int cols,
-              uint8_t *__restrict__ dst, int dpitch, size_t dstride, int src_aligned4)
+              uint8_t *__restrict__ dst, int dpitch, size_t dstride, int src_aligned16)
 {
-    const int x4 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+    const int x16 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 16;
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (y >= rows || x4 >= cols) return;
-    const uint8_t *s = src + (size_t)blockIdx.z * sstride + (size_t)y * spitch + x4;
-    uint32_t v;
-    if (src_aligned4 && x4 + 4 <= spitch) {
-        v = __ldg(reinterpret_cast<const uint32_t *>(s));
+    if (y >= rows || x16 >= cols) return;
+    const uint8_t *sp = src + (size_t)blockIdx.z * sstride + (size_t)y * spitch + x16;
+    uint4 v;
+    if (src_aligned16 && x16 + 16 <= spitch) {
+        v = __ldg(reinterpret_cast<const uint4 *>(sp));
     } else {
-        v = 0;
+        uint32_t wv[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (x4 + k < cols) v |= (uint32_t)__ldg(s + k) << (8 * k);
+        for (int k = 0; k < 16; k++)
+            if (x16 + k < cols) wv[k >> 2] |= (uint32_t)__ldg(sp + k) << (8 * (k & 3));
+        v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
     }
-    *reinterpret_cast<uint32_t *>(dst + (size_t)blockIdx.z * dstride + (size_t)y * dpitch + x4) = v;
+    // the right border of the destination absorbs the tail of the last chunk (filled afterwards)
+    *reinterpret_cast<uint4 *>(dst + (size_t)blockIdx.z * dstride + (size_t)y * dpitch + x16) = v;
 }
 
 // K2: int16 x2 Scharr derivative, reflect-101 (stage-by-stage parity entry point; the LK
@@ -182,7 +221,7 @@ int pmv_internal_pyr_plan(pmv_ctx *ctx, int which, int batch, int rows, int cols
     int r = rows, c = cols;
     for (int l = 0; l <= L; l++) {
         if (l > 0) { r = (r + 1) / 2; c = (c + 1) / 2; }
-        int pitch = align_up(bxl + c + border + 3, 128);
+        int pitch = align_up(bxl + c + border + 16, 128);   // +16: 16-byte stores may run past the right border
         size_t stride = (size_t)pitch * (r + 2 * border);
         off[l] = total + (size_t)border * pitch + bxl;  // interior origin of image 0
         total += stride * batch;
@@ -207,7 +246,7 @@ static int fill_borders(pmv_ctx *ctx, const PyrSet &set, int batch, cudaStream_t
         nmax = n > nmax ? n : nmax;
     }
     A.by = set.lv[0].border; A.bxl = set.lv[0].bxl; A.bxr = set.lv[0].border;
-    dim3 grid(min((nmax + 255) / 256, 96), batch, set.top + 1);
+    dim3 grid(min((nmax / 16 + 255) / 256 + 1, 24), batch, set.top + 1);
     border_fill_kernel<<<grid, 256, 0, s>>>(A);
     PMV_LAUNCH_CHECK(ctx, "border_fill_kernel");
     return PMV_OK;
@@ -223,8 +262,8 @@ int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, const uint8
         const int half = d_src2 ? batch / 2 : batch;
         const uint8_t *srcs[2] = {d_src, d_src2};
         for (int k = 0; k < (d_src2 ? 2 : 1); k++) {
-            int al = (((uintptr_t)srcs[k]) % 4 == 0) && (src_pitch % 4 == 0) && (src_stride % 4 == 0);
-            dim3 grid((l0.cols + 127) / 128, (l0.rows + 7) / 8, half);
+            int al = (((uintptr_t)srcs[k]) % 16 == 0) && (src_pitch % 16 == 0) && (src_stride % 16 == 0);
+            dim3 grid((l0.cols + 511) / 512, (l0.rows + 7) / 8, half);
             import_kernel<<<grid, 256, 0, s>>>(srcs[k], src_pitch, src_stride, l0.rows, l0.cols,
                                                const_cast<uint8_t *>(l0.ptr) + (size_t)k * half * l0.img_stride,
                                                l0.pitch, l0.img_stride, al);
