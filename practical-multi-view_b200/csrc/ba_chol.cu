@@ -24,7 +24,7 @@ constexpr int LDS_ = 68;          // shared-memory row stride (doubles): conflic
 // Factor the diagonal block S_kk = U_kk^T U_kk and solve z_k = U_kk^-T b_k.  One barrier per column:
 // every thread derives 1/sqrt(pivot) itself, the scaled row goes to a separate output tile.
 __global__ void __launch_bounds__(256)
-chol_diag_kernel(double *S, double *b, int n, int k0, BAState *st)
+chol_diag_kernel(double *S, double *b, int n, int k0, int fuse_nlim /* > 0: also solve the panel columns [k0+NB, fuse_nlim) */, BAState *st)
 {
     __shared__ double A[NB][NB + 1];
     __shared__ double U[NB][NB + 1];
@@ -75,6 +75,23 @@ chol_diag_kernel(double *S, double *b, int n, int k0, BAState *st)
     }
     if (tid < nb) b[k0 + tid] = z[tid];
     if (tid == 0) st->chol_ok = 1;
+    // narrow envelope (banded system): the same CTA solves the panel U_kj = U_kk^-T S_kj, one column per
+    // thread with its NB unknowns in registers -- saves a dependent launch per block step
+    for (int col = k0 + nb + tid; col < fuse_nlim; col += 256) {
+        double x[NB];
+#pragma unroll
+        for (int r = 0; r < NB; r++) x[r] = r < nb ? S[(size_t)(k0 + r) * n + col] : 0.0;
+#pragma unroll
+        for (int r = 0; r < NB; r++) {
+            double sacc = x[r];
+#pragma unroll
+            for (int t = 0; t < r; t++) sacc -= U[t][r] * x[t];
+            x[r] = sacc / (r < nb ? U[r][r] : 1.0);
+        }
+#pragma unroll
+        for (int r = 0; r < NB; r++)
+            if (r < nb) S[(size_t)(k0 + r) * n + col] = x[r];
+    }
 }
 
 // U_kj = U_kk^-T S_kj : one thread per column of the block row (columns k0+NB .. nlim-1)
@@ -238,13 +255,16 @@ int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_
         chol_gradient_check_kernel<<<1, 1, 0, s>>>(st);
         PMV_LAUNCH_CHECK(ctx, "chol_gradient_check_kernel");
         for (int k0 = 0, kb = 0; k0 < n; k0 += NB, kb++) {
-            chol_diag_kernel<<<1, 256, 0, s>>>(S, b, n, k0, st);
-            PMV_LAUNCH_CHECK(ctx, "chol_diag_kernel");
             const int t0 = k0 + NB;
             const int nlim = lim_host ? std::min(n, lim_host[kb]) : n;
+            const bool fuse = t0 < nlim && nlim - t0 <= 512;
+            chol_diag_kernel<<<1, 256, 0, s>>>(S, b, n, k0, fuse ? nlim : 0, st);
+            PMV_LAUNCH_CHECK(ctx, "chol_diag_kernel");
             if (t0 < nlim) {
-                chol_panel_kernel<<<(nlim - t0 + 127) / 128, 128, 0, s>>>(S, n, k0, nlim, st);
-                PMV_LAUNCH_CHECK(ctx, "chol_panel_kernel");
+                if (!fuse) {
+                    chol_panel_kernel<<<(nlim - t0 + 127) / 128, 128, 0, s>>>(S, n, k0, nlim, st);
+                    PMV_LAUNCH_CHECK(ctx, "chol_panel_kernel");
+                }
                 const int nt = (nlim - t0 + TW - 1) / TW;
                 chol_update_kernel<<<nt * (nt + 1) / 2, 256, 0, s>>>(S, b, n, k0, t0, nlim, st);
                 PMV_LAUNCH_CHECK(ctx, "chol_update_kernel");
