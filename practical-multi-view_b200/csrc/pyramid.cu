@@ -12,85 +12,83 @@
 // Kernels (all HBM-bound streaming kernels, DESIGN.md has the byte counts):
 //   import_kernel      caller image (any pitch) -> interior of the bordered level 0
 //   border_fill_kernel reflect-101 border of one level, all images of the batch
-//   pyr_down_kernel    one CTA = 128x16 output tile from a 288x35 staged input tile
-//                      (16 B vector loads), horizontal pass -> uint16 tile, vertical pass,
-//                      packed 4-byte stores
+//   pyr_down_kernel    register-resident: a warp = 60 x 8 outputs, packed 16-bit SIMD-in-register
+//                      arithmetic, neighbour sums by warp shuffles, no shared memory
 #include "common.cuh"
 
 namespace {
 
-constexpr int PT_W = 128;               // output tile width
-constexpr int PT_H = 16;                // output tile height
-constexpr int PIN_H = 2 * PT_H + 3;     // 35 input rows
-constexpr int PIN_W = 2 * PT_W + 32;    // 288 staged input bytes per row (16 B aligned superset)
-constexpr int PIN_X0 = 16;              // staged column c <-> interior column 2*tx0 - 16 + c
+constexpr int PW_OUT = 60;   // outputs per warp-row: lanes 1..30 produce two each (lanes 0 / 31 are halo)
+constexpr int PW_R = 8;      // output rows per warp
 
-// src: level interior pointer inside a bordered allocation (>= 16 addressable bytes left of column 0,
-// row_bytes_right addressable bytes from column 0).  Image edges are handled here (reflect-101), so the
-// kernel does not depend on the border having been filled.
+// One aligned 32-bit word of a level row; words touching columns outside [0, cols) are assembled
+// byte-wise with reflect-101 (edge lanes only).
+__device__ __forceinline__ uint32_t pyr_load_word(const uint8_t *__restrict__ row, int col0, int cols)
+{
+    if (col0 >= 0 && col0 + 4 <= cols) return __ldg(reinterpret_cast<const uint32_t *>(row + col0));
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int c = col0 + k;
+        c = c < -2 ? 0 : (c > cols + 1 ? cols - 1 : reflect101(c, cols));   // beyond the taps: any in-range byte
+        v |= (uint32_t)__ldg(row + c) << (8 * k);
+    }
+    return v;
+}
+
+// K1 pyrDown, register-resident: a warp owns 60 output columns x PW_R output rows.  Lane L holds the
+// 4-byte input word at columns 2*x0 - 4 + 4L; the vertical [1 4 6 4 1] pass runs on two packed 16-bit
+// lanes per register (even / odd input columns, sums <= 4080), the horizontal pass on packed output
+// pairs (sums <= 65280) with the neighbouring lanes' partial sums fetched by shuffles.  No shared
+// memory, no barriers; every input word is read once per warp (+ 2 halo lanes, + 3 halo rows per 16).
 __global__ void __launch_bounds__(256)
 pyr_down_kernel(const uint8_t *__restrict__ src, int srows, int scols, int spitch, size_t sstride,
-                int row_bytes_right,
                 uint8_t *__restrict__ dst, int drows, int dcols, int dpitch, size_t dstride)
 {
-    __shared__ __align__(16) uint8_t s_in[PIN_H][PIN_W];
-    __shared__ __align__(16) uint16_t s_h[PIN_H][PT_W];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * PW_OUT;                         // first output column of the warp
+    const int y0 = (blockIdx.y * 8 + warp) * PW_R;              // first output row of the warp
+    if (y0 >= drows) return;
+    src += (size_t)blockIdx.z * sstride;
+    dst += (size_t)blockIdx.z * dstride;
+    const int col0 = 2 * x0 - 4 + 4 * lane;                     // input column of byte 0 of this lane's word
+    const uint32_t M = 0x00ff00ffu;
 
-    const int b = blockIdx.z;
-    src += (size_t)b * sstride;
-    dst += (size_t)b * dstride;
-    const int tx0 = blockIdx.x * PT_W, ty0 = blockIdx.y * PT_H;
-    const int gx0 = 2 * tx0 - PIN_X0;  // interior column of staged column 0 (multiple of 16)
-    const int gy0 = 2 * ty0 - 2;       // interior row of staged row 0
-    const int tid = threadIdx.x;
-
-    for (int i = tid; i < PIN_H * (PIN_W / 16); i += 256) {
-        int r = i / (PIN_W / 16), ch = i % (PIN_W / 16);
-        int gy = reflect101(gy0 + r, srows);
-        int gx = gx0 + ch * 16;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (gx + 16 <= row_bytes_right)
-            v = __ldg(reinterpret_cast<const uint4 *>(src + (ptrdiff_t)gy * spitch + gx));
-        *reinterpret_cast<uint4 *>(&s_in[r][ch * 16]) = v;
+    // all 2*PW_R + 3 input rows of the warp are requested up front (independent loads: enough bytes in
+    // flight to cover HBM latency), rows past the image fold back through reflect-101 and are harmless
+    uint32_t win[2 * PW_R + 3];
+#pragma unroll
+    for (int k = 0; k < 2 * PW_R + 3; k++) {
+        const uint8_t *row = src + (size_t)reflect101(2 * y0 - 2 + k, srows) * spitch;
+        win[k] = pyr_load_word(row, col0, scols);
     }
-    // tiles touching the left / right image edge: columns outside [0, scols) come from their mirror
-    if (2 * tx0 - 2 < 0 || 2 * tx0 + 2 * PT_W + 2 > scols) {
-        __syncthreads();
-        for (int i = tid; i < PIN_H * (2 * PT_W + 3); i += 256) {
-            int r = i / (2 * PT_W + 3), c = PIN_X0 - 2 + i % (2 * PT_W + 3);
-            int gx = gx0 + c;
-            if (gx < 0 || gx >= scols) {
-                int gy = reflect101(gy0 + r, srows);
-                s_in[r][c] = src[(ptrdiff_t)gy * spitch + reflect101(gx, scols)];
+#pragma unroll
+    for (int r = 0; r < PW_R; r++) {
+        const int y = y0 + r;
+        if (y >= drows) break;                                  // warp-uniform
+        uint32_t e[5], o[5];                                    // rows 2y-2 .. 2y+2, even / odd columns
+#pragma unroll
+        for (int k = 0; k < 5; k++) { e[k] = win[2 * r + k] & M; o[k] = (win[2 * r + k] >> 8) & M; }
+        // vertical pass (two input columns per register)
+        const uint32_t VE = e[0] + e[4] + ((e[1] + e[3]) << 2) + e[2] * 6u;   // (V0, V2)
+        const uint32_t VO = o[0] + o[4] + ((o[1] + o[3]) << 2) + o[2] * 6u;   // (V1, V3)
+        const uint32_t VEl = __shfl_up_sync(0xffffffffu, VE, 1), VOl = __shfl_up_sync(0xffffffffu, VO, 1);
+        const uint32_t VEr = __shfl_down_sync(0xffffffffu, VE, 1);
+        // horizontal pass on the output pair (x, x+1), x = x0 + 2 (lane - 1)
+        const uint32_t A = __byte_perm(VEl, VE, 0x5432);        // (V[-2], V0)
+        const uint32_t B = __byte_perm(VOl, VO, 0x5432);        // (V[-1], V1)
+        const uint32_t F = __byte_perm(VE, VEr, 0x5432);        // (V2, V4)
+        const uint32_t res = A + F + ((B + VO) << 2) + VE * 6u + 0x00800080u;
+        const uint32_t two = __byte_perm((res >> 8) & M, 0u, 0x4420);   // out(x) | out(x+1) << 8
+        const uint32_t nb = __shfl_down_sync(0xffffffffu, two, 1);
+        if ((lane & 1) && lane < 31) {
+            const int ox = x0 + 2 * (lane - 1);
+            if (ox < dcols) {
+                const uint32_t four = two | (nb << 16);
+                // row pitch padding absorbs a partial word at the right edge (border fill follows)
+                *reinterpret_cast<uint32_t *>(dst + (size_t)y * dpitch + ox) = four;
             }
         }
-    }
-    __syncthreads();
-
-    // horizontal pass: s_h[r][x] = taps over s_in[r][2x-2 .. 2x+2]
-    for (int i = tid; i < PIN_H * PT_W; i += 256) {
-        int r = i / PT_W, x = i % PT_W;
-        const uint8_t *p = &s_in[r][PIN_X0 + 2 * x - 2];
-        s_h[r][x] = (uint16_t)(p[0] + p[4] + 4 * (p[1] + p[3]) + 6 * p[2]);
-    }
-    __syncthreads();
-
-    // vertical pass + store: a warp owns a row, a lane 4 consecutive outputs
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int yy = warp; yy < PT_H; yy += 8) {
-        int oy = ty0 + yy;
-        if (oy >= drows) break;
-        uint32_t packed = 0;
-        int ox = tx0 + lane * 4;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int x = lane * 4 + k;
-            int v = s_h[2 * yy][x] + s_h[2 * yy + 4][x] + 4 * (s_h[2 * yy + 1][x] + s_h[2 * yy + 3][x]) +
-                    6 * s_h[2 * yy + 2][x];
-            packed |= (uint32_t)((v + 128) >> 8) << (8 * k);
-        }
-        // the right border of the destination absorbs the partial word (filled afterwards)
-        if (ox < dcols) *reinterpret_cast<uint32_t *>(dst + (size_t)oy * dpitch + ox) = packed;
     }
 }
 
@@ -272,8 +270,8 @@ int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, const uint8
     }
     for (int l = 1; l <= set.top; l++) {
         const PyrLevel &a = set.lv[l - 1], &d = set.lv[l];
-        dim3 grid((d.cols + PT_W - 1) / PT_W, (d.rows + PT_H - 1) / PT_H, batch);
-        pyr_down_kernel<<<grid, 256, 0, s>>>(a.ptr, a.rows, a.cols, a.pitch, a.img_stride, a.pitch - a.bxl,
+        dim3 grid((d.cols + PW_OUT - 1) / PW_OUT, (d.rows + 8 * PW_R - 1) / (8 * PW_R), batch);
+        pyr_down_kernel<<<grid, 256, 0, s>>>(a.ptr, a.rows, a.cols, a.pitch, a.img_stride,
                                              const_cast<uint8_t *>(d.ptr), d.rows, d.cols, d.pitch, d.img_stride);
         PMV_LAUNCH_CHECK(ctx, "pyr_down_kernel");
     }
