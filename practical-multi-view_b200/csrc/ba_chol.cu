@@ -21,76 +21,73 @@ constexpr int NB = PMV_CHOL_NB;   // 32 rows per block step: panel columns keep 
 constexpr int TW = 64;            // trailing-update tile width
 constexpr int LDS_ = 68;          // shared-memory row stride (doubles): conflict-free DMMA fragment loads
 
-// Factor the diagonal block S_kk = U_kk^T U_kk and solve z_k = U_kk^-T b_k.  One barrier per column:
-// every thread derives 1/sqrt(pivot) itself, the scaled row goes to a separate output tile.
+// Factor the diagonal block S_kk = U_kk^T U_kk and solve z_k = U_kk^-T b_k -- warp-synchronous: lane j of
+// warp 0 holds column j in registers, pivots and row entries travel by shuffles (no barriers, ~2 us).
+// With fuse_nlim > 0 (banded system) the whole CTA then solves the panel U_kj = U_kk^-T S_kj.
 __global__ void __launch_bounds__(256)
 chol_diag_kernel(double *S, double *b, int n, int k0, int fuse_nlim /* > 0: also solve the panel columns [k0+NB, fuse_nlim) */, BAState *st)
 {
-    __shared__ double A[NB][NB + 1];
     __shared__ double U[NB][NB + 1];
-    __shared__ double z[NB];
+    __shared__ double invd[NB];
     __shared__ int ok;
     if (st->done) return;
     const int tid = threadIdx.x, nb = min(NB, n - k0);
     if (tid == 0) ok = (k0 == 0) ? 1 : st->chol_ok;
-    for (int i = tid; i < NB * NB; i += 256) {
-        int r = i / NB, c = i % NB;
-        A[r][c] = (r < nb && c < nb && c >= r) ? S[(size_t)(k0 + r) * n + k0 + c] : (r == c ? 1.0 : 0.0);
-        U[r][c] = 0.0;
-    }
-    if (tid < NB) z[tid] = tid < nb ? b[k0 + tid] : 0.0;
     __syncthreads();
     if (!ok) return;
-    for (int j = 0; j < nb; j++) {
-        const double piv = A[j][j];
-        if (!(piv > 0) || !isfinite(piv)) { ok = 0; break; }   // same value in every thread: uniform exit
-        const double inv = 1.0 / sqrt(piv);
-        const int m = nb - j - 1;
-        // row j of U
-        for (int c = j + tid; c < nb; c += 256) U[j][c] = A[j][c] * inv;
-        // trailing update with the unscaled row: A[r][c] -= A[j][r] A[j][c] / piv
-        const double ip = inv * inv;
-        for (int t = tid; t < m * m; t += 256) {
-            int rr = t / m, cc = t - rr * m;
-            if (cc >= rr) A[j + 1 + rr][j + 1 + cc] -= A[j][j + 1 + rr] * A[j][j + 1 + cc] * ip;
-        }
-        __syncthreads();
-    }
-    __syncthreads();
-    if (!ok) { if (tid == 0) st->chol_ok = 0; return; }
-    // z_k = U_kk^-T b_k (forward substitution with the lower-triangular U^T), one warp
     if (tid < 32) {
-        for (int j = 0; j < nb; j++) {
-            const double zj = z[j] / U[j][j];
-            __syncwarp();
-            if (tid == 0) z[j] = zj;
-            for (int c = j + 1 + tid; c < nb; c += 32) z[c] -= U[j][c] * zj;
-            __syncwarp();
+        const int j = tid;
+        double col[NB];
+#pragma unroll
+        for (int i = 0; i < NB; i++)
+            col[i] = (i < nb && j < nb && i <= j) ? S[(size_t)(k0 + i) * n + k0 + j] : (i == j ? 1.0 : 0.0);
+        double bj = j < nb ? b[k0 + j] : 0.0;
+        bool good = true;
+#pragma unroll
+        for (int k = 0; k < NB; k++) {
+            const double piv = __shfl_sync(0xffffffffu, col[k], k);
+            if (!(piv > 0) || !isfinite(piv)) good = false;      // warp-uniform
+            const double inv = 1.0 / sqrt(good ? piv : 1.0);
+            const double ukj = col[k] * inv;                      // U[k][j] (meaningful for j >= k)
+            col[k] = ukj;
+            if (j == k) invd[k] = inv;
+#pragma unroll
+            for (int i = k + 1; i < NB; i++) {
+                const double uki = __shfl_sync(0xffffffffu, ukj, i);
+                if (i <= j) col[i] -= uki * ukj;
+            }
+            // forward substitution of the right-hand side rides along: z_k = b_k / U_kk, b_j -= U_kj z_k
+            const double zk = __shfl_sync(0xffffffffu, bj, k) * inv;
+            if (j == k) bj = zk; else if (j > k) bj -= ukj * zk;
+        }
+        if (!good) { if (tid == 0) { ok = 0; st->chol_ok = 0; } }
+        else {
+#pragma unroll
+            for (int i = 0; i < NB; i++) {
+                U[i][j] = (i <= j) ? col[i] : 0.0;
+                if (i < nb && j < nb && i <= j) S[(size_t)(k0 + i) * n + k0 + j] = col[i];
+            }
+            if (j < nb) b[k0 + j] = bj;
+            if (tid == 0) st->chol_ok = 1;
         }
     }
     __syncthreads();
-    for (int i = tid; i < nb * nb; i += 256) {
-        int r = i / nb, c = i - r * nb;
-        if (c >= r) S[(size_t)(k0 + r) * n + k0 + c] = U[r][c];
-    }
-    if (tid < nb) b[k0 + tid] = z[tid];
-    if (tid == 0) st->chol_ok = 1;
-    // narrow envelope (banded system): the same CTA solves the panel U_kj = U_kk^-T S_kj, one column per
-    // thread with its NB unknowns in registers -- saves a dependent launch per block step
-    for (int col = k0 + nb + tid; col < fuse_nlim; col += 256) {
+    if (!ok) return;
+    // panel: one column per thread, its NB unknowns in registers, reciprocal diagonal from the factorisation
+    for (int colx = k0 + nb + tid; colx < fuse_nlim; colx += 256) {
         double x[NB];
 #pragma unroll
-        for (int r = 0; r < NB; r++) x[r] = r < nb ? S[(size_t)(k0 + r) * n + col] : 0.0;
+        for (int r = 0; r < NB; r++) x[r] = r < nb ? S[(size_t)(k0 + r) * n + colx] : 0.0;
 #pragma unroll
         for (int r = 0; r < NB; r++) {
             double sacc = x[r];
 #pragma unroll
             for (int t = 0; t < r; t++) sacc -= U[t][r] * x[t];
-            x[r] = sacc / (r < nb ? U[r][r] : 1.0);
+            x[r] = sacc * invd[r];
         }
 #pragma unroll
         for (int r = 0; r < NB; r++)
-            if (r < nb) S[(size_t)(k0 + r) * n + col] = x[r];
+            if (r < nb) S[(size_t)(k0 + r) * n + colx] = x[r];
     }
 }
 
