@@ -28,7 +28,7 @@ struct WinDev {
     double *camR;          // per (window, camera): R (9) | dR/da_0 (9) | dR/da_1 (9) | dR/da_2 (9)
     double *candR;         // per (window, camera): R of the candidate pose (9)
     int P;                 // points per chunk
-    int LD;                // row stride (doubles) of the chunk matrices, == 4 (mod 16)
+    int LD;                // stride (doubles) between k-columns of the chunk matrices, == 4 (mod 16)
     int passes;            // producer passes per chunk (1 or 2)
 };
 
@@ -174,11 +174,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D,
     double *sItem = sUnion;                  // P*Nc*20 : Jp (6) | r (2) | Jc (12) per item
     double *sPt = sItem + P * Nc * 20;       // P*12   : Vinv (6) | g (3) | pad
     double *sVg = sPt + P * 12;              // P*9    : raw V (6) | g (3) sums
-    // chunk buffers: Y and W as row-major [rows = 16*NS >= n][LD] matrices (row = 6*cam + a, column =
-    // 3*slot + b), two buffers; LD == 4 (mod 16) makes the fp64 mma fragment loads conflict-free
+    // chunk buffers: Y and W stored k-major, M[k = 3*slot + b][row = 6*cam + a] with row stride
+    // LD = 16*NS + 4 (== 4 mod 16): a producer writes 6 contiguous doubles per column and the fp64 mma
+    // fragment loads (lanes = 8 rows x 4 k) are conflict-free; two buffers
     const int NS = (n + 15) >> 4, LD = Wd.LD, KS = (3 * P + 3) >> 2;
     double *sYW = sVg + P * 9;
-    const size_t bufsz = (size_t)16 * NS * LD;
+    const size_t bufsz = (size_t)4 * KS * LD;
     unsigned *sMask = reinterpret_cast<unsigned *>(sYW + 4 * bufsz);   // 2 x P
     // phase B (factorisation) aliases the union region
     double *A = sUnion;                      // n x (n+1)
@@ -303,12 +304,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D,
                 for (int pass = 0; pass < passes; pass++) {
                     const int slot = pslot + pass * H;
                     if (!producer) break;
-                    double *Yo = sY + (size_t)(6 * pcam) * LD + 3 * slot, *Wo = sW + (size_t)(6 * pcam) * LD + 3 * slot;
+                    double *Yo = sY + (size_t)(3 * slot) * LD + 6 * pcam, *Wo = sW + (size_t)(3 * slot) * LD + 6 * pcam;
                     if (p0 + slot >= D.Np || !((mk[slot] >> pcam) & 1)) {
 #pragma unroll
                         for (int a = 0; a < 6; a++) {
-                            Yo[a * LD] = 0.0; Yo[a * LD + 1] = 0.0; Yo[a * LD + 2] = 0.0;
-                            Wo[a * LD] = 0.0; Wo[a * LD + 1] = 0.0; Wo[a * LD + 2] = 0.0;
+                            Yo[a] = 0.0; Yo[LD + a] = 0.0; Yo[2 * LD + a] = 0.0;
+                            Wo[a] = 0.0; Wo[LD + a] = 0.0; Wo[2 * LD + a] = 0.0;
                         }
                         continue;
                     }
@@ -327,10 +328,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D,
                     for (int a = 0; a < 6; a++) {
                         const double w0 = jc[a] * jp[0] + jc[6 + a] * jp[3], w1 = jc[a] * jp[1] + jc[6 + a] * jp[4],
                                      w2 = jc[a] * jp[2] + jc[6 + a] * jp[5];
-                        Wo[a * LD] = w0; Wo[a * LD + 1] = w1; Wo[a * LD + 2] = w2;
-                        Yo[a * LD] = w0 * pt[0] + w1 * pt[1] + w2 * pt[2];
-                        Yo[a * LD + 1] = w0 * pt[1] + w1 * pt[3] + w2 * pt[4];
-                        Yo[a * LD + 2] = w0 * pt[2] + w1 * pt[4] + w2 * pt[5];
+                        Wo[a] = w0; Wo[LD + a] = w1; Wo[2 * LD + a] = w2;
+                        Yo[a] = w0 * pt[0] + w1 * pt[1] + w2 * pt[2];
+                        Yo[LD + a] = w0 * pt[1] + w1 * pt[3] + w2 * pt[4];
+                        Yo[2 * LD + a] = w0 * pt[2] + w1 * pt[4] + w2 * pt[5];
                         accR[a] -= w0 * vg0 + w1 * vg1 + w2 * vg2;
                         accG[a] += jc[a] * r0 + jc[6 + a] * r1;
 #pragma unroll
@@ -381,8 +382,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D,
 #pragma unroll
                     for (int j = 0; j < WS_MAXST; j++) {
                         if (stI[j] < 0) continue;
-                        const double a0 = sY[(size_t)(16 * stI[j] + g) * LD + kc], a1 = sY[(size_t)(16 * stI[j] + 8 + g) * LD + kc];
-                        const double b0 = sW[(size_t)(16 * stJ[j] + g) * LD + kc], b1 = sW[(size_t)(16 * stJ[j] + 8 + g) * LD + kc];
+                        const double a0 = sY[(size_t)kc * LD + 16 * stI[j] + g], a1 = sY[(size_t)kc * LD + 16 * stI[j] + 8 + g];
+                        const double b0 = sW[(size_t)kc * LD + 16 * stJ[j] + g], b1 = sW[(size_t)kc * LD + 16 * stJ[j] + 8 + g];
                         win_dmma(C[j][0][0][0], C[j][0][0][1], a0, b0);
                         win_dmma(C[j][0][1][0], C[j][0][1][1], a0, b1);
                         win_dmma(C[j][1][0][0], C[j][1][0][1], a1, b0);
@@ -602,10 +603,10 @@ int pmv_internal_ba_window_iteration(pmv_ctx *ctx, const BADev &D, const unsigne
     Wd.passes = (Wd.P * Nc > WS_PRODUCERS) ? 2 : 1;
     const int wc = D.W * Nc;
     const size_t smem_col = sizeof(double) * (size_t)Nc * 45;
-    Wd.LD = 3 * Wd.P;
-    while (Wd.LD % 16 != 4) Wd.LD++;
     const int NS = (n + 15) / 16;
-    const size_t unionA = (size_t)Wd.P * Nc * 20 + (size_t)Wd.P * 21 + 4 * (size_t)16 * NS * Wd.LD + Wd.P + 2;
+    Wd.LD = 16 * NS + 4;
+    const int KS = (3 * Wd.P + 3) / 4;
+    const size_t unionA = (size_t)Wd.P * Nc * 20 + (size_t)Wd.P * 21 + 4 * (size_t)4 * KS * Wd.LD + Wd.P + 2;
     const size_t unionB = (size_t)n * (n + 1) + n;
     const size_t smem_schur = sizeof(double) * ((size_t)Nc * 78 + 8 + std::max(unionA, unionB) + 2);
     const size_t smem_back = sizeof(double) * (size_t)Nc * 63;
