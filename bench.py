@@ -72,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
         except Exception:
             self.proc = None
@@ -454,7 +454,7 @@ def main():
     ap.add_argument("--windows", type=int, default=4096)
     ap.add_argument("--ba-iters", type=int, default=5)
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="pmv", choices=["pmv", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
