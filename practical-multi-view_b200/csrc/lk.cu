@@ -64,6 +64,16 @@ __device__ __forceinline__ void bilinear_weights(float a, float b, int &iw00, in
     iw11 = 16384 - iw00 - iw01 - iw10;
 }
 
+// ((sum_i q_i * w_i + 256) >> 9) - ival with the four u8 neighbours packed in `quad`, the weights split
+// into signed high / unsigned low bytes and Iq = 512 * ival - 256.
+__device__ __forceinline__ int lk_interp_diff(unsigned quad, unsigned wlo, unsigned whi, int Iq)
+{
+    int t;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(t) : "r"(quad), "r"(whi), "r"(0));
+    const unsigned u = __dp4a(quad, wlo, (unsigned)(-Iq));
+    return (int)(((unsigned)t << 8) + u) >> 9;
+}
+
 // Copy the rows [y0, y0+nrows) x bytes [x0, x0+nbytes) of a bordered level into shared memory with
 // aligned 4-byte loads.  The smem copy keeps the global misalignment: pixel (r, c) of the region is
 // at dst[r*spitch + mis + c] with mis = x0 & 3 (returned).  Level interiors are 16 B aligned and
@@ -122,7 +132,10 @@ lk_track_kernel(const LKParams P)
     const float halfx = (w - 1) * 0.5f, halfy = (h - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (1 << 20);
 
-    int Iw[KPIX], dxw[KPIX], dyw[KPIX], joff[KPIX];
+    // per-lane template (pixel p = lane + 32k): pre-biased intensity, packed (dI/dx | dI/dy << 16), window
+    // offset, and the cached 2x2 neighbourhood of the next image (J00 | J01<<8 | J10<<16 | J11<<24)
+    int Iq[KPIX], dxy[KPIX], joff[KPIX];
+    unsigned quad[KPIX];
     unsigned valid = 0;
 #pragma unroll
     for (int k = 0; k < KPIX; k++) {
@@ -205,7 +218,8 @@ lk_track_kernel(const LKParams P)
             int iy = ((d00 >> 16) * iw00 + (d01 >> 16) * iw01 + (d10 >> 16) * iw10 +
                       (d11 >> 16) * iw11 + (1 << 13)) >> 14;
             if (!((valid >> k) & 1)) { ival = 0; ix = 0; iy = 0; }
-            Iw[k] = ival; dxw[k] = ix; dyw[k] = iy;
+            Iq[k] = 512 * ival - 256;                               // ((v + 256) >> 9) - ival == (v - Iq) >> 9
+            dxy[k] = (ix & 0xffff) | (int)((unsigned)iy << 16);
             sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
         }
         const float A11 = __fmul_rn((float)warp_sum_i64(sA11), FLT_SCALE);
@@ -229,32 +243,54 @@ lk_track_kernel(const LKParams P)
         __syncwarp();  // template reads of ps/ds are done before js overwrites them
         int jx0 = 0, jy0 = 0, jmis = 0;
         bool staged = false;
+        int qx = 0, qy = 0;           // integer position the cached quads belong to
+        bool have_quads = false;
         float pdx = 0.f, pdy = 0.f;
+        // (Re)load the 2x2 neighbourhoods for integer position (ix_, iy_); restages the window if needed.
+        auto load_quads = [&](int ix_, int iy_) {
+            int ox = ix_ - jx0, oy = iy_ - jy0;
+            if (!staged || ox < 0 || ox > 2 * LK_M || oy < 0 || oy > 2 * LK_M) {
+                __syncwarp();
+                jx0 = ix_ - LK_M; jy0 = iy_ - LK_M;
+                jmis = stage_region(reinterpret_cast<uint32_t *>(js), jp >> 2, Jimg, J.pitch, jx0, jy0, jw, jh, lane);
+                __syncwarp();
+                staged = true;
+                ox = LK_M; oy = LK_M;
+            }
+            const uint8_t *jb = js + oy * jp + ox + jmis;
+#pragma unroll
+            for (int k = 0; k < KPIX; k++) {
+                const uint8_t *q = jb + joff[k];
+                const unsigned lo = __byte_perm((unsigned)q[0], (unsigned)q[1], 0x0040);
+                const unsigned hi = __byte_perm((unsigned)q[jp], (unsigned)q[jp + 1], 0x0040);
+                quad[k] = __byte_perm(lo, hi, 0x5410);
+            }
+            qx = ix_; qy = iy_; have_quads = true;
+        };
+        // the fixed-point weights (iw11 can be -1 after rounding, iw00 can be 16384) are split as
+        // w = 256 * hi + lo with hi in [-1, 64] (signed bytes) and lo in [0, 255] (unsigned bytes), so the
+        // interpolation is two 4-way byte dot products: dp4a.u32.s32 (hi) and dp4a.u32.u32 (lo)
+        auto split_weights = [&](unsigned &wlo, unsigned &whi) {
+            wlo = (unsigned)(iw00 & 255) | ((unsigned)(iw01 & 255) << 8) | ((unsigned)(iw10 & 255) << 16) | ((unsigned)(iw11 & 255) << 24);
+            whi = (unsigned)((iw00 >> 8) & 255) | ((unsigned)((iw01 >> 8) & 255) << 8) | ((unsigned)((iw10 >> 8) & 255) << 16) |
+                  ((unsigned)((iw11 >> 8) & 255) << 24);
+        };
         for (int j = 0; j < P.max_count; j++) {
             const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
             if (inx < -w || inx >= J.cols || iny < -h || iny >= J.rows) {
                 if (level == 0) status = 0;
                 break;
             }
-            int ox = inx - jx0, oy = iny - jy0;
-            if (!staged || ox < 0 || ox > 2 * LK_M || oy < 0 || oy > 2 * LK_M) {
-                __syncwarp();
-                jx0 = inx - LK_M; jy0 = iny - LK_M;
-                jmis = stage_region(reinterpret_cast<uint32_t *>(js), jp >> 2, Jimg, J.pitch, jx0, jy0, jw, jh, lane);
-                __syncwarp();
-                staged = true;
-                ox = LK_M; oy = LK_M;
-            }
+            if (!have_quads || inx != qx || iny != qy) load_quads(inx, iny);
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), iw00, iw01, iw10, iw11);
-            const uint8_t *jb = js + oy * jp + ox + jmis;
+            unsigned wlo, whi;
+            split_weights(wlo, whi);
             int ib1 = 0, ib2 = 0;
 #pragma unroll
             for (int k = 0; k < KPIX; k++) {
-                const uint8_t *q = jb + joff[k];
-                int v = q[0] * iw00 + q[1] * iw01 + q[jp] * iw10 + q[jp + 1] * iw11;
-                int diff = ((v + (1 << 8)) >> 9) - Iw[k];
-                ib1 += diff * dxw[k];
-                ib2 += diff * dyw[k];
+                const int diff = lk_interp_diff(quad[k], wlo, whi, Iq[k]);
+                ib1 += diff * (int)(short)dxy[k];
+                ib2 += diff * (dxy[k] >> 16);
             }
             const float b1 = __fmul_rn((float)warp_sum_i64(ib1), FLT_SCALE);
             const float b2 = __fmul_rn((float)warp_sum_i64(ib2), FLT_SCALE);
@@ -279,23 +315,14 @@ lk_track_kernel(const LKParams P)
                 status = 0;
                 continue;
             }
-            int ox = inx - jx0, oy = iny - jy0;
-            if (!staged || ox < 0 || ox > 2 * LK_M || oy < 0 || oy > 2 * LK_M) {
-                __syncwarp();
-                jx0 = inx - LK_M; jy0 = iny - LK_M;
-                jmis = stage_region(reinterpret_cast<uint32_t *>(js), jp >> 2, Jimg, J.pitch, jx0, jy0, jw, jh, lane);
-                __syncwarp();
-                staged = true;
-                ox = LK_M; oy = LK_M;
-            }
+            if (!have_quads || inx != qx || iny != qy) load_quads(inx, iny);
             bilinear_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), iw00, iw01, iw10, iw11);
-            const uint8_t *jb = js + oy * jp + ox + jmis;
+            unsigned wlo, whi;
+            split_weights(wlo, whi);
             int e = 0;
 #pragma unroll
             for (int k = 0; k < KPIX; k++) {
-                const uint8_t *q = jb + joff[k];
-                int v = q[0] * iw00 + q[1] * iw01 + q[jp] * iw10 + q[jp + 1] * iw11;
-                int diff = ((v + (1 << 8)) >> 9) - Iw[k];
+                const int diff = lk_interp_diff(quad[k], wlo, whi, Iq[k]);
                 if ((valid >> k) & 1) e += abs(diff);
             }
             e = __reduce_add_sync(0xffffffffu, e);
