@@ -35,14 +35,28 @@ struct ImgView {            // uploaded patch of the parent image
     int rx, ry, rw, rh;     // ROI in parent coordinates
 };
 
-// stage ROI-coordinates [ty0-2, ty0+CT_H+2) x [tx0-2, tx0+CT_W+2) into s (u8, pitch CS_P)
+constexpr int CS_X0 = 4;   // staged column of ROI column tx0 (the tile starts on a 4-byte boundary at tx0 - 4)
+
+// stage ROI rows [ty0-2, ty0+CT_H+2) x ROI columns [tx0-4, tx0+CT_W+4) into s (u8, pitch CS_P = 72 B).
+// Interior tiles (no parent edge inside the halo) are copied with aligned 32-bit loads -- upload_roi puts ROI
+// column 0 on a 16-byte boundary; edge tiles fall back to byte gathers with reflect-101 at the PARENT's edges.
 __device__ __forceinline__ void stage_tile(uint8_t (*s)[CS_P], const ImgView &v, int tx0, int ty0, int tid)
 {
-    for (int i = tid; i < CS_H * CS_W; i += 256) {
-        int r = i / CS_W, c = i - r * CS_W;
-        int gy = reflect101(v.ry + ty0 - 2 + r, v.full_rows) - v.oy;
-        int gx = reflect101(v.rx + tx0 - 2 + c, v.full_cols) - v.ox;
-        s[r][c] = __ldg(v.ptr + (size_t)gy * v.pitch + gx);
+    const bool interior = (v.rx + tx0 - 2 >= 0) && (v.rx + tx0 + CT_W + 2 <= v.full_cols) &&
+                          (v.ry + ty0 - 2 >= 0) && (v.ry + ty0 + CT_H + 2 <= v.full_rows);
+    if (interior) {
+        const uint8_t *g = v.ptr + (ptrdiff_t)(v.ry + ty0 - 2 - v.oy) * v.pitch + (v.rx + tx0 - CS_X0 - v.ox);
+        for (int i = tid; i < CS_H * (CS_P / 4); i += 256) {
+            const int r = i / (CS_P / 4), wc = i - r * (CS_P / 4);
+            reinterpret_cast<uint32_t *>(&s[r][0])[wc] = __ldg(reinterpret_cast<const uint32_t *>(g + (ptrdiff_t)r * v.pitch) + wc);
+        }
+    } else {
+        for (int i = tid; i < CS_H * CS_W; i += 256) {
+            int r = i / CS_W, c = i - r * CS_W;
+            int gy = reflect101(v.ry + ty0 - 2 + r, v.full_rows) - v.oy;
+            int gx = reflect101(v.rx + tx0 - 2 + c, v.full_cols) - v.ox;
+            s[r][c + CS_X0 - 2] = __ldg(v.ptr + (ptrdiff_t)gy * v.pitch + gx);
+        }
     }
 }
 
@@ -74,9 +88,9 @@ mineig_kernel(const ImgView v, float *__restrict__ eig, int *__restrict__ max_bi
     for (int i = tid; i < CD_H * CD_W; i += 256) {
         int r = i / CD_W, c = i - r * CD_W;
         int y = reflect101(ty0 - 1 + r, v.rh), x = reflect101(tx0 - 1 + c, v.rw);
-        int sr = y - (ty0 - 2), sc = x - (tx0 - 2);   // staged indices of the centre
+        int sr = y - (ty0 - 2), sc = x - tx0 + CS_X0;   // staged indices of the centre
         int packed = 0;
-        if (sr >= 1 && sr < CS_H - 1 && sc >= 1 && sc < CS_W - 1) {
+        if (sr >= 1 && sr < CS_H - 1 && sc >= CS_X0 - 1 && sc <= CS_X0 + CT_W) {
             const uint8_t *p = &s_px[sr][sc];
             int a0 = p[-CS_P - 1], a1 = p[-CS_P], a2 = p[-CS_P + 1];
             int b0 = p[-1], b2 = p[1];
@@ -253,10 +267,10 @@ shitomasi_response_kernel(const ImgView v, int signed_quirk, double *__restrict_
     for (int i = tid; i < CD_H * CD_W; i += 256) {
         int r = i / CD_W, c = i - r * CD_W;
         int y = reflect101(ty0 - 1 + r, v.rh), x = reflect101(tx0 - 1 + c, v.rw);
-        int sr = y - (ty0 - 2), sc = x - (tx0 - 2);
+        int sr = y - (ty0 - 2), sc = x - tx0 + CS_X0;
         int packed = 0;
         // Frame.cpp:63-84: interior pixels only, rim gradients stay zero
-        if (y >= 1 && y < v.rh - 1 && x >= 1 && x < v.rw - 1 && sr >= 1 && sr < CS_H - 1 && sc >= 1 && sc < CS_W - 1) {
+        if (y >= 1 && y < v.rh - 1 && x >= 1 && x < v.rw - 1 && sr >= 1 && sr < CS_H - 1 && sc >= CS_X0 - 1 && sc <= CS_X0 + CT_W) {
             const uint8_t *p = &s_px[sr][sc];
             int l = p[-1], rr = p[1], u = p[-CS_P], d = p[CS_P];
             if (signed_quirk) { l = (signed char)l; rr = (signed char)rr; u = (signed char)u; d = (signed char)d; }
@@ -349,12 +363,14 @@ int upload_roi(pmv_ctx *ctx, const uint8_t *base, int full_rows, int full_cols, 
     int x1 = rx + rw + 2 > full_cols ? full_cols : rx + rw + 2;
     int y1 = ry + rh + 2 > full_rows ? full_rows : ry + rh + 2;
     int pw = x1 - x0, ph = y1 - y0;
-    int pitch = align_up(pw, 128);
-    cudaError_t e = ctx->img[0].reserve((size_t)pitch * ph);
+    const int lead = 16 - (rx - x0);                 // ROI column 0 lands on a 16-byte boundary (tile word loads)
+    int pitch = align_up(lead + pw + 16, 128);
+    cudaError_t e = ctx->img[0].reserve((size_t)pitch * ph + 256);
     if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "roi upload buffer", e);
-    PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->img[0].p, pitch, base + (size_t)y0 * step + x0, step, pw, ph,
+    uint8_t *p0 = ctx->img[0].as<uint8_t>() + lead;
+    PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(p0, pitch, base + (size_t)y0 * step + x0, step, pw, ph,
                                         cudaMemcpyHostToDevice, ctx->stream));
-    *v = ImgView{ctx->img[0].as<uint8_t>(), pitch, x0, y0, full_rows, full_cols, rx, ry, rw, rh};
+    *v = ImgView{p0, pitch, x0, y0, full_rows, full_cols, rx, ry, rw, rh};
     return PMV_OK;
 }
 

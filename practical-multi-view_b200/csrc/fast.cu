@@ -75,10 +75,19 @@ fast_kernel(const uint8_t *__restrict__ img, int rows, int cols, int pitch, int 
     __shared__ int s_sc[FC_H][FC_W + 1];
     const int tid = threadIdx.x;
     const int tx0 = blockIdx.x * FT_W, ty0 = blockIdx.y * FT_H;
-    for (int i = tid; i < FS_H * FS_W; i += 256) {
-        int r = i / FS_W, c = i - r * FS_W;
-        int gy = min(max(ty0 - 4 + r, 0), rows - 1), gx = min(max(tx0 - 4 + c, 0), cols - 1);
-        s_px[r][c] = __ldg(img + (size_t)gy * pitch + gx);   // clamped reads are never used by valid pixels
+    if (tx0 >= 4 && tx0 + FT_W + 4 <= pitch && ty0 >= 4 && ty0 + FT_H + 4 <= rows) {
+        // interior tile: the staged 72-byte rows start on a 4-byte boundary -> aligned 32-bit loads
+        const uint8_t *g = img + (size_t)(ty0 - 4) * pitch + (tx0 - 4);
+        for (int i = tid; i < FS_H * (FS_P / 4); i += 256) {
+            const int r = i / (FS_P / 4), wc = i - r * (FS_P / 4);
+            reinterpret_cast<uint32_t *>(&s_px[r][0])[wc] = __ldg(reinterpret_cast<const uint32_t *>(g + (size_t)r * pitch) + wc);
+        }
+    } else {
+        for (int i = tid; i < FS_H * FS_W; i += 256) {
+            int r = i / FS_W, c = i - r * FS_W;
+            int gy = min(max(ty0 - 4 + r, 0), rows - 1), gx = min(max(tx0 - 4 + c, 0), cols - 1);
+            s_px[r][c] = __ldg(img + (size_t)gy * pitch + gx);   // clamped reads are never used by valid pixels
+        }
     }
     __syncthreads();
     // scores on the tile + 1 halo; pixels outside rows/cols 3..dim-4 are not corners
