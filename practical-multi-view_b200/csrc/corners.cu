@@ -72,6 +72,109 @@ __device__ __forceinline__ float block_max_f(float v, float *s_red)
     return v;  // valid in thread 0
 }
 
+// Closed form of cornerMinEigenVal from the exact integer box sums of the Sobel products:
+// eig = k * (0.5 (Sxx + Syy) - sqrt(0.25 (Sxx - Syy)^2 + Sxy^2)),  k = (1/3060)^2.
+// Sxx +- Syy are formed in integers (no cancellation error), one approximate sqrt (<= 2 ulp).
+__device__ __forceinline__ float mineig_from_sums(int sxx, int sxy, int syy)
+{
+    const float kf = (float)((1.0 / 3060.0) * (1.0 / 3060.0));
+    const float Pf = (float)(sxx + syy), Qf = (float)(sxx - syy), Bf = (float)sxy;
+    const float t = fmaf(0.25f * Qf, Qf, Bf * Bf);
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    return kf * fmaf(0.5f, Pf, -r);
+}
+
+// Region of the register-resident fast kernel: a warp owns 120 columns x MF_R rows; it runs only where
+// neither the ROI's nor the parent's edge is within reach (the tile kernel covers the rest).
+constexpr int MF_W = 120, MF_R = 16;
+__host__ __device__ __forceinline__ bool mineig_fast_region(int x0, int y0, int rw, int rh)
+{
+    return rw >= 2 * MF_W && rh >= 2 * MF_R &&   // the host launches the fast kernel under the same condition
+           x0 >= 4 && x0 + MF_W + 4 <= rw && y0 >= 2 && y0 + MF_R + 2 <= rh;
+}
+// is the 64x32 tile of the tile kernel fully inside fast regions?
+__host__ __device__ __forceinline__ bool mineig_tile_is_fast(int tx0, int ty0, int rw, int rh)
+{
+    const int xa = (tx0 / MF_W) * MF_W, xb = ((tx0 + CT_W - 1) / MF_W) * MF_W;
+    for (int y = (ty0 / MF_R) * MF_R; y < ty0 + CT_H; y += MF_R)
+        if (!mineig_fast_region(xa, y, rw, rh) || !mineig_fast_region(xb, y, rw, rh)) return false;
+    return ty0 + CT_H <= rh && tx0 + CT_W <= rw;
+}
+
+// K4 (interior): lane L holds the 4 pixels at columns x0 - 4 + 4L of the current input row (one aligned
+// 32-bit load), the two missing neighbours come from the adjacent lanes; Sobel, products, the 3x3 box sum
+// and the closed form stay in registers while the warp walks down MF_R + 4 input rows.  Lanes 1..30 write
+// 4 responses each (16-byte stores when the map pitch allows).  HBM traffic: 1 B/px in, 4 B/px out.
+__global__ void __launch_bounds__(256)
+mineig_fast_kernel(const ImgView v, float *__restrict__ eig, int *__restrict__ max_bits)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * MF_W, y0 = (blockIdx.y * 8 + warp) * MF_R;
+    if (!mineig_fast_region(x0, y0, v.rw, v.rh)) return;      // warp-uniform
+    const int cx = x0 - 4 + 4 * lane;                          // ROI column of byte 0 of this lane's word
+    const uint8_t *g = v.ptr + (ptrdiff_t)(v.ry + y0 - 2 - v.oy) * v.pitch + (v.rx + cx - v.ox);
+    int dxp[2][4], smp[2][4];                                  // horizontal diff / smooth of the two previous rows
+    int Hxx[2][4], Hxy[2][4], Hyy[2][4];                       // horizontal 3-sums of the two previous gradient rows
+    float vmax = 0.f;
+    // all MF_R + 4 input rows are requested up front: independent loads cover the HBM latency
+    unsigned win[MF_R + 4];
+#pragma unroll
+    for (int it = 0; it < MF_R + 4; it++) win[it] = __ldg(reinterpret_cast<const unsigned *>(g + (ptrdiff_t)it * v.pitch));
+#pragma unroll
+    for (int it = 0; it < MF_R + 4; it++) {
+        // input row y0 - 2 + it ; after this row: gradient row y0 - 3 + it, box-sum (output) row y0 - 4 + it
+        const unsigned w = win[it];
+        const unsigned wl = __shfl_up_sync(0xffffffffu, w, 1), wr = __shfl_down_sync(0xffffffffu, w, 1);
+        int p[6];
+        p[0] = wl >> 24; p[1] = w & 255; p[2] = (w >> 8) & 255; p[3] = (w >> 16) & 255; p[4] = w >> 24; p[5] = wr & 255;
+        int dx[4], sm[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { dx[j] = p[j + 2] - p[j]; sm[j] = p[j] + 2 * p[j + 1] + p[j + 2]; }
+        if (it >= 2) {
+            int xx[4], xy[4], yy[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int sx = dxp[0][j] + 2 * dxp[1][j] + dx[j], sy = sm[j] - smp[0][j];
+                xx[j] = sx * sx; xy[j] = sx * sy; yy[j] = sy * sy;
+            }
+            // horizontal 3-sums; the outer terms come from the neighbouring lanes
+            const int lxx = __shfl_up_sync(0xffffffffu, xx[3], 1), lxy = __shfl_up_sync(0xffffffffu, xy[3], 1),
+                      lyy = __shfl_up_sync(0xffffffffu, yy[3], 1);
+            const int rxx = __shfl_down_sync(0xffffffffu, xx[0], 1), rxy = __shfl_down_sync(0xffffffffu, xy[0], 1),
+                      ryy = __shfl_down_sync(0xffffffffu, yy[0], 1);
+            int hxx[4], hxy[4], hyy[4];
+            hxx[0] = lxx + xx[0] + xx[1]; hxx[1] = xx[0] + xx[1] + xx[2]; hxx[2] = xx[1] + xx[2] + xx[3]; hxx[3] = xx[2] + xx[3] + rxx;
+            hxy[0] = lxy + xy[0] + xy[1]; hxy[1] = xy[0] + xy[1] + xy[2]; hxy[2] = xy[1] + xy[2] + xy[3]; hxy[3] = xy[2] + xy[3] + rxy;
+            hyy[0] = lyy + yy[0] + yy[1]; hyy[1] = yy[0] + yy[1] + yy[2]; hyy[2] = yy[1] + yy[2] + yy[3]; hyy[3] = yy[2] + yy[3] + ryy;
+            if (it >= 4) {
+                const int y = y0 + it - 4;
+                float e[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    e[j] = mineig_from_sums(Hxx[0][j] + Hxx[1][j] + hxx[j], Hxy[0][j] + Hxy[1][j] + hxy[j],
+                                            Hyy[0][j] + Hyy[1][j] + hyy[j]);
+                }
+                if (lane >= 1 && lane <= 30) {
+                    float *o = eig + (size_t)y * v.rw + cx;
+                    if ((v.rw & 3) == 0) *reinterpret_cast<float4 *>(o) = make_float4(e[0], e[1], e[2], e[3]);
+                    else { o[0] = e[0]; o[1] = e[1]; o[2] = e[2]; o[3] = e[3]; }
+                    vmax = fmaxf(vmax, fmaxf(fmaxf(e[0], e[1]), fmaxf(e[2], e[3])));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                Hxx[0][j] = Hxx[1][j]; Hxy[0][j] = Hxy[1][j]; Hyy[0][j] = Hyy[1][j];
+                Hxx[1][j] = hxx[j]; Hxy[1][j] = hxy[j]; Hyy[1][j] = hyy[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) { dxp[0][j] = dxp[1][j]; smp[0][j] = smp[1][j]; dxp[1][j] = dx[j]; smp[1][j] = sm[j]; }
+    }
+    for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0 && vmax > 0.f) atomicMax(max_bits, __float_as_int(vmax));
+}
+
 // K4: eig(y,x) over the ROI + global max (atomicMax on the bits of a non-negative float)
 __global__ void __launch_bounds__(256)
 mineig_kernel(const ImgView v, float *__restrict__ eig, int *__restrict__ max_bits)
@@ -81,6 +184,7 @@ mineig_kernel(const ImgView v, float *__restrict__ eig, int *__restrict__ max_bi
     __shared__ float s_red[8];
     const int tid = threadIdx.x;
     const int tx0 = blockIdx.x * CT_W, ty0 = blockIdx.y * CT_H;
+    if (mineig_tile_is_fast(tx0, ty0, v.rw, v.rh)) return;   // written by mineig_fast_kernel
     stage_tile(s_px, v, tx0, ty0, tid);
     __syncthreads();
     // Sobel at halo-1 positions; positions outside the ROI take the value of their reflect-101
@@ -117,18 +221,13 @@ mineig_kernel(const ImgView v, float *__restrict__ eig, int *__restrict__ max_bi
     };
     hsum(tyb + 0, hxx[0], hxy[0], hyy[0]);
     hsum(tyb + 1, hxx[1], hxy[1], hyy[1]);
-    const float kf = (float)((1.0 / 3060.0) * (1.0 / 3060.0));
     float vmax = 0.f;
 #pragma unroll
     for (int r = 0; r < CT_R; r++) {
         hsum(tyb + r + 2, hxx[(r + 2) % 3], hxy[(r + 2) % 3], hyy[(r + 2) % 3]);
         const int y = ty0 + tyb + r;
         if (x < v.rw && y < v.rh) {
-            float a = __fmul_rn(__fmul_rn((float)(hxx[0] + hxx[1] + hxx[2]), kf), 0.5f);
-            float b = __fmul_rn((float)(hxy[0] + hxy[1] + hxy[2]), kf);
-            float c = __fmul_rn(__fmul_rn((float)(hyy[0] + hyy[1] + hyy[2]), kf), 0.5f);
-            float amc = __fsub_rn(a, c);
-            float e = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(amc, amc), __fmul_rn(b, b))));
+            const float e = mineig_from_sums(hxx[0] + hxx[1] + hxx[2], hxy[0] + hxy[1] + hxy[2], hyy[0] + hyy[1] + hyy[2]);
             eig[(size_t)y * v.rw + x] = e;
             vmax = fmaxf(vmax, e);
         }
@@ -387,7 +486,12 @@ int run_mineig(pmv_ctx *ctx, const ImgView &v, float *d_eig, int *d_max, cudaStr
 {
     ProfScope ps(ctx, PMV_PHASE_RESPONSE, s);
     PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_max, 0, sizeof(int), s));
-    dim3 grid((v.rw + CT_W - 1) / CT_W, (v.rh + CT_H - 1) / CT_H);
+    if (v.rw >= 2 * MF_W && v.rh >= 2 * MF_R) {   // an interior exists: register-resident kernel (same predicate on device)
+        dim3 gridf((v.rw + MF_W - 1) / MF_W, (v.rh + 8 * MF_R - 1) / (8 * MF_R));
+        mineig_fast_kernel<<<gridf, 256, 0, s>>>(v, d_eig, d_max);
+        PMV_LAUNCH_CHECK(ctx, "mineig_fast_kernel");
+    }
+    dim3 grid((v.rw + CT_W - 1) / CT_W, (v.rh + CT_H - 1) / CT_H);   // edges (and small ROIs): tile kernel
     mineig_kernel<<<grid, 256, 0, s>>>(v, d_eig, d_max);
     PMV_LAUNCH_CHECK(ctx, "mineig_kernel");
     return PMV_OK;
