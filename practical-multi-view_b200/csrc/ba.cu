@@ -33,6 +33,9 @@ struct pmv_ba_problem {
     // one LM iteration is a fixed launch sequence (all decisions live in BAState on the device), so it is
     // captured once into a CUDA graph and replayed: removes the launch gaps of the ~600 dependent launches
     // of the blocked Cholesky
+    double *d_band = nullptr;                            // packed envelope of S + rhs (sharded all-reduce buffer)
+    long long *d_band_off = nullptr;
+    long long band_count = 0;
     cudaGraphExec_t graph_exec = nullptr;
     int graph_max_iters = -1;
     uint64_t graph_launches = 0;                         // kernel launches inside one replay
@@ -104,6 +107,26 @@ __global__ void ba_unpack_gmax_kernel(const BADev D, const double *buf)
     if (w < D.W) D.st[w].gmax = buf[w];
 }
 
+// Sharded solves exchange only the envelope of the upper triangle of S (plus rhs): row r contributes the
+// columns [r, lim(r)), packed back to back -- for the banded BAL-scale system 13 MB instead of 288 MB.
+__global__ void __launch_bounds__(256) ba_band_pack_kernel(const double *__restrict__ S, const double *__restrict__ rhs, int n,
+                                                           const int *__restrict__ lim, const long long *__restrict__ off,
+                                                           double *__restrict__ buf, int unpack, double *S_out, double *rhs_out)
+{
+    const int r = blockIdx.x;
+    if (r == n) {   // last block: the right-hand side
+        for (int j = threadIdx.x; j < n; j += 256) {
+            if (unpack) rhs_out[j] = buf[off[n] + j]; else buf[off[n] + j] = rhs[j];
+        }
+        return;
+    }
+    const int len = lim[r / PMV_CHOL_NB] - r;
+    const long long o = off[r];
+    for (int j = threadIdx.x; j < len; j += 256) {
+        if (unpack) S_out[(size_t)r * n + r + j] = buf[o + j]; else buf[o + j] = S[(size_t)r * n + r + j];
+    }
+}
+
 int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
 {
     pmv_ctx *ctx = p->ctx;
@@ -142,9 +165,13 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
         PMV_LAUNCH_CHECK(ctx, "ba_point_schur_kernel");
     }
     if (p->sharded) {
-        // [S | rhs] are contiguous per problem (W == 1 in sharded mode): one in-place sum over ranks
-        int rc = pmv_internal_ba_allreduce(ctx, D.S, D.S, (size_t)n * n + n, 0, s);
+        // sum the partial reduced camera systems over the ranks: envelope of the upper triangle + rhs
+        ba_band_pack_kernel<<<n + 1, 256, 0, s>>>(D.S, D.rhs, n, D.chol_lim, p->d_band_off, p->d_band, 0, nullptr, nullptr);
+        PMV_LAUNCH_CHECK(ctx, "ba_band_pack_kernel");
+        int rc = pmv_internal_ba_allreduce(ctx, p->d_band, p->d_band, (size_t)p->band_count, 0, s);
         if (rc) return rc;
+        ba_band_pack_kernel<<<n + 1, 256, 0, s>>>(nullptr, nullptr, n, D.chol_lim, p->d_band_off, p->d_band, 1, D.S, D.rhs);
+        PMV_LAUNCH_CHECK(ctx, "ba_band_pack_kernel");
         ba_pack_gmax_kernel<<<wblocks, 128, 0, s>>>(D, p->d_scal);
         PMV_LAUNCH_CHECK(ctx, "ba_pack_gmax_kernel");
         rc = pmv_internal_ba_allreduce(ctx, p->d_scal, p->d_scal_red, W, 1, s);
@@ -348,8 +375,20 @@ PMV_API pmv_ba_problem *pmv_ba_problem_create(pmv_ctx *ctx, const double *poses,
         int *d_lim = nullptr;
         if (dev_alloc(p, &d_lim, nblk) != PMV_OK) { pmv_ba_problem_destroy(p); return nullptr; }
         cudaMemcpyAsync(d_lim, p->chol_lim.data(), sizeof(int) * nblk, cudaMemcpyHostToDevice, s);
-        cudaStreamSynchronize(s);
         D.chol_lim = d_lim;
+        if (p->sharded) {
+            std::vector<long long> off(n + 1);
+            long long acc = 0;
+            for (size_t r = 0; r < n; r++) { off[r] = acc; acc += p->chol_lim[r / PMV_CHOL_NB] - (int)r; }
+            off[n] = acc;
+            p->band_count = acc + (long long)n;
+            if (dev_alloc(p, &p->d_band_off, n + 1) != PMV_OK || dev_alloc(p, &p->d_band, (size_t)p->band_count) != PMV_OK) {
+                pmv_ba_problem_destroy(p);
+                return nullptr;
+            }
+            cudaMemcpyAsync(p->d_band_off, off.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, s);
+        }
+        cudaStreamSynchronize(s);
     }
     if (pmv_ba_problem_reset(p, nullptr, nullptr) != PMV_OK) { pmv_ba_problem_destroy(p); return nullptr; }
     return p;

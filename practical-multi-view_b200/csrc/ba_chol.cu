@@ -12,6 +12,7 @@
 //   chol_backsub_kernel U y = z, one CTA walking the block rows from the bottom
 // The trailing update is the n^3/3 term and the only place the tensor pipe is used in this library.
 #include <algorithm>
+#include <cstdlib>
 
 #include "ba.cuh"
 
@@ -190,43 +191,65 @@ chol_update_kernel(double *S, double *b, int n, int k0, int t0 /* first trailing
 }
 
 // U y = z from the bottom block row upwards; one CTA (1024 threads).  Per block row: 32 warps form the dot
-// products with the known tail of y (inside the envelope), then one warp solves the 32x32 triangle from
-// shared memory.
+// products with the known tail of y (inside the envelope), then one warp solves the 32x32 triangle.
+// For narrow envelopes (banded systems) the NB x (envelope) block row is copied into shared memory with
+// cp.async one step AHEAD (it does not depend on y), so the 188 dependent steps see no HBM/L2 latency.
+constexpr int BS_MAXW = 321;   // widest envelope (columns from k0) staged in shared memory; odd stride: no bank conflicts down a column
+
 __global__ void __launch_bounds__(1024)
-chol_backsub_kernel(const double *S, const double *z, double *y, int n, const int *__restrict__ lim, BAState *st)
+chol_backsub_kernel(const double *S, const double *z, double *y, int n, const int *__restrict__ lim, BAState *st, int staged)
 {
-    __shared__ double Ukk[NB][NB + 1];
+    extern __shared__ double sbuf[];            // staged: 2 x NB x BS_MAXW
     __shared__ double yk[NB];
     __shared__ int fin;
     if (st->done || !st->chol_ok) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nblk = (n + NB - 1) / NB;
     if (tid == 0) fin = 1;
+    auto stage = [&](int kb, double *dst) {
+        const int k0 = kb * NB, nb = min(NB, n - k0), wdt = min(n, lim[kb]) - k0;
+        for (int i = tid; i < nb * wdt; i += 1024) {
+            const int r = i / wdt, c = i - r * wdt;
+            if (c >= r) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + r * BS_MAXW + c);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(S + (size_t)(k0 + r) * n + k0 + c));
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    if (staged) stage(nblk - 1, sbuf + ((nblk - 1) & 1 ? NB * BS_MAXW : 0));
     for (int kb = nblk - 1; kb >= 0; kb--) {
         const int k0 = kb * NB, nb = min(NB, n - k0);
-        {
-            int r = tid / NB, c = tid % NB;   // 1024 threads == NB*NB
-            Ukk[r][c] = (r < nb && c < nb && c >= r) ? S[(size_t)(k0 + r) * n + k0 + c] : 0.0;
-        }
         const int cend = min(n, lim[kb]);   // U_kj == 0 beyond the envelope
+        const double *U = nullptr;
+        if (staged) {
+            if (kb > 0) stage(kb - 1, sbuf + ((kb - 1) & 1 ? NB * BS_MAXW : 0));
+            if (kb > 0) asm volatile("cp.async.wait_group 1;"); else asm volatile("cp.async.wait_group 0;");
+            __syncthreads();
+            U = sbuf + (kb & 1 ? NB * BS_MAXW : 0);
+        }
         if (warp < nb) {
             double sacc = 0;
-            for (int c = k0 + nb + lane; c < cend; c += 32) sacc += S[(size_t)(k0 + warp) * n + c] * y[c];
+            if (staged) {
+                for (int c = nb + lane; c < cend - k0; c += 32) sacc += U[warp * BS_MAXW + c] * y[k0 + c];
+            } else {
+                for (int c = k0 + nb + lane; c < cend; c += 32) sacc += S[(size_t)(k0 + warp) * n + c] * y[c];
+            }
             for (int o = 16; o; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
             if (lane == 0) yk[warp] = z[k0 + warp] - sacc;
         }
         __syncthreads();
         if (warp == 0) {
+            // lane r keeps row r's unknown; column r of the triangle is read as needed
+            double mine = lane < nb ? yk[lane] : 0.0;
             for (int r = nb - 1; r >= 0; r--) {
-                const double v = yk[r] / Ukk[r][r];
-                __syncwarp();
-                if (lane == 0) { yk[r] = v; if (!isfinite(v)) fin = 0; }
-                if (lane < r) yk[lane] -= Ukk[lane][r] * v;
-                __syncwarp();
+                const double urr = staged ? U[r * BS_MAXW + r] : S[(size_t)(k0 + r) * n + k0 + r];
+                const double v = __shfl_sync(0xffffffffu, mine, r) / urr;
+                if (lane == r) { mine = v; if (!isfinite(v)) fin = 0; }
+                else if (lane < r) mine -= (staged ? U[lane * BS_MAXW + r] : S[(size_t)(k0 + lane) * n + k0 + r]) * v;
             }
+            if (lane < nb) y[k0 + lane] = mine;
         }
-        __syncthreads();
-        if (tid < nb) y[k0 + tid] = yk[tid];
         __syncthreads();
     }
     if (tid == 0 && !fin) st->chol_ok = 0;
@@ -267,8 +290,16 @@ int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_
                 PMV_LAUNCH_CHECK(ctx, "chol_update_kernel");
             }
         }
-        chol_backsub_kernel<<<1, 1024, 0, s>>>(S, b, y, n, D.chol_lim, st);
-        PMV_LAUNCH_CHECK(ctx, "chol_backsub_kernel");
+        {
+            int maxw = 0;
+            for (int k0 = 0, kb = 0; k0 < n; k0 += NB, kb++) maxw = std::max(maxw, (lim_host ? std::min(n, lim_host[kb]) : n) - k0);
+            const int staged = (maxw <= BS_MAXW) && !getenv("PMV_CHOL_NO_STAGE");
+            const size_t smem = staged ? sizeof(double) * 2 * NB * BS_MAXW : 0;
+            static bool attr = false;
+            if (!attr) { cudaFuncSetAttribute(chol_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+            chol_backsub_kernel<<<1, 1024, smem, s>>>(S, b, y, n, D.chol_lim, st, staged);
+            PMV_LAUNCH_CHECK(ctx, "chol_backsub_kernel");
+        }
     }
     return PMV_OK;
 }
