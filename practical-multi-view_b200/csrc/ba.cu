@@ -25,6 +25,12 @@ struct pmv_ba_problem {
     int sharded = 0;     // points sharded over ranks: reduce camera blocks / S / scalars with NCCL
     int rank = 0;
     std::vector<void *> allocs;
+    // one-shot solves (pmv_ba_solve / pmv_ba_solve_batched) carve their buffers out of a grow-only arena of
+    // the context instead of ~35 cudaMalloc/cudaFree pairs per call (the pipeline calls BA once per keyframe)
+    int transient = 0;           // created by a one-shot entry point
+    int arena_mode = 0;          // 0 cudaMalloc per buffer, 1 measuring pass, 2 carving pass
+    char *arena_base = nullptr;
+    size_t arena_off = 0;
     double *d_init_poses = nullptr, *d_init_points = nullptr;
     double *d_Uraw = nullptr, *d_Uraw_red = nullptr;   // 27 doubles per camera (+ W cost slots at the end)
     double *d_scal = nullptr, *d_scal_red = nullptr;   // per window: model_change, cand_cost, step_norm2, x_norm2
@@ -53,6 +59,12 @@ int dev_alloc(pmv_ba_problem *p, T **out, size_t count)
 {
     void *q = nullptr;
     size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    if (p->arena_mode) {
+        const size_t off = (p->arena_off + 255) & ~(size_t)255;
+        p->arena_off = off + bytes;
+        if (p->arena_mode == 2) { *out = reinterpret_cast<T *>(p->arena_base + off); p->bytes += bytes; }
+        return PMV_OK;
+    }
     cudaError_t e = cudaMalloc(&q, bytes);
     if (e != cudaSuccess) return p->ctx->fail(PMV_ERR_NOMEM, "ba problem allocation", e);
     p->allocs.push_back(q);
@@ -213,15 +225,10 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
     return PMV_OK;
 }
 
-}  // namespace
-
-extern "C" {
-
-PMV_API pmv_ba_problem *pmv_ba_problem_create(pmv_ctx *ctx, const double *poses, const double *points,
-                                              const double *obs, const int32_t *cam_idx, const int32_t *pt_idx,
-                                              const int32_t *obs_off, int W, int Nc, int Np, int No,
-                                              const double K[9], double huber_delta, int sharded_rank,
-                                              int sharded_nranks)
+pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const double *points, const double *obs,
+                                  const int32_t *cam_idx, const int32_t *pt_idx, const int32_t *obs_off, int W, int Nc,
+                                  int Np, int No, const double K[9], double huber_delta, int sharded_rank,
+                                  int sharded_nranks, bool transient)
 {
     if (!ctx) return nullptr;
     if (!poses || !points || (No > 0 && (!obs || !cam_idx || !pt_idx)) || !K || W <= 0 || Nc <= 0 || Np <= 0 || No < 0 ||
@@ -280,8 +287,14 @@ PMV_API pmv_ba_problem *pmv_ba_problem_create(pmv_ctx *ctx, const double *poses,
     }
     // PMV_BA_FORCE_GENERAL=1 (tests) keeps small problems on the general path so both are exercised
     const char *force_general = getenv("PMV_BA_FORCE_GENERAL");
+    // The window kernels give one CTA per window: they win once a batch fills a good part of the GPU, while
+    // a lone window (the per-keyframe call of the pipeline) is twice as fast spread over the SMs by the
+    // general path (tools/ba_latency.py: 0.61 vs 1.34 ms for 5 poses x 400 points x 5 iterations).
+    // PMV_BA_FORCE_WINDOW=1 (tests) keeps any eligible problem on the window path.
+    const char *force_window = getenv("PMV_BA_FORCE_WINDOW");
     bool window_ok = pmv_internal_ba_window_eligible(Nc, Np) && sharded_nranks <= 1 &&
-                     !(force_general && force_general[0] == '1');
+                     !(force_general && force_general[0] == '1') &&
+                     (W >= 4 || (force_window && force_window[0] == '1'));
     std::vector<unsigned> h_vis;
     if (window_ok) {
         h_vis.assign((size_t)W * Np, 0u);
@@ -315,13 +328,17 @@ PMV_API pmv_ba_problem *pmv_ba_problem_create(pmv_ctx *ctx, const double *poses,
     int *d_cam, *d_pt, *d_win, *d_ptoff, *d_camoff, *d_camobs;
     double *d_obs;
     int rc = 0;
+    const int nblk = ((int)n + PMV_CHOL_NB - 1) / PMV_CHOL_NB;
+    int *d_lim = nullptr;
+    double *d_sys = nullptr;
+    p->use_window = window_ok ? 1 : 0;
+    auto alloc_all = [&]() {
     rc |= dev_alloc(p, &d_cam, No); rc |= dev_alloc(p, &d_pt, No); rc |= dev_alloc(p, &d_win, No);
     rc |= dev_alloc(p, &d_obs, 2 * (size_t)No); rc |= dev_alloc(p, &d_ptoff, wp + 1); rc |= dev_alloc(p, &d_camoff, wc + 1);
     rc |= dev_alloc(p, &d_camobs, No);
     rc |= dev_alloc(p, &D.poses, wc * 6); rc |= dev_alloc(p, &D.points, wp * 3);
     rc |= dev_alloc(p, &D.cand_poses, wc * 6); rc |= dev_alloc(p, &D.cand_points, wp * 3);
     rc |= dev_alloc(p, &p->d_init_poses, wc * 6); rc |= dev_alloc(p, &p->d_init_points, wp * 3);
-    p->use_window = window_ok ? 1 : 0;
     if (!window_ok) {   // the window path never materialises the linearisation
         rc |= dev_alloc(p, &D.Lr, 2 * (size_t)No); rc |= dev_alloc(p, &D.Ljc, 12 * (size_t)No); rc |= dev_alloc(p, &D.Ljp, 6 * (size_t)No);
     } else {
@@ -331,13 +348,28 @@ PMV_API pmv_ba_problem *pmv_ba_problem_create(pmv_ctx *ctx, const double *poses,
     rc |= dev_alloc(p, &D.diag_c, wc * 6); rc |= dev_alloc(p, &D.diag_p, wp * 3);
     rc |= dev_alloc(p, &D.U, wc * 36); rc |= dev_alloc(p, &D.gc, wc * 6);
     // S and rhs contiguous ([S | rhs]) so a sharded solve reduces them with one collective
-    double *d_sys = nullptr;
     rc |= dev_alloc(p, &d_sys, window_ok ? 8 : (size_t)W * (n * n + n) + (n + 1) * 8);   // the window path keeps S on chip
     rc |= dev_alloc(p, &D.yc, (size_t)W * n);
     rc |= dev_alloc(p, &D.Vinv, wp * 6); rc |= dev_alloc(p, &D.gp, wp * 3);
     rc |= dev_alloc(p, &D.st, W);
     rc |= dev_alloc(p, &p->d_Uraw, 27 * wc + W); rc |= dev_alloc(p, &p->d_Uraw_red, 27 * wc + W);
     rc |= dev_alloc(p, &p->d_scal, 4 * (size_t)W); rc |= dev_alloc(p, &p->d_scal_red, 4 * (size_t)W);
+    rc |= dev_alloc(p, &d_lim, nblk);
+    };
+    p->transient = transient ? 1 : 0;
+    if (transient && !p->sharded) {
+        p->arena_mode = 1;
+        alloc_all();
+        const size_t total = p->arena_off + 256;
+        if (total <= ((size_t)64 << 20)) {
+            cudaError_t e = ctx->scratch[7].reserve(total);
+            if (e != cudaSuccess) { ctx->fail(PMV_ERR_NOMEM, "ba arena", e); delete p; return nullptr; }
+            p->arena_mode = 2; p->arena_base = reinterpret_cast<char *>(ctx->scratch[7].p); p->arena_off = 0;
+        } else {
+            p->arena_mode = 0;
+        }
+    }
+    alloc_all();
     if (rc) { pmv_ba_problem_destroy(p); return nullptr; }
     D.S = d_sys; D.rhs = d_sys + (size_t)W * n * n;
     D.obs_cam = d_cam; D.obs_pt = d_pt; D.obs_win = d_win; D.obs_xy = d_obs;
@@ -364,7 +396,6 @@ PMV_API pmv_ba_problem *pmv_ba_problem_create(pmv_ctx *ctx, const double *poses,
             cudaMemcpyAsync(emax.data(), d_e + Nc, sizeof(double) * Nc, cudaMemcpyDeviceToHost, s);
             if (cudaStreamSynchronize(s) != cudaSuccess) { ctx->fail(PMV_ERR_CUDA, "envelope exchange failed"); pmv_ba_problem_destroy(p); return nullptr; }
         }
-        const int nblk = ((int)n + PMV_CHOL_NB - 1) / PMV_CHOL_NB;
         p->chol_lim.assign(nblk, (int)n);
         int run = 0;
         for (int kb = 0; kb < nblk; kb++) {
@@ -372,8 +403,6 @@ PMV_API pmv_ba_problem *pmv_ba_problem_create(pmv_ctx *ctx, const double *poses,
             for (int c = c0; c <= c1; c++) run = std::max(run, (int)emax[c]);
             p->chol_lim[kb] = std::min((int)n, 6 * (run + 1));
         }
-        int *d_lim = nullptr;
-        if (dev_alloc(p, &d_lim, nblk) != PMV_OK) { pmv_ba_problem_destroy(p); return nullptr; }
         cudaMemcpyAsync(d_lim, p->chol_lim.data(), sizeof(int) * nblk, cudaMemcpyHostToDevice, s);
         D.chol_lim = d_lim;
         if (p->sharded) {
@@ -392,6 +421,20 @@ PMV_API pmv_ba_problem *pmv_ba_problem_create(pmv_ctx *ctx, const double *poses,
     }
     if (pmv_ba_problem_reset(p, nullptr, nullptr) != PMV_OK) { pmv_ba_problem_destroy(p); return nullptr; }
     return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+PMV_API pmv_ba_problem *pmv_ba_problem_create(pmv_ctx *ctx, const double *poses, const double *points,
+                                              const double *obs, const int32_t *cam_idx, const int32_t *pt_idx,
+                                              const int32_t *obs_off, int W, int Nc, int Np, int No,
+                                              const double K[9], double huber_delta, int sharded_rank,
+                                              int sharded_nranks)
+{
+    return ba_problem_create(ctx, poses, points, obs, cam_idx, pt_idx, obs_off, W, Nc, Np, No, K, huber_delta,
+                             sharded_rank, sharded_nranks, false);
 }
 
 PMV_API void pmv_ba_problem_destroy(pmv_ba_problem *p)
@@ -441,7 +484,9 @@ PMV_API int pmv_ba_problem_solve(pmv_ba_problem *p, int max_iters)
                              : ba_iteration(p, s);
     };
     const char *no_graph = getenv("PMV_BA_NO_GRAPH");
-    const bool want_graph = !(no_graph && no_graph[0] == '1');
+    // a one-shot solve of a small problem issues a handful of launches per iteration: capturing and
+    // instantiating a graph would cost more than it saves
+    const bool want_graph = !(no_graph && no_graph[0] == '1') && !(p->transient && p->D.n <= 160);
     if (want_graph && (!p->graph_exec || p->graph_max_iters != max_iters)) {
         if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
         // first iteration runs eagerly (sets function attributes, validates the launches) ...
@@ -516,8 +561,8 @@ PMV_API int pmv_ba_solve_batched(pmv_ctx *ctx, double *poses, double *points, co
                                  pmv_ba_summary *sums)
 {
     if (!ctx) return PMV_ERR_INVALID;
-    pmv_ba_problem *p = pmv_ba_problem_create(ctx, poses, points, obs, cam_idx, pt_idx, obs_off, W, Nc, Np, No, K,
-                                              huber_delta, 0, 1);
+    pmv_ba_problem *p = ba_problem_create(ctx, poses, points, obs, cam_idx, pt_idx, obs_off, W, Nc, Np, No, K,
+                                          huber_delta, 0, 1, true);
     if (!p) return PMV_ERR_INVALID;
     int rc = pmv_ba_problem_solve(p, max_iters);
     if (rc == PMV_OK) rc = pmv_ba_problem_download(p, poses, points, sums);

@@ -14,8 +14,10 @@ def ba_path(request, monkeypatch):
     """Run every solve twice: the window-batched kernels (Nc <= 22) and the general multi-kernel path."""
     if request.param == "general":
         monkeypatch.setenv("PMV_BA_FORCE_GENERAL", "1")
+        monkeypatch.delenv("PMV_BA_FORCE_WINDOW", raising=False)
     else:
         monkeypatch.delenv("PMV_BA_FORCE_GENERAL", raising=False)
+        monkeypatch.setenv("PMV_BA_FORCE_WINDOW", "1")   # a lone window defaults to the general path
     return request.param
 
 
