@@ -263,6 +263,9 @@ __global__ void chol_gradient_check_kernel(BAState *st)
 
 }  // namespace
 
+int pmv_internal_ba_cholesky_band(pmv_ctx *ctx, double *S, double *b, int n, const int *lim_host, const int *lim_dev,
+                                  BAState *st, cudaStream_t s);   // ba_chol_band.cu
+
 // lim_host[kb] / D.chol_lim[kb]: end column (exclusive, <= n) of the envelope of block row kb -- cumulative
 // maximum of the camera co-visibility reach, so fill-in stays inside it.  A banded reduced camera system
 // (BASELINE config 5: every point seen by 5 of the <= 40 nearest poses) is factorised in O(n * band^2).
@@ -274,7 +277,10 @@ int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_
         BAState *st = D.st + w;
         chol_gradient_check_kernel<<<1, 1, 0, s>>>(st);
         PMV_LAUNCH_CHECK(ctx, "chol_gradient_check_kernel");
-        for (int k0 = 0, kb = 0; k0 < n; k0 += NB, kb++) {
+        // banded systems: the whole factorisation in one cluster launch (ba_chol_band.cu)
+        const int band = pmv_internal_ba_cholesky_band(ctx, S, b, n, lim_host, D.chol_lim, st, s);
+        if (band < 0) return band;
+        for (int k0 = 0, kb = 0; k0 < n && !band; k0 += NB, kb++) {
             const int t0 = k0 + NB;
             const int nlim = lim_host ? std::min(n, lim_host[kb]) : n;
             const bool fuse = t0 < nlim && nlim - t0 <= 512;

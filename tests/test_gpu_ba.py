@@ -137,6 +137,25 @@ def test_large_reduced_system_uses_blocked_cholesky(ctx, synth):
     assert np.abs(p - po).max() < 1e-5
 
 
+@pytest.mark.parametrize("nposes,npts,span", [(40, 3000, 20), (100, 6000, 40), (30, 1500, 30), (67, 4000, 12), (200, 8000, 40)])
+def test_banded_cholesky_cluster_kernel(ctx, synth, monkeypatch, ba_path, nposes, npts, span):
+    """Banded reduced systems are factorised by one cluster launch (ba_chol_band.cu); it must agree with the
+    oracle and with the multi-launch blocked Cholesky (PMV_CHOL_NO_CLUSTER=1) on the same problem."""
+    if ba_path == "window":
+        pytest.skip("n > 160: one path")
+    w = synth.ba_large(11 + nposes, n_poses=nposes, n_points=npts, views=5, span=span)
+    monkeypatch.delenv("PMV_CHOL_NO_CLUSTER", raising=False)
+    p, x, s = ctx.ba_solve(*_args(w), 1.0, 4)
+    monkeypatch.setenv("PMV_CHOL_NO_CLUSTER", "1")
+    p2, x2, s2 = ctx.ba_solve(*_args(w), 1.0, 4)
+    po, xo, so = oracle.ba_solve(*_args(w), 1.0, 4)
+    assert s["iterations"] == so["iterations"] == s2["iterations"]
+    assert abs(s["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]
+    assert abs(s["final_cost"] - s2["final_cost"]) <= 1e-9 * so["final_cost"]
+    assert np.abs(p - po).max() < 1e-5
+    assert np.abs(x - xo).max() < 1e-4
+
+
 def test_resident_problem_reset_and_errors(ctx, pmv, synth):
     w = synth.ba_window(9, n_poses=5, n_points=100)
     prob = ctx.ba_problem(*_args(w))
