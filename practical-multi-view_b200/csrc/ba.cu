@@ -46,6 +46,10 @@ struct pmv_ba_problem {
     int graph_max_iters = -1;
     uint64_t graph_launches = 0;                         // kernel launches inside one replay
     size_t bytes = 0;
+    // block-organised point elimination (ba_pair_schur_kernel): segments of the per-camera-pair entry lists
+    BAPairSeg *d_segs = nullptr;
+    int2 *d_entries = nullptr;
+    int nsegs = 0;
     // window-batched path (ba_window.cu): Nc <= 22, every (point, camera) pair observed at most once
     int use_window = 0;
     unsigned *d_vis = nullptr;
@@ -173,8 +177,13 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
         PMV_LAUNCH_CHECK(ctx, "ba_clear_system_kernel");
     }
     if (wp > 0) {
-        ba_point_schur_kernel<<<std::min((wp + 3) / 4, 148 * 32), 128, 0, s>>>(D);
+        const int by_pairs = p->nsegs > 0;
+        ba_point_schur_kernel<<<std::min((wp + 3) / 4, 148 * 32), 128, 0, s>>>(D, by_pairs ? 0 : 1);
         PMV_LAUNCH_CHECK(ctx, "ba_point_schur_kernel");
+        if (by_pairs) {
+            ba_pair_schur_kernel<<<(p->nsegs + 3) / 4, 128, 0, s>>>(D, p->d_segs, p->nsegs, p->d_entries);
+            PMV_LAUNCH_CHECK(ctx, "ba_pair_schur_kernel");
+        }
     }
     if (p->sharded) {
         // sum the partial reduced camera systems over the ranks: envelope of the upper triangle + rhs
@@ -418,6 +427,53 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
             cudaMemcpyAsync(p->d_band_off, off.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, s);
         }
         cudaStreamSynchronize(s);
+    }
+    // ---- pair list: for every co-observed camera pair (ci <= ck) the observation pairs (i, k) of the points
+    // that see both, cut into segments of <= 512 entries (one warp each).  Large single problems only: below
+    // ~100 k observations the per-point kernel has more parallelism than there are segments.
+    {
+        const char *no_pairs = getenv("PMV_BA_NO_PAIRS");
+        const char *force_pairs = getenv("PMV_BA_FORCE_PAIRS");   // tests: small problems through the pair path
+        const bool want = W == 1 && !window_ok && p->arena_mode == 0 && (size_t)Nc * Nc <= ((size_t)16 << 20) &&
+                          (No >= 100000 || (force_pairs && force_pairs[0] == '1')) && !(no_pairs && no_pairs[0] == '1');
+        if (want) {
+            std::vector<unsigned> pcnt((size_t)Nc * Nc + 1, 0u);
+            for (size_t q = 0; q + 1 < pt_off.size(); q++)
+                for (int i = pt_off[q]; i < pt_off[q + 1]; i++)
+                    for (int k = pt_off[q]; k < pt_off[q + 1]; k++)
+                        if (h_cam[i] <= h_cam[k]) pcnt[(size_t)h_cam[i] * Nc + h_cam[k] + 1]++;
+            unsigned long long total = 0;
+            for (size_t a = 1; a < pcnt.size(); a++) total += pcnt[a];
+            if (total > 0 && total < (1ull << 31)) {
+                std::vector<BAPairSeg> segs;
+                std::vector<unsigned> cur((size_t)Nc * Nc);
+                unsigned run = 0;
+                for (size_t a = 0; a < (size_t)Nc * Nc; a++) {
+                    const unsigned c = pcnt[a + 1];
+                    cur[a] = run;
+                    for (unsigned o = 0; o < c; o += 512)
+                        segs.push_back({(int)(a / Nc), (int)(a % Nc), (int)(run + o), (int)(run + std::min(c, o + 512))});
+                    run += c;
+                }
+                std::vector<int2> ent((size_t)total);
+                for (size_t q = 0; q + 1 < pt_off.size(); q++)
+                    for (int i = pt_off[q]; i < pt_off[q + 1]; i++)
+                        for (int k = pt_off[q]; k < pt_off[q + 1]; k++)
+                            if (h_cam[i] <= h_cam[k]) ent[cur[(size_t)h_cam[i] * Nc + h_cam[k]]++] = make_int2(i, k);
+                if (dev_alloc(p, &p->d_segs, segs.size()) != PMV_OK || dev_alloc(p, &p->d_entries, ent.size()) != PMV_OK) {
+                    pmv_ba_problem_destroy(p);
+                    return nullptr;
+                }
+                cudaMemcpyAsync(p->d_segs, segs.data(), sizeof(BAPairSeg) * segs.size(), cudaMemcpyHostToDevice, s);
+                cudaMemcpyAsync(p->d_entries, ent.data(), sizeof(int2) * ent.size(), cudaMemcpyHostToDevice, s);
+                if (cudaStreamSynchronize(s) != cudaSuccess) {
+                    ctx->fail(PMV_ERR_CUDA, "pmv_ba_problem_create: pair list upload failed", cudaGetLastError());
+                    pmv_ba_problem_destroy(p);
+                    return nullptr;
+                }
+                p->nsegs = (int)segs.size();
+            }
+        }
     }
     if (pmv_ba_problem_reset(p, nullptr, nullptr) != PMV_OK) { pmv_ba_problem_destroy(p); return nullptr; }
     return p;

@@ -273,7 +273,7 @@ __global__ void ba_latch_cost_kernel(const BADev D)
 
 // ---- K9b point elimination: one warp per (window, point) -----------------------------------------------
 // V = sum J_p^T J_p + D_p^2, g = sum J_p^T r; S(ci,ck) -= W_i V^-1 W_k^T (ci <= ck); rhs_ci -= W_i V^-1 g.
-__global__ void __launch_bounds__(128) ba_point_schur_kernel(const BADev D)
+__global__ void __launch_bounds__(128) ba_point_schur_kernel(const BADev D, const int pass2 /* 0: V^-1 / g only, S comes from ba_pair_schur_kernel */)
 {
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * 4;
@@ -347,6 +347,7 @@ __global__ void __launch_bounds__(128) ba_point_schur_kernel(const BADev D)
         for (int k = 0; k < 6; k++) D.Vinv[6 * (size_t)wp + k] = Vi[k];
         D.gp[3 * (size_t)wp] = g[0]; D.gp[3 * (size_t)wp + 1] = g[1]; D.gp[3 * (size_t)wp + 2] = g[2];
     }
+    if (!pass2) continue;
     const double vg[3] = {Vi[0] * g[0] + Vi[1] * g[1] + Vi[2] * g[2], Vi[1] * g[0] + Vi[3] * g[1] + Vi[4] * g[2],
                           Vi[2] * g[0] + Vi[4] * g[1] + Vi[5] * g[2]};
     double *S = D.S + (size_t)w * D.n * D.n;
@@ -394,6 +395,95 @@ __global__ void __launch_bounds__(128) ba_point_schur_kernel(const BADev D)
     }
     }   // grid-stride loop over points
     if (gm_w >= 0 && lane == 0) atomic_max_pos_double(&D.st[gm_w].gmax, gm_acc);
+}
+
+// ---- K9b': the same elimination organised by BLOCK of S instead of by point (one problem, W == 1) ---------
+// The host lists, for every co-observed camera pair (ci <= ck), the observation pairs (i, k) of the points
+// that see both (ba.cu: pair list).  One warp sums a segment of <= 512 such entries of ONE pair in registers,
+// Y_i W_k^T = W_i V^-1 W_k^T (6x6), reduces over its lanes and adds the block to S once: 36 atomics per
+// segment instead of 36 per entry -- the per-point kernel above spends its time (4.5 ms at 1 M points) in
+// 570 M fp64 atomics on ~700 k addresses of S.  Entries with i == k also carry the right-hand side
+// rhs_ci -= W_i V^-1 g.  Needs V^-1 and g of every point (ba_point_schur_kernel with pass2 = 0).
+struct BAPairSeg { int ci, ck, begin, end; };
+
+__global__ void __launch_bounds__(128) ba_pair_schur_kernel(const BADev D, const BAPairSeg *__restrict__ segs, int nsegs,
+                                                            const int2 *__restrict__ entries)
+{
+    const int lane = threadIdx.x & 31;
+    const int sidx = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (sidx >= nsegs) return;
+    const BAState *st = &D.st[0];
+    if (st->done) return;
+    const BAPairSeg sg = segs[sidx];
+    double sci[6], sck[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { sci[k] = D.scale_c[6 * (size_t)sg.ci + k]; sck[k] = D.scale_c[6 * (size_t)sg.ck + k]; }
+    double acc[36], racc[6];
+#pragma unroll
+    for (int k = 0; k < 36; k++) acc[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) racc[k] = 0.0;
+    for (int e = sg.begin + lane; e < sg.end; e += 32) {
+        const int2 en = entries[e];
+        const int oi = en.x, ok = en.y;
+        const int pt = D.obs_pt[oi];
+        double sp[3], Vi[6];
+#pragma unroll
+        for (int k = 0; k < 3; k++) sp[k] = D.scale_p[3 * (size_t)pt + k];
+#pragma unroll
+        for (int k = 0; k < 6; k++) Vi[k] = D.Vinv[6 * (size_t)pt + k];
+        double Wi[18], Wk[18];
+        {
+            double jp[6];
+#pragma unroll
+            for (int k = 0; k < 3; k++) { jp[k] = D.Ljp[6 * (size_t)oi + k] * sp[k]; jp[3 + k] = D.Ljp[6 * (size_t)oi + 3 + k] * sp[k]; }
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                const double j0 = D.Ljc[12 * (size_t)oi + r] * sci[r], j1 = D.Ljc[12 * (size_t)oi + 6 + r] * sci[r];
+                Wi[3 * r] = j0 * jp[0] + j1 * jp[3]; Wi[3 * r + 1] = j0 * jp[1] + j1 * jp[4]; Wi[3 * r + 2] = j0 * jp[2] + j1 * jp[5];
+            }
+        }
+        if (ok == oi) {
+#pragma unroll
+            for (int k = 0; k < 18; k++) Wk[k] = Wi[k];
+            const double g0 = D.gp[3 * (size_t)pt], g1 = D.gp[3 * (size_t)pt + 1], g2 = D.gp[3 * (size_t)pt + 2];
+            const double vg0 = Vi[0] * g0 + Vi[1] * g1 + Vi[2] * g2, vg1 = Vi[1] * g0 + Vi[3] * g1 + Vi[4] * g2,
+                         vg2 = Vi[2] * g0 + Vi[4] * g1 + Vi[5] * g2;
+#pragma unroll
+            for (int r = 0; r < 6; r++) racc[r] += Wi[3 * r] * vg0 + Wi[3 * r + 1] * vg1 + Wi[3 * r + 2] * vg2;
+        } else {
+            double jp[6];
+#pragma unroll
+            for (int k = 0; k < 3; k++) { jp[k] = D.Ljp[6 * (size_t)ok + k] * sp[k]; jp[3 + k] = D.Ljp[6 * (size_t)ok + 3 + k] * sp[k]; }
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                const double j0 = D.Ljc[12 * (size_t)ok + c] * sck[c], j1 = D.Ljc[12 * (size_t)ok + 6 + c] * sck[c];
+                Wk[3 * c] = j0 * jp[0] + j1 * jp[3]; Wk[3 * c + 1] = j0 * jp[1] + j1 * jp[4]; Wk[3 * c + 2] = j0 * jp[2] + j1 * jp[5];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            const double y0 = Wi[3 * r] * Vi[0] + Wi[3 * r + 1] * Vi[1] + Wi[3 * r + 2] * Vi[2];
+            const double y1 = Wi[3 * r] * Vi[1] + Wi[3 * r + 1] * Vi[3] + Wi[3 * r + 2] * Vi[4];
+            const double y2 = Wi[3 * r] * Vi[2] + Wi[3 * r + 1] * Vi[4] + Wi[3 * r + 2] * Vi[5];
+#pragma unroll
+            for (int c = 0; c < 6; c++) acc[6 * r + c] += y0 * Wk[3 * c] + y1 * Wk[3 * c + 1] + y2 * Wk[3 * c + 2];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 36; k++) acc[k] = warp_sum_d(acc[k]);
+    double *S = D.S;
+    // lane l adds elements l and l + 32 of the 6x6 block (row major)
+#pragma unroll
+    for (int k = 0; k < 36; k++)
+        if (lane == (k & 31)) atomicAdd(&S[(size_t)(6 * sg.ci + k / 6) * D.n + 6 * sg.ck + k % 6], -acc[k]);
+    if (sg.ci == sg.ck) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) racc[k] = warp_sum_d(racc[k]);
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+            if (lane == k) atomicAdd(&D.rhs[6 * sg.ci + k], -racc[k]);
+    }
 }
 
 // after the optional cross-rank reduction of S / rhs: add the camera diagonal blocks U + D_c^2 and J_c^T r

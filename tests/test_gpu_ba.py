@@ -156,6 +156,32 @@ def test_banded_cholesky_cluster_kernel(ctx, synth, monkeypatch, ba_path, nposes
     assert np.abs(x - xo).max() < 1e-4
 
 
+@pytest.mark.parametrize("nposes,npts,span", [(40, 3000, 20), (12, 900, 12)])
+def test_pair_list_schur_matches_point_kernel(ctx, pmv, synth, monkeypatch, ba_path, nposes, npts, span):
+    """Large single problems eliminate the points block by block of S (ba_pair_schur_kernel, per-camera-pair
+    entry lists) instead of point by point with atomics; forced here on a small problem, both must agree with
+    the oracle.  A resident problem is used because one-shot solves of small problems live in the arena."""
+    if ba_path == "window":
+        pytest.skip("general path only")
+    w = synth.ba_large(5 + nposes, n_poses=nposes, n_points=npts, views=5, span=span)
+    po, xo, so = oracle.ba_solve(*_args(w), 1.0, 4)
+    res = {}
+    for mode in ("pairs", "points"):
+        if mode == "pairs":
+            monkeypatch.setenv("PMV_BA_FORCE_PAIRS", "1")
+        else:
+            monkeypatch.delenv("PMV_BA_FORCE_PAIRS", raising=False)
+        prob = ctx.ba_problem(*_args(w), 1.0)
+        prob.solve(4)
+        p, x, s = prob.download()
+        prob.close()
+        res[mode] = (p, x, s[0])
+        assert s[0]["iterations"] == so["iterations"]
+        assert abs(s[0]["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]
+        assert np.abs(p[0] - po).max() < 1e-5
+    assert abs(res["pairs"][2]["final_cost"] - res["points"][2]["final_cost"]) <= 1e-9 * so["final_cost"]
+
+
 def test_resident_problem_reset_and_errors(ctx, pmv, synth):
     w = synth.ba_window(9, n_poses=5, n_points=100)
     prob = ctx.ba_problem(*_args(w))
