@@ -178,8 +178,13 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
     }
     if (wp > 0) {
         const int by_pairs = p->nsegs > 0;
-        ba_point_schur_kernel<<<std::min((wp + 3) / 4, 148 * 32), 128, 0, s>>>(D, by_pairs ? 0 : 1);
-        PMV_LAUNCH_CHECK(ctx, "ba_point_schur_kernel");
+        if (by_pairs && D.No <= 8 * (long long)D.Np) {
+            ba_point_vinv_w1_kernel<8><<<std::min((wp + 15) / 16, 148 * 32), 128, 0, s>>>(D);
+            PMV_LAUNCH_CHECK(ctx, "ba_point_vinv_w1_kernel");
+        } else {
+            ba_point_schur_kernel<<<std::min((wp + 3) / 4, 148 * 32), 128, 0, s>>>(D, by_pairs ? 0 : 1);
+            PMV_LAUNCH_CHECK(ctx, "ba_point_schur_kernel");
+        }
         if (by_pairs) {
             ba_pair_schur_kernel<<<(p->nsegs + 3) / 4, 128, 0, s>>>(D, p->d_segs, p->nsegs, p->d_entries);
             PMV_LAUNCH_CHECK(ctx, "ba_pair_schur_kernel");
@@ -213,8 +218,13 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
     ba_cam_candidate_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D, p->sharded ? (p->rank == 0) : 1);
     PMV_LAUNCH_CHECK(ctx, "ba_cam_candidate_kernel");
     if (wp > 0) {
-        ba_backsub_kernel<<<std::min((wp + 3) / 4, 148 * 32), 128, 0, s>>>(D);
-        PMV_LAUNCH_CHECK(ctx, "ba_backsub_kernel");
+        if (W == 1 && (D.No >= 100000 || p->nsegs > 0) && D.No <= 8 * (long long)D.Np) {
+            ba_backsub_w1_kernel<8><<<std::min((wp + 15) / 16, 148 * 32), 128, 0, s>>>(D);
+            PMV_LAUNCH_CHECK(ctx, "ba_backsub_w1_kernel");
+        } else {
+            ba_backsub_kernel<<<std::min((wp + 3) / 4, 148 * 32), 128, 0, s>>>(D);
+            PMV_LAUNCH_CHECK(ctx, "ba_backsub_kernel");
+        }
     }
     if (p->sharded) {
         ba_pack_scalars_kernel<<<wblocks, 128, 0, s>>>(D, p->d_scal);

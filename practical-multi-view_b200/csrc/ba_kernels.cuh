@@ -397,6 +397,91 @@ __global__ void __launch_bounds__(128) ba_point_schur_kernel(const BADev D, cons
     if (gm_w >= 0 && lane == 0) atomic_max_pos_double(&D.st[gm_w].gmax, gm_acc);
 }
 
+// ---- single large problem (W == 1), few observations per point: G lanes per point instead of a whole warp ----
+// BAL-scale problems see every point from ~5 cameras; a warp per point leaves 27 of 32 lanes idle in the two
+// per-point kernels (1.5 ms each at 1 M points).  These variants put 32 / G points in a warp.
+template <int G>
+__device__ __forceinline__ double group_sum_d(double v)
+{
+#pragma unroll
+    for (int o = G / 2; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// V^-1, g, diag_p, scale_p and max |gradient| of every point (what ba_point_schur_kernel does before its pass 2)
+template <int G>
+__global__ void __launch_bounds__(128) ba_point_vinv_w1_kernel(const BADev D)
+{
+    BAState *st = &D.st[0];
+    if (st->done) return;
+    const bool lin = st->need_linearize != 0, scale_ready = st->scale_ready != 0;
+    const double radius = st->radius;
+    const int lane = threadIdx.x & 31, gl = lane % G, ppw = 32 / G;
+    const int nwarps = gridDim.x * 4;
+    double gm_acc = 0.0;
+    for (int base = (blockIdx.x * 4 + (threadIdx.x >> 5)) * ppw; base < D.Np; base += nwarps * ppw) {
+        const int wp = base + lane / G;
+        const bool valid = wp < D.Np;
+        const int o0 = valid ? D.pt_off[wp] : 0, o1 = valid ? D.pt_off[wp + 1] : 0;
+        const bool active = o1 > o0;
+        double a[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) a[k] = 0;
+        for (int i = o0 + gl; i < o1; i += G) {
+            double jp[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) jp[k] = D.Ljp[6 * (size_t)i + k];
+            const double r0 = D.Lr[2 * (size_t)i], r1 = D.Lr[2 * (size_t)i + 1];
+            a[0] += jp[0] * jp[0] + jp[3] * jp[3]; a[1] += jp[0] * jp[1] + jp[3] * jp[4]; a[2] += jp[0] * jp[2] + jp[3] * jp[5];
+            a[3] += jp[1] * jp[1] + jp[4] * jp[4]; a[4] += jp[1] * jp[2] + jp[4] * jp[5]; a[5] += jp[2] * jp[2] + jp[5] * jp[5];
+            a[6] += jp[0] * r0 + jp[3] * r1; a[7] += jp[1] * r0 + jp[4] * r1; a[8] += jp[2] * r0 + jp[5] * r1;
+        }
+#pragma unroll
+        for (int k = 0; k < 9; k++) a[k] = group_sum_d<G>(a[k]);
+        if (!active) continue;   // no shuffles below: groups of a warp may part here
+        double sp[3];
+        if (lin && !scale_ready) {
+            sp[0] = 1.0 / (1.0 + sqrt(a[0])); sp[1] = 1.0 / (1.0 + sqrt(a[3])); sp[2] = 1.0 / (1.0 + sqrt(a[5]));
+            if (gl == 0) { D.scale_p[3 * (size_t)wp] = sp[0]; D.scale_p[3 * (size_t)wp + 1] = sp[1]; D.scale_p[3 * (size_t)wp + 2] = sp[2]; }
+        } else {
+            sp[0] = D.scale_p[3 * (size_t)wp]; sp[1] = D.scale_p[3 * (size_t)wp + 1]; sp[2] = D.scale_p[3 * (size_t)wp + 2];
+        }
+        if (gl != 0) continue;
+        double V[6] = {a[0] * sp[0] * sp[0], a[1] * sp[0] * sp[1], a[2] * sp[0] * sp[2],
+                       a[3] * sp[1] * sp[1], a[4] * sp[1] * sp[2], a[5] * sp[2] * sp[2]};
+        const double g[3] = {a[6] * sp[0], a[7] * sp[1], a[8] * sp[2]};
+        double dp[3];
+        if (lin) {
+            dp[0] = fmin(fmax(V[0], 1e-6), 1e32); dp[1] = fmin(fmax(V[3], 1e-6), 1e32); dp[2] = fmin(fmax(V[5], 1e-6), 1e32);
+            D.diag_p[3 * (size_t)wp] = dp[0]; D.diag_p[3 * (size_t)wp + 1] = dp[1]; D.diag_p[3 * (size_t)wp + 2] = dp[2];
+            gm_acc = fmax(gm_acc, fmax(fabs(a[6]), fmax(fabs(a[7]), fabs(a[8]))));
+        } else {
+            dp[0] = D.diag_p[3 * (size_t)wp]; dp[1] = D.diag_p[3 * (size_t)wp + 1]; dp[2] = D.diag_p[3 * (size_t)wp + 2];
+        }
+        {
+            const double d0 = sqrt(dp[0] / radius), d1 = sqrt(dp[1] / radius), d2 = sqrt(dp[2] / radius);
+            V[0] += d0 * d0; V[3] += d1 * d1; V[5] += d2 * d2;
+        }
+        double Vi[6];
+        {
+            const double l00 = sqrt(V[0]), l10 = V[1] / l00, l20 = V[2] / l00;
+            const double l11 = sqrt(V[3] - l10 * l10), l21 = (V[4] - l20 * l10) / l11;
+            const double l22 = sqrt(V[5] - l20 * l20 - l21 * l21);
+            const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
+            const double i10 = -l10 * i00 * i11, i21 = -l21 * i11 * i22, i20 = -(l20 * i00 + l21 * i10) * i22;
+            Vi[0] = i00 * i00 + i10 * i10 + i20 * i20; Vi[1] = i10 * i11 + i20 * i21; Vi[2] = i20 * i22;
+            Vi[3] = i11 * i11 + i21 * i21; Vi[4] = i21 * i22; Vi[5] = i22 * i22;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) D.Vinv[6 * (size_t)wp + k] = Vi[k];
+        D.gp[3 * (size_t)wp] = g[0]; D.gp[3 * (size_t)wp + 1] = g[1]; D.gp[3 * (size_t)wp + 2] = g[2];
+    }
+    // one atomic per warp
+    __syncwarp();
+    for (int o = 16; o; o >>= 1) gm_acc = fmax(gm_acc, __shfl_xor_sync(0xffffffffu, gm_acc, o));
+    if (lane == 0 && gm_acc > 0.0) atomic_max_pos_double(&st->gmax, gm_acc);
+}
+
 // ---- K9b': the same elimination organised by BLOCK of S instead of by point (one problem, W == 1) ---------
 // The host lists, for every co-observed camera pair (ci <= ck), the observation pairs (i, k) of the points
 // that see both (ba.cu: pair list).  One warp sums a segment of <= 512 such entries of ONE pair in registers,
@@ -678,6 +763,89 @@ __global__ void __launch_bounds__(128) ba_backsub_kernel(const BADev D)
     a_mc += mc; a_cc += cc; a_sn += sn; a_xn += xn;
     }   // grid-stride loop over points
     flush();
+}
+
+// back-substitution, W == 1, G lanes per point (see ba_point_vinv_w1_kernel)
+template <int G>
+__global__ void __launch_bounds__(128) ba_backsub_w1_kernel(const BADev D)
+{
+    BAState *st = &D.st[0];
+    if (st->done || !st->chol_ok) return;
+    const int lane = threadIdx.x & 31, gl = lane % G, ppw = 32 / G;
+    const int nwarps = gridDim.x * 4;
+    const double *yc = D.yc;
+    double a_mc = 0, a_cc = 0, a_sn = 0, a_xn = 0;
+    for (int base = (blockIdx.x * 4 + (threadIdx.x >> 5)) * ppw; base < D.Np; base += nwarps * ppw) {
+        const int wp = base + lane / G;
+        const bool valid = wp < D.Np;
+        const int o0 = valid ? D.pt_off[wp] : 0, o1 = valid ? D.pt_off[wp + 1] : 0;
+        const bool active = o1 > o0;
+        double sp[3] = {1.0, 1.0, 1.0};
+        if (active) { sp[0] = D.scale_p[3 * (size_t)wp]; sp[1] = D.scale_p[3 * (size_t)wp + 1]; sp[2] = D.scale_p[3 * (size_t)wp + 2]; }
+        double t0 = 0, t1 = 0, t2 = 0;
+        for (int i = o0 + gl; i < o1; i += G) {
+            const int ci = D.obs_cam[i];
+            const double *sc = D.scale_c + 6 * (size_t)ci;
+            double jy0 = 0, jy1 = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const double y = yc[6 * ci + k] * sc[k];
+                jy0 += D.Ljc[12 * (size_t)i + k] * y; jy1 += D.Ljc[12 * (size_t)i + 6 + k] * y;
+            }
+            t0 -= D.Ljp[6 * (size_t)i] * sp[0] * jy0 + D.Ljp[6 * (size_t)i + 3] * sp[0] * jy1;
+            t1 -= D.Ljp[6 * (size_t)i + 1] * sp[1] * jy0 + D.Ljp[6 * (size_t)i + 4] * sp[1] * jy1;
+            t2 -= D.Ljp[6 * (size_t)i + 2] * sp[2] * jy0 + D.Ljp[6 * (size_t)i + 5] * sp[2] * jy1;
+        }
+        t0 = group_sum_d<G>(t0); t1 = group_sum_d<G>(t1); t2 = group_sum_d<G>(t2);
+        double yp[3] = {0, 0, 0}, cand[3] = {0, 0, 0}, sn = 0, xn = 0;
+        if (active) {
+            t0 += D.gp[3 * (size_t)wp]; t1 += D.gp[3 * (size_t)wp + 1]; t2 += D.gp[3 * (size_t)wp + 2];
+            const double *Vi = D.Vinv + 6 * (size_t)wp;
+            yp[0] = Vi[0] * t0 + Vi[1] * t1 + Vi[2] * t2; yp[1] = Vi[1] * t0 + Vi[3] * t1 + Vi[4] * t2;
+            yp[2] = Vi[2] * t0 + Vi[4] * t1 + Vi[5] * t2;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const double x = D.points[3 * (size_t)wp + k];
+                cand[k] = x + (-yp[k] * sp[k]);
+                const double d = x - cand[k];
+                sn += d * d; xn += x * x;
+            }
+            if (gl < 3) D.cand_points[3 * (size_t)wp + gl] = cand[gl];
+        } else if (valid && gl < 3) {
+            D.cand_points[3 * (size_t)wp + gl] = D.points[3 * (size_t)wp + gl];   // inactive point: candidate = x
+        }
+        double mc = 0, cc = 0;
+        for (int i = o0 + gl; i < o1; i += G) {
+            const int ci = D.obs_cam[i];
+            const double *sc = D.scale_c + 6 * (size_t)ci;
+            double m0 = 0, m1 = 0;  // J * step, step = -y
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const double y = yc[6 * ci + k] * sc[k];
+                m0 -= D.Ljc[12 * (size_t)i + k] * y; m1 -= D.Ljc[12 * (size_t)i + 6 + k] * y;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const double y = yp[k] * sp[k];
+                m0 -= D.Ljp[6 * (size_t)i + k] * y; m1 -= D.Ljp[6 * (size_t)i + 3 + k] * y;
+            }
+            mc -= m0 * (D.Lr[2 * (size_t)i] + m0 / 2.0) + m1 * (D.Lr[2 * (size_t)i + 1] + m1 / 2.0);
+            double r[2];
+            ba_residual_only(D.cand_poses + 6 * (size_t)ci, cand, D.obs_xy[2 * (size_t)i], D.obs_xy[2 * (size_t)i + 1],
+                             D.fx, D.cx, D.fy, D.cy, r);
+            double rho0, rho1;
+            ba_huber(D.delta, r[0] * r[0] + r[1] * r[1], rho0, rho1);
+            cc += 0.5 * rho0;
+        }
+        a_mc += mc; a_cc += cc;                      // per-lane partial sums, reduced once at the end
+        if (gl == 0) { a_sn += sn; a_xn += xn; }     // once per point
+    }
+    __syncwarp();
+    a_mc = warp_sum_d(a_mc); a_cc = warp_sum_d(a_cc); a_sn = warp_sum_d(a_sn); a_xn = warp_sum_d(a_xn);
+    if (lane == 0) {
+        atomicAdd(&st->model_change, a_mc); atomicAdd(&st->cand_cost, a_cc);
+        atomicAdd(&st->step_norm2, a_sn); atomicAdd(&st->x_norm2, a_xn);
+    }
 }
 
 // ---- trust-region bookkeeping: one thread per window (Ceres TrustRegionMinimizer / LM strategy) --------
