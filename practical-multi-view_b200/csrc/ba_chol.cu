@@ -190,13 +190,15 @@ chol_update_kernel(double *S, double *b, int n, int k0, int t0 /* first trailing
     }
 }
 
-// U y = z from the bottom block row upwards; one CTA (1024 threads).  Per block row: 32 warps form the dot
+// U y = z from the bottom block row upwards; one CTA (512 threads).  Per block row: 16 warps form the dot
 // products with the known tail of y (inside the envelope), then one warp solves the 32x32 triangle.
 // For narrow envelopes (banded systems) the NB x (envelope) block row is copied into shared memory with
 // cp.async one step AHEAD (it does not depend on y), so the 188 dependent steps see no HBM/L2 latency.
 constexpr int BS_MAXW = 321;   // widest envelope (columns from k0) staged in shared memory; odd stride: no bank conflicts down a column
 
-__global__ void __launch_bounds__(1024)
+constexpr int BS_THREADS = 512;
+
+__global__ void __launch_bounds__(BS_THREADS)
 chol_backsub_kernel(const double *S, const double *z, double *y, int n, const int *__restrict__ lim, BAState *st, int staged)
 {
     extern __shared__ double sbuf[];            // staged: 2 x NB x BS_MAXW
@@ -208,7 +210,7 @@ chol_backsub_kernel(const double *S, const double *z, double *y, int n, const in
     if (tid == 0) fin = 1;
     auto stage = [&](int kb, double *dst) {
         const int k0 = kb * NB, nb = min(NB, n - k0), wdt = min(n, lim[kb]) - k0;
-        for (int i = tid; i < nb * wdt; i += 1024) {
+        for (int i = tid; i < nb * wdt; i += BS_THREADS) {
             const int r = i / wdt, c = i - r * wdt;
             if (c >= r) {
                 const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + r * BS_MAXW + c);
@@ -217,24 +219,56 @@ chol_backsub_kernel(const double *S, const double *z, double *y, int n, const in
         }
         asm volatile("cp.async.commit_group;");
     };
-    if (staged) stage(nblk - 1, sbuf + ((nblk - 1) & 1 ? NB * BS_MAXW : 0));
+    if (staged) {
+        // banded system: block rows staged one step ahead, the known tail of y in a shared-memory ring, and a
+        // branch-free triangle solve (row in registers, reciprocal diagonal, ~46 cycles per unknown)
+        double *ysm = sbuf + 2 * NB * BS_MAXW;   // ring of the last 512 unknowns, indexed by column & 511
+        stage(nblk - 1, sbuf + ((nblk - 1) & 1 ? NB * BS_MAXW : 0));
+        for (int kb = nblk - 1; kb >= 0; kb--) {
+            const int k0 = kb * NB, nb = min(NB, n - k0);
+            const int wdt = min(n, lim[kb]) - k0;   // U_kj == 0 beyond the envelope
+            if (kb > 0) stage(kb - 1, sbuf + ((kb - 1) & 1 ? NB * BS_MAXW : 0));
+            if (kb > 0) asm volatile("cp.async.wait_group 1;"); else asm volatile("cp.async.wait_group 0;");
+            __syncthreads();   // block row kb landed; the triangle of step kb + 1 has published its unknowns
+            const double *U = sbuf + (kb & 1 ? NB * BS_MAXW : 0);
+            // warp 0 takes its triangle rows into registers BEFORE the barrier below: afterwards the other warps
+            // run ahead and refill this buffer's twin, and the triangle must not touch shared block rows any more
+            double urow[NB], myinv = 0.0;
+            if (warp == 0) {
+#pragma unroll
+                for (int r = 0; r < NB; r++) urow[r] = (lane < nb && r < nb && r > lane) ? U[lane * BS_MAXW + r] : 0.0;
+                myinv = lane < nb ? 1.0 / U[lane * BS_MAXW + lane] : 0.0;
+            }
+            for (int row = warp; row < nb; row += BS_THREADS / 32) {
+                double sacc = 0;
+                for (int c = nb + lane; c < wdt; c += 32) sacc += U[row * BS_MAXW + c] * ysm[(k0 + c) & 511];
+                for (int o = 16; o; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+                if (lane == 0) yk[row] = z[k0 + row] - sacc;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                // lane l keeps unknown l; rows >= nb of a partial last block are inert
+                double mine = lane < nb ? yk[lane] : 0.0;
+#pragma unroll
+                for (int r = NB - 1; r >= 0; r--) {
+                    const double v = __shfl_sync(0xffffffffu, mine * myinv, r);
+                    const double upd = fma(-urow[r], v, mine);
+                    mine = (lane == r) ? v : ((lane < r) ? upd : mine);
+                }
+                if (!isfinite(mine)) fin = 0;
+                if (lane < nb) { y[k0 + lane] = mine; ysm[(k0 + lane) & 511] = mine; }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && !fin) st->chol_ok = 0;
+        return;
+    }
     for (int kb = nblk - 1; kb >= 0; kb--) {
         const int k0 = kb * NB, nb = min(NB, n - k0);
         const int cend = min(n, lim[kb]);   // U_kj == 0 beyond the envelope
-        const double *U = nullptr;
-        if (staged) {
-            if (kb > 0) stage(kb - 1, sbuf + ((kb - 1) & 1 ? NB * BS_MAXW : 0));
-            if (kb > 0) asm volatile("cp.async.wait_group 1;"); else asm volatile("cp.async.wait_group 0;");
-            __syncthreads();
-            U = sbuf + (kb & 1 ? NB * BS_MAXW : 0);
-        }
         if (warp < nb) {
             double sacc = 0;
-            if (staged) {
-                for (int c = nb + lane; c < cend - k0; c += 32) sacc += U[warp * BS_MAXW + c] * y[k0 + c];
-            } else {
-                for (int c = k0 + nb + lane; c < cend; c += 32) sacc += S[(size_t)(k0 + warp) * n + c] * y[c];
-            }
+            for (int c = k0 + nb + lane; c < cend; c += 32) sacc += S[(size_t)(k0 + warp) * n + c] * y[c];
             for (int o = 16; o; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
             if (lane == 0) yk[warp] = z[k0 + warp] - sacc;
         }
@@ -243,10 +277,10 @@ chol_backsub_kernel(const double *S, const double *z, double *y, int n, const in
             // lane r keeps row r's unknown; column r of the triangle is read as needed
             double mine = lane < nb ? yk[lane] : 0.0;
             for (int r = nb - 1; r >= 0; r--) {
-                const double urr = staged ? U[r * BS_MAXW + r] : S[(size_t)(k0 + r) * n + k0 + r];
+                const double urr = S[(size_t)(k0 + r) * n + k0 + r];
                 const double v = __shfl_sync(0xffffffffu, mine, r) / urr;
                 if (lane == r) { mine = v; if (!isfinite(v)) fin = 0; }
-                else if (lane < r) mine -= (staged ? U[lane * BS_MAXW + r] : S[(size_t)(k0 + lane) * n + k0 + r]) * v;
+                else if (lane < r) mine -= S[(size_t)(k0 + lane) * n + k0 + r] * v;
             }
             if (lane < nb) y[k0 + lane] = mine;
         }
@@ -300,10 +334,10 @@ int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_
             int maxw = 0;
             for (int k0 = 0, kb = 0; k0 < n; k0 += NB, kb++) maxw = std::max(maxw, (lim_host ? std::min(n, lim_host[kb]) : n) - k0);
             const int staged = (maxw <= BS_MAXW) && !getenv("PMV_CHOL_NO_STAGE");
-            const size_t smem = staged ? sizeof(double) * 2 * NB * BS_MAXW : 0;
+            const size_t smem = staged ? sizeof(double) * (2 * NB * BS_MAXW + 512) : 0;
             static bool attr = false;
             if (!attr) { cudaFuncSetAttribute(chol_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-            chol_backsub_kernel<<<1, 1024, smem, s>>>(S, b, y, n, D.chol_lim, st, staged);
+            chol_backsub_kernel<<<1, BS_THREADS, smem, s>>>(S, b, y, n, D.chol_lim, st, staged);
             PMV_LAUNCH_CHECK(ctx, "chol_backsub_kernel");
         }
     }
