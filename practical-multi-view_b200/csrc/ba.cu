@@ -154,8 +154,13 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
         ba_linearize_kernel<<<(D.No + 127) / 128, 128, 0, s>>>(D);
         PMV_LAUNCH_CHECK(ctx, "ba_linearize_kernel");
     }
-    ba_cam_accumulate_kernel<<<(wc + 3) / 4, 128, 0, s>>>(D, p->d_Uraw);
-    PMV_LAUNCH_CHECK(ctx, "ba_cam_accumulate_kernel");
+    if (D.No >= 256LL * wc) {   // hundreds to thousands of observations per camera: a CTA per camera
+        ba_cam_accumulate_wide_kernel<<<wc, 256, 0, s>>>(D, p->d_Uraw);
+        PMV_LAUNCH_CHECK(ctx, "ba_cam_accumulate_wide_kernel");
+    } else {
+        ba_cam_accumulate_kernel<<<(wc + 3) / 4, 128, 0, s>>>(D, p->d_Uraw);
+        PMV_LAUNCH_CHECK(ctx, "ba_cam_accumulate_kernel");
+    }
     const double *Uraw = p->d_Uraw;
     if (p->sharded) {
         ba_pack_cost_kernel<<<wblocks, 128, 0, s>>>(D, p->d_Uraw + 27 * (size_t)wc);

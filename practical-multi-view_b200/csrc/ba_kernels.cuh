@@ -213,6 +213,48 @@ __global__ void __launch_bounds__(128) ba_cam_accumulate_kernel(const BADev D, d
     }
 }
 
+// Same sums for cameras with thousands of observations (BAL scale: 5 000 per camera): one CTA of 8 warps per
+// (window, camera) and a shared-memory reduction -- a single warp per camera leaves the GPU at 7 warps per SM
+// walking 156 dependent gathers each (0.69 ms at 1 000 cameras x 5 M observations).
+__global__ void __launch_bounds__(256) ba_cam_accumulate_wide_kernel(const BADev D, double *__restrict__ Uraw)
+{
+    __shared__ double part[8][27];
+    const int wc = blockIdx.x;
+    const int w = wc / D.Nc, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const BAState *st = &D.st[w];
+    if (st->done || !st->need_linearize) return;
+    double acc[27];
+#pragma unroll
+    for (int k = 0; k < 27; k++) acc[k] = 0;
+    for (int j = D.cam_off[wc] + threadIdx.x; j < D.cam_off[wc + 1]; j += 256) {
+        const size_t i = D.cam_obs[j];
+        double jc[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) jc[k] = D.Ljc[12 * i + k];
+        const double r0 = D.Lr[2 * i], r1 = D.Lr[2 * i + 1];
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+#pragma unroll
+            for (int b = a; b < 6; b++) acc[t++] += jc[a] * jc[b] + jc[6 + a] * jc[6 + b];
+        }
+#pragma unroll
+        for (int a = 0; a < 6; a++) acc[21 + a] += jc[a] * r0 + jc[6 + a] * r1;
+    }
+#pragma unroll
+    for (int k = 0; k < 27; k++) {
+        acc[k] = warp_sum_d(acc[k]);
+        if (lane == 0) part[warp][k] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 27) {
+        double v = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) v += part[q][threadIdx.x];
+        Uraw[27 * (size_t)wc + threadIdx.x] = v;
+    }
+}
+
 // finalize per camera (after the optional cross-rank reduction of Uraw): Jacobi scale, LM diagonal,
 // scaled U (36) and gradient.  One thread per (window, camera).
 __global__ void __launch_bounds__(128) ba_cam_finalize_kernel(const BADev D, const double *__restrict__ Uraw)
@@ -491,7 +533,7 @@ __global__ void __launch_bounds__(128) ba_point_vinv_w1_kernel(const BADev D)
 // rhs_ci -= W_i V^-1 g.  Needs V^-1 and g of every point (ba_point_schur_kernel with pass2 = 0).
 struct BAPairSeg { int ci, ck, begin, end; };
 
-__global__ void __launch_bounds__(128) ba_pair_schur_kernel(const BADev D, const BAPairSeg *__restrict__ segs, int nsegs,
+__global__ void __launch_bounds__(128, 3) ba_pair_schur_kernel(const BADev D, const BAPairSeg *__restrict__ segs, int nsegs,
                                                             const int2 *__restrict__ entries)
 {
     const int lane = threadIdx.x & 31;
