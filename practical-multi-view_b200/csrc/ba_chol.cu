@@ -208,14 +208,20 @@ chol_backsub_kernel(const double *S, const double *z, double *y, int n, const in
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nblk = (n + NB - 1) / NB;
     if (tid == 0) fin = 1;
+    double *zs_base = staged ? sbuf + 2 * NB * BS_MAXW + 512 : nullptr;   // [2][NB] staged right-hand sides
     auto stage = [&](int kb, double *dst) {
         const int k0 = kb * NB, nb = min(NB, n - k0), wdt = min(n, lim[kb]) - k0;
-        for (int i = tid; i < nb * wdt; i += BS_THREADS) {
-            const int r = i / wdt, c = i - r * wdt;
-            if (c >= r) {
-                const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + r * BS_MAXW + c);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(S + (size_t)(k0 + r) * n + k0 + c));
-            }
+        // 16 threads per row, no index arithmetic beyond an add (an i / wdt per element cost more than the copy)
+        const int r = tid >> 4;
+        if (r < nb) {
+            const double *src = S + (size_t)(k0 + r) * n + k0;
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + r * BS_MAXW);
+            for (int c = r + (tid & 15); c < wdt; c += 16)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + 8u * c), "l"(src + c));
+        }
+        if (zs_base && tid < nb) {   // the right-hand side of the block row rides along (no L2 round trip per step)
+            const unsigned za = (unsigned)__cvta_generic_to_shared(zs_base + (kb & 1) * NB + tid);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(za), "l"(z + k0 + tid));
         }
         asm volatile("cp.async.commit_group;");
     };
@@ -243,7 +249,7 @@ chol_backsub_kernel(const double *S, const double *z, double *y, int n, const in
                 double sacc = 0;
                 for (int c = nb + lane; c < wdt; c += 32) sacc += U[row * BS_MAXW + c] * ysm[(k0 + c) & 511];
                 for (int o = 16; o; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-                if (lane == 0) yk[row] = z[k0 + row] - sacc;
+                if (lane == 0) yk[row] = zs_base[(kb & 1) * NB + row] - sacc;
             }
             __syncthreads();
             if (warp == 0) {
@@ -334,7 +340,7 @@ int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_
             int maxw = 0;
             for (int k0 = 0, kb = 0; k0 < n; k0 += NB, kb++) maxw = std::max(maxw, (lim_host ? std::min(n, lim_host[kb]) : n) - k0);
             const int staged = (maxw <= BS_MAXW) && !getenv("PMV_CHOL_NO_STAGE");
-            const size_t smem = staged ? sizeof(double) * (2 * NB * BS_MAXW + 512) : 0;
+            const size_t smem = staged ? sizeof(double) * (2 * NB * BS_MAXW + 512 + 2 * NB) : 0;
             static bool attr = false;
             if (!attr) { cudaFuncSetAttribute(chol_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
             chol_backsub_kernel<<<1, BS_THREADS, smem, s>>>(S, b, y, n, D.chol_lim, st, staged);
