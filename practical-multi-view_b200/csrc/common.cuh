@@ -70,6 +70,18 @@ struct PyrLevel {
     int bxl;     // allocated bytes left of interior column 0 (>= border + 4, multiple of 16)
 };
 
+// Scharr derivative of one level for a batch of images, as OpenCV's derivative pyramid keeps it: one packed
+// word per pixel (dI/dx in the low, dI/dy in the high 16 bits), ZERO outside the image for `border` pixels on
+// all sides.  ptr = pixel (0, 0) of image 0; pitch / img_stride in words; rows 128 B aligned.
+struct DerivLevel {
+    const int *ptr;
+    int pitch;
+    size_t img_stride;
+};
+struct DerivSet {
+    DerivLevel lv[PMV_MAX_PYR_LEVELS];
+};
+
 struct PyrSet {  // all levels of one image batch
     PyrLevel lv[PMV_MAX_PYR_LEVELS];
     int top = 0;  // effective max level
@@ -107,6 +119,8 @@ struct pmv_ctx {
     // workspaces
     DevBuf img[2];    // uploaded level-0 images (prev / next)
     DevBuf pyr[2];    // reduced levels (prev / next)
+    DevBuf deriv;     // Scharr derivative levels of the prev images (LK)
+    unsigned long long deriv_sig = 0;   // geometry the zero borders of `deriv` were written for
     DevBuf pts[4];    // prev_xy, next_xy, status, err
     DevBuf scratch[8];
     PinBuf pin[4];
@@ -166,3 +180,7 @@ int pmv_internal_pyr_plan(pmv_ctx *ctx, int which, int batch, int rows, int cols
 // (src == nullptr), fill its border, then build levels 1..top with their borders.
 int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, const uint8_t *d_src, const uint8_t *d_src2,
                          int src_pitch, size_t src_stride, cudaStream_t s);
+// Plan (and zero, when the geometry changed) derivative storage matching the levels of `set`; then compute
+// the derivatives of all levels of `batch` images (borders of `set` must be filled).
+int pmv_internal_deriv_plan(pmv_ctx *ctx, const PyrSet &set, int batch, DerivSet *out, cudaStream_t s);
+int pmv_internal_deriv_run(pmv_ctx *ctx, const PyrSet &set, const DerivSet &d, int batch, cudaStream_t s);

@@ -30,6 +30,7 @@ constexpr int LK_M = 4;       // drift margin (px) of the staged next-image wind
 struct LKParams {
     PyrLevel prev[PMV_MAX_PYR_LEVELS];
     PyrLevel next[PMV_MAX_PYR_LEVELS];
+    DerivLevel dprev[PMV_MAX_PYR_LEVELS];   // Scharr derivative of prev (scharr_level_kernel), zero outside the image
     int top;
     const float *prev_xy;
     float *next_xy;
@@ -117,8 +118,8 @@ lk_track_kernel(const LKParams P)
 
     uint8_t *ws = smem + (size_t)warp * P.smem_per_warp;
     const int pp = P.pp, jp = P.jp, dp = w + 1;
-    uint8_t *ps = ws;                                            // prev patch (h+3) rows x pp bytes
-    int *ds = reinterpret_cast<int *>(ws + (h + 3) * pp);        // derivs (h+1) x (w+1), short2 packed
+    uint8_t *ps = ws;                                            // prev patch (h+1) rows x pp bytes
+    int *ds = reinterpret_cast<int *>(ws + (h + 1) * pp);        // derivs (h+1) x (w+1), short2 packed
     uint8_t *js = ws;                                            // next window, aliases ps/ds
     const int jw = w + 1 + 2 * LK_M, jh = h + 1 + 2 * LK_M;
 
@@ -169,37 +170,24 @@ lk_track_kernel(const LKParams P)
         int iw00, iw01, iw10, iw11;
         bilinear_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), iw00, iw01, iw10, iw11);
 
-        // ---- 1. stage prev patch: image rows ipy-1.., cols ipx-1.. ((h+3) x (w+3)) -----------
+        // ---- 1. stage the bilinear support of the template: prev patch and its Scharr derivative, rows
+        //         ipy.., cols ipx.. ((h+1) x (w+1)).  The derivative comes from the per-level plane built once
+        //         per image (scharr_level_kernel) -- as OpenCV's derivative pyramid, zero outside the image;
+        //         computing it here per feature cost 22 % of this kernel's instructions.
         __syncwarp();
-        const int pmis = stage_region(reinterpret_cast<uint32_t *>(ps), pp >> 2, Iimg, I.pitch,
-                                      ipx - 1, ipy - 1, w + 3, h + 3, lane);
-        __syncwarp();
-        // ---- 2. Scharr derivative on the bilinear support (zero outside the image) ------
-        // Lane = column of the staged patch, rows stream through a 3-deep register window; the
-        // horizontal neighbours come from shuffles (separable: t0 = 3(a+c)+10b, t1 = c-a per column).
-        for (int c0 = 0; c0 < w + 1; c0 += 30) {
-            const int pc = c0 + lane;                         // patch column held by this lane
-            const bool cin = pc < w + 3;
-            const uint8_t *col = ps + pmis + (cin ? pc : 0);
-            int v0 = col[0], v1 = col[pp];
-            const int xx = ipx + pc;                           // image x of the derivative this lane OUTPUTS
-            const bool xin = lane < 30 && pc < w + 1 && xx >= 0 && xx < I.cols;
-            for (int r = 0; r < h + 1; r++) {
-                const int v2 = col[(r + 2) * pp];
-                const int t0 = 3 * (v0 + v2) + 10 * v1, t1 = v2 - v0;
-                const int t0r = __shfl_down_sync(0xffffffffu, t0, 2);
-                const int t1m = __shfl_down_sync(0xffffffffu, t1, 1);
-                const int t1r = __shfl_down_sync(0xffffffffu, t1, 2);
-                const int yy = ipy + r;
-                if (lane < 30 && pc < w + 1) {
-                    int packed = 0;
-                    if (xin && yy >= 0 && yy < I.rows) {
-                        const int gx = t0r - t0, gy = 3 * (t1 + t1r) + 10 * t1m;
-                        packed = (gx & 0xffff) | (int)((unsigned)gy << 16);
-                    }
-                    ds[r * dp + pc] = packed;
+        const int pmis = stage_region(reinterpret_cast<uint32_t *>(ps), pp >> 2, Iimg, I.pitch, ipx, ipy, w + 1, h + 1, lane);
+        {
+            const DerivLevel &DL = P.dprev[level];
+            const int *dsrc = DL.ptr + (size_t)b * DL.img_stride + (ptrdiff_t)ipy * DL.pitch + ipx;
+            for (int c0 = 0; c0 < dp; c0 += 32) {
+                const int pc = c0 + lane;
+                if (pc < dp) {
+                    // plain load -> store loop with pointer increments: this kernel is instruction-issue bound and
+                    // 16 resident warps hide the latency (batching the loads in registers was slower)
+                    const int *src = dsrc + pc;
+                    int *dst = ds + pc;
+                    for (int r = 0; r <= h; r++) { *dst = __ldg(src); src += DL.pitch; dst += dp; }
                 }
-                v0 = v1; v1 = v2;
             }
         }
         __syncwarp();
@@ -209,7 +197,7 @@ lk_track_kernel(const LKParams P)
         for (int k = 0; k < KPIX; k++) {
             const int t = s_tab[lane + 32 * k];
             const int y = t >> 8, x = t & 255;
-            const uint8_t *q = ps + (y + 1) * pp + pmis + (x + 1);
+            const uint8_t *q = ps + y * pp + pmis + x;
             int ival = (q[0] * iw00 + q[1] * iw01 + q[pp] * iw10 + q[pp + 1] * iw11 + (1 << 8)) >> 9;
             const int *d = ds + y * dp + x;
             int d00 = d[0], d01 = d[1], d10 = d[dp], d11 = d[dp + 1];
@@ -371,17 +359,17 @@ int check_lk_args(pmv_ctx *ctx, int rows, int cols, int step, int n, int win_w, 
 // prev and next image sets share ONE bordered allocation of 2*batch images (prev = [0, batch),
 // next = [batch, 2*batch)), so import / pyrDown / border fill run once per step for both.
 int lk_plan(pmv_ctx *ctx, int batch, int rows, int cols, int win_w, int win_h, int max_level,
-            PyrSet *sp, PyrSet *sn)
+            PyrSet *sp, PyrSet *sn, DerivSet *dv, cudaStream_t s)
 {
     const int border = (win_w > win_h ? win_w : win_h) + LK_M + 2;
     int rc = pmv_internal_pyr_plan(ctx, 0, 2 * batch, rows, cols, border, win_w, win_h, max_level, sp);
     if (rc) return rc;
     *sn = *sp;
     for (int l = 0; l <= sp->top; l++) sn->lv[l].ptr = sp->lv[l].ptr + (size_t)batch * sp->lv[l].img_stride;
-    return PMV_OK;
+    return pmv_internal_deriv_plan(ctx, *sp, batch, dv, s);
 }
 
-int lk_enqueue(pmv_ctx *ctx, const PyrSet &sp, const PyrSet &sn, const uint8_t *d_prev, const uint8_t *d_next,
+int lk_enqueue(pmv_ctx *ctx, const PyrSet &sp, const PyrSet &sn, const DerivSet &dv, const uint8_t *d_prev, const uint8_t *d_next,
                int batch, size_t img_stride, int pitch, const float *d_prev_xy, int n, int win_w, int win_h,
                int max_count, double eps, int flags, double min_eig_thr,
                float *d_next_xy, uint8_t *d_status, float *d_err, cudaStream_t s)
@@ -398,12 +386,16 @@ int lk_enqueue(pmv_ctx *ctx, const PyrSet &sp, const PyrSet &sn, const uint8_t *
             rc = pmv_internal_pyr_run(ctx, sn, batch, d_next, nullptr, pitch, img_stride, s);
             if (rc) return rc;
         }
+        if (n > 0) {
+            rc = pmv_internal_deriv_run(ctx, sp, dv, batch, s);
+            if (rc) return rc;
+        }
     }
     if (n == 0) return PMV_OK;
     ProfScope pl(ctx, PMV_PHASE_LK, s);
     LKParams P;
     memset(&P, 0, sizeof P);
-    for (int l = 0; l <= sp.top; l++) { P.prev[l] = sp.lv[l]; P.next[l] = sn.lv[l]; }
+    for (int l = 0; l <= sp.top; l++) { P.prev[l] = sp.lv[l]; P.next[l] = sn.lv[l]; P.dprev[l] = dv.lv[l]; }
     P.top = sp.top;
     P.prev_xy = d_prev_xy; P.next_xy = d_next_xy; P.status = d_status; P.err = d_err;
     P.n = n; P.win_w = win_w; P.win_h = win_h;
@@ -412,9 +404,9 @@ int lk_enqueue(pmv_ctx *ctx, const PyrSet &sp, const PyrSet &sn, const uint8_t *
     if (eps < 0) eps = 0;
     if (eps > 10) eps = 10;
     P.max_count = max_count; P.eps2 = eps * eps; P.flags = flags; P.min_eig = (float)min_eig_thr;
-    P.pp = align_up(3 + win_w + 3 + 3, 4);
+    P.pp = align_up(3 + win_w + 1 + 3, 4);
     P.jp = align_up(3 + win_w + 1 + 2 * LK_M + 3, 4);
-    int tmpl = (win_h + 3) * P.pp + (win_h + 1) * (win_w + 1) * 4;
+    int tmpl = (win_h + 1) * P.pp + (win_h + 1) * (win_w + 1) * 4;
     int jwin = (win_h + 1 + 2 * LK_M) * P.jp;
     P.smem_per_warp = align_up(tmpl > jwin ? tmpl : jwin, 16);
     const int kmax = (win_w * win_h + 31) / 32;
@@ -447,9 +439,10 @@ PMV_API int pmv_lk_track_batched_dev(pmv_ctx *ctx, const uint8_t *d_prev, const 
     if (img_stride < (size_t)rows * step) return ctx->fail(PMV_ERR_INVALID, "lk: img_stride < rows*step");
     cudaSetDevice(ctx->device);
     PyrSet sp, sn;
-    rc = lk_plan(ctx, batch, rows, cols, win_w, win_h, max_level, &sp, &sn);
+    DerivSet dv;
+    rc = lk_plan(ctx, batch, rows, cols, win_w, win_h, max_level, &sp, &sn, &dv, ctx->stream);
     if (rc) return rc;
-    return lk_enqueue(ctx, sp, sn, d_prev, d_next, batch, img_stride, step, d_prev_xy, n, win_w, win_h,
+    return lk_enqueue(ctx, sp, sn, dv, d_prev, d_next, batch, img_stride, step, d_prev_xy, n, win_w, win_h,
                       max_count, eps, flags, min_eig_thr, d_next_xy, d_status, d_err, ctx->stream);
 }
 
@@ -472,7 +465,8 @@ PMV_API int pmv_lk_track_batched(pmv_ctx *ctx, const uint8_t *prev, const uint8_
     const int CH = batch <= 8 ? batch : 32;
     const int nchunks = (batch + CH - 1) / CH;
     PyrSet sp, sn;
-    rc = lk_plan(ctx, CH, rows, cols, win_w, win_h, max_level, &sp, &sn);
+    DerivSet dv;
+    rc = lk_plan(ctx, CH, rows, cols, win_w, win_h, max_level, &sp, &sn, &dv, ctx->stream);
     if (rc) return rc;
     const size_t raw_bytes = (size_t)batch * img_stride;
     cudaError_t e = ctx->pts[0].reserve((size_t)batch * n * 8 + 8);
@@ -508,7 +502,7 @@ PMV_API int pmv_lk_track_batched(pmv_ctx *ctx, const uint8_t *prev, const uint8_
             PMV_CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[c], cs));
             PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->chunk_ev[c], 0));
         }
-        rc = lk_enqueue(ctx, sp, sn, rawP + off, rawN + off, nb, img_stride, step, dpx + (size_t)b0 * n * 2, n, win_w,
+        rc = lk_enqueue(ctx, sp, sn, dv, rawP + off, rawN + off, nb, img_stride, step, dpx + (size_t)b0 * n * 2, n, win_w,
                         win_h, max_count, eps, flags, min_eig_thr, dnx + (size_t)b0 * n * 2, dst + (size_t)b0 * n,
                         der + (size_t)b0 * n, s);
         if (rc) return rc;

@@ -203,7 +203,81 @@ scharr_kernel(const uint8_t *__restrict__ src, int rows, int cols, int pitch, sh
     dst[(size_t)y * cols + x] = make_short2((short)(t0p - t0m), (short)(3 * (t1m + t1p) + 10 * t1c));
 }
 
+// K2 for the LK tracker: derivative of every pixel of a bordered level, 4 pixels per thread (three aligned
+// words per input row, one 16 B store).  Reads run 1 px into the reflect-101 border of the level, so the
+// values at the image edge are OpenCV's; pixels beyond the last column are written as zero (they belong
+// to the zero border of the derivative plane).
+__global__ void __launch_bounds__(256)
+scharr_level_kernel(const uint8_t *__restrict__ img, int rows, int cols, int pitch, size_t istride,
+                    int *__restrict__ der, int dpitch, size_t dstride)
+{
+    const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x0 >= cols || y >= rows) return;
+    const uint8_t *base = img + (size_t)blockIdx.z * istride + (size_t)(y - 1) * pitch + x0 - 4;
+    uint32_t wv[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) wv[r][k] = *reinterpret_cast<const uint32_t *>(base + (size_t)r * pitch + 4 * k);
+    int t0[6], t1[6];   // columns x0 - 1 .. x0 + 4
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        const int bi = c + 3;   // byte index in the 12-byte row
+        const int a0 = (wv[0][bi >> 2] >> (8 * (bi & 3))) & 255, a1 = (wv[1][bi >> 2] >> (8 * (bi & 3))) & 255,
+                  a2 = (wv[2][bi >> 2] >> (8 * (bi & 3))) & 255;
+        t0[c] = 3 * (a0 + a2) + 10 * a1;
+        t1[c] = a2 - a0;
+    }
+    int out[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int gx = t0[k + 2] - t0[k], gy = 3 * (t1[k] + t1[k + 2]) + 10 * t1[k + 1];
+        out[k] = (x0 + k < cols) ? ((gx & 0xffff) | (int)((unsigned)gy << 16)) : 0;
+    }
+    *reinterpret_cast<int4 *>(der + (size_t)blockIdx.z * dstride + (size_t)y * dpitch + x0) = make_int4(out[0], out[1], out[2], out[3]);
+}
+
 }  // namespace
+
+int pmv_internal_deriv_plan(pmv_ctx *ctx, const PyrSet &set, int batch, DerivSet *out, cudaStream_t s)
+{
+    size_t total = 0, off[PMV_MAX_PYR_LEVELS];
+    unsigned long long sig = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
+    mix((unsigned long long)batch); mix((unsigned long long)set.top);
+    for (int l = 0; l <= set.top; l++) {
+        const PyrLevel &a = set.lv[l];
+        const int bd = a.border, bl = align_up(bd, 4);
+        const int pitch = align_up(bl + a.cols + bd + 4, 32);   // +4: the last 16 B store may run past the last column
+        const size_t stride = (size_t)pitch * (a.rows + 2 * bd);
+        off[l] = total + (size_t)bd * pitch + bl;
+        total += stride * batch;
+        out->lv[l] = DerivLevel{nullptr, pitch, stride};
+        mix((unsigned long long)a.rows); mix((unsigned long long)a.cols); mix((unsigned long long)bd);
+    }
+    const void *before = ctx->deriv.p;
+    cudaError_t e = ctx->deriv.reserve(total * 4 + 256);
+    if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "derivative workspace", e);
+    if (ctx->deriv.p != before || ctx->deriv_sig != sig) {   // new geometry: (re)write the zero borders
+        PMV_CUDA_TRY(ctx, cudaMemsetAsync(ctx->deriv.p, 0, total * 4, s));
+        ctx->deriv_sig = sig;
+    }
+    for (int l = 0; l <= set.top; l++) out->lv[l].ptr = ctx->deriv.as<int>() + off[l];
+    return PMV_OK;
+}
+
+int pmv_internal_deriv_run(pmv_ctx *ctx, const PyrSet &set, const DerivSet &d, int batch, cudaStream_t s)
+{
+    for (int l = 0; l <= set.top; l++) {
+        const PyrLevel &a = set.lv[l];
+        dim3 grid((a.cols + 255) / 256, (a.rows + 3) / 4, batch);
+        scharr_level_kernel<<<grid, 256, 0, s>>>(a.ptr, a.rows, a.cols, a.pitch, a.img_stride,
+                                                 const_cast<int *>(d.lv[l].ptr), d.lv[l].pitch, d.lv[l].img_stride);
+        PMV_LAUNCH_CHECK(ctx, "scharr_level_kernel");
+    }
+    return PMV_OK;
+}
 
 // ------------------------------------------------------------------ internal planning ---
 int pmv_internal_pyr_plan(pmv_ctx *ctx, int which, int batch, int rows, int cols, int border,
