@@ -40,7 +40,11 @@ BATCH = 256
 # compulsory bytes per frame pair = 2 pyramids read once + points in/out
 PYR_BYTES = H * W + 188 * 621 + 94 * 311 + 47 * 156          # 619 930
 ALG_BYTES_PER_PAIR_LK = 2 * PYR_BYTES + N_FEAT * 21           # 1 281 860
+# the Scharr derivative is materialised once per prev image level, as OpenCV does:
+# + 4 B/px read by the tracker; the pyramid group reads W*H, writes 3 levels and (prev images only) 4 B/px of derivative
+ALG_BYTES_PER_PAIR_LK_DERIV = ALG_BYTES_PER_PAIR_LK + 4 * PYR_BYTES   # 3 761 580
 ALG_BYTES_PER_IMAGE_PYR = PYR_BYTES                            # read W*H + write 3 levels
+ALG_BYTES_PER_PREV_IMAGE_DERIV = 5 * PYR_BYTES                 # Scharr: 1 B/px read + 4 B/px written, all levels
 
 
 def make_workload(rank: int, batch: int):
@@ -650,17 +654,17 @@ def main():
     lk_ms, lk_n = prof.get("lk", (0.0, 0))
     py_ms, py_n = prof.get("pyramid", (0.0, 0))
     lk_avg = lk_ms / max(lk_n, 1)
-    lk_bytes = ALG_BYTES_PER_PAIR_LK * batch
+    lk_bytes = ALG_BYTES_PER_PAIR_LK_DERIV * batch
     lk_ach = lk_bytes / (lk_avg * 1e-3) / 1e9 if lk_avg else None
     py_avg = py_ms / max(py_n, 1)
-    py_bytes = ALG_BYTES_PER_IMAGE_PYR * 2 * batch
+    py_bytes = (ALG_BYTES_PER_IMAGE_PYR * 2 + ALG_BYTES_PER_PREV_IMAGE_DERIV) * batch
     py_ach = py_bytes / (py_avg * 1e-3) / 1e9 if py_avg else None
     # LK is bounded by instruction issue, not by HBM (SURVEY 8d asks for both figures): warp instructions per
     # feature and DRAM bytes per pair come from the ncu --set full capture of this kernel committed as
     # profiles/r1_lk_final_ncu_summary.txt (smsp__inst_executed.sum / 64 000 features; dram bytes / 32 pairs);
     # the issue peak is 148 SMs x 4 schedulers x 1 warp instruction per clock at the SM clock sampled during the run.
-    LK_WARP_INST_PER_FEATURE = 861060824 / 64000.0
-    LK_DRAM_BYTES_PER_PAIR = (48.039424e6 + 430.848e3) / 32.0
+    LK_WARP_INST_PER_FEATURE = 715446617 / 64000.0
+    LK_DRAM_BYTES_PER_PAIR = (132.067328e6 + 8.086784e6) / 32.0
     sm_hz = float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
     issue_peak = 148 * 4 * sm_hz
     issue_ach = LK_WARP_INST_PER_FEATURE * N_FEAT * batch / (lk_avg * 1e-3) if lk_avg else None
@@ -674,7 +678,7 @@ def main():
                 "avg_launch_ms": lk_avg, "algorithmic_bytes_per_launch": lk_bytes,
                 "share_of_step": lk_ms / ms if ms else None,
                 "note": "LK is integer-issue/LSU bound, not HBM bound (SURVEY §8d); HBM fraction reported as the contract asks",
-                "other_kernels": {"pyr_down_kernel(x6 launches/step)": {
+                "other_kernels": {"pyramid group (import x2, pyr_down x3, border_fill, scharr_level x4 per step)": {
                     "bound": "hbm", "achieved": py_ach, "peak": peak, "unit": "GB/s",
                     "frac": (py_ach / peak) if py_ach else None, "avg_group_ms": py_avg,
                     "algorithmic_bytes_per_group": py_bytes, "share_of_step": py_ms / ms if ms else None}}}

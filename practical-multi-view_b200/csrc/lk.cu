@@ -1,13 +1,16 @@
 // lk.cu -- K3: per-feature pyramidal Lucas-Kanade solve, one warp per feature.
 //
 // Replaces cv::calcOpticalFlowPyrLK as called at reference OpenCVLucasKanadeFM.cpp:15
-// (LKTrackerInvoker, SURVEY Appx A.3), with calcSharrDeriv (Appx A.2) fused in.
+// (LKTrackerInvoker, SURVEY Appx A.3); calcSharrDeriv (Appx A.2) runs once per image level in
+// scharr_level_kernel (pyramid.cu) and leaves OpenCV's derivative pyramid: packed (dI/dx | dI/dy << 16)
+// per pixel, zero outside the image.
 //
 // Design (B200): a warp owns one feature for ALL pyramid levels (one launch per batch, no
 // inter-level round trip through HBM).  Per level the warp
-//   1. stages the (w+3)x(h+3) u8 patch of the previous image in shared memory (reflect-101),
-//   2. computes the Scharr derivative at the (w+1)x(h+1) bilinear support on the fly
-//      (zero outside the image, exactly like OpenCV's zero-bordered derivative image),
+//   1. stages the (w+1)x(h+1) u8 patch of the previous image in shared memory (reflect-101 border
+//      of the level),
+//   2. stages the Scharr derivative of the same (w+1)x(h+1) bilinear support from the derivative
+//      plane (computing it per feature cost 22 % of this kernel's instructions),
 //   3. builds the template: 14-bit fixed-point bilinear samples of I, dI/dx, dI/dy kept in
 //      REGISTERS (pixel p = lane + 32k), structure tensor by exact per-lane int32 sums +
 //      REDUX warp reductions,
@@ -97,6 +100,13 @@ __device__ __forceinline__ int stage_region(uint32_t *dst, int spitch_words, con
     return mis;
 }
 
+// The dispatch picks the smallest KPIX in {4, 8, 11, 14, 17, 20, 24, 28, 32} that covers the window, so the
+// window has more than 32 * lk_kprev(KPIX) pixels: template slots k < lk_kprev(KPIX) hold a pixel in every lane.
+__host__ __device__ constexpr int lk_kprev(int kpix)
+{
+    return kpix <= 4 ? 0 : kpix <= 8 ? 4 : kpix <= 11 ? 8 : kpix <= 14 ? 11 : kpix <= 17 ? 14 : kpix <= 20 ? 17 : kpix <= 24 ? 20 : kpix <= 28 ? 24 : 28;
+}
+
 template <int KPIX>
 __global__ void __launch_bounds__(LK_WARPS * 32)
 lk_track_kernel(const LKParams P)
@@ -117,9 +127,11 @@ lk_track_kernel(const LKParams P)
     if (f >= P.n) return;  // warp-uniform; only __syncwarp below
 
     uint8_t *ws = smem + (size_t)warp * P.smem_per_warp;
-    const int pp = P.pp, jp = P.jp, dp = w + 1;
-    uint8_t *ps = ws;                                            // prev patch (h+1) rows x pp bytes
-    int *ds = reinterpret_cast<int *>(ws + (h + 1) * pp);        // derivs (h+1) x (w+1), short2 packed
+    // one pitch for all three staged buffers (jp bytes for the patches, jp words for the derivatives): pixel
+    // (y, x) sits at offset joff[k] = y * jp + x in each of them, so the template phase needs no table lookups
+    const int pp = P.jp, jp = P.jp, dp = P.jp;
+    uint8_t *ps = ws;                                            // prev patch (h+1) rows x jp bytes
+    int *ds = reinterpret_cast<int *>(ws + (h + 1) * pp);        // derivs (h+1) rows x jp words, short2 packed
     uint8_t *js = ws;                                            // next window, aliases ps/ds
     const int jw = w + 1 + 2 * LK_M, jh = h + 1 + 2 * LK_M;
 
@@ -179,9 +191,9 @@ lk_track_kernel(const LKParams P)
         {
             const DerivLevel &DL = P.dprev[level];
             const int *dsrc = DL.ptr + (size_t)b * DL.img_stride + (ptrdiff_t)ipy * DL.pitch + ipx;
-            for (int c0 = 0; c0 < dp; c0 += 32) {
+            for (int c0 = 0; c0 <= w; c0 += 32) {
                 const int pc = c0 + lane;
-                if (pc < dp) {
+                if (pc <= w) {
                     // plain load -> store loop with pointer increments: this kernel is instruction-issue bound and
                     // 16 resident warps hide the latency (batching the loads in registers was slower)
                     const int *src = dsrc + pc;
@@ -195,17 +207,15 @@ lk_track_kernel(const LKParams P)
         int sA11 = 0, sA12 = 0, sA22 = 0;
 #pragma unroll
         for (int k = 0; k < KPIX; k++) {
-            const int t = s_tab[lane + 32 * k];
-            const int y = t >> 8, x = t & 255;
-            const uint8_t *q = ps + y * pp + pmis + x;
+            const uint8_t *q = ps + pmis + joff[k];
             int ival = (q[0] * iw00 + q[1] * iw01 + q[pp] * iw10 + q[pp + 1] * iw11 + (1 << 8)) >> 9;
-            const int *d = ds + y * dp + x;
+            const int *d = ds + joff[k];
             int d00 = d[0], d01 = d[1], d10 = d[dp], d11 = d[dp + 1];
             int ix = ((int)(short)d00 * iw00 + (int)(short)d01 * iw01 + (int)(short)d10 * iw10 +
                       (int)(short)d11 * iw11 + (1 << 13)) >> 14;
             int iy = ((d00 >> 16) * iw00 + (d01 >> 16) * iw01 + (d10 >> 16) * iw10 +
                       (d11 >> 16) * iw11 + (1 << 13)) >> 14;
-            if (!((valid >> k) & 1)) { ival = 0; ix = 0; iy = 0; }
+            if (k >= lk_kprev(KPIX) && !((valid >> k) & 1)) { ival = 0; ix = 0; iy = 0; }   // padding exists only past the previous KPIX step
             Iq[k] = 512 * ival - 256;                               // ((v + 256) >> 9) - ival == (v - Iq) >> 9
             dxy[k] = (ix & 0xffff) | (int)((unsigned)iy << 16);
             sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
@@ -406,7 +416,7 @@ int lk_enqueue(pmv_ctx *ctx, const PyrSet &sp, const PyrSet &sn, const DerivSet 
     P.max_count = max_count; P.eps2 = eps * eps; P.flags = flags; P.min_eig = (float)min_eig_thr;
     P.pp = align_up(3 + win_w + 1 + 3, 4);
     P.jp = align_up(3 + win_w + 1 + 2 * LK_M + 3, 4);
-    int tmpl = (win_h + 1) * P.pp + (win_h + 1) * (win_w + 1) * 4;
+    int tmpl = (win_h + 1) * P.jp * 5;   // prev patch (bytes) + derivative support (words), both with pitch jp
     int jwin = (win_h + 1 + 2 * LK_M) * P.jp;
     P.smem_per_warp = align_up(tmpl > jwin ? tmpl : jwin, 16);
     const int kmax = (win_w * win_h + 31) / 32;
