@@ -663,8 +663,8 @@ def main():
     # feature and DRAM bytes per pair come from the ncu --set full capture of this kernel committed as
     # profiles/r1_lk_final_ncu_summary.txt (smsp__inst_executed.sum / 64 000 features; dram bytes / 32 pairs);
     # the issue peak is 148 SMs x 4 schedulers x 1 warp instruction per clock at the SM clock sampled during the run.
-    LK_WARP_INST_PER_FEATURE = 715446617 / 64000.0
-    LK_DRAM_BYTES_PER_PAIR = (132.067328e6 + 8.086784e6) / 32.0
+    LK_WARP_INST_PER_FEATURE = 668022617 / 64000.0
+    LK_DRAM_BYTES_PER_PAIR = (132.062464e6 + 4.643072e6) / 32.0
     sm_hz = float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
     issue_peak = 148 * 4 * sm_hz
     issue_ach = LK_WARP_INST_PER_FEATURE * N_FEAT * batch / (lk_avg * 1e-3) if lk_avg else None
