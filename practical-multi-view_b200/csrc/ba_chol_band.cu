@@ -582,6 +582,7 @@ int pmv_internal_ba_cholesky_band(pmv_ctx *ctx, double *S, double *b, int n, con
         const int je = std::min(nblk, (std::min(n, lim_host[kb]) + NB - 1) / NB);
         T = std::max(T, je - kb);
     }
+    if (T < 2) T = 2;   // a tile entering the window must not be needed in the step that loads it
     const int Tp = T + 1;
     if (Tp > MAXTP) return 0;
     int cnt[CL] = {0};

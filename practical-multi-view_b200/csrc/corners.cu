@@ -236,23 +236,41 @@ mineig_kernel(const ImgView v, float *__restrict__ eig, int *__restrict__ max_bi
     if (tid == 0 && vmax > 0.f) atomicMax(max_bits, __float_as_int(vmax));
 }
 
-// K6a: threshold + 3x3 NMS + unordered compaction of (response bits, index) records
+// K6a: threshold + 3x3 NMS + unordered compaction of (response bits, index) records.  A CTA sweeps a
+// 32 x 64 pixel tile and gathers its candidates in shared memory, so the global counter sees one atomic per
+// tile (an atomic per candidate on ONE address serialised in L2: 138 us for ~60 k candidates of a 4K frame).
+constexpr int GC_ROWS = 64;
+
 __global__ void __launch_bounds__(256)
 gftt_candidates_kernel(const float *__restrict__ eig, int rows, int cols, const int *__restrict__ max_bits,
                        double quality, Rec128 *__restrict__ out, int *__restrict__ count, int cap)
 {
+    __shared__ Rec128 s_rec[32 * GC_ROWS];   // every pixel of the tile may qualify (plateaus)
+    __shared__ int s_n, s_base;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x < 1 || y < 1 || x >= cols - 1 || y >= rows - 1) return;
     const float thr = (float)((double)__int_as_float(*max_bits) * quality);
-    const float *p = eig + (size_t)y * cols + x;
-    const float val = p[0];
-    if (!(val > thr)) return;
-    float m = fmaxf(fmaxf(p[-cols - 1], p[-cols]), fmaxf(p[-cols + 1], p[-1]));
-    m = fmaxf(m, fmaxf(fmaxf(p[1], p[cols - 1]), fmaxf(p[cols], p[cols + 1])));
-    if (val < m) return;  // val == dilate(thresholded) <=> val >= every neighbour
-    int slot = atomicAdd(count, 1);
-    if (slot < cap) out[slot] = Rec128{(unsigned long long)__float_as_uint(val), (unsigned long long)(y * cols + x)};
+    for (int ys = 0; ys < GC_ROWS; ys += 8) {
+        const int y = blockIdx.y * GC_ROWS + ys + (threadIdx.x >> 5);
+        if (x < 1 || y < 1 || x >= cols - 1 || y >= rows - 1) continue;
+        const float *p = eig + (size_t)y * cols + x;
+        const float val = p[0];
+        if (!(val > thr)) continue;
+        float m = fmaxf(fmaxf(p[-cols - 1], p[-cols]), fmaxf(p[-cols + 1], p[-1]));
+        m = fmaxf(m, fmaxf(fmaxf(p[1], p[cols - 1]), fmaxf(p[cols], p[cols + 1])));
+        if (val < m) continue;  // val == dilate(thresholded) <=> val >= every neighbour
+        const int slot = atomicAdd(&s_n, 1);
+        s_rec[slot] = Rec128{(unsigned long long)__float_as_uint(val), (unsigned long long)(y * cols + x)};
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n == 0) return;
+    if (threadIdx.x == 0) s_base = atomicAdd(count, n);
+    __syncthreads();
+    const int base = s_base;
+    for (int i = threadIdx.x; i < n; i += 256)
+        if (base + i < cap) out[base + i] = s_rec[i];
 }
 
 __global__ void __launch_bounds__(256)
@@ -615,7 +633,7 @@ PMV_API int pmv_gftt(pmv_ctx *ctx, const uint8_t *base, int full_rows, int full_
     int n_cand = 0;
     {
         ProfScope ps(ctx, PMV_PHASE_SELECT, s);
-        dim3 grid((roi_w + 31) / 32, (roi_h + 7) / 8);
+        dim3 grid((roi_w + 31) / 32, (roi_h + GC_ROWS - 1) / GC_ROWS);
         gftt_candidates_kernel<<<grid, 256, 0, s>>>(d_eig, roi_h, roi_w, d_misc, quality, d_rec, d_misc + 1, cap);
         PMV_LAUNCH_CHECK(ctx, "gftt_candidates_kernel");
         PMV_CUDA_TRY(ctx, cudaMemcpyAsync(h_misc, d_misc, 16, cudaMemcpyDeviceToHost, s));

@@ -73,6 +73,9 @@ fast_kernel(const uint8_t *__restrict__ img, int rows, int cols, int pitch, int 
 {
     __shared__ __align__(16) uint8_t s_px[FS_H][FS_P];
     __shared__ int s_sc[FC_H][FC_W + 1];
+    __shared__ Rec128 s_rec[FT_H * FT_W];
+    __shared__ int s_n, s_base;
+    if (threadIdx.x == 0) s_n = 0;   // the barriers below order it before the first use
     const int tid = threadIdx.x;
     const int tx0 = blockIdx.x * FT_W, ty0 = blockIdx.y * FT_H;
     if (tx0 >= 4 && tx0 + FT_W + 4 <= pitch && ty0 >= 4 && ty0 + FT_H + 4 <= rows) {
@@ -110,10 +113,18 @@ fast_kernel(const uint8_t *__restrict__ img, int rows, int cols, int pitch, int 
                         sc > s_sc[r + 1][c + 2] && sc > s_sc[r + 2][c] && sc > s_sc[r + 2][c + 1] && sc > s_sc[r + 2][c + 2];
             if (!keep) continue;
         }
-        int slot = atomicAdd(count, 1);
-        if (slot < cap)
-            out[slot] = Rec128{~(unsigned long long)(y * cols + x), (unsigned long long)(nonmax ? sc : 0)};
+        // gathered per tile: the global counter takes one atomic per CTA (same-address atomics serialise in L2)
+        const int slot = atomicAdd(&s_n, 1);
+        s_rec[slot] = Rec128{~(unsigned long long)(y * cols + x), (unsigned long long)(nonmax ? sc : 0)};
     }
+    __syncthreads();
+    const int nloc = s_n;
+    if (nloc == 0) return;
+    if (tid == 0) s_base = atomicAdd(count, nloc);
+    __syncthreads();
+    const int base = s_base;
+    for (int i = tid; i < nloc; i += 256)
+        if (base + i < cap) out[base + i] = s_rec[i];
 }
 
 __global__ void __launch_bounds__(256)
