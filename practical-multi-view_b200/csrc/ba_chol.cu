@@ -211,47 +211,55 @@ chol_backsub_kernel(const double *S, const double *z, double *y, int n, const in
     double *zs_base = staged ? sbuf + 2 * NB * BS_MAXW + 512 : nullptr;   // [2][NB] staged right-hand sides
     auto stage = [&](int kb, double *dst) {
         const int k0 = kb * NB, nb = min(NB, n - k0), wdt = min(n, lim[kb]) - k0;
-        // 16 threads per row, no index arithmetic beyond an add (an i / wdt per element cost more than the copy)
-        const int r = tid >> 4;
-        if (r < nb) {
+        // threads 32..511 (warps 1..15), 16 per row, 30 rows per pass; no index arithmetic beyond an add
+        const int t = tid - 32;
+        for (int r = t >> 4; r < nb; r += (BS_THREADS - 32) / 16) {
             const double *src = S + (size_t)(k0 + r) * n + k0;
             const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + r * BS_MAXW);
-            for (int c = r + (tid & 15); c < wdt; c += 16)
+            for (int c = r + (t & 15); c < wdt; c += 16)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + 8u * c), "l"(src + c));
         }
-        if (zs_base && tid < nb) {   // the right-hand side of the block row rides along (no L2 round trip per step)
-            const unsigned za = (unsigned)__cvta_generic_to_shared(zs_base + (kb & 1) * NB + tid);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(za), "l"(z + k0 + tid));
+        if (zs_base && t < nb) {   // the right-hand side of the block row rides along (no L2 round trip per step)
+            const unsigned za = (unsigned)__cvta_generic_to_shared(zs_base + (kb & 1) * NB + t);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(za), "l"(z + k0 + t));
         }
         asm volatile("cp.async.commit_group;");
     };
     if (staged) {
-        // banded system: block rows staged one step ahead, the known tail of y in a shared-memory ring, and a
-        // branch-free triangle solve (row in registers, reciprocal diagonal, ~46 cycles per unknown)
+        // Banded system.  Block rows are staged two steps ahead by warps 1..15, the known tail of y lives in a
+        // shared-memory ring, and the dot products of a block row are split: the part against unknowns that are
+        // two or more blocks old is formed by warps 1..15 WHILE warp 0 solves the triangle of the block above
+        // (branch-free, row in registers, reciprocal diagonal, ~46 cycles per unknown); only the 32 columns of
+        // the block just solved remain on the critical path.
         double *ysm = sbuf + 2 * NB * BS_MAXW;   // ring of the last 512 unknowns, indexed by column & 511
-        stage(nblk - 1, sbuf + ((nblk - 1) & 1 ? NB * BS_MAXW : 0));
+        double *sP = zs_base + 2 * NB;           // [NB] old-part sums of the block row about to be solved
+        auto ubuf = [&](int kb) { return sbuf + (kb & 1 ? NB * BS_MAXW : 0); };
+        if (tid < NB) sP[tid] = 0.0;             // the top block row has no columns beyond its triangle
+        if (warp > 0) {
+            stage(nblk - 1, ubuf(nblk - 1));
+            if (nblk > 1) stage(nblk - 2, ubuf(nblk - 2)); else asm volatile("cp.async.commit_group;");
+            asm volatile("cp.async.wait_group 1;");
+        }
+        __syncthreads();   // block row nblk - 1 landed
         for (int kb = nblk - 1; kb >= 0; kb--) {
             const int k0 = kb * NB, nb = min(NB, n - k0);
             const int wdt = min(n, lim[kb]) - k0;   // U_kj == 0 beyond the envelope
-            if (kb > 0) stage(kb - 1, sbuf + ((kb - 1) & 1 ? NB * BS_MAXW : 0));
-            if (kb > 0) asm volatile("cp.async.wait_group 1;"); else asm volatile("cp.async.wait_group 0;");
-            __syncthreads();   // block row kb landed; the triangle of step kb + 1 has published its unknowns
-            const double *U = sbuf + (kb & 1 ? NB * BS_MAXW : 0);
-            // warp 0 takes its triangle rows into registers BEFORE the barrier below: afterwards the other warps
-            // run ahead and refill this buffer's twin, and the triangle must not touch shared block rows any more
+            const double *U = ubuf(kb);
+            // warp 0 takes its triangle rows into registers BEFORE barrier A: afterwards this buffer is refilled
             double urow[NB], myinv = 0.0;
             if (warp == 0) {
 #pragma unroll
                 for (int r = 0; r < NB; r++) urow[r] = (lane < nb && r < nb && r > lane) ? U[lane * BS_MAXW + r] : 0.0;
                 myinv = lane < nb ? 1.0 / U[lane * BS_MAXW + lane] : 0.0;
             }
+            // (1) the 32 columns of the block solved in the previous step, one per lane
             for (int row = warp; row < nb; row += BS_THREADS / 32) {
-                double sacc = 0;
-                for (int c = nb + lane; c < wdt; c += 32) sacc += U[row * BS_MAXW + c] * ysm[(k0 + c) & 511];
+                const int c = NB + lane;
+                double sacc = (c < wdt) ? U[row * BS_MAXW + c] * ysm[(k0 + c) & 511] : 0.0;
                 for (int o = 16; o; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-                if (lane == 0) yk[row] = zs_base[(kb & 1) * NB + row] - sacc;
+                if (lane == 0) yk[row] = zs_base[(kb & 1) * NB + row] - sP[row] - sacc;
             }
-            __syncthreads();
+            __syncthreads();   // A: right-hand side of the triangle complete; block row kb no longer needed
             if (warp == 0) {
                 // lane l keeps unknown l; rows >= nb of a partial last block are inert
                 double mine = lane < nb ? yk[lane] : 0.0;
@@ -263,9 +271,25 @@ chol_backsub_kernel(const double *S, const double *z, double *y, int n, const in
                 }
                 if (!isfinite(mine)) fin = 0;
                 if (lane < nb) { y[k0 + lane] = mine; ysm[(k0 + lane) & 511] = mine; }
+            } else {
+                // (2) refill the buffer of block row kb with block row kb - 2, make block row kb - 1 visible, and
+                //     form its sums against the unknowns of blocks >= kb + 1 (all known)
+                if (kb >= 2) stage(kb - 2, ubuf(kb - 2)); else asm volatile("cp.async.commit_group;");
+                asm volatile("cp.async.wait_group 1;");
+                asm volatile("bar.sync 1, %0;" ::"n"(BS_THREADS - 32) : "memory");
+                if (kb >= 1) {
+                    const int k1 = k0 - NB, w1 = min(n, lim[kb - 1]) - k1;
+                    const double *U1 = ubuf(kb - 1);
+                    for (int row = warp - 1; row < NB; row += BS_THREADS / 32 - 1) {
+                        double sacc = 0;
+                        for (int c = 2 * NB + lane; c < w1; c += 32) sacc += U1[row * BS_MAXW + c] * ysm[(k1 + c) & 511];
+                        for (int o = 16; o; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+                        if (lane == 0) sP[row] = sacc;
+                    }
+                }
             }
+            __syncthreads();   // B: unknowns of block kb published, sums of block row kb - 1 ready
         }
-        __syncthreads();
         if (tid == 0 && !fin) st->chol_ok = 0;
         return;
     }
@@ -340,7 +364,7 @@ int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_
             int maxw = 0;
             for (int k0 = 0, kb = 0; k0 < n; k0 += NB, kb++) maxw = std::max(maxw, (lim_host ? std::min(n, lim_host[kb]) : n) - k0);
             const int staged = (maxw <= BS_MAXW) && !getenv("PMV_CHOL_NO_STAGE");
-            const size_t smem = staged ? sizeof(double) * (2 * NB * BS_MAXW + 512 + 2 * NB) : 0;
+            const size_t smem = staged ? sizeof(double) * (2 * NB * BS_MAXW + 512 + 3 * NB) : 0;
             static bool attr = false;
             if (!attr) { cudaFuncSetAttribute(chol_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
             chol_backsub_kernel<<<1, BS_THREADS, smem, s>>>(S, b, y, n, D.chol_lim, st, staged);
