@@ -1,4 +1,4 @@
-// ba_chol_band.cu -- K10 for BANDED reduced camera systems (BASELINE config 5: n = 6000, envelope ~270
+// ba_chol_band.cu -- K10 for BANDED reduced camera systems (BASELINE config 5: n = 6000, envelope ~150
 // columns): the whole U^T U factorisation and the forward substitution in ONE launch by one thread-block
 // cluster whose distributed shared memory holds the sliding window of the band.
 //
@@ -17,17 +17,28 @@
 // (retired the step before) are refilled from HBM with the tiles of index kb + T by dedicated loader warps,
 // one step ahead of their first use.  Slot {a, b} is owned by CTA (a + b) mod 8.
 //
-// One step (pivot block kb):
-//   A  the warp that last updated the diagonal tile factors it in registers (lane j = column j, pivots travel
-//      by shuffles), publishes U_kk, 1/diag and z_k = U_kk^-T b_k in its CTA's shared memory and writes the
-//      block row to HBM for the back substitution          -- done at the END of step kb - 1 by that warp
+// Warp roles in every CTA (12 warps): 8 COMPUTE warps (panel solves, trailing updates), 3 LOADER warps (HBM
+// traffic, right-hand side) and 1 FACTOR warp (the diagonal tile), so the 32 column registers of the
+// factorisation are not shared with other code.
+//
+// One step (pivot block kb), two cluster barriers:
+//   A  (end of step kb - 1) the factor warp of the CTA owning tile (kb, kb) subtracts U_(kb-1,kb)^T U_(kb-1,kb)
+//      from it and factors it in registers: lane j = column j, 32 pivots as shuffle -> rcp -> FMA chains in four
+//      sub-blocks of 8, the rows of the later sub-blocks updated on the fp64 tensor pipe; publishes U_kk and
+//      1/diag in its CTA's shared memory
 //   -- cluster barrier --
-//   B  owners of the panel tiles (kb, J) pull U_kk through DSMEM, solve U_kJ = U_kk^-T S_kJ (one column per
-//      lane), write U_kJ to HBM, fold b_J -= U_kJ^T z_k into the window's right-hand side
+//   B  compute warps owning a panel tile (kb, J) copy U_kk through DSMEM into a private buffer (17 coalesced
+//      requests) and solve U_kJ = U_kk^-T S_kJ (one column per lane); the tile stays in its slot with its columns
+//      permuted so that a lane's tensor-core fragment is one 32 B piece.  Meanwhile the loader warps write the
+//      previous block row to HBM, start the loads of the tiles of index kb + T, and one of them solves
+//      z_k = U_kk^-T b_k
 //   -- cluster barrier --
-//   C  owners of the trailing tiles (I, J) subtract U_kI^T U_kJ with fp64 tensor-core tiles
+//   C  compute warps subtract U_kI^T U_kJ from their trailing tiles (I, J) with fp64 tensor-core tiles
 //      (mma.sync.m8n8k4.f64 -> DMMA; tcgen05 has no fp64 kind), operands read from the panel owners' shared
-//      memory; the warp holding tile (kb+1, kb+1) goes straight on to phase A of the next step.
+//      memory; loader warps store the incoming tiles and fold b_J -= U_kJ^T z_k; the factor warp runs phase A of
+//      step kb + 1.
+// Measured on B200 (tools/lat_probe.cu, PMV_CHOL_TRACE=1): a step is 7.2 us = panel solve 2.7 + diagonal-tile
+// update 1.8 + factor 2.3 + barriers; remote shared-memory access is request-bound, hence the coalesced copies.
 #include <cooperative_groups.h>
 
 #include <algorithm>
