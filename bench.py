@@ -480,7 +480,8 @@ def run_pipeline(args, rank, world, local_rank):
     launches = ctx.launches - l0
     if rank == 0:
         import oracle
-        log_c, tf_c, tb_c = drive(replay.Cv2Backend(), lambda: oracle.ba_solve(*ba_args, 1.0, 5))
+        from oracle.replay_backend import Cv2Backend
+        log_c, tf_c, tb_c = drive(Cv2Backend(), lambda: oracle.ba_solve(*ba_args, 1.0, 5))
         same = all(a[0].shape == b[0].shape and np.array_equal(a[0], b[0]) for a, b in zip(log_g, log_c))
         fps_g, fps_c = nfr / (tf_g + tb_g), nfr / (tf_c + tb_c)
         out = {"metric": "frames_per_s_pipeline_pattern", "value": fps_g, "unit": "frames/s", "n_gpus": 1, "steps": 1, "warmup": 1,

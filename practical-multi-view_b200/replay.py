@@ -1,7 +1,8 @@
 """Python re-drive of the reference's front-end control flow (OdometryPipeline::addFrame,
 OdometryPipeline.cpp:329-374; initialise :428-482; getGridROI :674-692) with a pluggable backend, so the
 GPU extractor + matcher can be compared with OpenCV on the *pipeline's own call pattern* (BASELINE
-config 1) in a container that cannot build the C++ executable.  Harness code (tests / bench), not product.
+config 1) in a container that cannot build the C++ executable.  Harness code (tests / bench), not product;
+the OpenCV-plugin backend it is compared with lives in oracle/replay_backend.py (test infrastructure).
 
 Per frame:  LK(prev, frame, features of prev; win 32x32, maxLevel 4)  ->  keep status==1, truncate to int
             if fewer than `tol` (150) survive: split the PREVIOUS frame into 255x255 ROIs, extract
@@ -26,29 +27,6 @@ def grid_rois(rows: int, cols: int):
         for c in range(0, cols, GRID):
             out.append((c, r, min(GRID, cols - c), min(GRID, rows - r)))
     return out
-
-
-class Cv2Backend:
-    """The reference's own plugins: OpenCVGoodFeatureExtractor + OpenCVLucasKanadeFM (cv2 = same kernels)."""
-    name = "cv2"
-
-    def extract(self, img, roi, max_feats):
-        import cv2
-        x, y, w, h = roi
-        # numpy views lose cv::Mat ROI parentage; the C++ call reads parent pixels at the ROI rim -> crop a
-        # response computed on the parent (SURVEY §8c caveat) is what oracle.gftt does; cv2 on a copy is the
-        # isolated variant.  Use the oracle form so both backends follow the C++ semantics.
-        import oracle
-        xy, _ = oracle.gftt(img, max_feats, 0.01, 5.0, roi=roi)
-        return xy.astype(np.int32)
-
-    def track(self, prev, nxt, pts):
-        import cv2
-        if len(pts) == 0:
-            return np.zeros((0, 2), np.float32), np.zeros(0, np.uint8)
-        nx, st, _ = cv2.calcOpticalFlowPyrLK(prev, nxt, pts.astype(np.float32).reshape(-1, 1, 2), None,
-                                             winSize=WIN, maxLevel=MAX_LEVEL)
-        return nx.reshape(-1, 2), st.ravel()
 
 
 class GpuBackend:

@@ -25,3 +25,14 @@ def test_reference_arm_json_contract():
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"]
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may use it."""
+    import re
+    pkg = ROOT / "practical-multi-view_b200"
+    pat = re.compile(r"^\s*(import\s+oracle|from\s+oracle|from\s+\.+\s*oracle)", re.M)
+    offenders = [str(p.relative_to(ROOT)) for p in pkg.rglob("*.py") if pat.search(p.read_text())]
+    offenders += [str(p.relative_to(ROOT)) for p in list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.h"))
+                  if "oracle/" in p.read_text() and "#include" in "".join(l for l in p.read_text().splitlines(True) if "oracle/" in l)]
+    assert offenders == []

@@ -9,9 +9,10 @@ pytestmark = pytest.mark.gpu
 
 def test_front_end_replay_matches_opencv_plugins(ctx):
     pytest.importorskip("cv2")
+    from oracle.replay_backend import Cv2Backend
     from pmv_b200 import replay
     frames = replay.synthetic_sequence(12, stream=3)
-    ref = replay.run_front_end(frames, replay.Cv2Backend(), min_tracked=400, tol=10**6)   # tol raised: re-extraction on every frame
+    ref = replay.run_front_end(frames, Cv2Backend(), min_tracked=400, tol=10**6)   # tol raised: re-extraction on every frame
     got = replay.run_front_end(frames, replay.GpuBackend(ctx), min_tracked=400, tol=10**6)
     n_extract = 0
     for k, ((fr, tr, er), (fg, tg, eg)) in enumerate(zip(ref, got)):
