@@ -69,10 +69,20 @@ static void angle_axis_rotate_point(const jet aa[3], const jet pt[3], jet out[3]
     }
 }
 
+/* Optional evaluation hook (oracle/_ref): when set, every residual / Jacobian evaluation of the minimiser below goes
+ * to the callback instead of the restated functor -- oracle/ref_shim's ceres::Solve points it at the REFERENCE's own
+ * ceres::CostFunction::Evaluate (ProjectionResidual compiled unchanged under real Jets); `obs` is then an opaque
+ * per-observation payload (the residual-block id) that the minimiser only passes through. */
+typedef void (*orc_residual_hook_t)(const double pose[6], const double pt[3], const double obs[2], const double K[9],
+                                    double r[2], double *Jc, double *Jp);
+static orc_residual_hook_t g_residual_hook = 0;
+ORC_API void orc_ba_set_residual_hook(orc_residual_hook_t h) { g_residual_hook = h; }
+
 /* ProjectionResidual::operator()<Jet> (ProjectionResidual.h:38-58): r[2], J_pose 2x6, J_pt 2x3 (row major) */
 ORC_API void orc_ba_residual(const double pose[6], const double pt[3], const double obs[2], const double K[9],
                              double r[2], double Jc[12], double Jp[6])
 {
+    if (g_residual_hook) { g_residual_hook(pose, pt, obs, K, r, Jc, Jp); return; }
     jet tr[6], X[3];
     for (int i = 0; i < 6; i++) tr[i] = jvar(pose[i], i);
     for (int i = 0; i < 3; i++) X[i] = jvar(pt[i], 6 + i);
@@ -90,6 +100,7 @@ ORC_API void orc_ba_residual(const double pose[6], const double pt[3], const dou
 /* scalar-only residual (cost evaluation of the candidate point) */
 static void residual_only(const double pose[6], const double pt[3], const double obs[2], const double K[9], double r[2])
 {
+    if (g_residual_hook) { g_residual_hook(pose, pt, obs, K, r, 0, 0); return; }
     double q[3] = {pt[0] + pose[3], pt[1] + pose[4], pt[2] + pose[5]}, p[3];
     double t2 = pose[0] * pose[0] + pose[1] * pose[1] + pose[2] * pose[2];
     if (t2 > DBL_EPSILON) {

@@ -1,7 +1,9 @@
 """CPU: the C++ drop-in adapters (practical-multi-view_b200/host/pmv_adapters.h) must compile against the
 REFERENCE's own plugin headers (Base*.h, Frame.h, Feature.h, OdometryPipeline.h).  The image has no C++
-OpenCV / dlib, so tests/stubs/ provides declaration-only stand-ins and the check is -fsyntax-only; it runs
-only where /root/reference is mounted (this container), never on the GPU box."""
+OpenCV / dlib / Ceres; oracle/ref_shim/ is a small functional stand-in for the slice the reference uses.  This
+test is the syntax check (runs only where /root/reference is mounted); the adapters are also LINKED and RUN
+against the reference's own classes through oracle/_ref/libpmv_ref.so (tests/test_ref_pins.py on CPU for the
+reference side, tests/test_gpu_ref_plugins.py on the GPU box for reference-vs-adapter)."""
 import shutil
 import subprocess
 from pathlib import Path
@@ -21,7 +23,7 @@ def test_adapters_compile_against_reference_headers(tmp_path):
                   "BaseFeatureExtractor* e2() { return new GpuShiTomasiFeatureExtractor(); }\n"
                   "BaseFeatureExtractor* e3() { return new GpuFASTFeatureExtractor(); }\n"
                   "BaseOptimizer* b(OdometryPipeline* p) { return new GpuBundleAdjustment(p); }\n")
-    cmd = ["g++", "-std=c++11", "-fsyntax-only", "-I", str(ROOT / "tests" / "stubs"), "-I", str(REF),
+    cmd = ["g++", "-std=c++11", "-fsyntax-only", "-I", str(ROOT / "oracle" / "ref_shim"), "-I", str(REF),
            "-I", str(ROOT / "include"), "-I", str(ROOT / "practical-multi-view_b200" / "host"), str(tu)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
