@@ -49,7 +49,7 @@ ALG_BYTES_PER_PREV_IMAGE_DERIV = 5 * PYR_BYTES                 # Scharr: 1 B/px 
 
 def make_workload(rank: int, batch: int):
     """Synthetic KITTI-shaped pairs (SURVEY §8d generator); distinct pairs cycled to fill the batch."""
-    from pmv_b200 import synth
+    from harness import synth
     distinct = min(batch, int(os.environ.get("PMV_BENCH_DISTINCT", "32")))
     prev = np.empty((batch, H, W), np.uint8)
     nxt = np.empty((batch, H, W), np.uint8)
@@ -161,7 +161,7 @@ def run_ba_windows(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import pmv_b200
-    from pmv_b200 import synth
+    from harness import synth
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -265,7 +265,8 @@ def run_ba_large(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import pmv_b200
-    from pmv_b200 import sharding, synth
+    from pmv_b200 import sharding
+    from harness import synth
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -353,7 +354,7 @@ def run_extract(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import pmv_b200
-    from pmv_b200 import synth
+    from harness import synth
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -456,7 +457,7 @@ def run_pipeline(args, rank, world, local_rank):
     exactly as the adapters would issue them.  Reference arm beside it: cv2 + the oracle BA on the host cores."""
     import torch
     import pmv_b200
-    from pmv_b200 import replay, synth
+    from harness import replay, synth
     torch.cuda.set_device(local_rank)
     nfr = args.frames
     frames = replay.synthetic_sequence(nfr, stream=rank)

@@ -99,15 +99,21 @@ def ba_window(seed: int, n_poses=20, n_points=2000, width=1241, height=376, outl
             "poses_true": poses_t, "points_true": pts_t}
 
 
-def ba_large(seed: int, n_poses=1000, n_points=1_000_000, views=5, span=40, width=1241, height=376, K=KITTI_K):
-    """BASELINE config 5 (BAL scale): each point is seen by `views` poses chosen among the `span` poses
-    nearest to it along a straight trajectory; observations need not fall inside an image."""
+def ba_large(seed: int, n_poses=1000, n_points=1_000_000, views=5, span=40, width=1241, height=376, K=KITTI_K,
+             sort_by_anchor=False):
+    """BASELINE config 5 (BAL scale): each point is seen by `views` poses chosen among the `span` (40)
+    poses nearest to it along a straight trajectory -- the `span` poses up to and including its anchor, which all
+    have the point in front of them; observations need not fall inside an image.  sort_by_anchor orders the
+    points along the trajectory (as real SfM / BAL point lists are), so a contiguous point shard sees only a
+    contiguous run of cameras."""
     rng = np.random.default_rng(seed)
     poses_t = np.zeros((n_poses, 6))
     poses_t[:, 1] = rng.normal(0, 0.01, n_poses)
     poses_t[:, 5] = np.arange(n_poses) * 1.0
     poses_t[:, 3:] += rng.normal(0, 0.02, (n_poses, 3))
     anchor = rng.integers(0, n_poses, n_points)
+    if sort_by_anchor:
+        anchor = np.sort(anchor)
     depth = rng.uniform(8, 50, n_points)
     u = rng.uniform(0.2 * width, 0.8 * width, n_points); v = rng.uniform(0.2 * height, 0.8 * height, n_points)
     pc = np.stack([(u - K[0, 2]) / K[0, 0] * depth, (v - K[1, 2]) / K[1, 1] * depth, -depth], -1)
@@ -116,10 +122,10 @@ def ba_large(seed: int, n_poses=1000, n_points=1_000_000, views=5, span=40, widt
     for a in np.unique(anchor):
         m = anchor == a
         pts_t[m] = (_rodrigues(poses_t[a, :3]).T @ pc[m].T).T - poses_t[a, 3:]
-    # `views` distinct poses within [anchor-span/2, anchor+span/2) that stay in front of the point (z < 0)
-    offs = np.stack([rng.permutation(span // 2)[:views] for _ in range(1)], 0)  # same pattern base, shifted per point
-    shift = rng.integers(0, span // 2, n_points)
-    cams = (anchor[:, None] - ((offs + shift[:, None]) % (span // 2))).clip(0, n_poses - 1)
+    # `views` distinct poses within (anchor - span, anchor]: they all stay in front of the point (z < 0)
+    offs = np.stack([rng.permutation(span)[:views] for _ in range(1)], 0)  # same pattern base, shifted per point
+    shift = rng.integers(0, span, n_points)
+    cams = (anchor[:, None] - ((offs + shift[:, None]) % span)).clip(0, n_poses - 1)
     cams = np.sort(cams, 1)
     keep = np.ones_like(cams, bool)
     keep[:, 1:] = cams[:, 1:] != cams[:, :-1]

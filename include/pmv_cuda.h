@@ -79,6 +79,11 @@ PMV_API const char *pmv_version(void);
 PMV_API int pmv_profile_enable(pmv_ctx *ctx, int on);
 PMV_API int pmv_profile_collect(pmv_ctx *ctx, int n_phases, double *ms_sum, int *count);
 
+/* Measured fp64 peaks of this context's device ("fp64 ALU peaks must be measured on the box"): a DFMA
+ * chain and an mma.sync.m8n8k4.f64 (DMMA) chain, TFLOP/s.  Diagnostic for bench.py's fp64 rooflines (the window bundle
+ * adjuster, CeresBundleAdjustment.cpp:54-61, is fp64-bound); replaces nothing in the reference. */
+PMV_API int pmv_probe_fp64(pmv_ctx *ctx, double *dfma_tflops, double *dmma_tflops);
+
 /* ------------------------------------------------------------------ pyramid ---------- */
 /* Effective top level of cv::buildOpticalFlowPyramid(img, Size(win_w,win_h), max_level):
  * max_level is clipped when the next level would be <= the window (SURVEY Appx A.1).

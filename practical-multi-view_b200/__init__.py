@@ -48,6 +48,7 @@ _SIGS = {
     "pmv_launch_count": (C.c_uint64, [_vp]),
     "pmv_profile_enable": (_int, [_vp, _int]),
     "pmv_profile_collect": (_int, [_vp, _int, _f64p, _i32p]),
+    "pmv_probe_fp64": (_int, [_vp, _f64p, _f64p]),
     "pmv_pyr_levels": (_int, [_int] * 5),
     "pmv_pyramid_build": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _vp, _sz, _i32p]),
     "pmv_scharr": (_int, [_vp, _vp, _int, _int, _int, _vp]),
@@ -162,6 +163,12 @@ class Context:
         cnt = (C.c_int32 * 8)()
         self._chk(self.lib.pmv_profile_collect(self.h, 8, ms, cnt))
         return {p: (ms[i], cnt[i]) for i, p in enumerate(self.PHASES) if cnt[i]}
+
+    def probe_fp64(self):
+        """Measured (DFMA, DMMA) fp64 TFLOP/s of this device."""
+        a, b = C.c_double(0), C.c_double(0)
+        self._chk(self.lib.pmv_probe_fp64(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     # ------------------------------------------------------------------ pyramid
     def pyramid_build(self, img: np.ndarray, win=(21, 21), max_level=3):

@@ -349,7 +349,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     D.W = W; D.Nc = Nc; D.Np = Np; D.n = 6 * Nc; D.No = No;
     D.fx = K[0]; D.cx = K[2]; D.fy = K[4]; D.cy = K[5]; D.delta = huber_delta;
     const size_t wc = (size_t)W * Nc, wp = (size_t)W * Np, n = D.n;
-    int *d_cam, *d_pt, *d_win, *d_ptoff, *d_camoff, *d_camobs;
+    int *d_cam, *d_pt, *d_win, *d_ptoff, *d_camoff, *d_camobs, *d_camact;
     double *d_obs;
     int rc = 0;
     const int nblk = ((int)n + PMV_CHOL_NB - 1) / PMV_CHOL_NB;
@@ -359,7 +359,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     auto alloc_all = [&]() {
     rc |= dev_alloc(p, &d_cam, No); rc |= dev_alloc(p, &d_pt, No); rc |= dev_alloc(p, &d_win, No);
     rc |= dev_alloc(p, &d_obs, 2 * (size_t)No); rc |= dev_alloc(p, &d_ptoff, wp + 1); rc |= dev_alloc(p, &d_camoff, wc + 1);
-    rc |= dev_alloc(p, &d_camobs, No);
+    rc |= dev_alloc(p, &d_camobs, No); rc |= dev_alloc(p, &d_camact, wc);
     rc |= dev_alloc(p, &D.poses, wc * 6); rc |= dev_alloc(p, &D.points, wp * 3);
     rc |= dev_alloc(p, &D.cand_poses, wc * 6); rc |= dev_alloc(p, &D.cand_points, wp * 3);
     rc |= dev_alloc(p, &p->d_init_poses, wc * 6); rc |= dev_alloc(p, &p->d_init_points, wp * 3);
@@ -397,7 +397,9 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     if (rc) { pmv_ba_problem_destroy(p); return nullptr; }
     D.S = d_sys; D.rhs = d_sys + (size_t)W * n * n;
     D.obs_cam = d_cam; D.obs_pt = d_pt; D.obs_win = d_win; D.obs_xy = d_obs;
-    D.pt_off = d_ptoff; D.cam_off = d_camoff; D.cam_obs = d_camobs;
+    D.pt_off = d_ptoff; D.cam_off = d_camoff; D.cam_obs = d_camobs; D.cam_active = d_camact;
+    std::vector<int> h_camact(wc);
+    for (size_t q = 0; q < wc; q++) h_camact[q] = cam_off[q + 1] > cam_off[q] ? 1 : 0;
     cudaStream_t s = ctx->stream;
     bool ok = true;
     auto up = [&](void *dst, const void *src, size_t bytes) {
@@ -406,6 +408,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     up(d_cam, h_cam.data(), sizeof(int) * No); up(d_pt, h_pt.data(), sizeof(int) * No); up(d_win, h_win.data(), sizeof(int) * No);
     up(d_obs, h_obs.data(), sizeof(double) * 2 * No); up(d_ptoff, pt_off.data(), sizeof(int) * (wp + 1));
     up(d_camoff, cam_off.data(), sizeof(int) * (wc + 1)); up(d_camobs, cam_obs.data(), sizeof(int) * No);
+    up(d_camact, h_camact.data(), sizeof(int) * wc);
     up(p->d_init_poses, poses, sizeof(double) * wc * 6); up(p->d_init_points, points, sizeof(double) * wp * 3);
     if (window_ok) up(p->d_vis, h_vis.data(), sizeof(unsigned) * wp);
     if (ok && cudaStreamSynchronize(s) != cudaSuccess) ok = false;  // host vectors die at return
@@ -413,12 +416,19 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     {
         // envelope per 64-row block (global over ranks when the points are sharded)
         if (p->sharded) {
+            // one max-reduction over the ranks: the envelope (emax) and which cameras are observed at all -- a rank
+            // whose point shard never sees camera c must still move it with everybody else (replicated poses)
             double *d_e = nullptr;
-            if (dev_alloc(p, &d_e, 2 * (size_t)Nc) != PMV_OK) { pmv_ba_problem_destroy(p); return nullptr; }
-            cudaMemcpyAsync(d_e, emax.data(), sizeof(double) * Nc, cudaMemcpyHostToDevice, s);
-            if (pmv_internal_ba_allreduce(ctx, d_e, d_e + Nc, Nc, 1, s) != PMV_OK) { pmv_ba_problem_destroy(p); return nullptr; }
-            cudaMemcpyAsync(emax.data(), d_e + Nc, sizeof(double) * Nc, cudaMemcpyDeviceToHost, s);
+            if (dev_alloc(p, &d_e, 4 * (size_t)Nc) != PMV_OK) { pmv_ba_problem_destroy(p); return nullptr; }
+            std::vector<double> ex(2 * (size_t)Nc);
+            for (int c = 0; c < Nc; c++) { ex[c] = emax[c]; ex[Nc + c] = h_camact[c]; }
+            cudaMemcpyAsync(d_e, ex.data(), sizeof(double) * 2 * Nc, cudaMemcpyHostToDevice, s);
+            if (pmv_internal_ba_allreduce(ctx, d_e, d_e + 2 * Nc, 2 * (size_t)Nc, 1, s) != PMV_OK) { pmv_ba_problem_destroy(p); return nullptr; }
+            cudaMemcpyAsync(ex.data(), d_e + 2 * Nc, sizeof(double) * 2 * Nc, cudaMemcpyDeviceToHost, s);
             if (cudaStreamSynchronize(s) != cudaSuccess) { ctx->fail(PMV_ERR_CUDA, "envelope exchange failed"); pmv_ba_problem_destroy(p); return nullptr; }
+            for (int c = 0; c < Nc; c++) { emax[c] = ex[c]; h_camact[c] = ex[Nc + c] > 0.5 ? 1 : 0; }
+            cudaMemcpyAsync(d_camact, h_camact.data(), sizeof(int) * Nc, cudaMemcpyHostToDevice, s);
+            if (cudaStreamSynchronize(s) != cudaSuccess) { ctx->fail(PMV_ERR_CUDA, "camera activity upload failed"); pmv_ba_problem_destroy(p); return nullptr; }
         }
         p->chol_lim.assign(nblk, (int)n);
         int run = 0;
@@ -545,8 +555,8 @@ PMV_API int pmv_ba_problem_solve(pmv_ba_problem *p, int max_iters)
     cudaStream_t s = ctx->stream;
     p->D.max_iters = max_iters;
     if (p->D.n <= 160) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(ba_cholesky_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
+        if (ctx->attr_first(PMV_ATTR_CHOL_SMALL))
+            cudaFuncSetAttribute(ba_cholesky_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     }
     ProfScope ps(ctx, PMV_PHASE_BA, s);
     // iteration 0 evaluates the cost even when max_iters == 0 (Ceres: IterationZero)
@@ -634,7 +644,7 @@ PMV_API int pmv_ba_solve_batched(pmv_ctx *ctx, double *poses, double *points, co
     if (!ctx) return PMV_ERR_INVALID;
     pmv_ba_problem *p = ba_problem_create(ctx, poses, points, obs, cam_idx, pt_idx, obs_off, W, Nc, Np, No, K,
                                           huber_delta, 0, 1, true);
-    if (!p) return PMV_ERR_INVALID;
+    if (!p) return ctx->last_code ? ctx->last_code : PMV_ERR_INVALID;   // the status ba_problem_create failed with
     int rc = pmv_ba_problem_solve(p, max_iters);
     if (rc == PMV_OK) rc = pmv_ba_problem_download(p, poses, points, sums);
     pmv_ba_problem_destroy(p);

@@ -39,6 +39,7 @@ struct BADev {
     const int *pt_off;    // W*Np + 1
     const int *cam_off;   // W*Nc + 1
     const int *cam_obs;   // No, observation indices grouped by (window, camera)
+    const int *cam_active; // W*Nc: the camera has an observation on ANY rank (a sharded rank may hold none of them)
     double fx, cx, fy, cy, delta;
     // parameters
     double *poses, *points, *cand_poses, *cand_points;

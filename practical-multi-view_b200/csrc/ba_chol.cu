@@ -365,8 +365,8 @@ int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_
             for (int k0 = 0, kb = 0; k0 < n; k0 += NB, kb++) maxw = std::max(maxw, (lim_host ? std::min(n, lim_host[kb]) : n) - k0);
             const int staged = (maxw <= BS_MAXW) && !getenv("PMV_CHOL_NO_STAGE");
             const size_t smem = staged ? sizeof(double) * (2 * NB * BS_MAXW + 512 + 3 * NB) : 0;
-            static bool attr = false;
-            if (!attr) { cudaFuncSetAttribute(chol_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+            if (ctx->attr_first(PMV_ATTR_CHOL_BACKSUB))
+                cudaFuncSetAttribute(chol_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             chol_backsub_kernel<<<1, BS_THREADS, smem, s>>>(S, b, y, n, D.chol_lim, st, staged);
             PMV_LAUNCH_CHECK(ctx, "chol_backsub_kernel");
         }

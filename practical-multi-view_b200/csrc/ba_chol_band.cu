@@ -604,11 +604,9 @@ int pmv_internal_ba_cholesky_band(pmv_ctx *ctx, double *S, double *b, int n, con
                         (size_t)Tp * (UMAX * 4 + PMAX * 2 + LMAX * 2 + 3) + (size_t)nblk * 2 + (size_t)Tp * Tp + 32;
     if (nslots > UMAX || nblk > 65535) return 0;
     if (smem > 220 * 1024) return 0;
-    static bool attr = false;
-    if (!attr) {
+    if (ctx->attr_first(PMV_ATTR_CHOL_BAND)) {
         cudaError_t e = cudaFuncSetAttribute(chol_band_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return ctx->fail(PMV_ERR_CUDA, "chol_band_cluster_kernel attribute", e);
-        attr = true;
     }
     const char *tr = getenv("PMV_CHOL_TRACE");
     if (tr && tr[0] == '1') {

@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(128) ba_cam_candidate_kernel(const BADev D, in
     const int w = wc / D.Nc;
     BAState *st = &D.st[w];
     if (st->done || !st->chol_ok) return;
-    const bool active = D.cam_off[wc + 1] > D.cam_off[wc];
+    const bool active = D.cam_active[wc] != 0;   // global over ranks: every rank must move the same replicated poses
     double sn = 0, xn = 0;
     for (int a = 0; a < 6; a++) {
         const size_t j = 6 * (size_t)wc + a;
@@ -897,6 +897,11 @@ __global__ void ba_lm_update_kernel(const BADev D)
     if (w >= D.W) return;
     BAState *st = &D.st[w];
     if (st->done) { st->accepted = 0; return; }
+    if (D.max_iters == 0) {   // Ceres with max_num_iterations = 0: iteration zero evaluates the cost, no step is taken
+        st->done = 1; st->termination = 0; st->accepted = 0; st->need_linearize = 0;
+        st->new_cost = 0; st->cand_cost = 0; st->model_change = 0; st->step_norm2 = 0; st->x_norm2 = 0;
+        return;
+    }
     st->iter++;
     st->scale_ready = 1;
     const bool valid = st->chol_ok && isfinite(st->model_change) && st->model_change > 0.0;

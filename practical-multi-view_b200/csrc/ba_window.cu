@@ -610,11 +610,9 @@ int pmv_internal_ba_window_iteration(pmv_ctx *ctx, const BADev &D, const unsigne
     const size_t unionB = (size_t)n * (n + 1) + n;
     const size_t smem_schur = sizeof(double) * ((size_t)Nc * 78 + 8 + std::max(unionA, unionB) + 2);
     const size_t smem_back = sizeof(double) * (size_t)Nc * 63;
-    static bool attr = false;
-    if (!attr) {
+    if (ctx->attr_first(PMV_ATTR_WIN_SCHUR)) {
         cudaFuncSetAttribute(win_schur_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(win_schur_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        attr = true;
     }
     win_prepare_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D, Wd, 0);
     PMV_LAUNCH_CHECK(ctx, "win_prepare_kernel");

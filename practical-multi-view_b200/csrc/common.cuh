@@ -87,6 +87,8 @@ struct PyrSet {  // all levels of one image batch
     int top = 0;  // effective max level
 };
 
+enum { PMV_ATTR_CHOL_SMALL = 0, PMV_ATTR_CHOL_BACKSUB, PMV_ATTR_CHOL_BAND, PMV_ATTR_WIN_SCHUR, PMV_ATTR_LK_BASE /* + KPIX (<= 32) */ };
+
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // ------------------------------------------------------------------ context -------------
@@ -100,6 +102,10 @@ struct pmv_ctx {
     std::vector<cudaEvent_t> chunk_ev;  // upload/compute hand-off events of the chunked host paths
     std::string err;
     uint64_t launches = 0;
+    // cudaFuncSetAttribute is per DEVICE: remembered per context (= per device), never per process.
+    // One bit per kernel family (PMV_ATTR_*); attr_first() is true the first time a bit is asked for.
+    uint64_t attr_done = 0;
+    bool attr_first(int bit) { const uint64_t m = 1ull << bit; if (attr_done & m) return false; attr_done |= m; return true; }
     void *nccl_comm = nullptr;          // ncclComm_t of the sharded bundle adjuster (ba_nccl.cu)
     int nranks = 1, rank = 0;
 
@@ -125,8 +131,10 @@ struct pmv_ctx {
     DevBuf scratch[8];
     PinBuf pin[4];
 
+    int last_code = 0;   // status of the last failure (entry points that return a handle report it through this)
     int fail(int code, const char *what, cudaError_t e = cudaSuccess)
     {
+        last_code = code;
         char b[512];
         if (e != cudaSuccess)
             snprintf(b, sizeof b, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));

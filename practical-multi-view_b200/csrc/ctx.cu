@@ -32,6 +32,7 @@ PMV_API void pmv_destroy(pmv_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->copy_stream);
+    pmv_comm_destroy(c);   // the communicator belongs to the context (no-op when none was made)
     for (auto &b : c->img) b.release();
     for (auto &b : c->pyr) b.release();
     for (auto &b : c->pts) b.release();

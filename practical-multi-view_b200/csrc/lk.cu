@@ -340,11 +340,8 @@ template <int KPIX>
 int launch_lk(pmv_ctx *ctx, LKParams &P, int batch, cudaStream_t s)
 {
     size_t smem = (size_t)P.smem_per_warp * LK_WARPS;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (ctx->attr_first(PMV_ATTR_LK_BASE + KPIX))
         cudaFuncSetAttribute(lk_track_kernel<KPIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
     dim3 grid((P.n + LK_WARPS - 1) / LK_WARPS, batch);
     lk_track_kernel<KPIX><<<grid, LK_WARPS * 32, smem, s>>>(P);
     PMV_LAUNCH_CHECK(ctx, "lk_track_kernel");

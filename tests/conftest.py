@@ -29,5 +29,5 @@ def ctx(pmv):
 
 @pytest.fixture(scope="session")
 def synth(pmv):
-    from pmv_b200 import synth as s
+    from harness import synth as s
     return s

@@ -10,7 +10,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 import pmv_b200  # noqa: E402
-from pmv_b200 import synth  # noqa: E402
+from harness import synth  # noqa: E402
 
 OUT = Path(__file__).parent
 

@@ -14,7 +14,8 @@ import torch.distributed as dist
 
 import oracle
 import pmv_b200
-from pmv_b200 import sharding, synth
+from pmv_b200 import sharding
+from harness import synth
 
 
 def main():

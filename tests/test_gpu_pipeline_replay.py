@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 def test_front_end_replay_matches_opencv_plugins(ctx):
     pytest.importorskip("cv2")
     from oracle.replay_backend import Cv2Backend
-    from pmv_b200 import replay
+    from harness import replay
     frames = replay.synthetic_sequence(12, stream=3)
     ref = replay.run_front_end(frames, Cv2Backend(), min_tracked=400, tol=10**6)   # tol raised: re-extraction on every frame
     got = replay.run_front_end(frames, replay.GpuBackend(ctx), min_tracked=400, tol=10**6)
@@ -28,7 +28,7 @@ def test_front_end_replay_matches_opencv_plugins(ctx):
 
 
 def test_grid_rois_match_reference_tiling():
-    from pmv_b200 import replay
+    from harness import replay
     rois = replay.grid_rois(376, 1241)
     assert len(rois) == 10                                   # 5 x 2 tiles
     assert rois[4] == (1020, 0, 221, 255) and rois[9] == (1020, 255, 221, 121)

@@ -45,7 +45,8 @@ def _worker(rank, world, port, out):
     import torch
     import torch.distributed as dist
     import pmv_b200
-    from pmv_b200 import sharding, synth
+    from pmv_b200 import sharding
+    from harness import synth
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         w = synth.ba_window(5, n_poses=4, n_points=37)

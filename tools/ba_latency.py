@@ -12,7 +12,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pmv_b200 as pmv  # noqa: E402
-from pmv_b200 import synth  # noqa: E402
+from harness import synth  # noqa: E402
 
 
 def probe(label, n_poses=5, n_points=400, iters=5, reps=200):
