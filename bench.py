@@ -1,5 +1,8 @@
 #!/usr/bin/env python
-"""bench.py -- BASELINE.json config 2: pyramidal-LK micro-benchmark on B200.
+"""bench.py -- the VO hot path on B200.  Headline line = BASELINE.json config 2 (pyramidal-LK micro-benchmark); the
+same JSON line carries a `workloads` object with configs 3 (4K extract + LK), 4 (4096 BA windows) and 5 (BAL-scale
+BA, point-sharded over the ranks with the NCCL all-reduce when --gpus N > 1), each with value / e2e / roofline /
+cpu_baseline and a parity block computed in the run.  `--workload X` prints one workload alone.
 
 A *step* is one pass of the front-end hot path over one batch of synthetic input:
 256 independent 1241x376 frame pairs, 2 000 tracked features per pair, 21x21 window,
@@ -102,6 +105,44 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_peaks():
+    try:
+        return json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        return {}
+
+
+def hbm_peak():
+    """(GB/s, provenance): the driver-measured copy bandwidth when present, else the profiling recipe's fallback."""
+    p = measured_peaks()
+    if "hbm_gbs" in p:
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def max_over_ranks(x: float, world: int) -> float:
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed_port(fn, threads):
+    """Time the -O3 -march=native build of the BA port with `threads` OpenMP threads (cpu_baseline legs)."""
+    import oracle
+    oracle.use_fast(True)
+    try:
+        oracle.set_threads(threads)
+        t0 = time.perf_counter()
+        r = fn()
+        return r, time.perf_counter() - t0
+    finally:
+        oracle.set_threads(os.cpu_count() or 1)
+        oracle.use_fast(False)
+
+
 def cpu_reference_rate(prev, nxt, pts, pairs: int, repeats: int = 1):
     """cv2.calcOpticalFlowPyrLK (pyramids built inside, as the reference calls it) on `pairs` pairs."""
     import cv2
@@ -163,9 +204,7 @@ def run_ba_windows(args, rank, world, local_rank):
     import pmv_b200
     from harness import synth
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    W, iters = args.windows, args.ba_iters
+    W, iters, steps = args.windows, args.ba_iters, args.steps
     distinct = min(W, int(os.environ.get("PMV_BENCH_DISTINCT", "16")))
     ws = [synth.ba_window(100000 * rank + i) for i in range(distinct)]
     sel = [ws[i % distinct] for i in range(W)]
@@ -193,7 +232,7 @@ def run_ba_windows(args, rank, world, local_rank):
     barrier(); sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         prob.reset(); prob.solve(iters)
     e1.record(stream)
     barrier()
@@ -201,43 +240,52 @@ def run_ba_windows(args, rank, world, local_rank):
     ms = e0.elapsed_time(e1); prof = ctx.profile_collect(); ctx.profile(False)
     P, X, S = prob.download()
     done_iters = float(np.mean([s["iterations"] for s in S]))
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    value = world * W * done_iters * args.steps / (float(t.item()) * 1e-3)
+    ms_max = max_over_ranks(ms, world)
+    value = world * W * done_iters * steps / (ms_max * 1e-3)
     # e2e: host arrays in -> create (index + upload) + solve + download, every step
-    te = time.perf_counter()
+    barrier(); te = time.perf_counter()
     P2, X2, S2 = ctx.ba_solve_batched(poses, points, obs, cam, pt, off.astype(np.int32), K, 1.0, iters)
-    t_e2e = time.perf_counter() - te
+    t_e2e = max_over_ranks(time.perf_counter() - te, world)
     e2e_value = world * W * float(np.mean([s["iterations"] for s in S2])) / t_e2e
+    out = None
     if rank == 0:
         import oracle
         nthr = os.cpu_count() or 1
         nw = min(W, int(os.environ.get("PMV_BENCH_CPU_WINDOWS", str(2 * nthr))))
         o1 = int(off[nw])
-        tc = time.perf_counter()
-        _, _, So = oracle.ba_solve_batched(poses[:nw], points[:nw], obs[:o1], cam[:o1], pt[:o1], off[:nw + 1].astype(np.int32),
-                                           K, 1.0, iters, nthreads=nthr)
-        tcpu = time.perf_counter() - tc
-        cpu_rate = float(np.sum([s["iterations"] for s in So])) / tcpu
+        sub = (poses[:nw], points[:nw], obs[:o1], cam[:o1], pt[:o1], off[:nw + 1].astype(np.int32), K, 1.0, iters)
+        # parity: the checker build (-O2, no contraction) on the first nw windows
+        _, _, So = oracle.ba_solve_batched(*sub, nthreads=nthr)
         rel = max(abs(S[i]["final_cost"] - So[i]["final_cost"]) / So[i]["final_cost"] for i in range(nw))
-        peaks = {}
-        try:
-            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-        except Exception:
-            pass
+        same_iters = all(S[i]["iterations"] == So[i]["iterations"] for i in range(nw))
+        # baseline: the same port built -O3 -march=native, with every host core and with the reference's 4 threads
+        (_, _, Sf), tcpu = timed_port(lambda: oracle.ba_solve_batched(*sub, nthreads=nthr), nthr)
+        cpu_rate = float(np.sum([x["iterations"] for x in Sf])) / tcpu
+        n4 = min(nw, 8)
+        sub4 = (poses[:n4], points[:n4], obs[:int(off[n4])], cam[:int(off[n4])], pt[:int(off[n4])], off[:n4 + 1].astype(np.int32), K, 1.0, iters)
+        (_, _, S4), t4 = timed_port(lambda: oracle.ba_solve_batched(*sub4, nthreads=4), 4)
+        cpu_rate4 = float(np.sum([x["iterations"] for x in S4])) / t4
         ba_ms, ba_n = prof.get("ba", (0.0, 0))
         n_obs = int(off[-1])
-        # dominant kernel = win_schur_kernel: fp64 FMA-bound; report the HBM roofline the contract asks for
-        # on the compulsory bytes of one iteration (obs 16 B + idx 8 B + point 24 B/pt + pose 48 B/cam)
-        alg = n_obs * 24 + W * 2000 * 24 + W * 20 * 48
         per_iter_ms = (ba_ms / max(ba_n, 1)) / max(done_iters, 1)
-        ach = alg / (per_iter_ms * 1e-3) / 1e9 if per_iter_ms else None
-        peak = float(peaks.get("hbm_gbs", 6650.0))
+        # dominant kernel = win_schur_kernel: fp64-FMA bound (k^2*108 + k*54 + 90k FMA per point with k
+        # observing poses).  Roofline = algorithmic fp64 flop of the point elimination / iteration time against the DMMA
+        # (mma.sync m8n8k4 f64) peak measured on this GPU in this run; the HBM figure on compulsory bytes sits beside it.
+        try:
+            dfma, dmma = ctx.probe_fp64()
+        except Exception:
+            dfma, dmma = None, None
+        kk = np.bincount(np.concatenate([w["pt_idx"] for w in ws[:1]]), minlength=2000).astype(np.float64)   # poses per point
+        fma_pt = float((kk * kk * 108 + kk * 54 + kk * 90).sum())
+        flop_iter = 2.0 * fma_pt * W
+        ach_tf = flop_iter / (per_iter_ms * 1e-3) / 1e12 if per_iter_ms else None
+        alg = n_obs * 24 + W * 2000 * 24 + W * 20 * 48
+        hbm, hbm_src = hbm_peak()
+        ach_gb = alg / (per_iter_ms * 1e-3) / 1e9 if per_iter_ms else None
         out = {"metric": "ba_window_lm_iterations_per_s", "value": value, "unit": "window-iterations/s", "n_gpus": world,
-               "steps": args.steps, "warmup": warmup, "ms_per_step": float(t.item()) / args.steps, "higher_is_better": True,
+               "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": f"BASELINE config 4: windowed BA bundle_size=20, 2000 points/window, {W} windows batched, "
+               "config": {"workload": f"BASELINE config 4: windowed BA bundle_size=20, 2000 points/window, {W} windows batched per GPU, "
                                       f"Schur + LM, {iters} iterations, Huber(1.0)", "windows": W, "observations": n_obs,
                           "l2_policy": f"inputs ({n_obs * 24 / 1e6:.0f} MB of observations) larger than the 126 MB L2" if n_obs * 24 > 126e6 else "flush not needed: see observations",
                           "parallelism": "independent windows per GPU, no collective"},
@@ -245,17 +293,21 @@ def run_ba_windows(args, rank, world, local_rank):
                        "d2h_bytes_per_step": int(poses.nbytes + points.nbytes), "api": "pmv_ba_solve_batched (host buffers; includes indexing the problem)",
                        "create_s": t_create},
                "gpu_launches": int(launches),
-               "roofline": {"kernel": "win_schur_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                            "frac": (ach / peak) if ach else None, "traffic": None,
-                            "note": "fp64-FMA bound (k^2*108 FMA per point), not HBM bound; HBM fraction on compulsory bytes per the contract",
-                            "avg_iteration_ms": per_iter_ms},
+               "roofline": {"kernel": "win_schur_kernel", "bound": "fp64 tensor (DMMA)", "achieved": ach_tf, "peak": dmma, "unit": "TFLOP/s",
+                            "frac": (ach_tf / dmma) if (ach_tf and dmma) else None, "traffic": None,
+                            "peak_source": "pmv_probe_fp64: mma.sync.m8n8k4.f64 chain on this GPU in this run",
+                            "dfma_peak_tflops": dfma, "algorithmic_flop_per_iteration": flop_iter, "avg_iteration_ms": per_iter_ms,
+                            "hbm": {"achieved": ach_gb, "peak": hbm, "unit": "GB/s", "frac": (ach_gb / hbm) if ach_gb else None,
+                                    "algorithmic_bytes_per_iteration": alg, "peak_source": hbm_src,
+                                    "note": "compulsory bytes (obs 16 B + idx 8 B, point 24 B, pose 48 B): not the binding roof"}},
                "cpu_baseline": {"value": cpu_rate, "unit": "window-iterations/s", "cores": nthr, "kind": "port",
-                                "sample": f"{nw} of {W} windows, {iters} iterations, oracle LM+Schur (OpenMP over windows, {tcpu:.1f} s)"},
-               "clocks": clocks, "parity_spot_check": {"max_rel_final_cost_diff_vs_oracle": rel, "windows_checked": nw}}
-        print(json.dumps(out))
+                                "sample": f"{nw} of {W} windows, {iters} iterations, LM+Schur port built -O3 -march=native, OpenMP over windows ({tcpu:.1f} s)",
+                                "with_4_threads": {"value": cpu_rate4, "cores": 4, "sample": f"{n4} windows ({t4:.1f} s); the reference sets num_threads=4"}},
+               "clocks": clocks,
+               "parity": {"max_rel_final_cost_diff_vs_oracle": rel, "same_iteration_counts": bool(same_iters), "windows_checked": nw,
+                          "tolerance": 1e-6, "ok": bool(rel <= 1e-6 and same_iters)}}
     prob.close(); ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return out
 
 
 def run_ba_large(args, rank, world, local_rank):
@@ -268,9 +320,7 @@ def run_ba_large(args, rank, world, local_rank):
     from pmv_b200 import sharding
     from harness import synth
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    iters = args.ba_iters
+    iters, steps = args.ba_iters, args.steps
     w = synth.ba_large(7, n_poses=args.cams, n_points=args.points, views=5, span=40)
     ctx = pmv_b200.Context(local_rank)
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
@@ -296,54 +346,92 @@ def run_ba_large(args, rank, world, local_rank):
     barrier(); sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         prob.reset(); prob.solve(iters)
     e1.record(stream)
     barrier()
     clocks = sampler.stop(); launches = ctx.launches - l0
     ms = e0.elapsed_time(e1)
     P, X, S = prob.download()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = max_over_ranks(ms, world)
     done_iters = S[0]["iterations"]
-    value = done_iters * args.steps / (float(t.item()) * 1e-3)
+    value = done_iters * steps / (ms_max * 1e-3)
+    # every rank must hold bit-identical replicated poses and the same accept/reject history (tests/mgpu_ba_sharded.py)
+    ranks_agree = True
+    if world > 1:
+        tp = torch.from_numpy(np.ascontiguousarray(P[0])).cuda(); mx, mn = tp.clone(), tp.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        tc_ = torch.tensor([S[0]["final_cost"], float(done_iters)], dtype=torch.float64, device="cuda"); cx, cn = tc_.clone(), tc_.clone()
+        dist.all_reduce(cx, op=dist.ReduceOp.MAX); dist.all_reduce(cn, op=dist.ReduceOp.MIN)
+        ranks_agree = bool((mx == mn).all()) and bool((cx == cn).all())
     # e2e: host arrays in -> create (index + upload) + solve + download
     barrier(); te = time.perf_counter()
     prob2 = ctx.ba_problem(w["poses"], pl, ol, cl, ptl, w["K"], 1.0, rank=rank, nranks=world)
     prob2.solve(iters); P2, X2, S2 = prob2.download()
-    barrier(); t_e2e = time.perf_counter() - te
+    barrier(); t_e2e = max_over_ranks(time.perf_counter() - te, world)
     prob2.close()
+    out = None
     if rank == 0:
-        cpu = None
-        if world == 1 and not args.no_cpu:
-            import oracle
+        import oracle
+        full = (w["poses"], w["points"], w["obs"], w["cam_idx"], w["pt_idx"], w["K"], 1.0)
+        parity, cpu = None, None
+        if not args.no_cpu:
+            # parity at FULL size: the checker build runs the same `iters` LM iterations on the host
             tc = time.perf_counter()
-            po, xo, so = oracle.ba_solve(w["poses"], w["points"], w["obs"], w["cam_idx"], w["pt_idx"], w["K"], 1.0, 2)
-            tcpu = time.perf_counter() - tc
-            cpu = {"value": so["iterations"] / tcpu, "unit": "LM iterations/s", "cores": os.cpu_count(), "kind": "port",
-                   "sample": f"2 LM iterations of the full problem, oracle LM + Schur + envelope Cholesky ({tcpu:.1f} s; OpenMP linearisation)"}
+            po, xo, so = oracle.ba_solve(*full, iters)
+            t_chk = time.perf_counter() - tc
+            rel = abs(S[0]["final_cost"] - so["final_cost"]) / so["final_cost"]
+            parity = {"final_cost": S[0]["final_cost"], "oracle_final_cost": so["final_cost"], "rel_final_cost_diff_vs_oracle": rel,
+                      "iterations": done_iters, "oracle_iterations": so["iterations"],
+                      "successful_steps": S[0]["successful_steps"], "oracle_successful_steps": so["successful_steps"],
+                      "max_abs_pose_diff": float(np.abs(P[0] - po).max()), "max_abs_point_diff_local_shard": float(np.abs(X[0] - xo[lo:hi]).max()),
+                      "ranks_bit_identical": ranks_agree, "tolerance": 1e-6, "oracle_seconds": t_chk,
+                      "ok": bool(rel <= 1e-6 and done_iters == so["iterations"] and S[0]["successful_steps"] == so["successful_steps"] and ranks_agree)}
+            if world == 1:
+                nthr = os.cpu_count() or 1
+                (_, _, sf), tcpu = timed_port(lambda: oracle.ba_solve(*full, 2), nthr)
+                (_, _, s4), t4 = timed_port(lambda: oracle.ba_solve(*full, 1), 4)
+                cpu = {"value": sf["iterations"] / tcpu, "unit": "LM iterations/s", "cores": nthr, "kind": "port",
+                       "sample": f"2 LM iterations of the full problem, LM + Schur + envelope Cholesky port built -O3 -march=native ({tcpu:.1f} s)",
+                       "with_4_threads": {"value": s4["iterations"] / t4, "cores": 4, "sample": f"1 LM iteration ({t4:.1f} s); the reference sets num_threads=4"}}
+        else:
+            parity = {"final_cost": S[0]["final_cost"], "ranks_bit_identical": ranks_agree, "ok": bool(ranks_agree), "note": "--no-cpu: oracle not run"}
         n_obs = len(w["obs"])
         n = 6 * args.cams
+        mn = np.full(args.points, 1 << 30, np.int64); mx = np.full(args.points, -1, np.int64)
+        np.minimum.at(mn, w["pt_idx"], w["cam_idx"]); np.maximum.at(mx, w["pt_idx"], w["cam_idx"])
+        span_cols = int(6 * ((mx - mn).max() + 1))                  # widest co-visibility, in columns of S
+        band_bytes = 8 * n * min(n, span_cols)                       # upper band of S actually touched
+        # compulsory bytes of one LM iteration = observations + indices (24 B/obs) + points read and
+        # candidate points written (2 x 24 B/point) + the band of the reduced camera system written once
+        alg = n_obs * 24 + 2 * args.points * 24 + band_bytes
+        per_iter_ms = ms_max / steps / max(done_iters, 1)
+        hbm, hbm_src = hbm_peak()
+        ach = alg / (per_iter_ms * 1e-3) / 1e9
+        ar_bytes = int((n * min(n, span_cols + 64) + 2 * n + 8) * 8)
         out = {"metric": "ba_large_lm_iterations_per_s", "value": value, "unit": "LM iterations/s", "n_gpus": world,
-               "steps": args.steps, "warmup": warmup, "ms_per_step": float(t.item()) / args.steps, "higher_is_better": True,
+               "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps, "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": f"BASELINE config 5: BAL-scale BA, {args.cams} cameras, {args.points} points, {n_obs} observations, "
-                                      f"points sharded over {world} GPU(s), NCCL all-reduce of [S|rhs] ({(n * n + n) * 8 / 1e6:.0f} MB) per iteration, "
-                                      f"{iters} LM iterations", "l2_policy": f"linearisation ({n_obs * 160 / 1e6:.0f} MB) + S ({n * n * 8 / 1e6:.0f} MB) larger than the 126 MB L2",
-                          "parallelism": f"points sharded x{world}, poses replicated"},
+               "config": {"workload": f"BASELINE config 5: BAL-scale BA, {args.cams} cameras, {args.points} points, {n_obs} observations "
+                                      f"(5 views among the 40 nearest poses), points sharded over {world} GPU(s), NCCL all-reduce of the band of [S|rhs] per iteration, "
+                                      f"{iters} LM iterations", "l2_policy": f"observations + points ({(n_obs * 24 + args.points * 48) / 1e6:.0f} MB per iteration) larger than the 126 MB L2",
+                          "parallelism": f"points sharded x{world}, poses replicated", "allreduce_bytes_per_iteration_approx": ar_bytes if world > 1 else 0,
+                          "nccl_ranks_on_data_plane": world if world > 1 else 0},
                "e2e": {"value": S2[0]["iterations"] / t_e2e, "unit": "LM iterations/s",
                        "h2d_bytes_per_step": int(len(ol) * 28 + w["poses"].nbytes + pl.nbytes), "d2h_bytes_per_step": int(w["poses"].nbytes + pl.nbytes),
                        "api": "pmv_ba_problem_create + solve + download (host buffers; includes indexing)"},
-               "gpu_launches": int(launches), "roofline": None, "cpu_baseline": cpu, "clocks": clocks,
+               "gpu_launches": int(launches),
+               "roofline": {"kernel": "one LM iteration (linearise + point elimination + banded Cholesky + back-substitution + candidate cost)",
+                            "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                            "peak_source": hbm_src, "algorithmic_bytes_per_iteration": alg, "avg_iteration_ms": per_iter_ms,
+                            "note": "whole-iteration figure; the serial banded factorisation (latency-bound, one cluster) is inside it"},
+               "cpu_baseline": cpu, "clocks": clocks, "parity": parity,
                "final_cost": S[0]["final_cost"], "initial_cost": S[0]["initial_cost"], "iterations": done_iters}
-        print(json.dumps(out))
     prob.close()
     if world > 1:
         ctx.comm_destroy()
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return out
 
 
 def run_extract(args, rank, world, local_rank):
@@ -356,9 +444,8 @@ def run_extract(args, rank, world, local_rank):
     import pmv_b200
     from harness import synth
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     Hh, Ww, NF = 2160, 3840, 10000
+    steps = args.steps
     f0, f1 = synth.frame_pair(500 + rank, h=Hh, w=Ww)
     ctx = pmv_b200.Context(local_rank)
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
@@ -380,23 +467,22 @@ def run_extract(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank); ctx.profile(True); ctx.profile_collect(); l0 = ctx.launches
     barrier(); sampler.start()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         xy, (nx, st, err) = step()
     barrier()
     dt = time.perf_counter() - t0
     clocks = sampler.stop(); launches = ctx.launches - l0
     prof = ctx.profile_collect()
-    for _ in range(args.steps):
+    for _ in range(steps):
         ctx.shitomasi(f0, NF)
     prof_shi = ctx.profile_collect()
-    for _ in range(args.steps):
+    for _ in range(steps):
         ctx.fast(f0, 10, True, NF)
     prof_fast = ctx.profile_collect()
     ctx.profile(False)
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    value = world * args.steps / float(t.item())
+    dt_max = max_over_ranks(dt, world)
+    value = world * steps / dt_max
+    out = None
     if rank == 0:
         import cv2
         cv2.setNumThreads(os.cpu_count() or 1)
@@ -407,13 +493,20 @@ def run_extract(args, rank, world, local_rank):
             cv2.calcOpticalFlowPyrLK(f0, f1, c, None, winSize=WIN, maxLevel=MAX_LEVEL)
         tcpu = (time.perf_counter() - tc) / reps
         c = c.reshape(-1, 2)
-        same = bool(len(c) == len(xy) and np.array_equal(c, xy))
-        peaks = {}
-        try:
-            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
+        # parity in numbers (north_star: same corner set up to response ties within 1e-5; LK within 0.01 px, same status)
+        from harness import parity as hp
+        eig = cv2.cornerMinEigenVal(f0, 3, ksize=3)
+        par = hp.list_parity(xy, c, eig)
+        ok_ties, why = hp.gftt_valid_up_to_ties(f0, xy, NF, 0.01, 5, eig=eig)
+        c1, cst, _ = cv2.calcOpticalFlowPyrLK(f0, f1, xy.reshape(-1, 1, 2).astype(np.float32), None, winSize=WIN, maxLevel=MAX_LEVEL)
+        okm = (cst.ravel() == 1) & (st == 1)
+        par.update({"valid_gftt_output_up_to_ties_1e-5": bool(ok_ties), "violations": why,
+                    "lk_4k_status_equal_to_cv2": bool(np.array_equal(st, cst.ravel())),
+                    "lk_4k_max_abs_dpos_px": float(np.abs(nx[okm] - c1.reshape(-1, 2)[okm]).max()) if okm.any() else None,
+                    "tracked": int(st.sum())})
+        par["ok"] = bool(par["set_equal"] and par["swaps_within_tie"] and ok_ties and par["lk_4k_status_equal_to_cv2"]
+                         and (par["lk_4k_max_abs_dpos_px"] or 0) < 0.01)
+        peak, peak_src = hbm_peak()
         npx = Hh * Ww
 
         def frac(ms_n, nbytes):
@@ -429,8 +522,8 @@ def run_extract(args, rank, world, local_rank):
                 "pyramid group (2 images, import + 3 levels + borders)": frac(prof.get("pyramid", (0, 0)), 2 * 11016000),
                 "lk_track_kernel<14> (10k features)": frac(prof.get("lk", (0, 0)), 2 * 11016000 + NF * 21)}
         main_k = kern["mineig_kernel (1 B/px in + 4 B/px out)"]
-        out = {"metric": "frames_per_s_extract_plus_lk", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-               "warmup": warmup, "ms_per_step": 1e3 * float(t.item()) / args.steps, "higher_is_better": True, "scaling": "weak",
+        out = {"metric": "frames_per_s_extract_plus_lk", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps,
+               "warmup": warmup, "ms_per_step": 1e3 * dt_max / steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "u8/int32+fp32", "data": "synthetic",
                "config": {"workload": "BASELINE config 3: Shi-Tomasi (goodFeaturesToTrack 10000, .01, 5) + pyramidal LK 21x21/maxLevel 3 on "
                                       "3840x2160 frames, one stream per GPU, host buffers every step", "image": [Hh, Ww], "features": NF,
@@ -440,14 +533,12 @@ def run_extract(args, rank, world, local_rank):
                        "api": "pmv_gftt + pmv_lk_track (host buffers)"},
                "gpu_launches": int(launches),
                "roofline": {"kernel": "mineig_kernel", "bound": "hbm", "achieved": main_k["achieved_GBps"] if main_k else None, "peak": peak,
-                            "unit": "GB/s", "frac": main_k["frac_of_hbm_peak"] if main_k else None, "traffic": None, "kernels": kern},
+                            "unit": "GB/s", "frac": main_k["frac_of_hbm_peak"] if main_k else None, "traffic": None, "peak_source": peak_src, "kernels": kern},
                "cpu_baseline": {"value": 1.0 / tcpu, "unit": "frames/s", "cores": cv2.getNumThreads(), "kind": "reference",
                                 "sample": f"cv2 {cv2.__version__} goodFeaturesToTrack + calcOpticalFlowPyrLK on the same frame pair, mean of {reps}"},
-               "clocks": clocks, "parity_spot_check": {"gftt_ordered_list_identical_to_cv2": same, "tracked": int(st.sum())}}
-        print(json.dumps(out))
+               "clocks": clocks, "parity": par}
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return out
 
 
 def run_pipeline(args, rank, world, local_rank):
@@ -479,6 +570,7 @@ def run_pipeline(args, rank, world, local_rank):
     l0 = ctx.launches
     log_g, tf_g, tb_g = drive(gpu_b, lambda: ctx.ba_solve(*ba_args, 1.0, 5))
     launches = ctx.launches - l0
+    out = None
     if rank == 0:
         import oracle
         from oracle.replay_backend import Cv2Backend
@@ -497,58 +589,20 @@ def run_pipeline(args, rank, world, local_rank):
                "cpu_baseline": {"value": fps_c, "unit": "frames/s", "cores": os.cpu_count(), "kind": "reference+port",
                                 "sample": "same frames: cv2 calcOpticalFlowPyrLK / goodFeaturesToTrack-equivalent oracle per ROI + oracle LM/Schur BA",
                                 "front_end_ms_per_frame": 1e3 * tf_c / nfr, "ba_ms_per_call": 1e3 * tb_c / max(nfr // 2, 1)},
-               "parity_spot_check": {"feature_sets_identical_every_frame": bool(same), "frames": nfr,
-                                     "re_extractions": int(sum(1 for x in log_g if x[2]))}}
-        print(json.dumps(out))
+               "parity": {"feature_sets_identical_every_frame": bool(same), "frames": nfr,
+                          "re_extractions": int(sum(1 for x in log_g if x[2])), "ok": bool(same)}}
     ctx.close()
+    return out
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=100)
-    ap.add_argument("--workload", default="lk", choices=["lk", "ba_windows", "ba_large", "extract", "pipeline"])
-    ap.add_argument("--cams", type=int, default=1000)
-    ap.add_argument("--points", type=int, default=1_000_000)
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--windows", type=int, default=4096)
-    ap.add_argument("--ba-iters", type=int, default=5)
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="pmv", choices=["pmv", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
-    args = ap.parse_args()
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-    if args.workload == "ba_windows":
-        run_ba_windows(args, rank, world, local_rank)
-        return
-    if args.workload == "ba_large":
-        run_ba_large(args, rank, world, local_rank)
-        return
-    if args.workload == "extract":
-        run_extract(args, rank, world, local_rank)
-        return
-    if args.workload == "pipeline":
-        run_pipeline(args, rank, world, local_rank)
-        return
-
+def run_lk(args, rank, world, local_rank):
+    """BASELINE config 2 (the headline): 256 frame pairs per GPU per step, weak scaling, no collective."""
     import torch
     import torch.distributed as dist
     import pmv_b200
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    batch = args.batch
+    batch, steps = args.batch, args.steps
     warmup = max(args.warmup, 3)
 
     prev, nxt, pts = make_workload(rank, batch)
@@ -581,17 +635,22 @@ def main():
     for _ in range(warmup):
         step_dev()
     barrier()
-    # parity spot check (outside the timed region): pair 0 vs cv2, the reference's kernel
-    parity = None
-    try:
-        import cv2
-        c1, cst, _ = cv2.calcOpticalFlowPyrLK(prev[0], nxt[0], pts[0].reshape(-1, 1, 2), None, winSize=WIN, maxLevel=MAX_LEVEL)
-        g1, gst = d_nx[0].cpu().numpy(), d_st[0].cpu().numpy()
+    # parity (outside the timed region): every DISTINCT pair of the batch vs cv2, the reference's kernel, plus
+    # bit-equality of the repeated pairs among themselves (north_star: identical status, positions within 0.01 px)
+    import cv2
+    distinct = min(batch, int(os.environ.get("PMV_BENCH_DISTINCT", "32")))
+    g_nx, g_st = d_nx.cpu().numpy(), d_st.cpu().numpy()
+    st_eq, dmax, tracked = True, 0.0, 0
+    for b in range(distinct if rank == 0 else 0):
+        c1, cst, _ = cv2.calcOpticalFlowPyrLK(prev[b], nxt[b], pts[b].reshape(-1, 1, 2), None, winSize=WIN, maxLevel=MAX_LEVEL)
         ok = cst.ravel() == 1
-        parity = {"status_equal": bool(np.array_equal(gst, cst.ravel())),
-                  "max_abs_dpos_px": float(np.abs(g1[ok] - c1.reshape(-1, 2)[ok]).max()), "tracked": int(ok.sum())}
-    except Exception as e:  # cv2 missing: parity is covered by tests
-        parity = {"error": str(e)}
+        st_eq = st_eq and bool(np.array_equal(g_st[b], cst.ravel()))
+        dmax = max(dmax, float(np.abs(g_nx[b][ok] - c1.reshape(-1, 2)[ok]).max()))
+        tracked += int(ok.sum())
+    rep_eq = all(np.array_equal(g_nx[b], g_nx[b % distinct]) and np.array_equal(g_st[b], g_st[b % distinct]) for b in range(batch))
+    parity = {"pairs_checked_vs_cv2": distinct, "status_equal": st_eq, "max_abs_dpos_px": dmax, "tracked": tracked,
+              "repeated_pairs_bit_identical": bool(rep_eq), "tolerance_px": 0.01,
+              "ok": bool(st_eq and dmax < 0.01 and rep_eq)}
 
     # ---- timed region (device resident) -----------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -602,7 +661,7 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_dev()
     e1.record(stream)
     barrier()
@@ -611,11 +670,8 @@ def main():
     ms = e0.elapsed_time(e1)
     prof = ctx.profile_collect()
     ctx.profile(False)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * batch * args.steps / (ms_max * 1e-3)
+    ms_max = max_over_ranks(ms, world)
+    value = world * batch * steps / (ms_max * 1e-3)
 
     # ---- e2e: host-buffer C-ABI call, pinned host memory, copies inside the timed region ------
     h_prev = torch.from_numpy(prev).pin_memory()
@@ -628,7 +684,7 @@ def main():
     def step_e2e():
         ctx.lk_track_batched(h_prev.numpy(), h_next.numpy(), h_pts.numpy(), WIN, MAX_LEVEL, out=outs)
 
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(steps, 5))
     for _ in range(2):
         step_e2e()
     barrier()
@@ -638,21 +694,12 @@ def main():
     e1.record(stream)
     barrier()
     ms_e = e0.elapsed_time(e1)
-    t = torch.tensor([ms_e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * batch * e2e_steps / (float(t.item()) * 1e-3)
+    e2e_value = world * batch * e2e_steps / (max_over_ranks(ms_e, world) * 1e-3)
     h2d = 2 * batch * H * W + batch * N_FEAT * 8
     d2h = batch * N_FEAT * (8 + 1 + 4)
 
     # ---- roofline of the dominant kernel (+ the HBM-bound pyramid kernel for reference) -------
-    peaks = {}
-    try:
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    peak, peak_src = hbm_peak()
     lk_ms, lk_n = prof.get("lk", (0.0, 0))
     py_ms, py_n = prof.get("pyramid", (0.0, 0))
     lk_avg = lk_ms / max(lk_n, 1)
@@ -685,6 +732,7 @@ def main():
                     "frac": (py_ach / peak) if py_ach else None, "avg_group_ms": py_avg,
                     "algorithmic_bytes_per_group": py_bytes, "share_of_step": py_ms / ms if ms else None}}}
 
+    out = None
     if rank == 0:
         cpu_pairs = int(os.environ.get("PMV_BENCH_CPU_PAIRS", str(batch)))
         cpu = None
@@ -703,18 +751,88 @@ def main():
                              f"calcOpticalFlowPyrLK incl. pyramids ({secs:.2f} s per pass)", "host_cpus": os.cpu_count()}
         out = {
             "metric": "frame_pairs_tracked_per_s", "value": value, "unit": "pairs/s", "n_gpus": world,
-            "steps": args.steps, "warmup": warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32+fp32", "data": "synthetic",
             "config": workload_config(),
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "pmv_lk_track_batched (host pinned buffers)"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "parity_spot_check": parity,
+            "parity": parity,
         }
-        print(json.dumps(out))
     ctx.close()
+    return out
+
+
+
+def sub_args(args, **kw):
+    a = argparse.Namespace(**vars(args))
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=100)
+    ap.add_argument("--workload", default="all", choices=["all", "lk", "ba_windows", "ba_large", "extract", "pipeline"])
+    ap.add_argument("--cams", type=int, default=1000)
+    ap.add_argument("--points", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--windows", type=int, default=4096)
+    ap.add_argument("--ba-iters", type=int, default=5)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="pmv", choices=["pmv", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
     if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    legs = {"lk": run_lk, "ba_windows": run_ba_windows, "ba_large": run_ba_large, "extract": run_extract, "pipeline": run_pipeline}
+    failed = []
+    if args.workload != "all":
+        out = legs[args.workload](args, rank, world, local_rank)
+    else:
+        # headline = config 2; configs 3 / 4 / 5 ride along as sub-lines with their own (shorter) step counts.
+        # At --gpus N > 1 config 5 is ONE problem point-sharded over the N ranks with the NCCL all-reduce on the
+        # data plane (strong scaling); configs 2 / 3 / 4 run one independent batch / stream / window set per rank.
+        out = run_lk(args, rank, world, local_rank)
+        subs = {}
+        for name, fn, a in (("extract_4k", run_extract, sub_args(args, steps=min(args.steps, 10))),
+                            ("ba_windows", run_ba_windows, sub_args(args, steps=min(args.steps, 3))),
+                            ("ba_large", run_ba_large, sub_args(args, steps=min(args.steps, 5)))):
+            if os.environ.get("PMV_BENCH_SKIP", "").find(name) >= 0:
+                continue
+            subs[name] = fn(a, rank, world, local_rank)
+        if rank == 0:
+            out["workloads"] = subs
+    if rank == 0:
+        for name, line in [("headline", out)] + list((out.get("workloads") or {}).items()):
+            p = (line or {}).get("parity") or {}
+            if p and p.get("ok") is False:
+                failed.append(name)
+        print(json.dumps(out))
+        sys.stdout.flush()
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if failed:
+        print(f"bench.py: PARITY FAILED in {failed} -- the numbers of those legs are void", file=sys.stderr)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -503,6 +503,17 @@ done:
     return sum.termination;
 }
 
+/* Thread count of the OpenMP regions (bench.py times the port with the reference's 4 threads,
+ * CeresBundleAdjustment.cpp:58, and with every host core). */
+ORC_API void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* W independent windows (BASELINE config 4): window w uses poses[w], points[w], and the observation
  * slice [obs_off[w], obs_off[w+1]).  OpenMP over windows. */
 ORC_API void orc_ba_solve_batched(double *poses, double *points, const double *obs, const int *cam_idx,

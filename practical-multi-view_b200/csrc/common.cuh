@@ -187,8 +187,7 @@ int pmv_internal_pyr_plan(pmv_ctx *ctx, int which, int batch, int rows, int cols
 // Import level 0 from device memory (any pitch) / expect it already copied into the interior
 // (src == nullptr), fill its border, then build levels 1..top with their borders.
 int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, const uint8_t *d_src, const uint8_t *d_src2,
-                         int src_pitch, size_t src_stride, cudaStream_t s);
-// Plan (and zero, when the geometry changed) derivative storage matching the levels of `set`; then compute
-// the derivatives of all levels of `batch` images (borders of `set` must be filled).
+                         int src_pitch, size_t src_stride, const DerivSet *dv, int n_deriv, cudaStream_t s);
+// Plan (and zero, when the geometry changed) derivative storage matching the levels of `set`; the planes of the
+// first n_deriv images are written by pmv_internal_pyr_run in the same pass that builds the levels.
 int pmv_internal_deriv_plan(pmv_ctx *ctx, const PyrSet &set, int batch, DerivSet *out, cudaStream_t s);
-int pmv_internal_deriv_run(pmv_ctx *ctx, const PyrSet &set, const DerivSet &d, int batch, cudaStream_t s);

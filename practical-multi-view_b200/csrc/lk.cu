@@ -384,17 +384,14 @@ int lk_enqueue(pmv_ctx *ctx, const PyrSet &sp, const PyrSet &sn, const DerivSet 
     int rc;
     {
         ProfScope ps(ctx, PMV_PHASE_PYRAMID, s);
+        const DerivSet *dp = n > 0 ? &dv : nullptr;
         if (sn.lv[0].ptr == sp.lv[0].ptr + (size_t)batch * sp.lv[0].img_stride) {
-            rc = pmv_internal_pyr_run(ctx, sp, 2 * batch, d_prev, d_next, pitch, img_stride, s);
+            rc = pmv_internal_pyr_run(ctx, sp, 2 * batch, d_prev, d_next, pitch, img_stride, dp, batch, s);
             if (rc) return rc;
         } else {  // chunk smaller than the planned batch: the two sets are not adjacent -> two passes
-            rc = pmv_internal_pyr_run(ctx, sp, batch, d_prev, nullptr, pitch, img_stride, s);
+            rc = pmv_internal_pyr_run(ctx, sp, batch, d_prev, nullptr, pitch, img_stride, dp, batch, s);
             if (rc) return rc;
-            rc = pmv_internal_pyr_run(ctx, sn, batch, d_next, nullptr, pitch, img_stride, s);
-            if (rc) return rc;
-        }
-        if (n > 0) {
-            rc = pmv_internal_deriv_run(ctx, sp, dv, batch, s);
+            rc = pmv_internal_pyr_run(ctx, sn, batch, d_next, nullptr, pitch, img_stride, nullptr, 0, s);
             if (rc) return rc;
         }
     }

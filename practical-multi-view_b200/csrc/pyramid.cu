@@ -12,82 +12,163 @@
 // Kernels (all HBM-bound streaming kernels, DESIGN.md has the byte counts):
 //   import_kernel      caller image (any pitch) -> interior of the bordered level 0
 //   border_fill_kernel reflect-101 border of one level, all images of the batch
-//   pyr_down_kernel    register-resident: a warp = 60 x 8 outputs, packed 16-bit SIMD-in-register
-//                      arithmetic, neighbour sums by warp shuffles, no shared memory
+//   pyr_fused_kernel   one TMA box load per 128 x 32 tile of level l -> bordered level-0 copy, Scharr plane of level l
+//                      and level l + 1, all from the same shared-memory tile (one launch per level)
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int PW_OUT = 60;   // outputs per warp-row: lanes 1..30 produce two each (lanes 0 / 31 are halo)
-constexpr int PW_R = 8;      // output rows per warp
+// ------------------------------------------------------------------ fused level kernel ---
+// One CTA = one 128 x 32 tile of source level l of one image.  The tile and its halo (2 rows above / below, 8 bytes
+// left / right) arrive in shared memory through ONE TMA box load (cp.async.bulk.tensor, u8 tensor map over the
+// image interior: out-of-image bytes come back as zero and are patched to BORDER_REFLECT_101 in shared memory by the
+// edge tiles).  From that single pass over the source the CTA writes
+//   (COPY)  the interior of the bordered level-0 copy the tracker reads          16 B stores
+//   (deriv) the Scharr derivative plane of level l, one packed word per pixel    16 B stores
+//   (down)  level l + 1 = pyrDown(level l), packed 16-bit SIMD-in-register       4 B stores
+// so every level is read from HBM once and each output byte is written once.
+constexpr int FT_W = 128, FT_H = 32, FT_HX = 16, FT_HY = 2;   // the box must START on a 16-byte boundary (tools/tma_probe.cu)
+constexpr int FT_P = FT_W + 2 * FT_HX;      // 160: tile pitch = TMA box width (multiple of 16 B)
+constexpr int FT_R = FT_H + 2 * FT_HY;      // 36 rows
+constexpr uint32_t FT_BYTES = FT_P * FT_R;  // 5760
 
-// One aligned 32-bit word of a level row; words touching columns outside [0, cols) are assembled
-// byte-wise with reflect-101 (edge lanes only).
-__device__ __forceinline__ uint32_t pyr_load_word(const uint8_t *__restrict__ row, int col0, int cols)
-{
-    if (col0 >= 0 && col0 + 4 <= cols) return __ldg(reinterpret_cast<const uint32_t *>(row + col0));
-    uint32_t v = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int c = col0 + k;
-        c = c < -2 ? 0 : (c > cols + 1 ? cols - 1 : reflect101(c, cols));   // beyond the taps: any in-range byte
-        v |= (uint32_t)__ldg(row + c) << (8 * k);
-    }
-    return v;
-}
+struct FusedArgs {
+    int rows, cols;                 // source level
+    int n_first;                    // images [0, n_first) come from map A, the rest from map B (caller prev / next)
+    uint8_t *copy; int cpitch; size_t cstride;           // bordered level-0 interior (COPY)
+    int *der; int dpitch; size_t dstride; int n_deriv;   // derivative plane of images [0, n_deriv)
+    uint8_t *down; int drows, dcols, wpitch; size_t wstride;   // level l + 1 (nullptr: top level)
+};
 
-// K1 pyrDown, register-resident: a warp owns 60 output columns x PW_R output rows.  Lane L holds the
-// 4-byte input word at columns 2*x0 - 4 + 4L; the vertical [1 4 6 4 1] pass runs on two packed 16-bit
-// lanes per register (even / odd input columns, sums <= 4080), the horizontal pass on packed output
-// pairs (sums <= 65280) with the neighbouring lanes' partial sums fetched by shuffles.  No shared
-// memory, no barriers; every input word is read once per warp (+ 2 halo lanes, + 3 halo rows per 16).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool COPY>
 __global__ void __launch_bounds__(256)
-pyr_down_kernel(const uint8_t *__restrict__ src, int srows, int scols, int spitch, size_t sstride,
-                uint8_t *__restrict__ dst, int drows, int dcols, int dpitch, size_t dstride)
+pyr_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const FusedArgs A)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x0 = blockIdx.x * PW_OUT;                         // first output column of the warp
-    const int y0 = (blockIdx.y * 8 + warp) * PW_R;              // first output row of the warp
-    if (y0 >= drows) return;
-    src += (size_t)blockIdx.z * sstride;
-    dst += (size_t)blockIdx.z * dstride;
-    const int col0 = 2 * x0 - 4 + 4 * lane;                     // input column of byte 0 of this lane's word
-    const uint32_t M = 0x00ff00ffu;
-
-    // all 2*PW_R + 3 input rows of the warp are requested up front (independent loads: enough bytes in
-    // flight to cover HBM latency), rows past the image fold back through reflect-101 and are harmless
-    uint32_t win[2 * PW_R + 3];
-#pragma unroll
-    for (int k = 0; k < 2 * PW_R + 3; k++) {
-        const uint8_t *row = src + (size_t)reflect101(2 * y0 - 2 + k, srows) * spitch;
-        win[k] = pyr_load_word(row, col0, scols);
+    __shared__ __align__(128) uint8_t tile[FT_BYTES];
+    __shared__ __align__(8) uint64_t bar;
+    const int t = threadIdx.x;
+    const int x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H, z = blockIdx.z;
+    if (t == 0) {
+        const uint32_t b = smem_u32(&bar), d = smem_u32(tile);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(FT_BYTES) : "memory");
+        const bool first = z < A.n_first;
+        const CUtensorMap *m = first ? &mapA : &mapB;
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(d), "l"(m), "r"(x0 - FT_HX), "r"(y0 - FT_HY), "r"(first ? z : z - A.n_first), "r"(b) : "memory");
     }
-#pragma unroll
-    for (int r = 0; r < PW_R; r++) {
-        const int y = y0 + r;
-        if (y >= drows) break;                                  // warp-uniform
-        uint32_t e[5], o[5];                                    // rows 2y-2 .. 2y+2, even / odd columns
-#pragma unroll
-        for (int k = 0; k < 5; k++) { e[k] = win[2 * r + k] & M; o[k] = (win[2 * r + k] >> 8) & M; }
-        // vertical pass (two input columns per register)
-        const uint32_t VE = e[0] + e[4] + ((e[1] + e[3]) << 2) + e[2] * 6u;   // (V0, V2)
-        const uint32_t VO = o[0] + o[4] + ((o[1] + o[3]) << 2) + o[2] * 6u;   // (V1, V3)
-        const uint32_t VEl = __shfl_up_sync(0xffffffffu, VE, 1), VOl = __shfl_up_sync(0xffffffffu, VO, 1);
-        const uint32_t VEr = __shfl_down_sync(0xffffffffu, VE, 1);
-        // horizontal pass on the output pair (x, x+1), x = x0 + 2 (lane - 1)
-        const uint32_t A = __byte_perm(VEl, VE, 0x5432);        // (V[-2], V0)
-        const uint32_t B = __byte_perm(VOl, VO, 0x5432);        // (V[-1], V1)
-        const uint32_t F = __byte_perm(VE, VEr, 0x5432);        // (V2, V4)
-        const uint32_t res = A + F + ((B + VO) << 2) + VE * 6u + 0x00800080u;
-        const uint32_t two = __byte_perm((res >> 8) & M, 0u, 0x4420);   // out(x) | out(x+1) << 8
-        const uint32_t nb = __shfl_down_sync(0xffffffffu, two, 1);
-        if ((lane & 1) && lane < 31) {
-            const int ox = x0 + 2 * (lane - 1);
-            if (ox < dcols) {
-                const uint32_t four = two | (nb << 16);
-                // row pitch padding absorbs a partial word at the right edge (border fill follows)
-                *reinterpret_cast<uint32_t *>(dst + (size_t)y * dpitch + ox) = four;
+    __syncthreads();   // the initialised barrier is visible to every waiter
+    {
+        const uint32_t b = smem_u32(&bar);
+        asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@!p bra WAIT_%=;\n}" ::"r"(b) : "memory");
+    }
+    const int rows = A.rows, cols = A.cols;
+    // edge tiles: the (at most two) rows / columns beyond each image edge that the taps reach -> reflect-101
+    if (x0 == 0 || y0 == 0 || x0 + FT_W + 2 > cols || y0 + FT_H + 2 > rows) {
+        for (int i = t; i < 4 * FT_P + 4 * FT_R; i += 256) {
+            int r, c;   // tile coordinates
+            if (i < 4 * FT_P) {
+                const int k = i / FT_P;
+                c = i - k * FT_P;
+                const int y = k < 2 ? k - 2 : rows + (k - 2);   // image rows -2, -1, rows, rows + 1
+                r = y - (y0 - FT_HY);
+            } else {
+                const int j = i - 4 * FT_P, k = j / FT_R;
+                r = j - k * FT_R;
+                const int x = k < 2 ? k - 2 : cols + (k - 2);
+                c = x - (x0 - FT_HX);
             }
+            if (r < 0 || r >= FT_R || c < 0 || c >= FT_P) continue;
+            const int y = y0 - FT_HY + r, x = x0 - FT_HX + c;
+            if (y >= 0 && y < rows && x >= 0 && x < cols) continue;
+            const int sy = reflect101(y < -2 ? -2 : (y > rows + 1 ? rows + 1 : y), rows) - (y0 - FT_HY);
+            const int sx = reflect101(x < -2 ? -2 : (x > cols + 1 ? cols + 1 : x), cols) - (x0 - FT_HX);
+            if (sy >= 0 && sy < FT_R && sx >= 0 && sx < FT_P) tile[r * FT_P + c] = tile[sy * FT_P + sx];
+        }
+        __syncthreads();
+    }
+    if (COPY) {
+        const int r = t >> 3, ch = t & 7;
+        const int y = y0 + r, x = x0 + 16 * ch;
+        if (y < rows && x < cols) {
+            // the right border of the destination absorbs the tail of the last chunk (filled afterwards)
+            *reinterpret_cast<uint4 *>(A.copy + (size_t)z * A.cstride + (size_t)y * A.cpitch + x) =
+                *reinterpret_cast<const uint4 *>(tile + (r + FT_HY) * FT_P + FT_HX + 16 * ch);
+        }
+    }
+    if (z < A.n_deriv) {
+        // Scharr: 4 pixels x 4 rows per thread, three aligned words per source row (bytes x - 4 .. x + 7)
+        const int strip = t & 31, rg = t >> 5;
+        const int x = x0 + 4 * strip;
+        if (x < cols && y0 + 4 * rg < rows) {
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(tile + (4 * rg + FT_HY - 1) * FT_P + FT_HX - 4 + 4 * strip);
+            uint32_t w[6][3];
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int k = 0; k < 3; k++) w[r][k] = wp[r * (FT_P / 4) + k];
+            int *dp = A.der + (size_t)z * A.dstride + (size_t)(y0 + 4 * rg) * A.dpitch + x;
+#pragma unroll
+            for (int rr = 0; rr < 4; rr++) {
+                if (y0 + 4 * rg + rr >= rows) break;
+                int s0[6], s1[6];
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    const int bi = c + 3;
+                    const int a0 = (w[rr][bi >> 2] >> (8 * (bi & 3))) & 255, a1 = (w[rr + 1][bi >> 2] >> (8 * (bi & 3))) & 255,
+                              a2 = (w[rr + 2][bi >> 2] >> (8 * (bi & 3))) & 255;
+                    s0[c] = 3 * (a0 + a2) + 10 * a1;
+                    s1[c] = a2 - a0;
+                }
+                int out[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int gx = s0[k + 2] - s0[k], gy = 3 * (s1[k] + s1[k + 2]) + 10 * s1[k + 1];
+                    out[k] = (x + k < cols) ? ((gx & 0xffff) | (int)((unsigned)gy << 16)) : 0;
+                }
+                *reinterpret_cast<int4 *>(dp + (size_t)rr * A.dpitch) = make_int4(out[0], out[1], out[2], out[3]);
+            }
+        }
+    }
+    if (A.down) {
+        // pyrDown: 4 outputs per thread; vertical [1 4 6 4 1] on packed even / odd columns, horizontal on packed pairs
+        const int j = t & 15, orow = t >> 4;
+        const int ox = (x0 >> 1) + 4 * j, oy = (y0 >> 1) + orow;
+        if (ox < A.dcols && oy < A.drows) {
+            const uint32_t M = 0x00ff00ffu;
+            uint32_t VE[4], VO[4];   // the four words from source column 2 ox - 4 on (bytes 4 .. 19 of three 8-byte loads)
+            {
+                uint32_t e[5][4], o[5][4];
+#pragma unroll
+                for (int r = 0; r < 5; r++) {
+                    const uint2 *sp = reinterpret_cast<const uint2 *>(tile + (2 * orow + r) * FT_P + FT_HX - 8 + 8 * j);
+                    const uint2 q0 = sp[0], q1 = sp[1], q2 = sp[2];
+                    const uint32_t wv[4] = {q0.y, q1.x, q1.y, q2.x};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { e[r][k] = wv[k] & M; o[r][k] = (wv[k] >> 8) & M; }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    VE[k] = e[0][k] + e[4][k] + ((e[1][k] + e[3][k]) << 2) + e[2][k] * 6u;
+                    VO[k] = o[0][k] + o[4][k] + ((o[1][k] + o[3][k]) << 2) + o[2][k] * 6u;
+                }
+            }
+            // V index of word k (k = 0..3 <-> bytes 4 + 4k ..): VE[k] = (V[4+4k], V[6+4k]), VO[k] = (V[5+4k], V[7+4k]);
+            // output m is centred on V[8 + 2m]
+            const uint32_t A01 = __byte_perm(VE[0], VE[1], 0x5432);   // (V6,  V8)
+            const uint32_t F01 = __byte_perm(VE[1], VE[2], 0x5432);   // (V10, V12)
+            const uint32_t B01 = __byte_perm(VO[0], VO[1], 0x5432);   // (V7,  V9)
+            const uint32_t r01 = A01 + F01 + ((B01 + VO[1]) << 2) + VE[1] * 6u + 0x00800080u;
+            const uint32_t F23 = __byte_perm(VE[2], VE[3], 0x5432);   // (V14, V16)
+            const uint32_t B23 = __byte_perm(VO[1], VO[2], 0x5432);   // (V11, V13)
+            const uint32_t r23 = F01 + F23 + ((B23 + VO[2]) << 2) + VE[2] * 6u + 0x00800080u;
+            // row pitch padding absorbs a partial word at the right edge (border fill follows)
+            *reinterpret_cast<uint32_t *>(A.down + (size_t)z * A.wstride + (size_t)oy * A.wpitch + ox) = __byte_perm(r01, r23, 0x7531);
         }
     }
 }
@@ -203,41 +284,6 @@ scharr_kernel(const uint8_t *__restrict__ src, int rows, int cols, int pitch, sh
     dst[(size_t)y * cols + x] = make_short2((short)(t0p - t0m), (short)(3 * (t1m + t1p) + 10 * t1c));
 }
 
-// K2 for the LK tracker: derivative of every pixel of a bordered level, 4 pixels per thread (three aligned
-// words per input row, one 16 B store).  Reads run 1 px into the reflect-101 border of the level, so the
-// values at the image edge are OpenCV's; pixels beyond the last column are written as zero (they belong
-// to the zero border of the derivative plane).
-__global__ void __launch_bounds__(256)
-scharr_level_kernel(const uint8_t *__restrict__ img, int rows, int cols, int pitch, size_t istride,
-                    int *__restrict__ der, int dpitch, size_t dstride)
-{
-    const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x0 >= cols || y >= rows) return;
-    const uint8_t *base = img + (size_t)blockIdx.z * istride + (size_t)(y - 1) * pitch + x0 - 4;
-    uint32_t wv[3][3];
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int k = 0; k < 3; k++) wv[r][k] = *reinterpret_cast<const uint32_t *>(base + (size_t)r * pitch + 4 * k);
-    int t0[6], t1[6];   // columns x0 - 1 .. x0 + 4
-#pragma unroll
-    for (int c = 0; c < 6; c++) {
-        const int bi = c + 3;   // byte index in the 12-byte row
-        const int a0 = (wv[0][bi >> 2] >> (8 * (bi & 3))) & 255, a1 = (wv[1][bi >> 2] >> (8 * (bi & 3))) & 255,
-                  a2 = (wv[2][bi >> 2] >> (8 * (bi & 3))) & 255;
-        t0[c] = 3 * (a0 + a2) + 10 * a1;
-        t1[c] = a2 - a0;
-    }
-    int out[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int gx = t0[k + 2] - t0[k], gy = 3 * (t1[k] + t1[k + 2]) + 10 * t1[k + 1];
-        out[k] = (x0 + k < cols) ? ((gx & 0xffff) | (int)((unsigned)gy << 16)) : 0;
-    }
-    *reinterpret_cast<int4 *>(der + (size_t)blockIdx.z * dstride + (size_t)y * dpitch + x0) = make_int4(out[0], out[1], out[2], out[3]);
-}
-
 }  // namespace
 
 int pmv_internal_deriv_plan(pmv_ctx *ctx, const PyrSet &set, int batch, DerivSet *out, cudaStream_t s)
@@ -264,18 +310,6 @@ int pmv_internal_deriv_plan(pmv_ctx *ctx, const PyrSet &set, int batch, DerivSet
         ctx->deriv_sig = sig;
     }
     for (int l = 0; l <= set.top; l++) out->lv[l].ptr = ctx->deriv.as<int>() + off[l];
-    return PMV_OK;
-}
-
-int pmv_internal_deriv_run(pmv_ctx *ctx, const PyrSet &set, const DerivSet &d, int batch, cudaStream_t s)
-{
-    for (int l = 0; l <= set.top; l++) {
-        const PyrLevel &a = set.lv[l];
-        dim3 grid((a.cols + 255) / 256, (a.rows + 3) / 4, batch);
-        scharr_level_kernel<<<grid, 256, 0, s>>>(a.ptr, a.rows, a.cols, a.pitch, a.img_stride,
-                                                 const_cast<int *>(d.lv[l].ptr), d.lv[l].pitch, d.lv[l].img_stride);
-        PMV_LAUNCH_CHECK(ctx, "scharr_level_kernel");
-    }
     return PMV_OK;
 }
 
@@ -324,30 +358,103 @@ static int fill_borders(pmv_ctx *ctx, const PyrSet &set, int batch, cudaStream_t
     return PMV_OK;
 }
 
+// ------------------------------------------------------------------ tensor maps ---------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static bool tma_ok(const void *ptr, int pitch, size_t stride, int nimg)
+{
+    return ((uintptr_t)ptr % 16 == 0) && (pitch % 16 == 0) && (nimg == 1 || stride % 16 == 0);
+}
+
+// u8 images [nimg][rows][cols] (row pitch / image stride in bytes), box = one fused tile with its halo
+static int make_image_map(pmv_ctx *ctx, CUtensorMap *m, const uint8_t *ptr, int rows, int cols, int pitch, size_t stride, int nimg)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return ctx->fail(PMV_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    if (nimg == 1 || stride % 16) stride = (size_t)pitch * (rows > 0 ? rows : 1);
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)nimg};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)stride};
+    const cuuint32_t box[3] = {FT_P, FT_R, 1}, es[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ctx->fail(PMV_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    return PMV_OK;
+}
+
 // d_src / d_src2: caller images for the first / second half of the batch (prev / next image sets share one
-// bordered allocation so every pyramid kernel runs once per step); d_src2 == nullptr -> one source.
+// bordered allocation so every pyramid kernel runs once per step); d_src2 == nullptr -> one source;
+// d_src == nullptr -> level 0 was already copied into the planned interior.  dv != nullptr: the Scharr planes of
+// images [0, n_deriv) are written from the same pass.  One fused launch per level, then one border launch.
 int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, const uint8_t *d_src, const uint8_t *d_src2,
-                         int src_pitch, size_t src_stride, cudaStream_t s)
+                         int src_pitch, size_t src_stride, const DerivSet *dv, int n_deriv, cudaStream_t s)
 {
     const PyrLevel &l0 = set.lv[0];
-    if (d_src) {
-        const int half = d_src2 ? batch / 2 : batch;
+    const int half = d_src2 ? batch / 2 : batch;
+    bool direct = d_src && tma_ok(d_src, src_pitch, src_stride, half) && (!d_src2 || tma_ok(d_src2, src_pitch, src_stride, half));
+    if (d_src && !direct) {   // unaligned caller images: import first, then the fused pass reads our own level 0
         const uint8_t *srcs[2] = {d_src, d_src2};
         for (int k = 0; k < (d_src2 ? 2 : 1); k++) {
-            int al = (((uintptr_t)srcs[k]) % 16 == 0) && (src_pitch % 16 == 0) && (src_stride % 16 == 0);
             dim3 grid((l0.cols + 511) / 512, (l0.rows + 7) / 8, half);
             import_kernel<<<grid, 256, 0, s>>>(srcs[k], src_pitch, src_stride, l0.rows, l0.cols,
                                                const_cast<uint8_t *>(l0.ptr) + (size_t)k * half * l0.img_stride,
-                                               l0.pitch, l0.img_stride, al);
+                                               l0.pitch, l0.img_stride, 0);
             PMV_LAUNCH_CHECK(ctx, "import_kernel");
         }
     }
-    for (int l = 1; l <= set.top; l++) {
-        const PyrLevel &a = set.lv[l - 1], &d = set.lv[l];
-        dim3 grid((d.cols + PW_OUT - 1) / PW_OUT, (d.rows + 8 * PW_R - 1) / (8 * PW_R), batch);
-        pyr_down_kernel<<<grid, 256, 0, s>>>(a.ptr, a.rows, a.cols, a.pitch, a.img_stride,
-                                             const_cast<uint8_t *>(d.ptr), d.rows, d.cols, d.pitch, d.img_stride);
-        PMV_LAUNCH_CHECK(ctx, "pyr_down_kernel");
+    if (!dv) n_deriv = 0;
+    for (int l = 0; l <= set.top; l++) {
+        const PyrLevel &a = set.lv[l];
+        const bool down = l < set.top;
+        if (!down && n_deriv == 0) break;
+        FusedArgs A;
+        memset(&A, 0, sizeof A);
+        A.rows = a.rows; A.cols = a.cols; A.n_first = batch;
+        CUtensorMap mA, mB;
+        int rc;
+        const bool copy = (l == 0 && direct);
+        if (copy) {
+            rc = make_image_map(ctx, &mA, d_src, a.rows, a.cols, src_pitch, src_stride, half);
+            if (rc) return rc;
+            mB = mA;
+            if (d_src2) {
+                rc = make_image_map(ctx, &mB, d_src2, a.rows, a.cols, src_pitch, src_stride, half);
+                if (rc) return rc;
+                A.n_first = half;
+            }
+            A.copy = const_cast<uint8_t *>(a.ptr); A.cpitch = a.pitch; A.cstride = a.img_stride;
+        } else {
+            rc = make_image_map(ctx, &mA, a.ptr, a.rows, a.cols, a.pitch, a.img_stride, batch);
+            if (rc) return rc;
+            mB = mA;
+        }
+        if (n_deriv > 0) {
+            A.der = const_cast<int *>(dv->lv[l].ptr); A.dpitch = dv->lv[l].pitch; A.dstride = dv->lv[l].img_stride; A.n_deriv = n_deriv;
+        }
+        // the top level only carries derivatives: no CTA for images without them
+        const int nz = down ? batch : n_deriv;
+        if (down) {
+            const PyrLevel &d = set.lv[l + 1];
+            A.down = const_cast<uint8_t *>(d.ptr); A.drows = d.rows; A.dcols = d.cols; A.wpitch = d.pitch; A.wstride = d.img_stride;
+        }
+        dim3 grid((a.cols + FT_W - 1) / FT_W, (a.rows + FT_H - 1) / FT_H, nz);
+        if (copy) pyr_fused_kernel<true><<<grid, 256, 0, s>>>(mA, mB, A);
+        else pyr_fused_kernel<false><<<grid, 256, 0, s>>>(mA, mB, A);
+        PMV_LAUNCH_CHECK(ctx, "pyr_fused_kernel");
     }
     return fill_borders(ctx, set, batch, s);
 }
@@ -382,7 +489,7 @@ PMV_API int pmv_pyramid_build(pmv_ctx *ctx, const uint8_t *img, int rows, int co
     const PyrLevel &l0 = set.lv[0];
     PMV_CUDA_TRY(ctx, cudaMemcpy2DAsync(const_cast<uint8_t *>(l0.ptr), l0.pitch, img, step, cols, rows,
                                         cudaMemcpyHostToDevice, ctx->stream));
-    rc = pmv_internal_pyr_run(ctx, set, 1, nullptr, nullptr, 0, 0, ctx->stream);
+    rc = pmv_internal_pyr_run(ctx, set, 1, nullptr, nullptr, 0, 0, nullptr, 0, ctx->stream);
     if (rc) return rc;
     size_t need = 0;
     for (int l = 1; l <= set.top; l++) need += (size_t)set.lv[l].rows * set.lv[l].cols;
