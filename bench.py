@@ -727,7 +727,7 @@ def run_lk(args, rank, world, local_rank):
                 "avg_launch_ms": lk_avg, "algorithmic_bytes_per_launch": lk_bytes,
                 "share_of_step": lk_ms / ms if ms else None,
                 "note": "LK is integer-issue/LSU bound, not HBM bound (SURVEY §8d); HBM fraction reported as the contract asks",
-                "other_kernels": {"pyramid group (import x2, pyr_down x3, border_fill, scharr_level x4 per step)": {
+                "other_kernels": {"pyramid group (pyr_fused_kernel x4 per step: TMA tile -> level-0 copy + borders + Scharr planes + next level)": {
                     "bound": "hbm", "achieved": py_ach, "peak": peak, "unit": "GB/s",
                     "frac": (py_ach / peak) if py_ach else None, "avg_group_ms": py_avg,
                     "algorithmic_bytes_per_group": py_bytes, "share_of_step": py_ms / ms if ms else None}}}

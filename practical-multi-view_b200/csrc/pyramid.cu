@@ -11,7 +11,6 @@
 //
 // Kernels (all HBM-bound streaming kernels, DESIGN.md has the byte counts):
 //   import_kernel      caller image (any pitch) -> interior of the bordered level 0
-//   border_fill_kernel reflect-101 border of one level, all images of the batch
 //   pyr_fused_kernel   one TMA box load per 128 x 32 tile of level l -> bordered level-0 copy, Scharr plane of level l
 //                      and level l + 1, all from the same shared-memory tile (one launch per level)
 #include <cuda.h>
@@ -21,13 +20,14 @@
 namespace {
 
 // ------------------------------------------------------------------ fused level kernel ---
-// One CTA = one 128 x 32 tile of source level l of one image.  The tile and its halo (2 rows above / below, 8 bytes
+// One CTA = one 128 x 32 tile of source level l of one image.  The tile and its halo (2 rows above / below, 16 bytes
 // left / right) arrive in shared memory through ONE TMA box load (cp.async.bulk.tensor, u8 tensor map over the
 // image interior: out-of-image bytes come back as zero and are patched to BORDER_REFLECT_101 in shared memory by the
 // edge tiles).  From that single pass over the source the CTA writes
-//   (COPY)  the interior of the bordered level-0 copy the tracker reads          16 B stores
-//   (deriv) the Scharr derivative plane of level l, one packed word per pixel    16 B stores
-//   (down)  level l + 1 = pyrDown(level l), packed 16-bit SIMD-in-register       4 B stores
+//   (COPY)   the interior of the bordered level-0 copy the tracker reads         16 B stores
+//   (deriv)  the Scharr derivative plane of level l, one packed word per pixel   16 B stores, byte dot products
+//   (down)   level l + 1 = pyrDown(level l): 25 taps as ten 4-way byte dot products   4 B stores
+//   (border) edge tiles: the reflect-101 border of level l next to their tile     16 B stores
 // so every level is read from HBM once and each output byte is written once.
 constexpr int FT_W = 128, FT_H = 32, FT_HX = 16, FT_HY = 2;   // the box must START on a 16-byte boundary (tools/tma_probe.cu)
 constexpr int FT_P = FT_W + 2 * FT_HX;      // 160: tile pitch = TMA box width (multiple of 16 B)
@@ -36,210 +36,274 @@ constexpr uint32_t FT_BYTES = FT_P * FT_R;  // 5760
 
 struct FusedArgs {
     int rows, cols;                 // source level
-    int n_first;                    // images [0, n_first) come from map A, the rest from map B (caller prev / next)
+    int n_first;                    // images [0, n_first) come from map A / srcA, the rest from map B / srcB (caller prev / next)
     uint8_t *copy; int cpitch; size_t cstride;           // bordered level-0 interior (COPY)
     int *der; int dpitch; size_t dstride; int n_deriv;   // derivative plane of images [0, n_deriv)
     uint8_t *down; int drows, dcols, wpitch; size_t wstride;   // level l + 1 (nullptr: top level)
+    // border of level l: read from the source interior, written around `bdst` (COPY: the level-0 copy; else in place)
+    const uint8_t *srcA, *srcB; int spitch; size_t sstride;
+    uint8_t *bdst; int bpitch; size_t bstride;
+    int by, bxl, bxr;               // border rows (top = bottom), allocated bytes on the left (multiple of 16), border columns on the right
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-template <bool COPY>
-__global__ void __launch_bounds__(256)
-pyr_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const FusedArgs A)
+// reflect-101 with one fold on the fast path (the overshoot is almost always smaller than the image)
+__device__ __forceinline__ int reflect101_fast(int p, int len)
 {
-    __shared__ __align__(128) uint8_t tile[FT_BYTES];
-    __shared__ __align__(8) uint64_t bar;
-    const int t = threadIdx.x;
-    const int x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H, z = blockIdx.z;
-    if (t == 0) {
-        const uint32_t b = smem_u32(&bar), d = smem_u32(tile);
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(FT_BYTES) : "memory");
-        const bool first = z < A.n_first;
-        const CUtensorMap *m = first ? &mapA : &mapB;
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                     ::"r"(d), "l"(m), "r"(x0 - FT_HX), "r"(y0 - FT_HY), "r"(first ? z : z - A.n_first), "r"(b) : "memory");
-    }
-    __syncthreads();   // the initialised barrier is visible to every waiter
-    {
-        const uint32_t b = smem_u32(&bar);
-        asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@!p bra WAIT_%=;\n}" ::"r"(b) : "memory");
-    }
+    const int q = p < 0 ? -p : (p >= len ? 2 * len - 2 - p : p);
+    return (unsigned)q < (unsigned)len ? q : reflect101(p, len);
+}
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)   // unsigned pixels x signed coefficients
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__host__ __device__ constexpr int pk4(int b0, int b1, int b2, int b3)
+{
+    return (b0 & 255) | ((b1 & 255) << 8) | ((b2 & 255) << 16) | (int)((unsigned)(b3 & 255) << 24);
+}
+
+// Can the left / right border of the rows of a tile be built from the staged tile itself?  (the mirrored columns must
+// lie inside the 128 columns + 16-byte halo the tile holds)
+__device__ __forceinline__ bool fused_lr_from_tile(const FusedArgs &A, int x0)
+{
+    const int cols = A.cols;
+    const bool xlast = x0 + FT_W >= cols;
+    return A.bxl + 4 <= FT_W && A.bxl + 4 <= cols && (!xlast || (cols - x0 + FT_HX >= A.bxr + 20 && A.bxr + 20 <= cols));
+}
+
+// Border of level l around one tile (edge tiles only), straight from the source in global memory (it runs while the
+// tile's box load is in flight).  Part 1: rows above / below the image over the tile's image columns, whole 16-byte
+// chunks.  Part 2: everything left of column 0 and from the chunk that straddles the right image edge on (that chunk
+// belongs here, not to the copy phase), for all rows of the tile's outward extension.
+__device__ __forceinline__ void fused_border(const FusedArgs &A, int x0, int y0, int z, bool first, int t)
+{
     const int rows = A.rows, cols = A.cols;
-    // edge tiles: the (at most two) rows / columns beyond each image edge that the taps reach -> reflect-101
-    if (x0 == 0 || y0 == 0 || x0 + FT_W + 2 > cols || y0 + FT_H + 2 > rows) {
-        for (int i = t; i < 4 * FT_P + 4 * FT_R; i += 256) {
-            int r, c;   // tile coordinates
-            if (i < 4 * FT_P) {
-                const int k = i / FT_P;
-                c = i - k * FT_P;
-                const int y = k < 2 ? k - 2 : rows + (k - 2);   // image rows -2, -1, rows, rows + 1
-                r = y - (y0 - FT_HY);
-            } else {
-                const int j = i - 4 * FT_P, k = j / FT_R;
-                r = j - k * FT_R;
-                const int x = k < 2 ? k - 2 : cols + (k - 2);
-                c = x - (x0 - FT_HX);
+    const bool xlast = x0 + FT_W >= cols, ylast = y0 + FT_H >= rows;
+    if (x0 == 0 || y0 == 0 || xlast || ylast) {
+        const uint8_t *src = (first ? A.srcA : A.srcB) + (size_t)(first ? z : z - A.n_first) * A.sstride;
+        uint8_t *dst = A.bdst + (size_t)z * A.bstride;
+        const int ca = cols & ~15;
+        if (y0 == 0 || ylast) {
+            const int nch = ((x0 + FT_W < ca ? x0 + FT_W : ca) - x0) >> 4;
+            const int ntop = y0 == 0 ? A.by : 0, nrow = ntop + (ylast ? A.by : 0);
+            for (int i = t; i < nrow * 8; i += 256) {
+                const int k = i >> 3, ch = i & 7;
+                if (ch < nch) {
+                    const int y = k < ntop ? k - ntop : rows + (k - ntop);
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)reflect101_fast(y, rows) * A.spitch + x0 + 16 * ch));
+                    *reinterpret_cast<uint4 *>(dst + (ptrdiff_t)y * A.bpitch + x0 + 16 * ch) = v;
+                }
             }
-            if (r < 0 || r >= FT_R || c < 0 || c >= FT_P) continue;
-            const int y = y0 - FT_HY + r, x = x0 - FT_HX + c;
-            if (y >= 0 && y < rows && x >= 0 && x < cols) continue;
-            const int sy = reflect101(y < -2 ? -2 : (y > rows + 1 ? rows + 1 : y), rows) - (y0 - FT_HY);
+        }
+        // Part 2.  Regular case (the mirrored columns lie inside this tile): the rows of the tile itself are written
+        // from the staged tile by fused_tile; here only the corner rows above / below the image remain.
+        const bool regular = fused_lr_from_tile(A, x0);
+        int ey0 = y0 == 0 ? -A.by : y0, ey1 = ylast ? rows + A.by : y0 + FT_H;
+        for (int part = 0; part < 2; part++) {
+            int ya = ey0, yb = ey1;
+            if (regular) {   // part 0: rows above the image, part 1: rows below
+                if (part == 0) { ya = ey0; yb = ey0 < 0 ? 0 : ey0; } else { ya = ey1 > rows ? rows : ey1; yb = ey1; }
+            } else if (part == 1) break;
+            if (ya >= yb) continue;
+            const int wl = x0 == 0 ? A.bxl >> 2 : 0;
+            const int nw = wl + (xlast ? ((cols + A.bxr + 15 - ca) >> 4) << 2 : 0);
+            for (int w = t & 31; w < nw; w += 32) {      // a lane keeps its word column: the four source columns are fixed
+                const int xw = w < wl ? 4 * w - A.bxl : ca + 4 * (w - wl);
+                const int c0 = reflect101_fast(xw, cols), c1 = reflect101_fast(xw + 1, cols), c2 = reflect101_fast(xw + 2, cols),
+                          c3 = reflect101_fast(xw + 3, cols);
+                for (int y = ya + (t >> 5); y < yb; y += 8) {
+                    const uint8_t *srow = src + (size_t)reflect101_fast(y, rows) * A.spitch;
+                    const uint32_t q = (uint32_t)__ldg(srow + c0) | ((uint32_t)__ldg(srow + c1) << 8) | ((uint32_t)__ldg(srow + c2) << 16) |
+                                       ((uint32_t)__ldg(srow + c3) << 24);
+                    *reinterpret_cast<uint32_t *>(dst + (ptrdiff_t)y * A.bpitch + xw) = q;
+                }
+            }
+        }
+    }
+}
+
+// Everything that is computed from one staged tile: edge patch, level-0 copy, Scharr plane, next level.
+template <bool COPY>
+__device__ __forceinline__ void fused_tile(const FusedArgs &A, uint8_t *tile, int x0, int y0, int z, int t)
+{
+    const int rows = A.rows, cols = A.cols;
+    // left / right border of this tile's rows from the staged image columns (regular case; see fused_border):
+    // 16-byte chunks, the mirror image of four columns is a byte permutation of two neighbouring words
+    if ((x0 == 0 || x0 + FT_W >= cols) && fused_lr_from_tile(A, x0)) {
+        uint8_t *dst = A.bdst + (size_t)z * A.bstride;
+        const int nl = x0 == 0 ? A.bxl >> 4 : 0;                                       // chunks left of column 0
+        const int ca = cols & ~15;
+        const int nr = x0 + FT_W >= cols ? (cols + A.bxr + 15 - ca) >> 4 : 0;          // chunks from `ca` on
+        for (int i = t; i < (nl + nr) * FT_H; i += 256) {
+            const int r = i & (FT_H - 1), ch = i >> 5;
+            const int y = y0 + r;
+            if (y >= rows) continue;
+            const uint8_t *trow = tile + (r + FT_HY) * FT_P + FT_HX - x0;              // trow[x] = image column x
+            uint32_t q[4];
+            int x16;
+            if (ch < nl) {
+                x16 = -16 * (ch + 1);                                                 // destination bytes x16 .. x16 + 15 <- columns -x16 .. -x16 - 15
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(trow - x16 - 16);   // w[0] = columns -x16-16 .. ; w[4] = columns -x16 ..
+#pragma unroll
+                for (int k = 0; k < 4; k++) q[k] = __byte_perm(w[3 - k], w[4 - k], 0x1234);
+            } else {
+                x16 = ca + 16 * (ch - nl);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int xw = x16 + 4 * k;
+                    if (xw + 4 <= cols) {
+                        q[k] = *reinterpret_cast<const uint32_t *>(trow + xw);
+                    } else if (xw >= cols) {
+                        const int a4 = 2 * cols - 5 - xw;                              // columns a4 .. a4 + 3, reversed
+                        const uint32_t *w = reinterpret_cast<const uint32_t *>(trow + (a4 & ~3));
+                        q[k] = __byte_perm(__funnelshift_r(w[0], w[1], 8 * (a4 & 3)), 0u, 0x0123);
+                    } else {
+                        uint32_t v = 0;
+#pragma unroll
+                        for (int b = 0; b < 4; b++) { const int x = xw + b; v |= (uint32_t)trow[x < cols ? x : 2 * cols - 2 - x] << (8 * b); }
+                        q[k] = v;
+                    }
+                }
+            }
+            *reinterpret_cast<uint4 *>(dst + (ptrdiff_t)y * A.bpitch + x16) = make_uint4(q[0], q[1], q[2], q[3]);
+        }
+    }
+    // edge tiles: the two rows / columns beyond each image edge that the taps reach -> reflect-101 inside the tile
+    if (x0 == 0 || y0 == 0 || x0 + FT_W + 2 > cols || y0 + FT_H + 2 > rows) {
+        if (t < FT_P) {   // rows -2, -1, rows, rows + 1: one tile column per thread (columns reflected too)
+            const int c = t, x = x0 - FT_HX + c;
             const int sx = reflect101(x < -2 ? -2 : (x > cols + 1 ? cols + 1 : x), cols) - (x0 - FT_HX);
-            if (sy >= 0 && sy < FT_R && sx >= 0 && sx < FT_P) tile[r * FT_P + c] = tile[sy * FT_P + sx];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int y = k < 2 ? k - 2 : rows + (k - 2);
+                const int r = y - (y0 - FT_HY);
+                if (r >= 0 && r < FT_R) {
+                    const int sy = reflect101(y, rows) - (y0 - FT_HY);
+                    if (sy >= 0 && sy < FT_R && sx >= 0 && sx < FT_P) tile[r * FT_P + c] = tile[sy * FT_P + sx];
+                }
+            }
+        }
+        // columns: 4 candidate columns x 36 rows = 144 items on threads 0..143
+        if (t < 4 * FT_R) {
+            const int k = t / FT_R, r = t - k * FT_R;
+            const int x = k < 2 ? k - 2 : cols + (k - 2);
+            const int c = x - (x0 - FT_HX);
+            const int y = y0 - FT_HY + r;
+            if (c >= 0 && c < FT_P && y >= 0 && y < rows) {   // rows outside the image were done above (with reflected columns)
+                const int sx = reflect101(x, cols) - (x0 - FT_HX);
+                if (sx >= 0 && sx < FT_P) tile[r * FT_P + c] = tile[r * FT_P + sx];
+            }
         }
         __syncthreads();
     }
     if (COPY) {
         const int r = t >> 3, ch = t & 7;
         const int y = y0 + r, x = x0 + 16 * ch;
-        if (y < rows && x < cols) {
-            // the right border of the destination absorbs the tail of the last chunk (filled afterwards)
+        if (y < rows && x + 16 <= cols)
             *reinterpret_cast<uint4 *>(A.copy + (size_t)z * A.cstride + (size_t)y * A.cpitch + x) =
                 *reinterpret_cast<const uint4 *>(tile + (r + FT_HY) * FT_P + FT_HX + 16 * ch);
-        }
     }
     if (z < A.n_deriv) {
-        // Scharr: 4 pixels x 4 rows per thread, three aligned words per source row (bytes x - 4 .. x + 7)
+        // Scharr: 4 pixels x 4 rows per thread.  Per source row three aligned words -> the byte windows
+        // (x-1 .. x+2), (x .. x+3), (x+2 .. x+5); d/dx and d/dy are byte dot products against signed coefficient words.
         const int strip = t & 31, rg = t >> 5;
         const int x = x0 + 4 * strip;
         if (x < cols && y0 + 4 * rg < rows) {
             const uint32_t *wp = reinterpret_cast<const uint32_t *>(tile + (4 * rg + FT_HY - 1) * FT_P + FT_HX - 4 + 4 * strip);
-            uint32_t w[6][3];
+            uint32_t Wa[6], Wc[6], Wb[6];
 #pragma unroll
-            for (int r = 0; r < 6; r++)
-#pragma unroll
-                for (int k = 0; k < 3; k++) w[r][k] = wp[r * (FT_P / 4) + k];
+            for (int r = 0; r < 6; r++) {
+                const uint32_t w0 = wp[r * (FT_P / 4)], w1 = wp[r * (FT_P / 4) + 1], w2 = wp[r * (FT_P / 4) + 2];
+                Wa[r] = __funnelshift_r(w0, w1, 24); Wc[r] = w1; Wb[r] = __funnelshift_r(w1, w2, 16);
+            }
+            constexpr int X3 = pk4(-3, 0, 3, 0), X10 = pk4(-10, 0, 10, 0), YP = pk4(3, 10, 3, 0), YN = pk4(-3, -10, -3, 0);
+            constexpr int X3s = pk4(0, -3, 0, 3), X10s = pk4(0, -10, 0, 10), YPs = pk4(0, 3, 10, 3), YNs = pk4(0, -3, -10, -3);
             int *dp = A.der + (size_t)z * A.dstride + (size_t)(y0 + 4 * rg) * A.dpitch + x;
 #pragma unroll
             for (int rr = 0; rr < 4; rr++) {
                 if (y0 + 4 * rg + rr >= rows) break;
-                int s0[6], s1[6];
-#pragma unroll
-                for (int c = 0; c < 6; c++) {
-                    const int bi = c + 3;
-                    const int a0 = (w[rr][bi >> 2] >> (8 * (bi & 3))) & 255, a1 = (w[rr + 1][bi >> 2] >> (8 * (bi & 3))) & 255,
-                              a2 = (w[rr + 2][bi >> 2] >> (8 * (bi & 3))) & 255;
-                    s0[c] = 3 * (a0 + a2) + 10 * a1;
-                    s1[c] = a2 - a0;
-                }
+                int gx[4], gy[4];
+                gx[0] = dp4a_us(Wa[rr], X3, dp4a_us(Wa[rr + 1], X10, dp4a_us(Wa[rr + 2], X3, 0)));
+                gy[0] = dp4a_us(Wa[rr + 2], YP, dp4a_us(Wa[rr], YN, 0));
+                gx[1] = dp4a_us(Wc[rr], X3, dp4a_us(Wc[rr + 1], X10, dp4a_us(Wc[rr + 2], X3, 0)));
+                gy[1] = dp4a_us(Wc[rr + 2], YP, dp4a_us(Wc[rr], YN, 0));
+                gx[2] = dp4a_us(Wc[rr], X3s, dp4a_us(Wc[rr + 1], X10s, dp4a_us(Wc[rr + 2], X3s, 0)));
+                gy[2] = dp4a_us(Wc[rr + 2], YPs, dp4a_us(Wc[rr], YNs, 0));
+                gx[3] = dp4a_us(Wb[rr], X3, dp4a_us(Wb[rr + 1], X10, dp4a_us(Wb[rr + 2], X3, 0)));
+                gy[3] = dp4a_us(Wb[rr + 2], YP, dp4a_us(Wb[rr], YN, 0));
                 int out[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int gx = s0[k + 2] - s0[k], gy = 3 * (s1[k] + s1[k + 2]) + 10 * s1[k + 1];
-                    out[k] = (x + k < cols) ? ((gx & 0xffff) | (int)((unsigned)gy << 16)) : 0;
+                for (int k = 0; k < 4; k++) out[k] = (int)__byte_perm((uint32_t)gx[k], (uint32_t)gy[k], 0x5410);
+                if (x + 3 >= cols) {   // last strip of the row: the zero border of the plane starts at `cols`
+#pragma unroll
+                    for (int k = 0; k < 4; k++) out[k] = (x + k < cols) ? out[k] : 0;
                 }
                 *reinterpret_cast<int4 *>(dp + (size_t)rr * A.dpitch) = make_int4(out[0], out[1], out[2], out[3]);
             }
         }
     }
     if (A.down) {
-        // pyrDown: 4 outputs per thread; vertical [1 4 6 4 1] on packed even / odd columns, horizontal on packed pairs
+        // pyrDown: 4 outputs per thread; every output is (sum of ten byte dot products + 128) >> 8 -- the separable
+        // [1 4 6 4 1] x [1 4 6 4 1] taps with the row weight folded into the coefficient words (all exact integers)
         const int j = t & 15, orow = t >> 4;
         const int ox = (x0 >> 1) + 4 * j, oy = (y0 >> 1) + orow;
         if (ox < A.dcols && oy < A.drows) {
-            const uint32_t M = 0x00ff00ffu;
-            uint32_t VE[4], VO[4];   // the four words from source column 2 ox - 4 on (bytes 4 .. 19 of three 8-byte loads)
-            {
-                uint32_t e[5][4], o[5][4];
+            uint32_t acc[4] = {128u, 128u, 128u, 128u};
 #pragma unroll
-                for (int r = 0; r < 5; r++) {
-                    const uint2 *sp = reinterpret_cast<const uint2 *>(tile + (2 * orow + r) * FT_P + FT_HX - 8 + 8 * j);
-                    const uint2 q0 = sp[0], q1 = sp[1], q2 = sp[2];
-                    const uint32_t wv[4] = {q0.y, q1.x, q1.y, q2.x};
-#pragma unroll
-                    for (int k = 0; k < 4; k++) { e[r][k] = wv[k] & M; o[r][k] = (wv[k] >> 8) & M; }
-                }
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    VE[k] = e[0][k] + e[4][k] + ((e[1][k] + e[3][k]) << 2) + e[2][k] * 6u;
-                    VO[k] = o[0][k] + o[4][k] + ((o[1][k] + o[3][k]) << 2) + o[2][k] * 6u;
-                }
+            for (int r = 0; r < 5; r++) {
+                const uint32_t wr = r == 2 ? 6u : ((r == 1 || r == 3) ? 4u : 1u);
+                const uint32_t ca = wr * 0x04010000u, cb = wr * 0x00010406u, cc = wr * 0x04060401u, cd = wr * 0x00000001u;
+                const uint2 *sp = reinterpret_cast<const uint2 *>(tile + (2 * orow + r) * FT_P + FT_HX - 8 + 8 * j);
+                const uint2 q0 = sp[0], q1 = sp[1], q2 = sp[2];
+                // source columns relative to 2 ox: q0.y = -4..-1, q1.x = 0..3, q1.y = 4..7, q2.x = 8..11
+                acc[0] = __dp4a(q0.y, ca, __dp4a(q1.x, cb, acc[0]));   // taps -2 .. 2
+                acc[1] = __dp4a(q1.x, cc, __dp4a(q1.y, cd, acc[1]));   // taps  0 .. 4
+                acc[2] = __dp4a(q1.x, ca, __dp4a(q1.y, cb, acc[2]));   // taps  2 .. 6
+                acc[3] = __dp4a(q1.y, cc, __dp4a(q2.x, cd, acc[3]));   // taps  4 .. 8
             }
-            // V index of word k (k = 0..3 <-> bytes 4 + 4k ..): VE[k] = (V[4+4k], V[6+4k]), VO[k] = (V[5+4k], V[7+4k]);
-            // output m is centred on V[8 + 2m]
-            const uint32_t A01 = __byte_perm(VE[0], VE[1], 0x5432);   // (V6,  V8)
-            const uint32_t F01 = __byte_perm(VE[1], VE[2], 0x5432);   // (V10, V12)
-            const uint32_t B01 = __byte_perm(VO[0], VO[1], 0x5432);   // (V7,  V9)
-            const uint32_t r01 = A01 + F01 + ((B01 + VO[1]) << 2) + VE[1] * 6u + 0x00800080u;
-            const uint32_t F23 = __byte_perm(VE[2], VE[3], 0x5432);   // (V14, V16)
-            const uint32_t B23 = __byte_perm(VO[1], VO[2], 0x5432);   // (V11, V13)
-            const uint32_t r23 = F01 + F23 + ((B23 + VO[2]) << 2) + VE[2] * 6u + 0x00800080u;
-            // row pitch padding absorbs a partial word at the right edge (border fill follows)
-            *reinterpret_cast<uint32_t *>(A.down + (size_t)z * A.wstride + (size_t)oy * A.wpitch + ox) = __byte_perm(r01, r23, 0x7531);
+            const uint32_t lo = __byte_perm(acc[0], acc[1], 0x0051), hi = __byte_perm(acc[2], acc[3], 0x0051);
+            // row pitch padding absorbs a partial word at the right edge (the next launch writes that border)
+            *reinterpret_cast<uint32_t *>(A.down + (size_t)z * A.wstride + (size_t)oy * A.wpitch + ox) = __byte_perm(lo, hi, 0x5410);
         }
     }
 }
 
-// Reflect-101 border of ALL levels of a batch in one launch (grid.y = image, grid.z = level):
-// bands top / bottom (full bordered width) and left / right.
-struct BorderArgs {
-    uint8_t *ptr[PMV_MAX_PYR_LEVELS];
-    int rows[PMV_MAX_PYR_LEVELS], cols[PMV_MAX_PYR_LEVELS], pitch[PMV_MAX_PYR_LEVELS];
-    size_t stride[PMV_MAX_PYR_LEVELS];
-    int by, bxl, bxr;
-};
+constexpr int FT_NT = 2;   // vertically adjacent tiles per CTA: both box loads are issued up front, the second lands while the first is processed
 
-// Work item = one aligned 16-byte chunk of a destination row.  Border rows (above / below the image) copy
-// whole chunks from their mirror row with one uint4 load where the chunk lies inside [0, cols); everything
-// else (left / right margins, row ends) is assembled byte-wise with reflect-101.
-__global__ void __launch_bounds__(256) border_fill_kernel(const BorderArgs A)
+template <bool COPY>
+__global__ void __launch_bounds__(256, 6)
+pyr_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const FusedArgs A)
 {
-    const int l = blockIdx.z;
-    const int rows = A.rows[l], cols = A.cols[l], pitch = A.pitch[l];
-    uint8_t *base = A.ptr[l] + (size_t)blockIdx.y * A.stride[l];
-    const int by = A.by, bxl = A.bxl, bxr = A.bxr;
-    const int row_chunks = (bxl + cols + bxr + 15) >> 4;          // chunks of a full bordered row
-    const int right0 = cols & ~15;                                // first chunk (interior x) touching the right margin
-    const int side_chunks = (bxl >> 4) + ((cols + bxr + 15 - right0) >> 4);
-    const int n_tb = 2 * by * row_chunks, n_lr = rows * side_chunks;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < n_tb + n_lr; i += gridDim.x * 256) {
-        int y, x0;
-        if (i < n_tb) {
-            const int r = i / row_chunks;
-            x0 = (i - r * row_chunks) * 16 - bxl;
-            y = r < by ? r - by : rows + (r - by);
-        } else {
-            const int j = i - n_tb;
-            y = j / side_chunks;
-            const int c = j - y * side_chunks;
-            x0 = c < (bxl >> 4) ? c * 16 - bxl : right0 + (c - (bxl >> 4)) * 16;
+    __shared__ __align__(128) uint8_t tile[FT_NT][FT_BYTES];
+    __shared__ __align__(8) uint64_t bar[FT_NT];
+    const int t = threadIdx.x;
+    const int x0 = blockIdx.x * FT_W, yb = blockIdx.y * (FT_NT * FT_H), z = blockIdx.z;
+    const bool first = z < A.n_first;
+    if (t == 0) {
+        const CUtensorMap *m = first ? &mapA : &mapB;
+#pragma unroll
+        for (int s = 0; s < FT_NT; s++) {
+            if (yb + s * FT_H >= A.rows) break;
+            const uint32_t b = smem_u32(&bar[s]), d = smem_u32(tile[s]);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(FT_BYTES) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(d), "l"(m), "r"(x0 - FT_HX), "r"(yb + s * FT_H - FT_HY), "r"(first ? z : z - A.n_first), "r"(b) : "memory");
         }
-        const uint8_t *srow = base + (ptrdiff_t)reflect101(y, rows) * pitch;
-        uint8_t *drow = base + (ptrdiff_t)y * pitch;
-        if (x0 >= 0 && x0 + 16 <= cols) {
-            if (y < 0 || y >= rows) *reinterpret_cast<uint4 *>(drow + x0) = *reinterpret_cast<const uint4 *>(srow + x0);
-        } else {
-            uint32_t wv[4];
+    }
+    __syncthreads();   // the initialised barriers are visible to every waiter
 #pragma unroll
-            for (int k4 = 0; k4 < 4; k4++) {
-                uint32_t v = 0;
+    for (int s = 0; s < FT_NT; s++)
+        if (yb + s * FT_H < A.rows) fused_border(A, x0, yb + s * FT_H, z, first, t);
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int x = x0 + 4 * k4 + k;
-                    v |= (uint32_t)srow[reflect101(x, cols)] << (8 * k);
-                }
-                wv[k4] = v;
-            }
-            if (y >= 0 && y < rows && (x0 + 16 <= 0 || (x0 >= cols && x0 + 16 <= cols + bxr))) {
-                *reinterpret_cast<uint4 *>(drow + x0) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-            } else if (y >= 0 && y < rows) {
-                // interior row: keep the image bytes of a chunk that straddles the edge
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    const int x = x0 + k;
-                    if ((x < 0 || x >= cols) && x < cols + bxr) drow[x] = (uint8_t)(wv[k >> 2] >> (8 * (k & 3)));
-                }
-            } else if (x0 + 16 <= cols + bxr) {
-                *reinterpret_cast<uint4 *>(drow + x0) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 16; k++)
-                    if (x0 + k < cols + bxr) drow[x0 + k] = (uint8_t)(wv[k >> 2] >> (8 * (k & 3)));
-            }
-        }
+    for (int s = 0; s < FT_NT; s++) {
+        if (yb + s * FT_H >= A.rows) break;
+        const uint32_t b = smem_u32(&bar[s]);
+        asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@!p bra WAIT_%=;\n}" ::"r"(b) : "memory");
+        fused_tile<COPY>(A, tile[s], x0, yb + s * FT_H, z, t);
     }
 }
 
@@ -339,25 +403,6 @@ int pmv_internal_pyr_plan(pmv_ctx *ctx, int which, int batch, int rows, int cols
     return PMV_OK;
 }
 
-static int fill_borders(pmv_ctx *ctx, const PyrSet &set, int batch, cudaStream_t s)
-{
-    BorderArgs A;
-    memset(&A, 0, sizeof A);
-    int nmax = 0;
-    for (int l = 0; l <= set.top; l++) {
-        const PyrLevel &d = set.lv[l];
-        A.ptr[l] = const_cast<uint8_t *>(d.ptr); A.rows[l] = d.rows; A.cols[l] = d.cols; A.pitch[l] = d.pitch;
-        A.stride[l] = d.img_stride;
-        int n = 2 * d.border * (d.bxl + d.cols + d.border) + d.rows * (d.bxl + d.border);
-        nmax = n > nmax ? n : nmax;
-    }
-    A.by = set.lv[0].border; A.bxl = set.lv[0].bxl; A.bxr = set.lv[0].border;
-    dim3 grid(min((nmax / 16 + 255) / 256 + 1, 24), batch, set.top + 1);
-    border_fill_kernel<<<grid, 256, 0, s>>>(A);
-    PMV_LAUNCH_CHECK(ctx, "border_fill_kernel");
-    return PMV_OK;
-}
-
 // ------------------------------------------------------------------ tensor maps ---------
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -399,7 +444,7 @@ static int make_image_map(pmv_ctx *ctx, CUtensorMap *m, const uint8_t *ptr, int 
 // d_src / d_src2: caller images for the first / second half of the batch (prev / next image sets share one
 // bordered allocation so every pyramid kernel runs once per step); d_src2 == nullptr -> one source;
 // d_src == nullptr -> level 0 was already copied into the planned interior.  dv != nullptr: the Scharr planes of
-// images [0, n_deriv) are written from the same pass.  One fused launch per level, then one border launch.
+// images [0, n_deriv) are written from the same pass.  One fused launch per level (borders included).
 int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, const uint8_t *d_src, const uint8_t *d_src2,
                          int src_pitch, size_t src_stride, const DerivSet *dv, int n_deriv, cudaStream_t s)
 {
@@ -420,7 +465,6 @@ int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, const uint8
     for (int l = 0; l <= set.top; l++) {
         const PyrLevel &a = set.lv[l];
         const bool down = l < set.top;
-        if (!down && n_deriv == 0) break;
         FusedArgs A;
         memset(&A, 0, sizeof A);
         A.rows = a.rows; A.cols = a.cols; A.n_first = batch;
@@ -445,18 +489,22 @@ int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, const uint8
         if (n_deriv > 0) {
             A.der = const_cast<int *>(dv->lv[l].ptr); A.dpitch = dv->lv[l].pitch; A.dstride = dv->lv[l].img_stride; A.n_deriv = n_deriv;
         }
-        // the top level only carries derivatives: no CTA for images without them
-        const int nz = down ? batch : n_deriv;
+        // border of level l: from the caller images into the level-0 copy, or in place around our own interior
+        if (copy) { A.srcA = d_src; A.srcB = d_src2 ? d_src2 : d_src; A.spitch = src_pitch; A.sstride = src_stride; }
+        else { A.srcA = A.srcB = a.ptr; A.spitch = a.pitch; A.sstride = a.img_stride; }
+        A.bdst = const_cast<uint8_t *>(a.ptr); A.bpitch = a.pitch; A.bstride = a.img_stride;
+        A.by = a.border; A.bxl = a.bxl; A.bxr = a.border;
+        const int nz = batch;   // the top level runs for every image too: its border is written by this launch
         if (down) {
             const PyrLevel &d = set.lv[l + 1];
             A.down = const_cast<uint8_t *>(d.ptr); A.drows = d.rows; A.dcols = d.cols; A.wpitch = d.pitch; A.wstride = d.img_stride;
         }
-        dim3 grid((a.cols + FT_W - 1) / FT_W, (a.rows + FT_H - 1) / FT_H, nz);
+        dim3 grid((a.cols + FT_W - 1) / FT_W, (a.rows + FT_NT * FT_H - 1) / (FT_NT * FT_H), nz);
         if (copy) pyr_fused_kernel<true><<<grid, 256, 0, s>>>(mA, mB, A);
         else pyr_fused_kernel<false><<<grid, 256, 0, s>>>(mA, mB, A);
         PMV_LAUNCH_CHECK(ctx, "pyr_fused_kernel");
     }
-    return fill_borders(ctx, set, batch, s);
+    return PMV_OK;
 }
 
 // ------------------------------------------------------------------ C ABI ---------------
