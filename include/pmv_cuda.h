@@ -131,6 +131,29 @@ PMV_API int pmv_lk_track_batched_dev(pmv_ctx *ctx, const uint8_t *d_prev, const 
                                      double min_eig_thr,
                                      float *d_next_xy, uint8_t *d_status, float *d_err);
 
+/* ------------------------------------------------------------------ resident front end -- */
+/* One handle for the front end of OdometryPipeline::addFrame (OdometryPipeline.cpp:329-374) with the images, both
+ * pyramids, the Scharr planes and the track list RESIDENT on the device between frames.  Per frame: one upload, one
+ * fused pyramid build (the reference reduces every frame twice, OpenCVLucasKanadeFM.cpp:15), the LK solve from the
+ * resident features of the previous frame, the status filter + Feature(int, int) truncation
+ * (OpenCVLucasKanadeFM.cpp:23-29), and -- when fewer than tracked_tol survive -- the ROI-grid goodFeaturesToTrack
+ * re-extraction on the PREVIOUS frame (getGridROI, OdometryPipeline.cpp:351,674-692) with Frame::hasNeighbor
+ * de-duplication (Frame.cpp:3-12; candidates tested in ROI-local coordinates, offset added afterwards, :361-364),
+ * then one small download.  pmv_tracker_init is initialise()'s extraction on the first frame (:440-459).
+ * Defaults of the reference: win 32x32, max_level 4, min_tracked 400, tracked_tol 150, grid 255, quality 0.01,
+ * min_dist 5, neighbor_dist 5. */
+typedef struct pmv_tracker pmv_tracker;
+PMV_API pmv_tracker *pmv_tracker_create(pmv_ctx *ctx, int rows, int cols, int win_w, int win_h, int max_level, int capacity,
+                                        int min_tracked, int tracked_tol, int grid, double quality, double min_dist,
+                                        int neighbor_dist);
+PMV_API void pmv_tracker_destroy(pmv_tracker *t);
+PMV_API int pmv_tracker_init(pmv_tracker *t, const uint8_t *frame, int step, int *n_features);
+/* xy: capacity x (column, row) int32 of the new frame's features (tracked ones first, in the order of the previous
+ * list, then newly extracted ones); prev_index: position of each in the previous frame's list, -1 = new. */
+PMV_API int pmv_tracker_add_frame(pmv_tracker *t, const uint8_t *frame, int step, int *n_tracked, int *n_features,
+                                  int *extracted, int32_t *xy, int32_t *prev_index, int capacity);
+PMV_API int pmv_tracker_features(pmv_tracker *t, int32_t *xy, int capacity, int *n);
+
 /* ------------------------------------------------------------------ corner detectors -- */
 /* Image arguments of the extractors: `base` is the PARENT image (full_rows x full_cols, row step
  * `step` bytes) and (roi_x, roi_y, roi_w, roi_h) the view the pipeline passes

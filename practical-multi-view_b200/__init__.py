@@ -58,6 +58,11 @@ _SIGS = {
                                     _int, _int, _dbl, _int, _dbl, _vp, _vp, _vp]),
     "pmv_lk_track_batched_dev": (_int, [_vp, _vp, _vp, _int, _sz, _int, _int, _int, _vp, _int, _int, _int,
                                         _int, _int, _dbl, _int, _dbl, _vp, _vp, _vp]),
+    "pmv_tracker_create": (_vp, [_vp, _int, _int, _int, _int, _int, _int, _int, _int, _int, C.c_double, C.c_double, _int]),
+    "pmv_tracker_destroy": (None, [_vp]),
+    "pmv_tracker_init": (_int, [_vp, _vp, _int, _i32p]),
+    "pmv_tracker_add_frame": (_int, [_vp, _vp, _int, _i32p, _i32p, _i32p, _vp, _vp, _int]),
+    "pmv_tracker_features": (_int, [_vp, _vp, _int, _i32p]),
     "pmv_min_eigen_val": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp]),
     "pmv_gftt": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _dbl, _dbl, _int, _int,
                         _vp, _vp, _i32p]),
@@ -234,6 +239,11 @@ class Context:
                                                     step, _ptr(d_pts), n, win[0], win[1], max_level, max_count,
                                                     eps, flags, min_eig, _ptr(d_next), _ptr(d_status), _ptr(d_err)))
 
+    def tracker(self, rows, cols, win=(32, 32), max_level=4, capacity=4096, min_tracked=400, tracked_tol=150, grid=255,
+                quality=0.01, min_dist=5.0, neighbor_dist=5):
+        """Device-resident front end (pmv_tracker_*): OdometryPipeline::addFrame without the host round trips."""
+        return Tracker(self, rows, cols, win, max_level, capacity, min_tracked, tracked_tol, grid, quality, min_dist, neighbor_dist)
+
     # ------------------------------------------------------------------ corner detectors
     @staticmethod
     def _roi(img, roi):
@@ -333,6 +343,52 @@ class Context:
 
     def comm_destroy(self):
         self._chk(self.lib.pmv_comm_destroy(self.h))
+
+
+class Tracker:
+    """pmv_tracker handle: frames in, (features, n_tracked, extracted) out; pyramids and tracks stay on the device."""
+
+    def __init__(self, ctx, rows, cols, win, max_level, capacity, min_tracked, tracked_tol, grid, quality, min_dist, neighbor_dist):
+        self.ctx, self.rows, self.cols, self.cap = ctx, rows, cols, capacity
+        self.h = ctx.lib.pmv_tracker_create(ctx.h, rows, cols, win[0], win[1], max_level, capacity, min_tracked, tracked_tol, grid,
+                                            quality, min_dist, neighbor_dist)
+        if not self.h:
+            raise PmvError(-1, ctx.lib.pmv_last_error(ctx.h).decode())
+        self._xy = np.zeros((capacity, 2), np.int32)
+        self._pi = np.zeros(capacity, np.int32)
+
+    def _img(self, img):
+        assert img.dtype == np.uint8 and img.shape == (self.rows, self.cols) and img.strides[1] == 1
+        return img
+
+    def init(self, img):
+        n = C.c_int(0)
+        self.ctx._chk(self.ctx.lib.pmv_tracker_init(self.h, _ptr(self._img(img)), img.strides[0], C.byref(n)))
+        return self.features()
+
+    def features(self):
+        n = C.c_int(0)
+        self.ctx._chk(self.ctx.lib.pmv_tracker_features(self.h, _ptr(self._xy), self.cap, C.byref(n)))
+        return self._xy[:n.value].copy()
+
+    def add_frame(self, img):
+        """Returns (features (n, 2) int32 [column, row], prev_index (n,), n_tracked, extracted)."""
+        nt, nf, ex = C.c_int(0), C.c_int(0), C.c_int(0)
+        self.ctx._chk(self.ctx.lib.pmv_tracker_add_frame(self.h, _ptr(self._img(img)), img.strides[0], C.byref(nt), C.byref(nf),
+                                                         C.byref(ex), _ptr(self._xy), _ptr(self._pi), self.cap))
+        n = min(nf.value, self.cap)
+        return self._xy[:n].copy(), self._pi[:n].copy(), nt.value, bool(ex.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.pmv_tracker_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class BAProblem:

@@ -184,6 +184,9 @@ __host__ __device__ __forceinline__ int reflect101(int p, int len)
 // Plan bordered storage for levels 0..L of `batch` images in ctx->pyr[which].
 int pmv_internal_pyr_plan(pmv_ctx *ctx, int which, int batch, int rows, int cols, int border,
                           int win_w, int win_h, int max_level, PyrSet *out);
+// the same in a buffer the caller owns (pmv_tracker keeps two pyramids alive between calls)
+int pmv_internal_pyr_plan_buf(pmv_ctx *ctx, DevBuf *buf, int batch, int rows, int cols, int border,
+                              int win_w, int win_h, int max_level, PyrSet *out);
 // Import level 0 from device memory (any pitch) / expect it already copied into the interior
 // (src == nullptr), fill its border, then build levels 1..top with their borders.
 int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, const uint8_t *d_src, const uint8_t *d_src2,
@@ -191,3 +194,15 @@ int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, const uint8
 // Plan (and zero, when the geometry changed) derivative storage matching the levels of `set`; the planes of the
 // first n_deriv images are written by pmv_internal_pyr_run in the same pass that builds the levels.
 int pmv_internal_deriv_plan(pmv_ctx *ctx, const PyrSet &set, int batch, DerivSet *out, cudaStream_t s);
+int pmv_internal_deriv_plan_buf(pmv_ctx *ctx, DevBuf *buf, unsigned long long *sig, const PyrSet &set, int batch, DerivSet *out,
+                                cudaStream_t s);
+// internal cross-file entry points (defined in lk.cu): border the tracker needs around every level, and the tracking
+// launch alone on pyramids / derivative planes that are already built (device pointers, asynchronous on s)
+int pmv_internal_lk_border(int win_w, int win_h);
+int pmv_internal_lk_launch(pmv_ctx *ctx, const PyrSet &sp, const PyrSet &sn, const DerivSet &dv, int batch,
+                           const float *d_prev_xy, int n, int win_w, int win_h, int max_count, double eps, int flags,
+                           double min_eig_thr, float *d_next_xy, uint8_t *d_status, float *d_err, cudaStream_t s);
+// defined in corners.cu: goodFeaturesToTrack of an ROI of an image that is ALREADY on the device (bordered or not:
+// reads outside the parent are reflected).  Results stay on the device (xy: n x 2 float ROI-local, score), *n on the host.
+int pmv_internal_gftt_device(pmv_ctx *ctx, const uint8_t *d_img, int pitch, int full_rows, int full_cols, int rx, int ry, int rw,
+                             int rh, int max_corners, double quality, double min_dist, float **d_xy, float **d_score, int *n);

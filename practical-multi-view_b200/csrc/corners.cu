@@ -33,6 +33,8 @@ struct ImgView {            // uploaded patch of the parent image
     int ox, oy;             // parent coordinates of patch pixel (0,0)
     int full_rows, full_cols;  // parent size (reflect-101 happens at the PARENT's edges)
     int rx, ry, rw, rh;     // ROI in parent coordinates
+    int word_ok = 1;        // ROI column 0 sits on a 4-byte boundary of `ptr` rows (upload_roi guarantees it; a view of a
+                            // resident image at an arbitrary ROI does not) -> aligned word loads allowed
 };
 
 constexpr int CS_X0 = 4;   // staged column of ROI column tx0 (the tile starts on a 4-byte boundary at tx0 - 4)
@@ -44,7 +46,7 @@ __device__ __forceinline__ void stage_tile(uint8_t (*s)[CS_P], const ImgView &v,
 {
     const bool interior = (v.rx + tx0 - 2 >= 0) && (v.rx + tx0 + CT_W + 2 <= v.full_cols) &&
                           (v.ry + ty0 - 2 >= 0) && (v.ry + ty0 + CT_H + 2 <= v.full_rows);
-    if (interior) {
+    if (interior && v.word_ok) {
         const uint8_t *g = v.ptr + (ptrdiff_t)(v.ry + ty0 - 2 - v.oy) * v.pitch + (v.rx + tx0 - CS_X0 - v.ox);
         for (int i = tid; i < CS_H * (CS_P / 4); i += 256) {
             const int r = i / (CS_P / 4), wc = i - r * (CS_P / 4);
@@ -111,7 +113,7 @@ mineig_fast_kernel(const ImgView v, float *__restrict__ eig, int *__restrict__ m
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x0 = blockIdx.x * MF_W, y0 = (blockIdx.y * 8 + warp) * MF_R;
-    if (!mineig_fast_region(x0, y0, v.rw, v.rh)) return;      // warp-uniform
+    if (!v.word_ok || !mineig_fast_region(x0, y0, v.rw, v.rh)) return;      // warp-uniform
     const int cx = x0 - 4 + 4 * lane;                          // ROI column of byte 0 of this lane's word
     const uint8_t *g = v.ptr + (ptrdiff_t)(v.ry + y0 - 2 - v.oy) * v.pitch + (v.rx + cx - v.ox);
     int dxp[2][4], smp[2][4];                                  // horizontal diff / smooth of the two previous rows
@@ -184,7 +186,7 @@ mineig_kernel(const ImgView v, float *__restrict__ eig, int *__restrict__ max_bi
     __shared__ float s_red[8];
     const int tid = threadIdx.x;
     const int tx0 = blockIdx.x * CT_W, ty0 = blockIdx.y * CT_H;
-    if (mineig_tile_is_fast(tx0, ty0, v.rw, v.rh)) return;   // written by mineig_fast_kernel
+    if (v.word_ok && mineig_tile_is_fast(tx0, ty0, v.rw, v.rh)) return;   // written by mineig_fast_kernel
     stage_tile(s_px, v, tx0, ty0, tid);
     __syncthreads();
     // Sobel at halo-1 positions; positions outside the ROI take the value of their reflect-101
@@ -558,7 +560,7 @@ int run_mineig(pmv_ctx *ctx, const ImgView &v, float *d_eig, int *d_max, cudaStr
 {
     ProfScope ps(ctx, PMV_PHASE_RESPONSE, s);
     PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_max, 0, sizeof(int), s));
-    if (v.rw >= 2 * MF_W && v.rh >= 2 * MF_R) {   // an interior exists: register-resident kernel (same predicate on device)
+    if (v.word_ok && v.rw >= 2 * MF_W && v.rh >= 2 * MF_R) {   // an interior exists: register-resident kernel (same predicate on device)
         dim3 gridf((v.rw + MF_W - 1) / MF_W, (v.rh + 8 * MF_R - 1) / (8 * MF_R));
         mineig_fast_kernel<<<gridf, 256, 0, s>>>(v, d_eig, d_max);
         PMV_LAUNCH_CHECK(ctx, "mineig_fast_kernel");
@@ -569,7 +571,81 @@ int run_mineig(pmv_ctx *ctx, const ImgView &v, float *d_eig, int *d_max, cudaStr
     return PMV_OK;
 }
 
+// goodFeaturesToTrack on a view that is already on the device; the corner list stays there (scratch[5]).
+int gftt_run(pmv_ctx *ctx, const ImgView &v, int max_corners, double quality, double min_dist, float **out_xy, float **out_sc,
+             int *n_out)
+{
+    cudaStream_t s = ctx->stream;
+    int rc;
+    const size_t npx = (size_t)v.rw * v.rh;
+    const int cap = (int)npx;  // plateaus of equal responses can make every pixel a candidate
+    const int cap2 = sort_capacity(cap);
+    cudaError_t e = ctx->scratch[0].reserve(npx * 4);                 // eig map
+    if (e == cudaSuccess) e = ctx->scratch[1].reserve(256);          // max bits, count, n_out
+    if (e == cudaSuccess) e = ctx->scratch[2].reserve((size_t)cap2 * sizeof(Rec128));
+    if (e == cudaSuccess) e = ctx->scratch[3].reserve(npx * 4);      // rank map
+    if (e == cudaSuccess) e = ctx->scratch[4].reserve(2 * (size_t)cap + 64);   // status | neighbour counts
+    if (e == cudaSuccess) e = ctx->pin[0].reserve(64);
+    if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "gftt workspace", e);
+    float *d_eig = ctx->scratch[0].as<float>();
+    int *d_misc = ctx->scratch[1].as<int>();   // [0] max bits, [1] count, [2] n_out
+    Rec128 *d_rec = ctx->scratch[2].as<Rec128>();
+    int *d_rank = ctx->scratch[3].as<int>();
+    unsigned char *d_status = ctx->scratch[4].as<unsigned char>();
+    int *h_misc = ctx->pin[0].as<int>();
+
+    PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_misc, 0, 16, s));
+    rc = run_mineig(ctx, v, d_eig, d_misc, s);
+    if (rc) return rc;
+    int n_cand = 0;
+    {
+        ProfScope ps(ctx, PMV_PHASE_SELECT, s);
+        dim3 grid((v.rw + 31) / 32, (v.rh + GC_ROWS - 1) / GC_ROWS);
+        gftt_candidates_kernel<<<grid, 256, 0, s>>>(d_eig, v.rh, v.rw, d_misc, quality, d_rec, d_misc + 1, cap);
+        PMV_LAUNCH_CHECK(ctx, "gftt_candidates_kernel");
+        PMV_CUDA_TRY(ctx, cudaMemcpyAsync(h_misc, d_misc, 16, cudaMemcpyDeviceToHost, s));
+        PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+        n_cand = h_misc[1] < cap ? h_misc[1] : cap;
+        const int want = max_corners > 0 ? max_corners : n_cand;
+        if (n_cand > 0) {
+            rc = sort_desc_128(ctx, d_rec, n_cand, s);
+            if (rc) return rc;
+            PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_rank, 0xff, npx * 4, s));
+            PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_status, 0, n_cand, s));
+            rank_scatter_kernel<<<(n_cand + 255) / 256, 256, 0, s>>>(d_rec, n_cand, d_rank);
+            PMV_LAUNCH_CHECK(ctx, "rank_scatter_kernel");
+            e = ctx->scratch[5].reserve((size_t)want * 12 + 16);
+            if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "gftt output", e);
+            float *d_xy = ctx->scratch[5].as<float>();
+            float *d_sc = d_xy + 2 * (size_t)want;
+            e = ctx->scratch[6].reserve((size_t)n_cand * GF_NBMAX * 4 + 16);
+            if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "gftt neighbour lists", e);
+            int *d_nb = ctx->scratch[6].as<int>();
+            unsigned char *d_nbc = d_status + cap;
+            gftt_neighbors_kernel<<<(n_cand + 255) / 256, 256, 0, s>>>(d_rec, n_cand, v.rh, v.rw, d_rank, (float)min_dist, d_nb, d_nbc);
+            PMV_LAUNCH_CHECK(ctx, "gftt_neighbors_kernel");
+            gftt_select_kernel<<<1, 1024, 0, s>>>(d_rec, n_cand, v.rh, v.rw, d_rank, d_nb, d_nbc, d_status, (float)min_dist,
+                                                  max_corners, d_xy, d_sc, d_misc + 2);
+            PMV_LAUNCH_CHECK(ctx, "gftt_select_kernel");
+            PMV_CUDA_TRY(ctx, cudaMemcpyAsync(h_misc, d_misc, 16, cudaMemcpyDeviceToHost, s));
+            PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+            *out_xy = d_xy; *out_sc = d_sc; *n_out = h_misc[2];
+            return PMV_OK;
+        }
+    }
+    *n_out = 0;
+    return PMV_OK;
+}
+
 }  // namespace
+
+int pmv_internal_gftt_device(pmv_ctx *ctx, const uint8_t *d_img, int pitch, int full_rows, int full_cols, int rx, int ry, int rw,
+                             int rh, int max_corners, double quality, double min_dist, float **d_xy, float **d_score, int *n)
+{
+    ImgView v{d_img, pitch, 0, 0, full_rows, full_cols, rx, ry, rw, rh};
+    v.word_ok = (((uintptr_t)d_img | (uintptr_t)pitch | (uintptr_t)rx) & 3) == 0;
+    return gftt_run(ctx, v, max_corners, quality, min_dist, d_xy, d_score, n);
+}
 
 extern "C" {
 
@@ -610,69 +686,16 @@ PMV_API int pmv_gftt(pmv_ctx *ctx, const uint8_t *base, int full_rows, int full_
     ImgView v;
     rc = upload_roi(ctx, base, full_rows, full_cols, step, roi_x, roi_y, roi_w, roi_h, &v);
     if (rc) return rc;
-    const size_t npx = (size_t)roi_w * roi_h;
-    const int cap = (int)npx;  // plateaus of equal responses can make every pixel a candidate
-    const int cap2 = sort_capacity(cap);
-    cudaError_t e = ctx->scratch[0].reserve(npx * 4);                 // eig map
-    if (e == cudaSuccess) e = ctx->scratch[1].reserve(256);          // max bits, count, n_out
-    if (e == cudaSuccess) e = ctx->scratch[2].reserve((size_t)cap2 * sizeof(Rec128));
-    if (e == cudaSuccess) e = ctx->scratch[3].reserve(npx * 4);      // rank map
-    if (e == cudaSuccess) e = ctx->scratch[4].reserve(2 * (size_t)cap + 64);   // status | neighbour counts
-    if (e == cudaSuccess) e = ctx->pin[0].reserve(64);
-    if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "gftt workspace", e);
-    float *d_eig = ctx->scratch[0].as<float>();
-    int *d_misc = ctx->scratch[1].as<int>();   // [0] max bits, [1] count, [2] n_out
-    Rec128 *d_rec = ctx->scratch[2].as<Rec128>();
-    int *d_rank = ctx->scratch[3].as<int>();
-    unsigned char *d_status = ctx->scratch[4].as<unsigned char>();
-    int *h_misc = ctx->pin[0].as<int>();
-
-    PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_misc, 0, 16, s));
-    rc = run_mineig(ctx, v, d_eig, d_misc, s);
+    float *d_xy = nullptr, *d_sc = nullptr;
+    int n = 0;
+    rc = gftt_run(ctx, v, max_corners, quality, min_dist, &d_xy, &d_sc, &n);
     if (rc) return rc;
-    int n_cand = 0;
-    {
-        ProfScope ps(ctx, PMV_PHASE_SELECT, s);
-        dim3 grid((roi_w + 31) / 32, (roi_h + GC_ROWS - 1) / GC_ROWS);
-        gftt_candidates_kernel<<<grid, 256, 0, s>>>(d_eig, roi_h, roi_w, d_misc, quality, d_rec, d_misc + 1, cap);
-        PMV_LAUNCH_CHECK(ctx, "gftt_candidates_kernel");
-        PMV_CUDA_TRY(ctx, cudaMemcpyAsync(h_misc, d_misc, 16, cudaMemcpyDeviceToHost, s));
+    if (n > 0) {
+        if (xy) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(xy, d_xy, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        if (score) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(score, d_sc, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
         PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
-        n_cand = h_misc[1] < cap ? h_misc[1] : cap;
-        const int want = max_corners > 0 ? max_corners : n_cand;
-        if (n_cand > 0) {
-            rc = sort_desc_128(ctx, d_rec, n_cand, s);
-            if (rc) return rc;
-            PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_rank, 0xff, npx * 4, s));
-            PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_status, 0, n_cand, s));
-            rank_scatter_kernel<<<(n_cand + 255) / 256, 256, 0, s>>>(d_rec, n_cand, d_rank);
-            PMV_LAUNCH_CHECK(ctx, "rank_scatter_kernel");
-            e = ctx->scratch[5].reserve((size_t)want * 12 + 16);
-            if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "gftt output", e);
-            float *d_xy = ctx->scratch[5].as<float>();
-            float *d_sc = d_xy + 2 * (size_t)want;
-            e = ctx->scratch[6].reserve((size_t)n_cand * GF_NBMAX * 4 + 16);
-            if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "gftt neighbour lists", e);
-            int *d_nb = ctx->scratch[6].as<int>();
-            unsigned char *d_nbc = d_status + cap;
-            gftt_neighbors_kernel<<<(n_cand + 255) / 256, 256, 0, s>>>(d_rec, n_cand, roi_h, roi_w, d_rank, (float)min_dist, d_nb, d_nbc);
-            PMV_LAUNCH_CHECK(ctx, "gftt_neighbors_kernel");
-            gftt_select_kernel<<<1, 1024, 0, s>>>(d_rec, n_cand, roi_h, roi_w, d_rank, d_nb, d_nbc, d_status, (float)min_dist,
-                                                  max_corners, d_xy, d_sc, d_misc + 2);
-            PMV_LAUNCH_CHECK(ctx, "gftt_select_kernel");
-            PMV_CUDA_TRY(ctx, cudaMemcpyAsync(h_misc, d_misc, 16, cudaMemcpyDeviceToHost, s));
-            PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
-            int n = h_misc[2];
-            if (n > 0) {
-                if (xy) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(xy, d_xy, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
-                if (score) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(score, d_sc, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-                PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
-            }
-            *n_out = n;
-            return PMV_OK;
-        }
     }
-    *n_out = 0;
+    *n_out = n;
     return PMV_OK;
 }
 

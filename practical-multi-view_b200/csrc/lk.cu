@@ -368,7 +368,7 @@ int check_lk_args(pmv_ctx *ctx, int rows, int cols, int step, int n, int win_w, 
 int lk_plan(pmv_ctx *ctx, int batch, int rows, int cols, int win_w, int win_h, int max_level,
             PyrSet *sp, PyrSet *sn, DerivSet *dv, cudaStream_t s)
 {
-    const int border = (win_w > win_h ? win_w : win_h) + LK_M + 2;
+    const int border = pmv_internal_lk_border(win_w, win_h);
     int rc = pmv_internal_pyr_plan(ctx, 0, 2 * batch, rows, cols, border, win_w, win_h, max_level, sp);
     if (rc) return rc;
     *sn = *sp;
@@ -395,6 +395,18 @@ int lk_enqueue(pmv_ctx *ctx, const PyrSet &sp, const PyrSet &sn, const DerivSet 
             if (rc) return rc;
         }
     }
+    return pmv_internal_lk_launch(ctx, sp, sn, dv, batch, d_prev_xy, n, win_w, win_h, max_count, eps, flags, min_eig_thr,
+                                  d_next_xy, d_status, d_err, s);
+}
+
+}  // namespace
+
+int pmv_internal_lk_border(int win_w, int win_h) { return (win_w > win_h ? win_w : win_h) + LK_M + 2; }
+
+int pmv_internal_lk_launch(pmv_ctx *ctx, const PyrSet &sp, const PyrSet &sn, const DerivSet &dv, int batch,
+                           const float *d_prev_xy, int n, int win_w, int win_h, int max_count, double eps, int flags,
+                           double min_eig_thr, float *d_next_xy, uint8_t *d_status, float *d_err, cudaStream_t s)
+{
     if (n == 0) return PMV_OK;
     ProfScope pl(ctx, PMV_PHASE_LK, s);
     LKParams P;
@@ -424,8 +436,6 @@ int lk_enqueue(pmv_ctx *ctx, const PyrSet &sp, const PyrSet &sn, const DerivSet 
     if (kmax <= 28) return launch_lk<28>(ctx, P, batch, s);
     return launch_lk<32>(ctx, P, batch, s);
 }
-
-}  // namespace
 
 extern "C" {
 

@@ -352,6 +352,12 @@ scharr_kernel(const uint8_t *__restrict__ src, int rows, int cols, int pitch, sh
 
 int pmv_internal_deriv_plan(pmv_ctx *ctx, const PyrSet &set, int batch, DerivSet *out, cudaStream_t s)
 {
+    return pmv_internal_deriv_plan_buf(ctx, &ctx->deriv, &ctx->deriv_sig, set, batch, out, s);
+}
+
+int pmv_internal_deriv_plan_buf(pmv_ctx *ctx, DevBuf *buf, unsigned long long *bsig, const PyrSet &set, int batch, DerivSet *out,
+                                cudaStream_t s)
+{
     size_t total = 0, off[PMV_MAX_PYR_LEVELS];
     unsigned long long sig = 1469598103934665603ull;
     auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
@@ -366,20 +372,26 @@ int pmv_internal_deriv_plan(pmv_ctx *ctx, const PyrSet &set, int batch, DerivSet
         out->lv[l] = DerivLevel{nullptr, pitch, stride};
         mix((unsigned long long)a.rows); mix((unsigned long long)a.cols); mix((unsigned long long)bd);
     }
-    const void *before = ctx->deriv.p;
-    cudaError_t e = ctx->deriv.reserve(total * 4 + 256);
+    const void *before = buf->p;
+    cudaError_t e = buf->reserve(total * 4 + 256);
     if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "derivative workspace", e);
-    if (ctx->deriv.p != before || ctx->deriv_sig != sig) {   // new geometry: (re)write the zero borders
-        PMV_CUDA_TRY(ctx, cudaMemsetAsync(ctx->deriv.p, 0, total * 4, s));
-        ctx->deriv_sig = sig;
+    if (buf->p != before || *bsig != sig) {   // new geometry: (re)write the zero borders
+        PMV_CUDA_TRY(ctx, cudaMemsetAsync(buf->p, 0, total * 4, s));
+        *bsig = sig;
     }
-    for (int l = 0; l <= set.top; l++) out->lv[l].ptr = ctx->deriv.as<int>() + off[l];
+    for (int l = 0; l <= set.top; l++) out->lv[l].ptr = buf->as<int>() + off[l];
     return PMV_OK;
 }
 
 // ------------------------------------------------------------------ internal planning ---
 int pmv_internal_pyr_plan(pmv_ctx *ctx, int which, int batch, int rows, int cols, int border,
                           int win_w, int win_h, int max_level, PyrSet *out)
+{
+    return pmv_internal_pyr_plan_buf(ctx, &ctx->pyr[which], batch, rows, cols, border, win_w, win_h, max_level, out);
+}
+
+int pmv_internal_pyr_plan_buf(pmv_ctx *ctx, DevBuf *buf, int batch, int rows, int cols, int border,
+                              int win_w, int win_h, int max_level, PyrSet *out)
 {
     int L = pmv_pyr_levels(rows, cols, win_w, win_h, max_level);
     if (L < 0 || L >= PMV_MAX_PYR_LEVELS) return ctx->fail(PMV_ERR_UNSUPPORTED, "max_level too large");
@@ -397,9 +409,9 @@ int pmv_internal_pyr_plan(pmv_ctx *ctx, int which, int batch, int rows, int cols
         total += stride * batch;
         out->lv[l] = PyrLevel{nullptr, r, c, pitch, stride, border, bxl};
     }
-    cudaError_t e = ctx->pyr[which].reserve(total + 256);
+    cudaError_t e = buf->reserve(total + 256);
     if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "pyramid workspace", e);
-    for (int l = 0; l <= L; l++) out->lv[l].ptr = ctx->pyr[which].as<uint8_t>() + off[l];
+    for (int l = 0; l <= L; l++) out->lv[l].ptr = buf->as<uint8_t>() + off[l];
     return PMV_OK;
 }
 
