@@ -11,6 +11,7 @@
 
 #include "ba.cuh"
 #include "ba_kernels.cuh"
+#include "ba_runs.cuh"
 
 int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_host, cudaStream_t s);  // ba_chol.cu
 int pmv_internal_ba_allreduce(pmv_ctx *ctx, const double *send, double *recv, size_t count, int op_max,
@@ -50,6 +51,10 @@ struct pmv_ba_problem {
     BAPairSeg *d_segs = nullptr;
     int2 *d_entries = nullptr;
     int nsegs = 0;
+    // run-organised path of one large problem (ba_runs.cuh): points sorted by camera tuple, runs of equal tuples
+    int *d_run_off = nullptr, *d_run_pt = nullptr;
+    int nruns = 0;
+    int run_kbegin[RUN_MAXK + 2] = {};                  // runs are ordered by tuple size: [kbegin[k], kbegin[k+1]) have k observations
     // window-batched path (ba_window.cu): Nc <= 22, every (point, camera) pair observed at most once
     int use_window = 0;
     unsigned *d_vis = nullptr;
@@ -150,11 +155,17 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
     const int W = D.W, n = D.n;
     const int wc = W * D.Nc, wp = W * D.Np;
     const int wblocks = (W + 127) / 128;
-    if (D.No > 0) {
+    if (p->nruns > 0) {
+        // runs of equal camera tuples: cost + raw camera blocks straight from the observations (nothing materialised)
+        PMV_CUDA_TRY(ctx, cudaMemsetAsync(p->d_Uraw, 0, sizeof(double) * 27 * (size_t)wc, s));
+        ba_run_cam_kernel<<<(p->nruns + 3) / 4, 128, 0, s>>>(D, p->d_run_off, p->d_run_pt, p->nruns, p->d_Uraw);
+        PMV_LAUNCH_CHECK(ctx, "ba_run_cam_kernel");
+    } else if (D.No > 0) {
         ba_linearize_kernel<<<(D.No + 127) / 128, 128, 0, s>>>(D);
         PMV_LAUNCH_CHECK(ctx, "ba_linearize_kernel");
     }
-    if (D.No >= 256LL * wc) {   // hundreds to thousands of observations per camera: a CTA per camera
+    if (p->nruns > 0) {
+    } else if (D.No >= 256LL * wc) {   // hundreds to thousands of observations per camera: a CTA per camera
         ba_cam_accumulate_wide_kernel<<<wc, 256, 0, s>>>(D, p->d_Uraw);
         PMV_LAUNCH_CHECK(ctx, "ba_cam_accumulate_wide_kernel");
     } else {
@@ -181,7 +192,10 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
         ba_clear_system_kernel<<<grid, 256, 0, s>>>(D);
         PMV_LAUNCH_CHECK(ctx, "ba_clear_system_kernel");
     }
-    if (wp > 0) {
+    if (wp > 0 && p->nruns > 0) {
+        int rc = launch_run_schur_all(ctx, D, p->d_run_off, p->d_run_pt, p->run_kbegin, s);
+        if (rc) return rc;
+    } else if (wp > 0) {
         const int by_pairs = p->nsegs > 0;
         if (by_pairs && D.No <= 8 * (long long)D.Np) {
             ba_point_vinv_w1_kernel<8><<<std::min((wp + 15) / 16, 148 * 32), 128, 0, s>>>(D);
@@ -223,7 +237,7 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
     ba_cam_candidate_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D, p->sharded ? (p->rank == 0) : 1);
     PMV_LAUNCH_CHECK(ctx, "ba_cam_candidate_kernel");
     if (wp > 0) {
-        if (W == 1 && (D.No >= 100000 || p->nsegs > 0) && D.No <= 8 * (long long)D.Np) {
+        if (p->nruns > 0 || (W == 1 && (D.No >= 100000 || p->nsegs > 0) && D.No <= 8 * (long long)D.Np)) {
             ba_backsub_w1_kernel<8><<<std::min((wp + 15) / 16, 148 * 32), 128, 0, s>>>(D);
             PMV_LAUNCH_CHECK(ctx, "ba_backsub_w1_kernel");
         } else {
@@ -340,6 +354,55 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     } else {
         for (int c = 0; c < Nc; c++) emax[c] = Nc - 1;   // batched windows use the small-n kernels anyway
     }
+    // ---- runs of points with the same camera tuple (ba_runs.cuh): one large problem whose points see <= 8 cameras.
+    // PMV_BA_NO_RUNS=1 keeps the pair-list path, PMV_BA_FORCE_RUNS=1 (tests) sends small problems through the runs.
+    std::vector<int> run_off, run_pt;
+    int run_kbegin[RUN_MAXK + 2] = {};
+    {
+        const char *no_runs = getenv("PMV_BA_NO_RUNS"), *force_runs = getenv("PMV_BA_FORCE_RUNS");
+        const bool forced = force_runs && force_runs[0] == '1';
+        bool want = W == 1 && !window_ok && !transient && !(no_runs && no_runs[0] == '1') && (No >= 100000 || forced);
+        std::vector<std::pair<unsigned long long, int>> keys;
+        if (want) {
+            keys.reserve(Np);
+            for (int q = 0; q < Np && want; q++) {
+                const int a = pt_off[q], b = pt_off[q + 1];
+                if (b == a) continue;
+                if (b - a > RUN_MAXK) { want = false; break; }
+                unsigned long long h = 1469598103934665603ull;
+                for (int d = a; d < b; d++) h = (h ^ (unsigned long long)(unsigned)h_cam[d]) * 1099511628211ull;
+                keys.push_back({((unsigned long long)(b - a) << 60) | (h >> 4), q});   // tuple size first, then the tuple
+            }
+        }
+        if (want && !keys.empty()) {
+            std::sort(keys.begin(), keys.end());
+            auto same_tuple = [&](int qa, int qb) {
+                const int a = pt_off[qa], b = pt_off[qb], ka = pt_off[qa + 1] - a;
+                if (ka != pt_off[qb + 1] - b) return false;
+                for (int d = 0; d < ka; d++) if (h_cam[a + d] != h_cam[b + d]) return false;
+                return true;
+            };
+            run_pt.resize(keys.size());
+            for (size_t i = 0; i < keys.size(); i++) {
+                run_pt[i] = keys[i].second;
+                const bool brk = i == 0 || keys[i].first != keys[i - 1].first || (int)i - run_off.back() >= RUN_MAXLEN ||
+                                 !same_tuple(keys[i].second, keys[i - 1].second);
+                if (brk) run_off.push_back((int)i);
+            }
+            run_off.push_back((int)keys.size());
+            {   // first run of every tuple size
+                int r = 0;
+                const int nr = (int)run_off.size() - 1;
+                for (int k = 1; k <= RUN_MAXK + 1; k++) {
+                    while (r < nr && (int)(keys[run_off[r]].first >> 60) < k) r++;
+                    run_kbegin[k] = r;
+                }
+            }
+            // short runs would put ~540 atomics per point on S again: the pair lists handle that case better
+            if (!forced && keys.size() < 3 * (run_off.size() - 1)) { run_off.clear(); run_pt.clear(); }
+        }
+    }
+    const bool use_runs = !run_off.empty();
     pmv_ba_problem *p = new pmv_ba_problem();
     p->ctx = ctx;
     p->sharded = sharded_nranks > 1;
@@ -363,7 +426,9 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     rc |= dev_alloc(p, &D.poses, wc * 6); rc |= dev_alloc(p, &D.points, wp * 3);
     rc |= dev_alloc(p, &D.cand_poses, wc * 6); rc |= dev_alloc(p, &D.cand_points, wp * 3);
     rc |= dev_alloc(p, &p->d_init_poses, wc * 6); rc |= dev_alloc(p, &p->d_init_points, wp * 3);
-    if (!window_ok) {   // the window path never materialises the linearisation
+    if (use_runs) {     // residuals and Jacobians are recomputed where they are used: no linearisation buffers
+        rc |= dev_alloc(p, &p->d_run_off, run_off.size()); rc |= dev_alloc(p, &p->d_run_pt, run_pt.size());
+    } else if (!window_ok) {   // the window path never materialises the linearisation
         rc |= dev_alloc(p, &D.Lr, 2 * (size_t)No); rc |= dev_alloc(p, &D.Ljc, 12 * (size_t)No); rc |= dev_alloc(p, &D.Ljp, 6 * (size_t)No);
     } else {
         rc |= dev_alloc(p, &p->d_vis, wp); rc |= dev_alloc(p, &p->d_camR, wc * 36); rc |= dev_alloc(p, &p->d_candR, wc * 9);
@@ -411,6 +476,11 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     up(d_camact, h_camact.data(), sizeof(int) * wc);
     up(p->d_init_poses, poses, sizeof(double) * wc * 6); up(p->d_init_points, points, sizeof(double) * wp * 3);
     if (window_ok) up(p->d_vis, h_vis.data(), sizeof(unsigned) * wp);
+    if (use_runs) {
+        up(p->d_run_off, run_off.data(), sizeof(int) * run_off.size()); up(p->d_run_pt, run_pt.data(), sizeof(int) * run_pt.size());
+        p->nruns = (int)run_off.size() - 1;
+        for (int k = 0; k < RUN_MAXK + 2; k++) p->run_kbegin[k] = run_kbegin[k];
+    }
     if (ok && cudaStreamSynchronize(s) != cudaSuccess) ok = false;  // host vectors die at return
     if (!ok) { ctx->fail(PMV_ERR_CUDA, "pmv_ba_problem_create: upload failed", cudaGetLastError()); pmv_ba_problem_destroy(p); return nullptr; }
     {
@@ -459,7 +529,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     {
         const char *no_pairs = getenv("PMV_BA_NO_PAIRS");
         const char *force_pairs = getenv("PMV_BA_FORCE_PAIRS");   // tests: small problems through the pair path
-        const bool want = W == 1 && !window_ok && p->arena_mode == 0 && (size_t)Nc * Nc <= ((size_t)16 << 20) &&
+        const bool want = !use_runs && W == 1 && !window_ok && p->arena_mode == 0 && (size_t)Nc * Nc <= ((size_t)16 << 20) &&
                           (No >= 100000 || (force_pairs && force_pairs[0] == '1')) && !(no_pairs && no_pairs[0] == '1');
         if (want) {
             std::vector<unsigned> pcnt((size_t)Nc * Nc + 1, 0u);

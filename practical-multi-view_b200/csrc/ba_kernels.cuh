@@ -807,7 +807,30 @@ __global__ void __launch_bounds__(128) ba_backsub_kernel(const BADev D)
     flush();
 }
 
-// back-substitution, W == 1, G lanes per point (see ba_point_vinv_w1_kernel)
+// back-substitution, W == 1, G lanes per point (see ba_point_vinv_w1_kernel).  On the run-organised path (ba_runs.cuh,
+// D.Ljc == nullptr) the linearisation of an observation is recomputed here instead of read back (24 B instead of
+// 160 B per observation).
+__device__ __forceinline__ void backsub_fetch(const BADev &D, int i, int ci, const double *X, double r[2], double jc[12], double jp[6])
+{
+    if (D.Ljc) {
+        r[0] = D.Lr[2 * (size_t)i]; r[1] = D.Lr[2 * (size_t)i + 1];
+#pragma unroll
+        for (int k = 0; k < 12; k++) jc[k] = D.Ljc[12 * (size_t)i + k];
+#pragma unroll
+        for (int k = 0; k < 6; k++) jp[k] = D.Ljp[6 * (size_t)i + k];
+    } else {
+        ba_residual_jac(D.poses + 6 * (size_t)ci, X, D.obs_xy[2 * (size_t)i], D.obs_xy[2 * (size_t)i + 1], D.fx, D.cx, D.fy, D.cy, r, jc, jp);
+        double rho0, rho1;
+        ba_huber(D.delta, r[0] * r[0] + r[1] * r[1], rho0, rho1);
+        const double sr = sqrt(rho1);
+        r[0] = r[0] * sr; r[1] = r[1] * sr;
+#pragma unroll
+        for (int k = 0; k < 12; k++) jc[k] = jc[k] * sr;
+#pragma unroll
+        for (int k = 0; k < 6; k++) jp[k] = jp[k] * sr;
+    }
+}
+
 template <int G>
 __global__ void __launch_bounds__(128) ba_backsub_w1_kernel(const BADev D)
 {
@@ -825,18 +848,21 @@ __global__ void __launch_bounds__(128) ba_backsub_w1_kernel(const BADev D)
         double sp[3] = {1.0, 1.0, 1.0};
         if (active) { sp[0] = D.scale_p[3 * (size_t)wp]; sp[1] = D.scale_p[3 * (size_t)wp + 1]; sp[2] = D.scale_p[3 * (size_t)wp + 2]; }
         double t0 = 0, t1 = 0, t2 = 0;
+        double Lr[2] = {0, 0}, Ljc[12], Ljp[6];   // linearisation of this lane's observation (kept for the second loop)
+        const bool single = o1 - o0 <= G;
         for (int i = o0 + gl; i < o1; i += G) {
             const int ci = D.obs_cam[i];
             const double *sc = D.scale_c + 6 * (size_t)ci;
+            backsub_fetch(D, i, ci, D.points + 3 * (size_t)wp, Lr, Ljc, Ljp);
             double jy0 = 0, jy1 = 0;
 #pragma unroll
             for (int k = 0; k < 6; k++) {
                 const double y = yc[6 * ci + k] * sc[k];
-                jy0 += D.Ljc[12 * (size_t)i + k] * y; jy1 += D.Ljc[12 * (size_t)i + 6 + k] * y;
+                jy0 += Ljc[k] * y; jy1 += Ljc[6 + k] * y;
             }
-            t0 -= D.Ljp[6 * (size_t)i] * sp[0] * jy0 + D.Ljp[6 * (size_t)i + 3] * sp[0] * jy1;
-            t1 -= D.Ljp[6 * (size_t)i + 1] * sp[1] * jy0 + D.Ljp[6 * (size_t)i + 4] * sp[1] * jy1;
-            t2 -= D.Ljp[6 * (size_t)i + 2] * sp[2] * jy0 + D.Ljp[6 * (size_t)i + 5] * sp[2] * jy1;
+            t0 -= Ljp[0] * sp[0] * jy0 + Ljp[3] * sp[0] * jy1;
+            t1 -= Ljp[1] * sp[1] * jy0 + Ljp[4] * sp[1] * jy1;
+            t2 -= Ljp[2] * sp[2] * jy0 + Ljp[5] * sp[2] * jy1;
         }
         t0 = group_sum_d<G>(t0); t1 = group_sum_d<G>(t1); t2 = group_sum_d<G>(t2);
         double yp[3] = {0, 0, 0}, cand[3] = {0, 0, 0}, sn = 0, xn = 0;
@@ -860,18 +886,19 @@ __global__ void __launch_bounds__(128) ba_backsub_w1_kernel(const BADev D)
         for (int i = o0 + gl; i < o1; i += G) {
             const int ci = D.obs_cam[i];
             const double *sc = D.scale_c + 6 * (size_t)ci;
+            if (!single) backsub_fetch(D, i, ci, D.points + 3 * (size_t)wp, Lr, Ljc, Ljp);
             double m0 = 0, m1 = 0;  // J * step, step = -y
 #pragma unroll
             for (int k = 0; k < 6; k++) {
                 const double y = yc[6 * ci + k] * sc[k];
-                m0 -= D.Ljc[12 * (size_t)i + k] * y; m1 -= D.Ljc[12 * (size_t)i + 6 + k] * y;
+                m0 -= Ljc[k] * y; m1 -= Ljc[6 + k] * y;
             }
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 const double y = yp[k] * sp[k];
-                m0 -= D.Ljp[6 * (size_t)i + k] * y; m1 -= D.Ljp[6 * (size_t)i + 3 + k] * y;
+                m0 -= Ljp[k] * y; m1 -= Ljp[3 + k] * y;
             }
-            mc -= m0 * (D.Lr[2 * (size_t)i] + m0 / 2.0) + m1 * (D.Lr[2 * (size_t)i + 1] + m1 / 2.0);
+            mc -= m0 * (Lr[0] + m0 / 2.0) + m1 * (Lr[1] + m1 / 2.0);
             double r[2];
             ba_residual_only(D.cand_poses + 6 * (size_t)ci, cand, D.obs_xy[2 * (size_t)i], D.obs_xy[2 * (size_t)i + 1],
                              D.fx, D.cx, D.fy, D.cy, r);

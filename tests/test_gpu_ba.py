@@ -182,6 +182,52 @@ def test_pair_list_schur_matches_point_kernel(ctx, pmv, synth, monkeypatch, ba_p
     assert abs(res["pairs"][2]["final_cost"] - res["points"][2]["final_cost"]) <= 1e-9 * so["final_cost"]
 
 
+@pytest.mark.parametrize("nposes,npts,span,views", [(40, 3000, 20, 5), (12, 900, 12, 5), (30, 2500, 16, 3), (24, 1500, 24, 8)])
+def test_run_organised_schur_matches_oracle(ctx, pmv, synth, monkeypatch, ba_path, nposes, npts, span, views):
+    """BAL-scale problems walk RUNS of points that share their camera tuple (ba_runs.cuh): residuals and Jacobians are
+    recomputed per observation, the blocks of a tuple are kept in registers and S is touched once per run.  Forced
+    here on small problems (tuple sizes 1..8 occur near the ends of the trajectory); compared with the oracle, with
+    the point-by-point kernel, and on a problem with rejected steps."""
+    if ba_path == "window":
+        pytest.skip("general path only")
+    w = synth.ba_large(11 + nposes, n_poses=nposes, n_points=npts, views=views, span=span)
+    po, xo, so = oracle.ba_solve(*_args(w), 1.0, 4)
+    res = {}
+    for mode in ("runs", "points"):
+        if mode == "runs":
+            monkeypatch.setenv("PMV_BA_FORCE_RUNS", "1")
+        else:
+            monkeypatch.delenv("PMV_BA_FORCE_RUNS", raising=False)
+        prob = ctx.ba_problem(*_args(w), 1.0)
+        prob.solve(4)
+        p, x, s = prob.download()
+        prob.close()
+        res[mode] = (p, x, s[0])
+        assert s[0]["iterations"] == so["iterations"] and s[0]["successful_steps"] == so["successful_steps"]
+        assert abs(s[0]["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]
+        assert abs(s[0]["initial_cost"] - so["initial_cost"]) <= 1e-9 * so["initial_cost"]
+        assert np.abs(p[0] - po).max() < 1e-5 and np.abs(x[0] - xo).max() < 1e-4
+    assert abs(res["runs"][2]["final_cost"] - res["points"][2]["final_cost"]) <= 1e-9 * so["final_cost"]
+    monkeypatch.delenv("PMV_BA_FORCE_RUNS", raising=False)
+
+
+def test_run_organised_rejected_steps(ctx, synth, monkeypatch):
+    """A badly initialised problem makes LM reject steps: the run path re-solves with the same linearisation
+    (recomputed, not stored) and must follow the oracle's accept / reject sequence."""
+    monkeypatch.setenv("PMV_BA_FORCE_RUNS", "1")
+    w = synth.ba_large(3, n_poses=16, n_points=1200, views=4, span=12)
+    rng = np.random.default_rng(0)
+    pts = w["points"] + rng.normal(0, 2.0, w["points"].shape)
+    args = (w["poses"], pts, w["obs"], w["cam_idx"], w["pt_idx"], w["K"])
+    po, xo, so = oracle.ba_solve(*args, 1.0, 8)
+    prob = ctx.ba_problem(*args, 1.0)
+    prob.solve(8)
+    p, x, s = prob.download()
+    prob.close()
+    assert s[0]["iterations"] == so["iterations"] and s[0]["successful_steps"] == so["successful_steps"]
+    assert abs(s[0]["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]
+
+
 def test_resident_problem_reset_and_errors(ctx, pmv, synth):
     w = synth.ba_window(9, n_poses=5, n_points=100)
     prob = ctx.ba_problem(*_args(w))
