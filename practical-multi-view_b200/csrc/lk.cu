@@ -23,6 +23,8 @@
 //
 // Roofline: NOT HBM bound (1.28 MB compulsory bytes per 2 000-feature pair vs ~6e8 integer
 // ops); the limiter is the integer/LSU issue rate -- see DESIGN.md.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -79,9 +81,17 @@ __device__ __forceinline__ int lk_interp_diff(unsigned quad, unsigned wlo, unsig
 }
 
 // Copy the rows [y0, y0+nrows) x bytes [x0, x0+nbytes) of a bordered level into shared memory with
-// aligned 4-byte loads.  The smem copy keeps the global misalignment: pixel (r, c) of the region is
+// aligned 4-byte asynchronous copies.  The smem copy keeps the global misalignment: pixel (r, c) of the region is
 // at dst[r*spitch + mis + c] with mis = x0 & 3 (returned).  Level interiors are 16 B aligned and
 // pitched to 128 B, so the misalignment is the same for every row.
+__device__ __forceinline__ void cp_async_4(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// The copies are ASYNCHRONOUS (cp.async, LDGSTS): global -> shared memory without a register round trip, so the
+// issuing warp does not stall per word; the caller waits once (cp_async_wait_all + __syncwarp) before reading.
 __device__ __forceinline__ int stage_region(uint32_t *dst, int spitch_words, const uint8_t *img, int pitch,
                                             int x0, int y0, int nbytes, int nrows, int lane)
 {
@@ -93,7 +103,7 @@ __device__ __forceinline__ int stage_region(uint32_t *dst, int spitch_words, con
     const int qd = 32 / nw, rm = 32 - qd * nw;
     int r = lane / nw, cw = lane - r * nw;
     for (int i = lane; i < total; i += 32) {
-        dst[r * spitch_words + cw] = __ldg(g + r * gp + cw);
+        cp_async_4(dst + r * spitch_words + cw, g + r * gp + cw);
         cw += rm; r += qd;
         if (cw >= nw) { cw -= nw; r++; }
     }
@@ -194,14 +204,14 @@ lk_track_kernel(const LKParams P)
             for (int c0 = 0; c0 <= w; c0 += 32) {
                 const int pc = c0 + lane;
                 if (pc <= w) {
-                    // plain load -> store loop with pointer increments: this kernel is instruction-issue bound and
-                    // 16 resident warps hide the latency (batching the loads in registers was slower)
+                    // one asynchronous 4-byte copy per word (LDGSTS): no register round trip, one wait after the loop
                     const int *src = dsrc + pc;
                     int *dst = ds + pc;
-                    for (int r = 0; r <= h; r++) { *dst = __ldg(src); src += DL.pitch; dst += dp; }
+                    for (int r = 0; r <= h; r++) { cp_async_4(dst, src); src += DL.pitch; dst += dp; }
                 }
             }
         }
+        cp_async_wait_all();
         __syncwarp();
         // ---- 3. template + structure tensor --------------------------------------------
         int sA11 = 0, sA12 = 0, sA22 = 0;
@@ -251,6 +261,7 @@ lk_track_kernel(const LKParams P)
                 __syncwarp();
                 jx0 = ix_ - LK_M; jy0 = iy_ - LK_M;
                 jmis = stage_region(reinterpret_cast<uint32_t *>(js), jp >> 2, Jimg, J.pitch, jx0, jy0, jw, jh, lane);
+                cp_async_wait_all();
                 __syncwarp();
                 staged = true;
                 ox = LK_M; oy = LK_M;
@@ -476,7 +487,8 @@ PMV_API int pmv_lk_track_batched(pmv_ctx *ctx, const uint8_t *prev, const uint8_
 
     // Chunked pipeline: raw image bytes go up on the copy stream (one contiguous transfer per chunk and
     // image set), the compute stream imports / builds pyramids / tracks chunk c while chunk c+1 is in flight.
-    const int CH = batch <= 8 ? batch : 32;
+    const char *ch_env = getenv("PMV_LK_CHUNK");   // tuning knob (tools/): images per upload chunk
+    const int CH = batch <= 8 ? batch : (ch_env && atoi(ch_env) > 0 ? atoi(ch_env) : 32);
     const int nchunks = (batch + CH - 1) / CH;
     PyrSet sp, sn;
     DerivSet dv;
