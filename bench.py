@@ -734,9 +734,10 @@ def run_lk(args, rank, world, local_rank):
     py_ach = py_bytes / (py_avg * 1e-3) / 1e9 if py_avg else None
     # LK is bounded by instruction issue, not by HBM (SURVEY 8d asks for both figures): warp instructions per
     # feature and DRAM bytes per pair come from the ncu --set full capture of this kernel committed as
-    # profiles/r1_lk_final_ncu_summary.txt (smsp__inst_executed.sum / 64 000 features; dram bytes / 32 pairs);
+    # profiles/r2_lk_ncu_summary.txt (smsp__inst_executed.sum / 512 000 features); DRAM bytes per pair from the cold-cache
+    # round-1 capture profiles/r1_lk_final_ncu_summary.txt (dram bytes / 32 pairs; the image traffic did not change);
     # the issue peak is 148 SMs x 4 schedulers x 1 warp instruction per clock at the SM clock sampled during the run.
-    LK_WARP_INST_PER_FEATURE = 668022617 / 64000.0
+    LK_WARP_INST_PER_FEATURE = 5283148656 / 512000.0
     LK_DRAM_BYTES_PER_PAIR = (132.062464e6 + 4.643072e6) / 32.0
     sm_hz = float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
     issue_peak = 148 * 4 * sm_hz
@@ -747,7 +748,7 @@ def run_lk(args, rank, world, local_rank):
                           "achieved": issue_ach / 1e9 if issue_ach else None, "peak": issue_peak / 1e9,
                           "unit": "G warp-instructions/s", "frac": (issue_ach / issue_peak) if issue_ach else None,
                           "warp_instructions_per_feature": LK_WARP_INST_PER_FEATURE,
-                          "source": "ncu smsp__inst_executed.sum, profiles/r1_lk_final_ncu_summary.txt"},
+                          "source": "ncu smsp__inst_executed.sum, profiles/r2_lk_ncu_summary.txt"},
                 "avg_launch_ms": lk_avg, "algorithmic_bytes_per_launch": lk_bytes,
                 "share_of_step": lk_ms / ms if ms else None,
                 "note": "LK is integer-issue/LSU bound, not HBM bound (SURVEY §8d); HBM fraction reported as the contract asks",
