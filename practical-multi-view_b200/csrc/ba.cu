@@ -13,7 +13,8 @@
 #include "ba_kernels.cuh"
 #include "ba_runs.cuh"
 
-int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_host, cudaStream_t s);  // ba_chol.cu
+int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_host, const BASplit *split, cudaStream_t s);  // ba_chol.cu
+int pmv_internal_ba_cholesky_band_T(int n, const int *lim_host);                                    // ba_chol_band.cu
 int pmv_internal_ba_allreduce(pmv_ctx *ctx, const double *send, double *recv, size_t count, int op_max,
                               cudaStream_t s);                                      // ba_nccl.cu
 bool pmv_internal_ba_window_eligible(int Nc, int Np);                               // ba_window.cu
@@ -55,6 +56,9 @@ struct pmv_ba_problem {
     int *d_run_off = nullptr, *d_run_pt = nullptr;
     int nruns = 0;
     int run_kbegin[RUN_MAXK + 2] = {};                  // runs are ordered by tuple size: [kbegin[k], kbegin[k+1]) have k observations
+    // two-sided solve of the banded reduced camera system (BASplit, ba.cuh)
+    BASplit split;
+    std::vector<int> split_lim[3];
     // window-batched path (ba_window.cu): Nc <= 22, every (point, camera) pair observed at most once
     int use_window = 0;
     unsigned *d_vis = nullptr;
@@ -231,7 +235,7 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
         ba_cholesky_small_kernel<<<W, 256, smem, s>>>(D);
         PMV_LAUNCH_CHECK(ctx, "ba_cholesky_small_kernel");
     } else {
-        int rc = pmv_internal_ba_cholesky_large(ctx, D, p->chol_lim.empty() ? nullptr : p->chol_lim.data(), s);
+        int rc = pmv_internal_ba_cholesky_large(ctx, D, p->chol_lim.empty() ? nullptr : p->chol_lim.data(), &p->split, s);
         if (rc) return rc;
     }
     ba_cam_candidate_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D, p->sharded ? (p->rank == 0) : 1);
@@ -509,6 +513,64 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
         }
         cudaMemcpyAsync(d_lim, p->chol_lim.data(), sizeof(int) * nblk, cudaMemcpyHostToDevice, s);
         D.chol_lim = d_lim;
+        // ---- two-sided solve: separator of w columns in the middle of a long banded system
+        {
+            const char *no_split = getenv("PMV_CHOL_NO_SPLIT");
+            const int NBk = PMV_CHOL_NB, nn = (int)n;
+            int maxw = 0;
+            for (int kb = 0; kb < nblk; kb++) maxw = std::max(maxw, p->chol_lim[kb] - kb * NBk);
+            const int w = (maxw + NBk - 1) / NBk * NBk;
+            const int a = ((nn - w) / 2) / NBk * NBk;
+            const bool want = W == 1 && !window_ok && p->arena_mode == 0 && !(no_split && no_split[0] == '1') && nn >= 1024 && w > 0 && 6 * w <= nn && a >= 2 * w &&
+                              pmv_internal_ba_cholesky_band_T(nn, p->chol_lim.data()) > 0;
+            if (want) {
+                BASplit &P = p->split;
+                P.a = a; P.w = w; P.h1 = a + w; P.h2 = nn - a;
+                std::vector<int> &l1 = p->split_lim[0], &l2 = p->split_lim[1], &l3 = p->split_lim[2];
+                const int nb1 = (P.h1 + NBk - 1) / NBk, nb2 = (P.h2 + NBk - 1) / NBk, nb3 = (w + NBk - 1) / NBk;
+                l1.resize(nb1); l2.assign(nb2, 0); l3.assign(nb3, w);
+                for (int kb = 0; kb < nb1; kb++) l1[kb] = std::min(p->chol_lim[kb], P.h1);
+                // reversed system: row i' <-> original index r = n-1-i' ; it reaches the reversed image of the first
+                // original row whose envelope covers r
+                {
+                    std::vector<int> first(nn);
+                    int kb = 0;
+                    for (int r = 0; r < nn; r++) {
+                        while (kb < nblk && p->chol_lim[kb] <= r) kb++;
+                        first[r] = std::min(r, kb * NBk);
+                    }
+                    int run2 = 0;
+                    for (int ip = 0; ip < P.h2; ip++) {
+                        const int r = nn - 1 - ip;
+                        const int reach = nn - first[r];               // one past the last reversed column
+                        run2 = std::max(run2, std::min(reach, P.h2));
+                        l2[ip / NBk] = std::max(l2[ip / NBk], run2);
+                    }
+                    for (int q = 1; q < nb2; q++) l2[q] = std::max(l2[q], l2[q - 1]);
+                }
+                const bool elig = pmv_internal_ba_cholesky_band_T(P.h1, l1.data()) > 0 && pmv_internal_ba_cholesky_band_T(P.h2, l2.data()) > 0 &&
+                                  pmv_internal_ba_cholesky_band_T(w, l3.data()) > 0;
+                if (elig) {
+                    int rc2 = 0;
+                    rc2 |= dev_alloc(p, &P.S2, (size_t)P.h2 * P.h2); rc2 |= dev_alloc(p, &P.b2, (size_t)P.h2); rc2 |= dev_alloc(p, &P.y2, (size_t)P.h2);
+                    rc2 |= dev_alloc(p, &P.AM, (size_t)w * w); rc2 |= dev_alloc(p, &P.bM, (size_t)w);
+                    rc2 |= dev_alloc(p, &P.S3, (size_t)w * w); rc2 |= dev_alloc(p, &P.b3, (size_t)w); rc2 |= dev_alloc(p, &P.y3, (size_t)w);
+                    rc2 |= dev_alloc(p, &P.lim1, nb1); rc2 |= dev_alloc(p, &P.lim2, nb2); rc2 |= dev_alloc(p, &P.lim3, nb3);
+                    rc2 |= dev_alloc(p, &P.st3, 3);
+                    if (rc2) { pmv_ba_problem_destroy(p); return nullptr; }
+                    cudaMemsetAsync(P.S2, 0, sizeof(double) * (size_t)P.h2 * P.h2, s);   // entries outside the envelope are never written
+                    cudaMemcpyAsync(P.lim1, l1.data(), sizeof(int) * nb1, cudaMemcpyHostToDevice, s);
+                    cudaMemcpyAsync(P.lim2, l2.data(), sizeof(int) * nb2, cudaMemcpyHostToDevice, s);
+                    cudaMemcpyAsync(P.lim3, l3.data(), sizeof(int) * nb3, cudaMemcpyHostToDevice, s);
+                    P.lim1_h = l1.data(); P.lim2_h = l2.data(); P.lim3_h = l3.data();
+                    P.lim_orig = d_lim;
+                    bool okc = cudaStreamCreateWithFlags(&P.s2, cudaStreamNonBlocking) == cudaSuccess;
+                    for (auto &e : P.ev) okc = okc && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+                    if (!okc) { ctx->fail(PMV_ERR_CUDA, "split solve: stream / events"); pmv_ba_problem_destroy(p); return nullptr; }
+                    P.enabled = 1;
+                }
+            }
+        }
         if (p->sharded) {
             std::vector<long long> off(n + 1);
             long long acc = 0;
@@ -594,6 +656,8 @@ PMV_API void pmv_ba_problem_destroy(pmv_ba_problem *p)
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+    if (p->split.s2) { cudaStreamSynchronize(p->split.s2); cudaStreamDestroy(p->split.s2); }
+    for (auto &e : p->split.ev) if (e) cudaEventDestroy(e);
     for (void *q : p->allocs) cudaFree(q);
     delete p;
 }

@@ -54,3 +54,23 @@ struct BADev {
     const int *chol_lim;         // per PMV_CHOL_NB-row block of S: end column of its envelope (blocked Cholesky)
     int max_iters;
 };
+
+// Two-sided elimination of a banded reduced camera system (ba_chol.cu: split solve).  The band is cut at a separator M
+// of w columns (w >= the envelope width) in the middle: the part above and the part below do not couple, so the
+// leading system [top | M] is factorised top-down and the trailing system [bottom | M], index-reversed, also
+// top-down -- concurrently, by two clusters -- and the separator's Schur complement is assembled from the two
+// partial factors and solved last.  Halves the chain of dependent block steps of the factorisation and of the
+// back-substitution.
+struct BASplit {
+    int enabled = 0;
+    int a = 0, w = 0, h1 = 0, h2 = 0;            // separator [a, a + w); h1 = a + w rows of the leading system, h2 = n - a of the reversed one
+    double *S2 = nullptr, *b2 = nullptr, *y2 = nullptr;      // reversed trailing system (h2 x h2, own leading dimension), rhs, solution
+    double *AM = nullptr, *bM = nullptr;                     // saved separator block (w x w) and rhs
+    double *S3 = nullptr, *b3 = nullptr, *y3 = nullptr;      // separator Schur complement, rhs, solution
+    int *lim1 = nullptr, *lim2 = nullptr, *lim3 = nullptr;   // envelopes of the three systems (device)
+    const int *lim_orig = nullptr;
+    BAState *st3 = nullptr;                                  // [3]: private status of the three factorisations
+    int *lim1_h = nullptr, *lim2_h = nullptr, *lim3_h = nullptr;   // host copies (owned by the problem)
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};

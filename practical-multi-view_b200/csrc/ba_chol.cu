@@ -199,7 +199,7 @@ constexpr int BS_MAXW = 321;   // widest envelope (columns from k0) staged in sh
 constexpr int BS_THREADS = 512;
 
 __global__ void __launch_bounds__(BS_THREADS)
-chol_backsub_kernel(const double *S, const double *z, double *y, int n, const int *__restrict__ lim, BAState *st, int staged)
+chol_backsub_kernel(const double *S, const double *z, double *y, int n, size_t ld, const int *__restrict__ lim, BAState *st, int staged)
 {
     extern __shared__ double sbuf[];            // staged: 2 x NB x BS_MAXW
     __shared__ double yk[NB];
@@ -214,7 +214,7 @@ chol_backsub_kernel(const double *S, const double *z, double *y, int n, const in
         // threads 32..511 (warps 1..15), 16 per row, 30 rows per pass; no index arithmetic beyond an add
         const int t = tid - 32;
         for (int r = t >> 4; r < nb; r += (BS_THREADS - 32) / 16) {
-            const double *src = S + (size_t)(k0 + r) * n + k0;
+            const double *src = S + (size_t)(k0 + r) * ld + k0;
             const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + r * BS_MAXW);
             for (int c = r + (t & 15); c < wdt; c += 16)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + 8u * c), "l"(src + c));
@@ -298,7 +298,7 @@ chol_backsub_kernel(const double *S, const double *z, double *y, int n, const in
         const int cend = min(n, lim[kb]);   // U_kj == 0 beyond the envelope
         if (warp < nb) {
             double sacc = 0;
-            for (int c = k0 + nb + lane; c < cend; c += 32) sacc += S[(size_t)(k0 + warp) * n + c] * y[c];
+            for (int c = k0 + nb + lane; c < cend; c += 32) sacc += S[(size_t)(k0 + warp) * ld + c] * y[c];
             for (int o = 16; o; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
             if (lane == 0) yk[warp] = z[k0 + warp] - sacc;
         }
@@ -307,10 +307,10 @@ chol_backsub_kernel(const double *S, const double *z, double *y, int n, const in
             // lane r keeps row r's unknown; column r of the triangle is read as needed
             double mine = lane < nb ? yk[lane] : 0.0;
             for (int r = nb - 1; r >= 0; r--) {
-                const double urr = S[(size_t)(k0 + r) * n + k0 + r];
+                const double urr = S[(size_t)(k0 + r) * ld + k0 + r];
                 const double v = __shfl_sync(0xffffffffu, mine, r) / urr;
                 if (lane == r) { mine = v; if (!isfinite(v)) fin = 0; }
-                else if (lane < r) mine -= S[(size_t)(k0 + lane) * n + k0 + r] * v;
+                else if (lane < r) mine -= S[(size_t)(k0 + lane) * ld + k0 + r] * v;
             }
             if (lane < nb) y[k0 + lane] = mine;
         }
@@ -325,24 +325,182 @@ __global__ void chol_gradient_check_kernel(BAState *st)
     if (!st->done && st->need_linearize && !(st->gmax > 1e-10)) { st->done = 1; st->termination = 3; }
 }
 
+// ---- split solve (BASplit): small kernels around the two concurrent half factorisations -----------------------
+// 1. private status blocks, saved separator block / rhs, and the index-reversed copy of the trailing system.
+//    S2[i'][j'] = S[n-1-j'][n-1-i'] inside the reversed envelope (whole 32-column tiles, zero where S has no entry).
+__global__ void __launch_bounds__(256)
+split_prepare_kernel(const double *__restrict__ S, const double *__restrict__ b, int n, const int *__restrict__ lim, BASplit P, const BAState *st)
+{
+    if (st->done) return;
+    const int a = P.a, w = P.w, h2 = P.h2;
+    const int row = blockIdx.x;
+    if (row < h2) {
+        const int ip = row, r_or = n - 1 - ip;                         // reversed row i' <-> original column index r_or
+        int cend = min(h2, P.lim2[ip / PMV_CHOL_NB]);
+        cend = min(h2, (cend + PMV_CHOL_NB - 1) / PMV_CHOL_NB * PMV_CHOL_NB);
+        for (int jp = ip + threadIdx.x; jp < cend; jp += 256) {
+            const int c_or = n - 1 - jp;                               // original row (c_or <= r_or)
+            const bool inside = r_or < min(n, lim[c_or / PMV_CHOL_NB]);
+            P.S2[(size_t)ip * h2 + jp] = inside ? S[(size_t)c_or * n + r_or] : 0.0;
+        }
+        if (threadIdx.x == 0) P.b2[ip] = b[r_or];
+    } else if (row < h2 + w) {
+        const int i = row - h2;
+        for (int j = threadIdx.x; j < w; j += 256) P.AM[(size_t)i * w + j] = j >= i ? S[(size_t)(a + i) * n + a + j] : 0.0;
+        if (threadIdx.x == 0) P.bM[i] = b[a + i];
+    } else if (threadIdx.x < 3) {
+        BAState t = *st;
+        t.chol_ok = 0;
+        P.st3[threadIdx.x] = t;
+    }
+}
+
+// 2. separator: A3 = U1^T U1 + flip(U2^T U2) - A_M and b3 = U1^T z1 + flip(U2^T z2) - b_M, where U1 / U2 are the
+//    trailing w x w blocks of the two partial factors (each equals A_M minus that side's Schur update, factorised).
+__global__ void __launch_bounds__(256)
+split_middle_kernel(const double *__restrict__ S, const double *__restrict__ z1, int n, BASplit P)
+{
+    if (!P.st3[0].chol_ok || !P.st3[1].chol_ok || P.st3[0].done) return;
+    __shared__ double colU1[512], colU2[512];
+    __shared__ double red[8];
+    const int i = blockIdx.x, w = P.w, a = P.a, h2 = P.h2, o2 = h2 - w;
+    const int ip = w - 1 - i;
+    for (int k = threadIdx.x; k < w; k += 256) {
+        colU1[k] = k <= i ? S[(size_t)(a + k) * n + a + i] : 0.0;                  // column i of U1
+        colU2[k] = k <= ip ? P.S2[(size_t)(o2 + k) * h2 + o2 + ip] : 0.0;           // column i' of U2
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < w; j += 256) {
+        double v = 0.0;
+        if (j >= i) {
+            const int jp = w - 1 - j;                                               // jp <= ip
+            double s1 = 0.0, s2 = 0.0;
+            for (int k = 0; k <= i; k++) s1 = fma(colU1[k], S[(size_t)(a + k) * n + a + j], s1);
+            for (int k = 0; k <= jp; k++) s2 = fma(P.S2[(size_t)(o2 + k) * h2 + o2 + jp], colU2[k], s2);
+            v = (s1 + s2) - P.AM[(size_t)i * w + j];
+        }
+        P.S3[(size_t)i * w + j] = v;
+    }
+    double t = 0.0;
+    for (int k = threadIdx.x; k < w; k += 256) t += colU1[k] * z1[a + k] + colU2[k] * P.b2[o2 + k];
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int q = 0; q < 8; q++) v += red[q];
+        P.b3[i] = v - P.bM[i];
+    }
+}
+
+// 3. with the separator solved (y3): the separator rows of the two forward-substituted right-hand sides become
+//    U y3, so the ordinary back-substitutions of the two half systems continue upwards from it.
+__global__ void __launch_bounds__(256)
+split_fix_kernel(const double *__restrict__ S, double *__restrict__ z1, int n, BASplit P)
+{
+    if (!P.st3[2].chol_ok || P.st3[2].done) return;
+    __shared__ double red[8];
+    const int w = P.w, a = P.a, h2 = P.h2, o2 = h2 - w;
+    const int i = blockIdx.x % w, side = blockIdx.x / w;
+    double t = 0.0;
+    if (side == 0) { for (int j = i + threadIdx.x; j < w; j += 256) t += S[(size_t)(a + i) * n + a + j] * P.y3[j]; }
+    else { for (int j = i + threadIdx.x; j < w; j += 256) t += P.S2[(size_t)(o2 + i) * h2 + o2 + j] * P.y3[w - 1 - j]; }
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int q = 0; q < 8; q++) v += red[q];
+        if (side == 0) z1[a + i] = v; else P.b2[o2 + i] = v;
+    }
+}
+
+// 4. solution of the bottom part back into original order; overall status
+__global__ void __launch_bounds__(256) split_finish_kernel(double *__restrict__ y, int n, BASplit P, BAState *st)
+{
+    if (st->done) return;
+    const int nb = P.h2 - P.w;
+    for (int ip = blockIdx.x * 256 + threadIdx.x; ip < nb; ip += gridDim.x * 256) y[n - 1 - ip] = P.y2[ip];
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->chol_ok = P.st3[0].chol_ok && P.st3[1].chol_ok && P.st3[2].chol_ok;
+}
+
 }  // namespace
 
-int pmv_internal_ba_cholesky_band(pmv_ctx *ctx, double *S, double *b, int n, const int *lim_host, const int *lim_dev,
+int pmv_internal_ba_cholesky_band(pmv_ctx *ctx, double *S, double *b, int n, size_t ld, const int *lim_host, const int *lim_dev,
                                   BAState *st, cudaStream_t s);   // ba_chol_band.cu
 
 // lim_host[kb] / D.chol_lim[kb]: end column (exclusive, <= n) of the envelope of block row kb -- cumulative
 // maximum of the camera co-visibility reach, so fill-in stays inside it.  A banded reduced camera system
 // (BASELINE config 5: every point seen by 5 of the <= 40 nearest poses) is factorised in O(n * band^2).
-int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_host, cudaStream_t s)
+static int launch_backsub(pmv_ctx *ctx, const double *S, const double *z, double *y, int n, size_t ld, const int *lim_host, const int *lim_dev,
+                          BAState *st, cudaStream_t s)
+{
+    int maxw = 0;
+    for (int k0 = 0, kb = 0; k0 < n; k0 += NB, kb++) maxw = std::max(maxw, (lim_host ? std::min(n, lim_host[kb]) : n) - k0);
+    const int staged = (maxw <= BS_MAXW) && !getenv("PMV_CHOL_NO_STAGE");
+    const size_t smem = staged ? sizeof(double) * (2 * NB * BS_MAXW + 512 + 3 * NB) : 0;
+    if (ctx->attr_first(PMV_ATTR_CHOL_BACKSUB))
+        cudaFuncSetAttribute(chol_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    chol_backsub_kernel<<<1, BS_THREADS, smem, s>>>(S, z, y, n, ld, lim_dev, st, staged);
+    PMV_LAUNCH_CHECK(ctx, "chol_backsub_kernel");
+    return PMV_OK;
+}
+
+// Two-sided solve of a banded system (BASplit, ba.cuh).  Returns 1 when done, 0 when a cluster launch is not possible
+// for one of the three systems (caller falls back to the one-sided path; nothing has been modified), < 0 on error.
+static int split_solve(pmv_ctx *ctx, const BADev &D, const BASplit &P, cudaStream_t s)
 {
     const int n = D.n;
+    double *S = D.S, *b = D.rhs, *y = D.yc;
+    BAState *st = D.st;
+    split_prepare_kernel<<<P.h2 + P.w + 1, 256, 0, s>>>(S, b, n, P.lim_orig, P, st);
+    PMV_LAUNCH_CHECK(ctx, "split_prepare_kernel");
+    // fork: leading system on s (in place in S), reversed trailing system on s2
+    PMV_CUDA_TRY(ctx, cudaEventRecord(P.ev[0], s));
+    PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(P.s2, P.ev[0], 0));
+    int r1 = pmv_internal_ba_cholesky_band(ctx, S, b, P.h1, (size_t)n, P.lim1_h, P.lim1, P.st3 + 0, s);
+    int r2 = pmv_internal_ba_cholesky_band(ctx, P.S2, P.b2, P.h2, (size_t)P.h2, P.lim2_h, P.lim2, P.st3 + 1, P.s2);
+    PMV_CUDA_TRY(ctx, cudaEventRecord(P.ev[1], P.s2));
+    PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(s, P.ev[1], 0));
+    if (r1 < 0 || r2 < 0) return r1 < 0 ? r1 : r2;
+    if (r1 == 0 || r2 == 0) return ctx->fail(PMV_ERR_UNSUPPORTED, "split solve: half system not eligible for the cluster kernel");
+    split_middle_kernel<<<P.w, 256, 0, s>>>(S, b, n, P);
+    PMV_LAUNCH_CHECK(ctx, "split_middle_kernel");
+    int r3 = pmv_internal_ba_cholesky_band(ctx, P.S3, P.b3, P.w, (size_t)P.w, P.lim3_h, P.lim3, P.st3 + 2, s);
+    if (r3 <= 0) return r3 < 0 ? r3 : ctx->fail(PMV_ERR_UNSUPPORTED, "split solve: separator not eligible for the cluster kernel");
+    int rc = launch_backsub(ctx, P.S3, P.b3, P.y3, P.w, (size_t)P.w, P.lim3_h, P.lim3, P.st3 + 2, s);
+    if (rc) return rc;
+    split_fix_kernel<<<2 * P.w, 256, 0, s>>>(S, b, n, P);
+    PMV_LAUNCH_CHECK(ctx, "split_fix_kernel");
+    PMV_CUDA_TRY(ctx, cudaEventRecord(P.ev[2], s));
+    PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(P.s2, P.ev[2], 0));
+    rc = launch_backsub(ctx, S, b, y, P.h1, (size_t)n, P.lim1_h, P.lim1, P.st3 + 0, s);
+    if (rc) return rc;
+    rc = launch_backsub(ctx, P.S2, P.b2, P.y2, P.h2, (size_t)P.h2, P.lim2_h, P.lim2, P.st3 + 1, P.s2);
+    if (rc) return rc;
+    PMV_CUDA_TRY(ctx, cudaEventRecord(P.ev[3], P.s2));
+    PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(s, P.ev[3], 0));
+    split_finish_kernel<<<8, 256, 0, s>>>(y, n, P, st);
+    PMV_LAUNCH_CHECK(ctx, "split_finish_kernel");
+    return 1;
+}
+
+int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_host, const BASplit *split, cudaStream_t s)
+{
+    const int n = D.n;
+    if (split && split->enabled && D.W == 1) {
+        chol_gradient_check_kernel<<<1, 1, 0, s>>>(D.st);
+        PMV_LAUNCH_CHECK(ctx, "chol_gradient_check_kernel");
+        const int r = split_solve(ctx, D, *split, s);
+        return r < 0 ? r : PMV_OK;
+    }
     for (int w = 0; w < D.W; w++) {
         double *S = D.S + (size_t)w * n * n, *b = D.rhs + (size_t)w * n, *y = D.yc + (size_t)w * n;
         BAState *st = D.st + w;
         chol_gradient_check_kernel<<<1, 1, 0, s>>>(st);
         PMV_LAUNCH_CHECK(ctx, "chol_gradient_check_kernel");
         // banded systems: the whole factorisation in one cluster launch (ba_chol_band.cu)
-        const int band = pmv_internal_ba_cholesky_band(ctx, S, b, n, lim_host, D.chol_lim, st, s);
+        const int band = pmv_internal_ba_cholesky_band(ctx, S, b, n, (size_t)n, lim_host, D.chol_lim, st, s);
         if (band < 0) return band;
         for (int k0 = 0, kb = 0; k0 < n && !band; k0 += NB, kb++) {
             const int t0 = k0 + NB;
@@ -367,7 +525,7 @@ int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_
             const size_t smem = staged ? sizeof(double) * (2 * NB * BS_MAXW + 512 + 3 * NB) : 0;
             if (ctx->attr_first(PMV_ATTR_CHOL_BACKSUB))
                 cudaFuncSetAttribute(chol_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            chol_backsub_kernel<<<1, BS_THREADS, smem, s>>>(S, b, y, n, D.chol_lim, st, staged);
+            chol_backsub_kernel<<<1, BS_THREADS, smem, s>>>(S, b, y, n, (size_t)n, D.chol_lim, st, staged);
             PMV_LAUNCH_CHECK(ctx, "chol_backsub_kernel");
         }
     }

@@ -108,14 +108,14 @@ __device__ __forceinline__ BandSmem carve(double *base, int nslots, int Tp, int 
 
 // HBM -> registers -> shared: tile (I, J) of S, zero outside the matrix, identity on the padded diagonal.
 // Split in two so the loader warps keep the loads in flight across a cluster barrier.
-__device__ __forceinline__ void tile_fetch(const double *__restrict__ S, int n, int I, int J, double2 (&v)[16], int lane)
+__device__ __forceinline__ void tile_fetch(const double *__restrict__ S, int n, size_t ld, int I, int J, double2 (&v)[16], int lane)
 {
 #pragma unroll
     for (int it = 0; it < 16; it++) {
         const int chunk = it * 32 + lane, r = chunk >> 4, c2 = (chunk & 15) * 2;
         const int gr = I * NB + r, gc = J * NB + c2;
         double2 x = make_double2(0.0, 0.0);
-        if (gr < n && gc < n) x = *reinterpret_cast<const double2 *>(S + (size_t)gr * n + gc);
+        if (gr < n && gc < n) x = *reinterpret_cast<const double2 *>(S + (size_t)gr * ld + gc);
         else if (I == J) { if (r == c2) x.x = 1.0; if (r == c2 + 1) x.y = 1.0; }
         v[it] = x;
     }
@@ -128,10 +128,10 @@ __device__ __forceinline__ void tile_store(double *dst, const double2 (&v)[16], 
         *reinterpret_cast<double2 *>(dst + r * TLD + c2) = v[it];
     }
 }
-__device__ __forceinline__ void load_tile(const double *__restrict__ S, int n, int I, int J, double *dst, int lane)
+__device__ __forceinline__ void load_tile(const double *__restrict__ S, int n, size_t ld, int I, int J, double *dst, int lane)
 {
     double2 v[16];
-    tile_fetch(S, n, I, J, v, lane);
+    tile_fetch(S, n, ld, I, J, v, lane);
     tile_store(dst, v, lane);
 }
 
@@ -278,12 +278,12 @@ __device__ __forceinline__ void panel_rhs(const double *tile, const double *rz /
 
 // The factored block row leaves for HBM (the back substitution reads it) from a loader warp, off the
 // critical path: U_kk from the published copy, z_k likewise.
-__device__ __forceinline__ void diag_writeback(const double *dU, double *S, int n, int kb, int lane)
+__device__ __forceinline__ void diag_writeback(const double *dU, double *S, int n, size_t ld, int kb, int lane)
 {
     const int k0 = kb * NB, nb = min(NB, n - k0), j = lane;
 #pragma unroll 8
     for (int i = 0; i < NB; i++)
-        if (i < nb && j < nb && i <= j) S[(size_t)(k0 + i) * n + k0 + j] = dU[i * ULD + j];
+        if (i < nb && j < nb && i <= j) S[(size_t)(k0 + i) * ld + k0 + j] = dU[i * ULD + j];
 }
 
 // Phase B: U_kJ = U_kk^-T S_kJ for one panel tile (one warp, lane = column), right-looking so the dependent
@@ -328,12 +328,12 @@ __device__ __forceinline__ void panel_solve(const double *__restrict__ rU /* rem
 }
 
 // A solved panel tile (column-permuted in its slot) leaves for HBM from a loader warp one step later
-__device__ __forceinline__ void panel_writeback(const double *tile, double *S, int n, int k0, int J, int lane)
+__device__ __forceinline__ void panel_writeback(const double *tile, double *S, int n, size_t ld, int k0, int J, int lane)
 {
     const int col = J * NB + lane, pc = pcol(lane);
     if (col >= n) return;
 #pragma unroll 8
-    for (int r = 0; r < NB; r++) S[(size_t)(k0 + r) * n + col] = tile[r * TLD + pc];   // pivot blocks with a panel are full
+    for (int r = 0; r < NB; r++) S[(size_t)(k0 + r) * ld + col] = tile[r * TLD + pc];   // pivot blocks with a panel are full
 }
 
 // Phase C: C -= PI^T PJ for one trailing tile (one warp), PI / PJ possibly in another CTA's shared memory.
@@ -383,7 +383,7 @@ __device__ __forceinline__ void update_tile(double *C, const double *PI, const d
 }
 
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
-chol_band_cluster_kernel(double *S, double *b, int n, const int *__restrict__ lim, BAState *st, int T, int nslots,
+chol_band_cluster_kernel(double *S, double *b, int n, size_t ld, const int *__restrict__ lim, BAState *st, int T, int nslots,
                          long long *trace /* PMV_CHOL_TRACE=1: per-warp clock64 stamps of 8 steps, else nullptr */)
 {
     extern __shared__ __align__(16) double band_smem[];
@@ -444,7 +444,7 @@ chol_band_cluster_kernel(double *S, double *b, int n, const int *__restrict__ li
             const int je = min((int)m.jend[I], wend);
             for (int J = I; J < je; J++) {
                 if (owner_of(I, J) != me) continue;
-                if (idx++ % NW == warp) load_tile(S, n, I, J, tile_ptr(I, J), lane);
+                if (idx++ % NW == warp) load_tile(S, n, ld, I, J, tile_ptr(I, J), lane);
             }
             if (owner_of(I, I) == me && warp == I % NW)
                 m.bwin[I * NB + lane] = (I * NB + lane < n) ? b[I * NB + lane] : 0.0;
@@ -498,7 +498,7 @@ chol_band_cluster_kernel(double *S, double *b, int n, const int *__restrict__ li
             int rn = r0 + T; if (rn >= Tp) rn -= Tp;
             if (owner_of(r0, r0) == me) {
                 if (lw == LW - 1) z_solve(m.dU + par * NB * ULD, m.dinv + par * NB, m.bwin + r0 * NB, m.dz + par * NB, b, n, kb, lane);
-                if (lw == LW - 2) diag_writeback(m.dU + par * NB * ULD, S, n, kb, lane);
+                if (lw == LW - 2) diag_writeback(m.dU + par * NB * ULD, S, n, ld, kb, lane);
             }
             {
                 // slot {rd, rn}: held panel tile (kb - 1, kb + d) of the previous step (d <= T - 2) -> HBM;
@@ -509,8 +509,8 @@ chol_band_cluster_kernel(double *S, double *b, int n, const int *__restrict__ li
                     const uchar2 t = m.llist[r0 * LMAX + e];
                     const int d = t.x, J = kb + d;
                     double *slot = tile_ptr(t.y, rn);
-                    if (kb > 0 && d <= T - 2 && J < jprev) panel_writeback(slot, S, n, (kb - 1) * NB, J, lane);
-                    if (d >= 1 && Jn < nblk && Jn < (int)m.jend[J]) { tile_fetch(S, n, J, Jn, lv, lane); ldst = slot; }
+                    if (kb > 0 && d <= T - 2 && J < jprev) panel_writeback(slot, S, n, ld, (kb - 1) * NB, J, lane);
+                    if (d >= 1 && Jn < nblk && Jn < (int)m.jend[J]) { tile_fetch(S, n, ld, J, Jn, lv, lane); ldst = slot; }
                 }
                 if (Jn < nblk && owner_of(rn, rn) == me && lw == 0) { lb = (Jn * NB + lane < n) ? b[Jn * NB + lane] : 0.0; lb_set = true; }
             }
@@ -579,9 +579,32 @@ chol_band_cluster_kernel(double *S, double *b, int n, const int *__restrict__ li
 
 }  // namespace
 
+// Window width T (in tiles) the cluster kernel would use for an n x n system with this envelope; 0 = not eligible.
+int pmv_internal_ba_cholesky_band_T(int n, const int *lim_host)
+{
+    if (!lim_host) return 0;
+    const int nblk = (n + NB - 1) / NB;
+    int T = 1;
+    for (int kb = 0; kb < nblk; kb++) {
+        const int je = std::min(nblk, (std::min(n, lim_host[kb]) + NB - 1) / NB);
+        T = std::max(T, je - kb);
+    }
+    if (T < 2) T = 2;
+    const int Tp = T + 1;
+    if (Tp > MAXTP) return 0;
+    int cnt[CL] = {0};
+    for (int x = 0; x < Tp; x++)
+        for (int y = x; y < Tp; y++) cnt[owner_of(x, y)]++;
+    const int nslots = *std::max_element(cnt, cnt + CL);
+    const size_t smem = sizeof(double) * ((size_t)nslots * TSZ + PMAX * UBSZ + 2 * NB * ULD + 4 * NB + (size_t)Tp * NB + NB * UTLD + 24 * CSLD) +
+                        (size_t)Tp * (UMAX * 4 + PMAX * 2 + LMAX * 2 + 3) + (size_t)nblk * 2 + (size_t)Tp * Tp + 32;
+    if (nslots > UMAX || nblk > 65535 || smem > 220 * 1024) return 0;
+    return T;
+}
+
 // Host side: eligibility (window width from the envelope) and launch.  Returns 1 when the cluster kernel was
 // launched, 0 when the system is too wide for it (caller falls back to the multi-launch path), < 0 on error.
-int pmv_internal_ba_cholesky_band(pmv_ctx *ctx, double *S, double *b, int n, const int *lim_host, const int *lim_dev,
+int pmv_internal_ba_cholesky_band(pmv_ctx *ctx, double *S, double *b, int n, size_t ld, const int *lim_host, const int *lim_dev,
                                   BAState *st, cudaStream_t s)
 {
     if (!lim_host || !lim_dev) return 0;
@@ -616,7 +639,7 @@ int pmv_internal_ba_cholesky_band(pmv_ctx *ctx, double *S, double *b, int n, con
         std::vector<long long> h(cnt);
         cudaMalloc(&d_tr, cnt * 8);
         cudaMemsetAsync(d_tr, 0, cnt * 8, s);
-        chol_band_cluster_kernel<<<CL, THREADS, smem, s>>>(S, b, n, lim_dev, st, T, nslots, d_tr);
+        chol_band_cluster_kernel<<<CL, THREADS, smem, s>>>(S, b, n, ld, lim_dev, st, T, nslots, d_tr);
         cudaStreamSynchronize(s);
         cudaMemcpy(h.data(), d_tr, cnt * 8, cudaMemcpyDeviceToHost);
         cudaFree(d_tr);
@@ -637,7 +660,7 @@ int pmv_internal_ba_cholesky_band(pmv_ctx *ctx, double *S, double *b, int n, con
         ctx->launches++;
         return 1;
     }
-    chol_band_cluster_kernel<<<CL, THREADS, smem, s>>>(S, b, n, lim_dev, st, T, nslots, nullptr);
+    chol_band_cluster_kernel<<<CL, THREADS, smem, s>>>(S, b, n, ld, lim_dev, st, T, nslots, nullptr);
     PMV_LAUNCH_CHECK(ctx, "chol_band_cluster_kernel");
     return 1;
 }

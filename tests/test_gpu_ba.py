@@ -228,6 +228,34 @@ def test_run_organised_rejected_steps(ctx, synth, monkeypatch):
     assert abs(s[0]["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]
 
 
+@pytest.mark.parametrize("nposes,npts,span", [(400, 20000, 20), (250, 12000, 30)])
+def test_two_sided_band_solve_matches_one_sided_and_oracle(ctx, pmv, synth, monkeypatch, ba_path, nposes, npts, span):
+    """Long banded reduced camera systems are cut at a separator in the middle: the leading system and the
+    index-reversed trailing system are factorised concurrently by two clusters, the separator's Schur complement is
+    solved last (BASplit).  Same iterates as the one-sided factorisation and as the oracle."""
+    if ba_path == "window":
+        pytest.skip("general path only")
+    w = synth.ba_large(31, n_poses=nposes, n_points=npts, views=5, span=span)
+    po, xo, so = oracle.ba_solve(*_args(w), 1.0, 3)
+    res = {}
+    for mode in ("split", "one_sided"):
+        if mode == "split":
+            monkeypatch.delenv("PMV_CHOL_NO_SPLIT", raising=False)
+        else:
+            monkeypatch.setenv("PMV_CHOL_NO_SPLIT", "1")
+        prob = ctx.ba_problem(*_args(w), 1.0)
+        prob.solve(3)
+        p, x, s = prob.download()
+        prob.close()
+        res[mode] = (p, s[0])
+        assert s[0]["iterations"] == so["iterations"] and s[0]["successful_steps"] == so["successful_steps"]
+        assert abs(s[0]["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]
+        assert np.abs(p[0] - po).max() < 1e-5
+    monkeypatch.delenv("PMV_CHOL_NO_SPLIT", raising=False)
+    assert np.abs(res["split"][0] - res["one_sided"][0]).max() < 1e-8
+    assert abs(res["split"][1]["final_cost"] - res["one_sided"][1]["final_cost"]) <= 1e-10 * so["final_cost"]
+
+
 def test_resident_problem_reset_and_errors(ctx, pmv, synth):
     w = synth.ba_window(9, n_poses=5, n_points=100)
     prob = ctx.ba_problem(*_args(w))
