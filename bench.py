@@ -480,6 +480,26 @@ def run_extract(args, rank, world, local_rank):
         ctx.fast(f0, 10, True, NF)
     prof_fast = ctx.profile_collect()
     ctx.profile(False)
+    # response kernels on a batch that fills the GPU: 8 resident 4K frames per launch (device pointers), CUDA events
+    NB8 = 8
+    pitch8 = (Ww + 15) // 16 * 16
+    d8 = torch.zeros(NB8, Hh, pitch8, dtype=torch.uint8, device="cuda")
+    for b in range(NB8):
+        d8[b, :, :Ww] = torch.from_numpy(synth.frame_pair(600 + 10 * rank + b, h=Hh, w=Ww)[0]).cuda()
+    eig8 = torch.empty(NB8, Hh, Ww, dtype=torch.float32, device="cuda"); emax8 = torch.zeros(NB8, dtype=torch.float32, device="cuda")
+    R8 = torch.empty(NB8, Hh, Ww, dtype=torch.float64, device="cuda"); rmax8 = torch.zeros(NB8, dtype=torch.float64, device="cuda")
+
+    def timed8(fn, reps=10):
+        for _ in range(3):
+            fn()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record(stream)
+        for _ in range(reps):
+            fn()
+        eb.record(stream); torch.cuda.synchronize()
+        return ea.elapsed_time(eb) / reps
+    ms_eig8 = timed8(lambda: ctx.min_eigen_val_batched_dev(d8.data_ptr(), NB8, Hh * pitch8, Hh, Ww, pitch8, eig8.data_ptr(), emax8.data_ptr()))
+    ms_shi8 = timed8(lambda: ctx.shitomasi_response_batched_dev(d8.data_ptr(), NB8, Hh * pitch8, Hh, Ww, pitch8, R8.data_ptr(), rmax8.data_ptr()))
     dt_max = max_over_ranks(dt, world)
     value = world * steps / dt_max
     out = None
@@ -521,7 +541,9 @@ def run_extract(args, rank, world, local_rank):
                 "fast_kernel (1 B/px in + 12 B/keypoint)": frac(prof_fast.get("fast", (0, 0)), npx),
                 "pyramid group (2 images, import + 3 levels + borders)": frac(prof.get("pyramid", (0, 0)), 2 * 11016000),
                 "lk_track_kernel<14> (10k features)": frac(prof.get("lk", (0, 0)), 2 * 11016000 + NF * 21)}
-        main_k = kern["mineig_kernel (1 B/px in + 4 B/px out)"]
+        kern["mineig kernels, 8 resident 4K frames per launch (1 B/px in + 4 B/px out; inputs + outputs 332 MB > L2)"] = frac((ms_eig8, 1), NB8 * npx * 5)
+        kern["shitomasi_response_kernel, 8 resident 4K frames per launch (1 B/px in + 8 B/px out; 597 MB > L2)"] = frac((ms_shi8, 1), NB8 * npx * 9)
+        main_k = kern["mineig kernels, 8 resident 4K frames per launch (1 B/px in + 4 B/px out; inputs + outputs 332 MB > L2)"]
         out = {"metric": "frames_per_s_extract_plus_lk", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps,
                "warmup": warmup, "ms_per_step": 1e3 * dt_max / steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "u8/int32+fp32", "data": "synthetic",
@@ -532,7 +554,7 @@ def run_extract(args, rank, world, local_rank):
                "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": int(3 * npx), "d2h_bytes_per_step": int(NF * 12 + NF * 13),
                        "api": "pmv_gftt + pmv_lk_track (host buffers)"},
                "gpu_launches": int(launches),
-               "roofline": {"kernel": "mineig_kernel", "bound": "hbm", "achieved": main_k["achieved_GBps"] if main_k else None, "peak": peak,
+               "roofline": {"kernel": "mineig_fast_kernel + mineig_kernel (edges), batch of 8 resident 4K frames", "bound": "hbm", "achieved": main_k["achieved_GBps"] if main_k else None, "peak": peak,
                             "unit": "GB/s", "frac": main_k["frac_of_hbm_peak"] if main_k else None, "traffic": None, "peak_source": peak_src, "kernels": kern},
                "cpu_baseline": {"value": 1.0 / tcpu, "unit": "frames/s", "cores": cv2.getNumThreads(), "kind": "reference",
                                 "sample": f"cv2 {cv2.__version__} goodFeaturesToTrack + calcOpticalFlowPyrLK on the same frame pair, mean of {reps}"},

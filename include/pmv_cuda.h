@@ -167,6 +167,15 @@ PMV_API int pmv_tracker_features(pmv_tracker *t, int32_t *xy, int capacity, int 
 PMV_API int pmv_min_eigen_val(pmv_ctx *ctx, const uint8_t *base, int full_rows, int full_cols, int step,
                               int roi_x, int roi_y, int roi_w, int roi_h, float *eig);
 
+/* Response stages on `batch` images RESIDENT in HBM (device pointers; asynchronous on the context stream): the
+ * cornerMinEigenVal map (OpenCVGoodFeatureExtractor.cpp:7) and the reference's own fp64 response
+ * (ShiTomasiFeatureExtractor.cpp:49-75 + Frame.cpp:58-138) of every image, plus each map's maximum (the threshold base
+ * of both extractors).  Image b starts at d_imgs + b*img_stride; map b at d_eig / d_R + b*rows*cols. */
+PMV_API int pmv_min_eigen_val_batched_dev(pmv_ctx *ctx, const uint8_t *d_imgs, int batch, size_t img_stride, int rows, int cols,
+                                          int step, float *d_eig, float *d_max);
+PMV_API int pmv_shitomasi_response_batched_dev(pmv_ctx *ctx, const uint8_t *d_imgs, int batch, size_t img_stride, int rows,
+                                               int cols, int step, int signed_quirk, double *d_R, double *d_max);
+
 /* == cv::goodFeaturesToTrack(view, corners, max_corners, quality, min_dist, Mat(), block_size,
  *    ksize, false, 0.04) as called at OpenCVGoodFeatureExtractor.cpp:7 (max, 0.01, 5, 3, 3).
  * xy: max_corners x (x,y) floats (integer valued), strongest first; score: the response

@@ -63,6 +63,8 @@ _SIGS = {
     "pmv_tracker_init": (_int, [_vp, _vp, _int, _i32p]),
     "pmv_tracker_add_frame": (_int, [_vp, _vp, _int, _i32p, _i32p, _i32p, _vp, _vp, _int]),
     "pmv_tracker_features": (_int, [_vp, _vp, _int, _i32p]),
+    "pmv_min_eigen_val_batched_dev": (_int, [_vp, _vp, _int, _sz, _int, _int, _int, _vp, _vp]),
+    "pmv_shitomasi_response_batched_dev": (_int, [_vp, _vp, _int, _sz, _int, _int, _int, _int, _vp, _vp]),
     "pmv_min_eigen_val": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp]),
     "pmv_gftt": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _dbl, _dbl, _int, _int,
                         _vp, _vp, _i32p]),
@@ -257,6 +259,14 @@ class Context:
         self._chk(self.lib.pmv_min_eigen_val(self.h, _ptr(img), img.shape[0], img.shape[1], img.strides[0],
                                              x, y, w, h, _ptr(out)))
         return out
+
+    def min_eigen_val_batched_dev(self, d_imgs: int, batch, img_stride, rows, cols, step, d_eig: int, d_max: int):
+        """Device pointers (ints); asynchronous.  d_eig: batch*rows*cols float32, d_max: batch float32."""
+        self._chk(self.lib.pmv_min_eigen_val_batched_dev(self.h, _ptr(d_imgs), batch, img_stride, rows, cols, step, _ptr(d_eig), _ptr(d_max)))
+
+    def shitomasi_response_batched_dev(self, d_imgs: int, batch, img_stride, rows, cols, step, d_R: int, d_max: int, signed_quirk=True):
+        self._chk(self.lib.pmv_shitomasi_response_batched_dev(self.h, _ptr(d_imgs), batch, img_stride, rows, cols, step,
+                                                              int(signed_quirk), _ptr(d_R), _ptr(d_max)))
 
     def gftt(self, img, max_corners, quality=0.01, min_dist=5.0, roi=None, block_size=3, ksize=3):
         x, y, w, h = self._roi(img, roi)

@@ -109,8 +109,9 @@ __host__ __device__ __forceinline__ bool mineig_tile_is_fast(int tx0, int ty0, i
 // and the closed form stay in registers while the warp walks down MF_R + 4 input rows.  Lanes 1..30 write
 // 4 responses each (16-byte stores when the map pitch allows).  HBM traffic: 1 B/px in, 4 B/px out.
 __global__ void __launch_bounds__(256)
-mineig_fast_kernel(const ImgView v, float *__restrict__ eig, int *__restrict__ max_bits)
+mineig_fast_kernel(ImgView v, float *__restrict__ eig, int *__restrict__ max_bits, size_t vstride, size_t estride)
 {
+    v.ptr += (size_t)blockIdx.z * vstride; eig += (size_t)blockIdx.z * estride; max_bits += blockIdx.z;   // image of a batch
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x0 = blockIdx.x * MF_W, y0 = (blockIdx.y * 8 + warp) * MF_R;
     if (!v.word_ok || !mineig_fast_region(x0, y0, v.rw, v.rh)) return;      // warp-uniform
@@ -179,13 +180,16 @@ mineig_fast_kernel(const ImgView v, float *__restrict__ eig, int *__restrict__ m
 
 // K4: eig(y,x) over the ROI + global max (atomicMax on the bits of a non-negative float)
 __global__ void __launch_bounds__(256)
-mineig_kernel(const ImgView v, float *__restrict__ eig, int *__restrict__ max_bits)
+mineig_kernel(ImgView v, float *__restrict__ eig, int *__restrict__ max_bits, size_t vstride, size_t estride,
+              const ushort2 *__restrict__ tiles)
 {
+    v.ptr += (size_t)blockIdx.z * vstride; eig += (size_t)blockIdx.z * estride; max_bits += blockIdx.z;
     __shared__ __align__(16) uint8_t s_px[CS_H][CS_P];
     __shared__ int s_d[CD_H][CD_W];   // Sobel (sx | sy << 16) at ROI coords (ty0-1+r, tx0-1+c)
     __shared__ float s_red[8];
     const int tid = threadIdx.x;
-    const int tx0 = blockIdx.x * CT_W, ty0 = blockIdx.y * CT_H;
+    // tiles != nullptr: the launch enumerates only the tiles the register-resident kernel does not cover
+    const int tx0 = (tiles ? tiles[blockIdx.x].x : blockIdx.x) * CT_W, ty0 = (tiles ? tiles[blockIdx.x].y : blockIdx.y) * CT_H;
     if (v.word_ok && mineig_tile_is_fast(tx0, ty0, v.rw, v.rh)) return;   // written by mineig_fast_kernel
     stage_tile(s_px, v, tx0, ty0, tid);
     __syncthreads();
@@ -427,9 +431,10 @@ gftt_select_kernel(const Rec128 *__restrict__ recs, int n, int rows, int cols, c
 // R(y,x) in fp64 + global max (bits of a non-negative double).  The view is isolated (fresh Mats in
 // the reference): gradient zero on the rim, blur reflects at the view's own edges, last column 0.
 __global__ void __launch_bounds__(256)
-shitomasi_response_kernel(const ImgView v, int signed_quirk, double *__restrict__ R,
-                          unsigned long long *__restrict__ max_bits)
+shitomasi_response_kernel(ImgView v, int signed_quirk, double *__restrict__ R,
+                          unsigned long long *__restrict__ max_bits, size_t vstride, size_t rstride)
 {
+    v.ptr += (size_t)blockIdx.z * vstride; R += (size_t)blockIdx.z * rstride; max_bits += blockIdx.z;
     __shared__ __align__(16) uint8_t s_px[CS_H][CS_P];
     __shared__ int s_d[CD_H][CD_W];   // (2*gx) | (2*gy) << 16 at view coords (ty0-1+r, tx0-1+c)
     __shared__ double s_redd[8];
@@ -556,17 +561,37 @@ int check_roi(pmv_ctx *ctx, const void *base, int full_rows, int full_cols, int 
     return PMV_OK;
 }
 
-int run_mineig(pmv_ctx *ctx, const ImgView &v, float *d_eig, int *d_max, cudaStream_t s)
+int run_mineig(pmv_ctx *ctx, const ImgView &v, float *d_eig, int *d_max, cudaStream_t s, int batch = 1, size_t vstride = 0, size_t estride = 0)
 {
     ProfScope ps(ctx, PMV_PHASE_RESPONSE, s);
-    PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_max, 0, sizeof(int), s));
+    PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_max, 0, sizeof(int) * batch, s));
     if (v.word_ok && v.rw >= 2 * MF_W && v.rh >= 2 * MF_R) {   // an interior exists: register-resident kernel (same predicate on device)
-        dim3 gridf((v.rw + MF_W - 1) / MF_W, (v.rh + 8 * MF_R - 1) / (8 * MF_R));
-        mineig_fast_kernel<<<gridf, 256, 0, s>>>(v, d_eig, d_max);
+        dim3 gridf((v.rw + MF_W - 1) / MF_W, (v.rh + 8 * MF_R - 1) / (8 * MF_R), batch);
+        mineig_fast_kernel<<<gridf, 256, 0, s>>>(v, d_eig, d_max, vstride, estride);
         PMV_LAUNCH_CHECK(ctx, "mineig_fast_kernel");
     }
-    dim3 grid((v.rw + CT_W - 1) / CT_W, (v.rh + CT_H - 1) / CT_H);   // edges (and small ROIs): tile kernel
-    mineig_kernel<<<grid, 256, 0, s>>>(v, d_eig, d_max);
+    dim3 grid((v.rw + CT_W - 1) / CT_W, (v.rh + CT_H - 1) / CT_H, batch);   // edges (and small ROIs): tile kernel
+    const ushort2 *tiles = nullptr;
+    if (v.word_ok && v.rw >= 2 * MF_W && v.rh >= 2 * MF_R && grid.x * grid.y > 64) {
+        // large view: launch only the edge tiles (most of a 4K frame belongs to the register-resident kernel).  The
+        // list depends on the view size alone and is cached in the context.
+        const unsigned long long sig = ((unsigned long long)v.rw << 32) | (unsigned)v.rh;
+        if (ctx->mineig_tiles_sig != sig) {
+            std::vector<ushort2> h;
+            for (unsigned ty = 0; ty < grid.y; ty++)
+                for (unsigned tx = 0; tx < grid.x; tx++)
+                    if (!mineig_tile_is_fast(tx * CT_W, ty * CT_H, v.rw, v.rh)) h.push_back(make_ushort2((unsigned short)tx, (unsigned short)ty));
+            cudaError_t e = ctx->mineig_tiles.reserve(h.size() * sizeof(ushort2) + 16);
+            if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "edge tile list", e);
+            PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));   // the list may still be in use by an earlier launch
+            PMV_CUDA_TRY(ctx, cudaMemcpy(ctx->mineig_tiles.p, h.data(), h.size() * sizeof(ushort2), cudaMemcpyHostToDevice));
+            ctx->mineig_tiles_sig = sig;
+            ctx->mineig_tiles_n = (int)h.size();
+        }
+        tiles = ctx->mineig_tiles.as<ushort2>();
+        grid = dim3(ctx->mineig_tiles_n, 1, batch);
+    }
+    if (grid.x > 0) mineig_kernel<<<grid, 256, 0, s>>>(v, d_eig, d_max, vstride, estride, tiles);
     PMV_LAUNCH_CHECK(ctx, "mineig_kernel");
     return PMV_OK;
 }
@@ -671,6 +696,38 @@ PMV_API int pmv_min_eigen_val(pmv_ctx *ctx, const uint8_t *base, int full_rows, 
     return PMV_OK;
 }
 
+PMV_API int pmv_min_eigen_val_batched_dev(pmv_ctx *ctx, const uint8_t *d_imgs, int batch, size_t img_stride, int rows, int cols,
+                                          int step, float *d_eig, float *d_max)
+{
+    if (!ctx) return PMV_ERR_INVALID;
+    if (!d_imgs || !d_eig || !d_max || batch <= 0 || rows <= 0 || cols <= 0 || step < cols || img_stride < (size_t)rows * step)
+        return ctx->fail(PMV_ERR_INVALID, "pmv_min_eigen_val_batched_dev: bad argument");
+    cudaSetDevice(ctx->device);
+    ImgView v{d_imgs, step, 0, 0, rows, cols, 0, 0, cols, rows};
+    v.word_ok = (((uintptr_t)d_imgs | (uintptr_t)step | (uintptr_t)img_stride) & 3) == 0;
+    // the running maxima are the bits of non-negative floats: d_max doubles as the int buffer of the kernels
+    return run_mineig(ctx, v, d_eig, reinterpret_cast<int *>(d_max), ctx->stream, batch, img_stride, (size_t)rows * cols);
+}
+
+PMV_API int pmv_shitomasi_response_batched_dev(pmv_ctx *ctx, const uint8_t *d_imgs, int batch, size_t img_stride, int rows,
+                                               int cols, int step, int signed_quirk, double *d_R, double *d_max)
+{
+    if (!ctx) return PMV_ERR_INVALID;
+    if (!d_imgs || !d_R || !d_max || batch <= 0 || rows <= 0 || cols <= 0 || step < cols || img_stride < (size_t)rows * step)
+        return ctx->fail(PMV_ERR_INVALID, "pmv_shitomasi_response_batched_dev: bad argument");
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    ImgView v{d_imgs, step, 0, 0, rows, cols, 0, 0, cols, rows};
+    v.word_ok = (((uintptr_t)d_imgs | (uintptr_t)step | (uintptr_t)img_stride) & 3) == 0;
+    ProfScope ps(ctx, PMV_PHASE_RESPONSE, s);
+    PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_max, 0, sizeof(double) * batch, s));
+    dim3 grid((cols + CT_W - 1) / CT_W, (rows + CT_H - 1) / CT_H, batch);
+    shitomasi_response_kernel<<<grid, 256, 0, s>>>(v, signed_quirk, d_R, reinterpret_cast<unsigned long long *>(d_max), img_stride,
+                                                   (size_t)rows * cols);
+    PMV_LAUNCH_CHECK(ctx, "shitomasi_response_kernel");
+    return PMV_OK;
+}
+
 PMV_API int pmv_gftt(pmv_ctx *ctx, const uint8_t *base, int full_rows, int full_cols, int step,
                      int roi_x, int roi_y, int roi_w, int roi_h, int max_corners, double quality,
                      double min_dist, int block_size, int ksize, float *xy, float *score, int *n_out)
@@ -718,7 +775,7 @@ PMV_API int pmv_shitomasi_response(pmv_ctx *ctx, const uint8_t *img, int rows, i
     PMV_CUDA_TRY(ctx, cudaMemsetAsync(ctx->scratch[1].p, 0, 16, s));
     dim3 grid((cols + CT_W - 1) / CT_W, (rows + CT_H - 1) / CT_H);
     shitomasi_response_kernel<<<grid, 256, 0, s>>>(v, signed_quirk, ctx->scratch[0].as<double>(),
-                                                   ctx->scratch[1].as<unsigned long long>());
+                                                   ctx->scratch[1].as<unsigned long long>(), 0, 0);
     PMV_LAUNCH_CHECK(ctx, "shitomasi_response_kernel");
     PMV_CUDA_TRY(ctx, cudaMemcpyAsync(R, ctx->scratch[0].p, n * 8, cudaMemcpyDeviceToHost, s));
     PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
@@ -753,7 +810,7 @@ PMV_API int pmv_shitomasi(pmv_ctx *ctx, const uint8_t *img, int rows, int cols, 
     {
         ProfScope ps(ctx, PMV_PHASE_RESPONSE, s);
         dim3 grid((cols + CT_W - 1) / CT_W, (rows + CT_H - 1) / CT_H);
-        shitomasi_response_kernel<<<grid, 256, 0, s>>>(v, signed_quirk, d_R, d_max);
+        shitomasi_response_kernel<<<grid, 256, 0, s>>>(v, signed_quirk, d_R, d_max, 0, 0);
         PMV_LAUNCH_CHECK(ctx, "shitomasi_response_kernel");
     }
     ProfScope ps(ctx, PMV_PHASE_SELECT, s);

@@ -144,3 +144,27 @@ def test_corner_golden_fixture(ctx):
     col, row, ssc = ctx.shitomasi(img, 50)
     assert np.array_equal(col, g["shi_col"]) and np.array_equal(row, g["shi_row"])
     assert np.allclose(ssc, g["shi_score"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("shape", [(376, 1241), (97, 333)])
+def test_batched_resident_responses_match_single_image_calls(ctx, synth, shape):
+    """pmv_min_eigen_val_batched_dev / pmv_shitomasi_response_batched_dev (images resident in HBM, one launch for the
+    batch) == the single-image host entry points, bit for bit, maxima included."""
+    import torch
+    h, w = shape
+    B = 3
+    imgs = np.stack([synth.frame_pair(40 + b, h=h, w=w)[0] for b in range(B)])
+    pitch = (w + 15) // 16 * 16
+    d = torch.zeros(B, h, pitch, dtype=torch.uint8, device="cuda")
+    d[:, :, :w] = torch.from_numpy(imgs).cuda()
+    eig = torch.zeros(B, h, w, dtype=torch.float32, device="cuda"); emax = torch.zeros(B, dtype=torch.float32, device="cuda")
+    R = torch.zeros(B, h, w, dtype=torch.float64, device="cuda"); rmax = torch.zeros(B, dtype=torch.float64, device="cuda")
+    ctx.min_eigen_val_batched_dev(d.data_ptr(), B, h * pitch, h, w, pitch, eig.data_ptr(), emax.data_ptr())
+    ctx.shitomasi_response_batched_dev(d.data_ptr(), B, h * pitch, h, w, pitch, R.data_ptr(), rmax.data_ptr())
+    ctx.sync()
+    for b in range(B):
+        e1 = ctx.min_eigen_val(imgs[b])
+        r1 = ctx.shitomasi_response(imgs[b])
+        assert np.array_equal(eig[b].cpu().numpy(), e1)
+        assert np.array_equal(R[b].cpu().numpy(), r1)
+        assert float(emax[b]) == float(e1.max()) and float(rmax[b]) == float(r1.max())
