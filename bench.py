@@ -613,6 +613,14 @@ def run_pipeline(args, rank, world, local_rank):
         ctx.ba_solve(*ba_args, 1.0, 5)
     tb_g = time.perf_counter() - t0
     launches = ctx.launches - l0
+    # pose from 3-D / 2-D correspondences (BasePnPSolver): the call between LK and BA, 300 tracked points
+    from harness import pnp_scene
+    sc = pnp_scene.scene(77, n=300)
+    pn = lambda: ctx.pnp_ransac(sc["X"], sc["uv"], sc["K"], sc["guess_r"], sc["guess_t"], True, 100, 8.0, 0.99)
+    pn(); t0 = time.perf_counter()
+    for _ in range(50):
+        g_ok, g_r, g_t, g_inl = pn()
+    t_pnp_g = (time.perf_counter() - t0) / 50
     same_cbc = all(a[0].shape == b[0].shape and np.array_equal(a[0], b[0]) for a, b in zip(log_g, log_cbc))
     out = None
     if rank == 0:
@@ -620,6 +628,16 @@ def run_pipeline(args, rank, world, local_rank):
         from oracle.replay_backend import Cv2Backend
         log_c, tf_c, tb_c = drive(Cv2Backend(), lambda: oracle.ba_solve(*ba_args, 1.0, 5))
         same = all(a[0].shape == b[0].shape and np.array_equal(a[0], b[0]) for a, b in zip(log_g, log_c))
+        import cv2
+        cvp = lambda: cv2.solvePnPRansac(sc["X"], sc["uv"], sc["K"], None, sc["guess_r"].reshape(3, 1).copy(), sc["guess_t"].reshape(3, 1).copy(),
+                                         True, 100, 8.0, 0.99)
+        cvp(); t0 = time.perf_counter()
+        for _ in range(50):
+            c_ok, c_r, c_t, c_inl = cvp()
+        t_pnp_c = (time.perf_counter() - t0) / 50
+        pnp_par = {"inlier_sets_equal": bool(np.array_equal(g_inl, c_inl.ravel())), "max_abs_drvec": float(np.abs(g_r - c_r.ravel()).max()),
+                   "max_abs_dtvec": float(np.abs(g_t - c_t.ravel()).max()), "gpu_ms_per_call": 1e3 * t_pnp_g, "cv2_ms_per_call": 1e3 * t_pnp_c,
+                   "points": 300}
         fps_g, fps_c = nfr / (tf_g + tb_g), nfr / (tf_c + tb_c)
         out = {"metric": "frames_per_s_pipeline_pattern", "value": fps_g, "unit": "frames/s", "n_gpus": 1, "steps": 1, "warmup": 1,
                "ms_per_step": 1e3 * (tf_g + tb_g) / nfr, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -636,7 +654,8 @@ def run_pipeline(args, rank, world, local_rank):
                                 "sample": "same frames: cv2 calcOpticalFlowPyrLK / goodFeaturesToTrack-equivalent oracle per ROI + oracle LM/Schur BA",
                                 "front_end_ms_per_frame": 1e3 * tf_c / nfr, "ba_ms_per_call": 1e3 * tb_c / max(nfr // 2, 1)},
                "parity": {"feature_sets_identical_every_frame": bool(same), "frames": nfr,
-                          "re_extractions": int(sum(1 for x in log_g if x[2])), "resident_tracker_identical_to_call_by_call": bool(same_cbc), "ok": bool(same and same_cbc)}}
+                          "re_extractions": int(sum(1 for x in log_g if x[2])), "resident_tracker_identical_to_call_by_call": bool(same_cbc), "pnp_ransac_vs_cv2": pnp_par,
+                          "ok": bool(same and same_cbc and pnp_par["inlier_sets_equal"] and pnp_par["max_abs_dtvec"] < 1e-6)}}
     ctx.close()
     return out
 

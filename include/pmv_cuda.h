@@ -154,6 +154,18 @@ PMV_API int pmv_tracker_add_frame(pmv_tracker *t, const uint8_t *frame, int step
                                   int *extracted, int32_t *xy, int32_t *prev_index, int capacity);
 PMV_API int pmv_tracker_features(pmv_tracker *t, int32_t *xy, int capacity, int *n);
 
+/* ------------------------------------------------------------------ pose from 3-D / 2-D correspondences -- */
+/* == cv::solvePnPRansac(obj, img, K, noArray(), rvec, tvec, use_extrinsic_guess, iterations, reproj_err, confidence,
+ *    inliers) with the default SOLVEPNP_ITERATIVE flag, as OpenCVEPnPSolver::solvePnP calls it
+ * (OpenCVEPnPSolver.cpp:34-35: true, 100, 8, .99): 5-point EPnP hypotheses on cv::RNG((uint64)-1) subsets, float
+ * reprojection-error inlier test, RANSACUpdateNumIters, then the minimisation of the reprojection error over the
+ * inliers starting from the caller's pose.  obj_xyz: n x 3 float (cv::Point3f), img_xy: n x 2 float; rvec / tvec:
+ * in = guess, out = pose (unchanged when no model is found: *n_inliers = 0, OpenCV returns false); inlier_mask:
+ * n bytes (optional).  n >= 6. */
+PMV_API int pmv_pnp_ransac(pmv_ctx *ctx, const float *obj_xyz, const float *img_xy, int n, const double K[9], double rvec[3],
+                           double tvec[3], int use_extrinsic_guess, int iterations, float reproj_err, double confidence,
+                           uint8_t *inlier_mask, int *n_inliers);
+
 /* ------------------------------------------------------------------ corner detectors -- */
 /* Image arguments of the extractors: `base` is the PARENT image (full_rows x full_cols, row step
  * `step` bytes) and (roi_x, roi_y, roi_w, roi_h) the view the pipeline passes

@@ -217,3 +217,17 @@ def ba_apply(R, t, points, obs_frame, obs_point, obs_col, obs_row, K, bundle_siz
                             _p(pts, C.c_float), len(of), _p(of, C.c_int), _p(op, C.c_int), _p(oc, C.c_int), _p(orow, C.c_int), apply_frame,
                             _p(s, C.c_double)))
     return R.reshape(-1, 3, 3), t, pts, {"initial_cost": s[0], "final_cost": s[1], "iterations": int(s[2]), "successful_steps": int(s[3])}
+
+
+def pnp_solve(K, R1, t1, points, src_cr, next_cr, R_guess, t_guess, impl=0):
+    """pnpsolver->solvePnP(src, next, R, t) on a synthetic pipeline state (impl 0: OpenCVEPnPSolver compiled from the
+    reference, cv2.solvePnPRansac behind the shim; impl 1: GpuEPnPSolver).  Returns (R, t, kept mask, len(next.map))."""
+    K = np.ascontiguousarray(K, np.float64).ravel(); R1 = np.ascontiguousarray(R1, np.float64).ravel(); t1 = np.ascontiguousarray(t1, np.float64).ravel()
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    s_cr = np.ascontiguousarray(src_cr, np.int32).reshape(-1, 2); n_cr = np.ascontiguousarray(next_cr, np.int32).reshape(-1, 2)
+    R = np.array(R_guess, np.float64, order="C").reshape(9).copy(); t = np.array(t_guess, np.float64, order="C").reshape(3).copy()
+    kept = np.zeros(len(pts), np.int32)
+    n_next = lib().ref_pnp_solve(impl, _p(K, C.c_double), _p(R1, C.c_double), _p(t1, C.c_double), len(pts), _p(pts, C.c_float), _p(s_cr, C.c_int),
+                                 _p(n_cr, C.c_int), _p(R, C.c_double), _p(t, C.c_double), _p(kept, C.c_int))
+    _chk(min(n_next, 0))
+    return R.reshape(3, 3), t, kept.astype(bool), n_next

@@ -15,6 +15,7 @@
 
 #include "CeresBundleAdjustment.h"
 #include "OdometryPipeline.h"
+#include "OpenCVEPnPSolver.h"
 #include "OpenCVFASTFeatureExtractor.h"
 #include "OpenCVGoodFeatureExtractor.h"
 #include "OpenCVLucasKanadeFM.h"
@@ -185,5 +186,47 @@ REF_API int ref_ba_apply(int impl, int n_frames, int bundle_size, int ba_iterati
         for (int a = 0; a < 3; a++) { for (int b = 0; b < 3; b++) R[9 * i + 3 * a + b] = pipe.R[i].at<double>(a, b); t[3 * i + a] = pipe.t[i].at<double>(a); }
     for (int p = 0; p < n_points; p++) { cv::Point3f q = pipe.feats3d[p]->getPoint(); points[3 * p] = q.x; points[3 * p + 1] = q.y; points[3 * p + 2] = q.z; }
     return 0;
+    REF_CATCH
+}
+
+// ---- f2: pnpsolver->solvePnP(src, next, R, t) as OdometryPipeline::estimatePose calls it, on a synthetic pipeline state:
+// n 3-D points in WORLD coordinates (Feature3D, float), src frame index 1 with pose (R1, t1), each point tracked from
+// (src_col, src_row) to (next_col, next_row).  R / t: in = guess, out = estimate; kept[i] = point i survived the outlier
+// removal (still in OdometryPipeline::feats3d).
+REF_API int ref_pnp_solve(int impl, const double* K, const double* R1, const double* t1, int n, const float* points,
+                          const int* src_cr, const int* next_cr, double* R, double* t, int* kept)
+{
+    REF_TRY
+    OdometryPipeline pipe;
+    pipe.verbose = false;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) pipe.camera.at<double>(i, j) = K[3 * i + j];
+    cv::Mat tiny(1, 1, CV_8UC3);
+    Frame src(tiny), next(tiny);
+    src.frame = 1; next.frame = 2;
+    cv::Mat I(3, 3, CV_64FC1), z(3, 1, CV_64FC1), Rs(3, 3, CV_64FC1), ts(3, 1, CV_64FC1);
+    for (int a = 0; a < 3; a++) {
+        for (int b = 0; b < 3; b++) { Rs.at<double>(a, b) = R1[3 * a + b]; I.at<double>(a, b) = a == b ? 1.0 : 0.0; }
+        ts.at<double>(a) = t1[a]; z.at<double>(a) = 0.0;
+    }
+    pipe.R.push_back(I); pipe.t.push_back(z); pipe.R.push_back(Rs); pipe.t.push_back(ts);
+    std::vector<std::shared_ptr<Feature>> keep_alive;
+    for (int p = 0; p < n; p++) {
+        auto f3 = std::make_shared<Feature3D>(cv::Point3f(points[3 * p], points[3 * p + 1], points[3 * p + 2]));
+        pipe.feats3d.push_back(f3);
+        auto fs = std::make_shared<Feature>(Feature(src_cr[2 * p], src_cr[2 * p + 1]));
+        auto fn = std::make_shared<Feature>(Feature(next_cr[2 * p], next_cr[2 * p + 1]));
+        keep_alive.push_back(fs); keep_alive.push_back(fn);
+        src.map[fs] = std::weak_ptr<Feature3D>(f3);
+        src.feat_corr[fs] = fn;
+    }
+    std::vector<std::shared_ptr<Feature3D>> all(pipe.feats3d.begin(), pipe.feats3d.end());
+    cv::Mat Rm(3, 3, CV_64FC1), tm(3, 1, CV_64FC1);
+    for (int a = 0; a < 3; a++) { for (int b = 0; b < 3; b++) Rm.at<double>(a, b) = R[3 * a + b]; tm.at<double>(a) = t[a]; }
+    std::unique_ptr<BasePnPSolver> s;
+    if (impl == 0) s.reset(new OpenCVEPnPSolver(&pipe)); else s.reset(new GpuEPnPSolver(&pipe));
+    s->solvePnP(src, next, Rm, tm);
+    for (int a = 0; a < 3; a++) { for (int b = 0; b < 3; b++) R[3 * a + b] = Rm.at<double>(a, b); t[a] = tm.at<double>(a); }
+    for (int p = 0; p < n; p++) kept[p] = std::find(pipe.feats3d.begin(), pipe.feats3d.end(), all[p]) != pipe.feats3d.end();
+    return (int)next.map.size();
     REF_CATCH
 }

@@ -63,6 +63,7 @@ _SIGS = {
     "pmv_tracker_init": (_int, [_vp, _vp, _int, _i32p]),
     "pmv_tracker_add_frame": (_int, [_vp, _vp, _int, _i32p, _i32p, _i32p, _vp, _vp, _int]),
     "pmv_tracker_features": (_int, [_vp, _vp, _int, _i32p]),
+    "pmv_pnp_ransac": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _vp, _int, _int, C.c_float, C.c_double, _vp, _i32p]),
     "pmv_min_eigen_val_batched_dev": (_int, [_vp, _vp, _int, _sz, _int, _int, _int, _vp, _vp]),
     "pmv_shitomasi_response_batched_dev": (_int, [_vp, _vp, _int, _sz, _int, _int, _int, _int, _vp, _vp]),
     "pmv_min_eigen_val": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp]),
@@ -240,6 +241,21 @@ class Context:
         self._chk(self.lib.pmv_lk_track_batched_dev(self.h, _ptr(d_prev), _ptr(d_nxt), B, img_stride, rows, cols,
                                                     step, _ptr(d_pts), n, win[0], win[1], max_level, max_count,
                                                     eps, flags, min_eig, _ptr(d_next), _ptr(d_status), _ptr(d_err)))
+
+    def pnp_ransac(self, obj, img, K, rvec=None, tvec=None, use_guess=True, iterations=100, reproj_err=8.0, confidence=0.99):
+        """== cv2.solvePnPRansac(obj, img, K, None, rvec, tvec, use_guess, iterations, reproj_err, confidence).
+        Returns (ok, rvec (3,), tvec (3,), inlier indices)."""
+        obj = np.ascontiguousarray(obj, np.float32).reshape(-1, 3); img = np.ascontiguousarray(img, np.float32).reshape(-1, 2)
+        n = len(obj)
+        assert len(img) == n
+        K = np.ascontiguousarray(K, np.float64).reshape(9)
+        r = np.zeros(3) if rvec is None else np.array(rvec, np.float64).reshape(3).copy()
+        t = np.zeros(3) if tvec is None else np.array(tvec, np.float64).reshape(3).copy()
+        mask = np.zeros(max(n, 1), np.uint8)
+        ni = C.c_int(0)
+        self._chk(self.lib.pmv_pnp_ransac(self.h, _ptr(obj), _ptr(img), n, _ptr(K), _ptr(r), _ptr(t), int(use_guess), iterations,
+                                          reproj_err, confidence, _ptr(mask), C.byref(ni)))
+        return ni.value > 0, r, t, np.nonzero(mask[:n])[0].astype(np.int32)
 
     def tracker(self, rows, cols, win=(32, 32), max_level=4, capacity=4096, min_tracked=400, tracked_tol=150, grid=255,
                 quality=0.01, min_dist=5.0, neighbor_dist=5):

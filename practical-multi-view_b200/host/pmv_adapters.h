@@ -4,7 +4,8 @@
 //     extractor = new GpuGoodFeatureExtractor();      // was OpenCVGoodFeatureExtractor
 //     matcher   = new GpuLucasKanadeFM();             // was OpenCVLucasKanadeFM
 //     ba        = new GpuBundleAdjustment(this);      // was CeresBundleAdjustment
-//     (pnpsolver / triangulator unchanged: BasePnPSolver / BaseTriangulator implementations stay)
+//     pnpsolver = new GpuEPnPSolver(this);            // was OpenCVEPnPSolver
+//     (triangulator unchanged: the BaseTriangulator implementation stays)
 //
 // Each class mirrors the reference class it replaces -- same members, defaults, Feature fields it
 // fills, iteration order over Frame::map -- and only swaps the OpenCV / Ceres call for the C-ABI
@@ -14,6 +15,7 @@
 #ifndef PMV_ADAPTERS_H
 #define PMV_ADAPTERS_H
 
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -28,6 +30,7 @@
 #include "BaseFeatureExtractor.h"
 #include "BaseFeatureMatcher.h"
 #include "BaseOptimizer.h"
+#include "BasePnPSolver.h"
 #include "OdometryPipeline.h"
 #include "pmv_cuda.h"
 
@@ -283,6 +286,61 @@ public:
             tracker->t[ps.first] = -_t.clone();
         }
         for (int j = 0; j < Np; j++) point_ptr[j]->update(points[3 * j], points[3 * j + 1], points[3 * j + 2]);
+    }
+private:
+    pmv::Handle gpu;
+};
+
+// ---- drop-in for OpenCVEPnPSolver (.h / .cpp:4-50) ---------------------------------------------------------
+class GpuEPnPSolver : public BasePnPSolver
+{
+public:
+    OdometryPipeline* tracker;
+
+    GpuEPnPSolver(OdometryPipeline* tracker) : tracker(tracker) {}
+
+    void solvePnP(Frame& src, Frame& next, cv::Mat& R_out, cv::Mat& t_out)
+    {
+        int j = src.frame;
+        std::vector<float> obj, img;
+        cv::Mat _R_rod;
+        cv::Rodrigues(R_out, _R_rod);
+        std::vector<std::weak_ptr<Feature3D>> local_feats3d;
+
+        for (auto& p : src.map) {                                          // same walk as .cpp:13-32
+            if (p.second.expired()) continue;
+            std::shared_ptr<Feature3D> f3d = p.second.lock();
+            if (src.feat_corr[p.first].expired()) continue;
+            std::shared_ptr<Feature> f = src.feat_corr[p.first].lock();
+            next.map[f] = std::weak_ptr<Feature3D>(f3d);
+            f3d->transformInv(tracker->R[j], tracker->t[j]);
+            cv::Point3f p3f = f3d->getPoint();
+            p3f.z *= -1;
+            obj.push_back(p3f.x); obj.push_back(p3f.y); obj.push_back(p3f.z);
+            cv::Point2f q = f->getPoint();
+            img.push_back(q.x); img.push_back(q.y);
+            f3d->transform(tracker->R[j], tracker->t[j]);
+            local_feats3d.push_back(f3d);
+        }
+        const int n = (int)local_feats3d.size();
+        double K[9], rv[3], tv[3];
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) K[3 * r + c] = tracker->camera.at<double>(r, c);
+        for (int k = 0; k < 3; k++) { rv[k] = _R_rod.at<double>(k); tv[k] = t_out.at<double>(k); }
+        std::vector<uint8_t> mask(n > 0 ? n : 1, 0);
+        int n_inliers = 0;
+        // solvePnPRansac(obj, img, camera, Mat(), rod, t, true, 100, 8, .99, inliers)  (.cpp:34-35)
+        gpu.check(pmv_pnp_ransac(gpu.get(), obj.data(), img.data(), n, K, rv, tv, 1, 100, 8.f, .99, mask.data(), &n_inliers), "pmv_pnp_ransac");
+        for (int k = 0; k < 3; k++) { _R_rod.at<double>(k) = rv[k]; t_out.at<double>(k) = tv[k]; }
+        cv::Rodrigues(_R_rod, R_out);
+
+        // Removing RANSAC outliers (.cpp:38-48)
+        for (int i = 0; i < n; i++) {
+            if (!mask[i]) {
+                if (local_feats3d[i].expired()) continue;
+                std::shared_ptr<Feature3D> f3d = local_feats3d[i].lock();
+                tracker->feats3d.erase(std::find(tracker->feats3d.begin(), tracker->feats3d.end(), f3d));
+            }
+        }
     }
 private:
     pmv::Handle gpu;

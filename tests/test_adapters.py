@@ -22,7 +22,8 @@ def test_adapters_compile_against_reference_headers(tmp_path):
                   "BaseFeatureExtractor* e1() { return new GpuGoodFeatureExtractor(); }\n"
                   "BaseFeatureExtractor* e2() { return new GpuShiTomasiFeatureExtractor(); }\n"
                   "BaseFeatureExtractor* e3() { return new GpuFASTFeatureExtractor(); }\n"
-                  "BaseOptimizer* b(OdometryPipeline* p) { return new GpuBundleAdjustment(p); }\n")
+                  "BaseOptimizer* b(OdometryPipeline* p) { return new GpuBundleAdjustment(p); }\n"
+                  "BasePnPSolver* s(OdometryPipeline* p) { return new GpuEPnPSolver(p); }\n")
     cmd = ["g++", "-std=c++11", "-fsyntax-only", "-I", str(ROOT / "oracle" / "ref_shim"), "-I", str(REF),
            "-I", str(ROOT / "include"), "-I", str(ROOT / "practical-multi-view_b200" / "host"), str(tu)]
     r = subprocess.run(cmd, capture_output=True, text=True)

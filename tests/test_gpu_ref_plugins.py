@@ -68,3 +68,23 @@ def test_bundle_adjuster_adapter_vs_reference(synth, n_poses, n_points, bundle, 
     assert abs(s0["final_cost"] - s1["final_cost"]) <= 1e-6 * s0["final_cost"]      # north_star gate
     assert np.abs(R0 - R1).max() < 1e-7 and np.abs(t0 - t1).max() < 1e-6
     assert np.abs(p0 - p1).max() <= 1e-4 * max(1.0, np.abs(p0).max())               # float32 storage of Feature3D
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_pnp_solver_adapter_vs_reference(seed):
+    """pnpsolver->solvePnP(src, next, R, t): OpenCVEPnPSolver compiled unchanged from the reference (cv2.solvePnPRansac behind
+    the shim) vs GpuEPnPSolver, on the same Frame / OdometryPipeline state: same pose, same 3-D points dropped as outliers,
+    same next.map size."""
+    import cv2
+    from harness import pnp_scene
+    sc = pnp_scene.scene(4000 + seed)
+    n = len(sc["X"])
+    pts = sc["X"].copy(); pts[:, 2] *= -1                      # the pipeline stores z < 0 in front of the camera (.cpp:26 flips it back)
+    src_cr = np.stack([np.arange(n) % 1241, np.arange(n) // 7], 1)
+    next_cr = sc["uv"].astype(np.int32)
+    Rg = cv2.Rodrigues(sc["guess_r"])[0]
+    out = [ref.pnp_solve(sc["K"], np.eye(3), np.zeros(3), pts, src_cr, next_cr, Rg, sc["guess_t"], impl=i) for i in (0, 1)]
+    (R0, t0, k0, n0), (R1, t1, k1, n1) = out
+    assert n0 == n1 == n
+    assert np.array_equal(k0, k1) and k0.sum() >= n - len(sc["outliers"]) - 6 and not k0[sc["outliers"]].any()
+    assert np.abs(R0 - R1).max() < 1e-7 and np.abs(t0 - t1).max() < 1e-6
