@@ -242,10 +242,13 @@ def run_ba_windows(args, rank, world, local_rank):
     done_iters = float(np.mean([s["iterations"] for s in S]))
     ms_max = max_over_ranks(ms, world)
     value = world * W * done_iters * steps / (ms_max * 1e-3)
-    # e2e: host arrays in -> create (index + upload) + solve + download, every step
-    barrier(); te = time.perf_counter()
-    P2, X2, S2 = ctx.ba_solve_batched(poses, points, obs, cam, pt, off.astype(np.int32), K, 1.0, iters)
-    t_e2e = max_over_ranks(time.perf_counter() - te, world)
+    # e2e: host arrays in -> create (index + upload) + solve + download, every call (steady state: the resident problem
+    # is closed and one untimed call has filled the context's memory pool)
+    prob.close()
+    for rep in range(2):
+        barrier(); te = time.perf_counter()
+        P2, X2, S2 = ctx.ba_solve_batched(poses, points, obs, cam, pt, off.astype(np.int32), K, 1.0, iters)
+        t_e2e = max_over_ranks(time.perf_counter() - te, world)
     e2e_value = world * W * float(np.mean([s["iterations"] for s in S2])) / t_e2e
     out = None
     if rank == 0:
@@ -306,7 +309,7 @@ def run_ba_windows(args, rank, world, local_rank):
                "clocks": clocks,
                "parity": {"max_rel_final_cost_diff_vs_oracle": rel, "same_iteration_counts": bool(same_iters), "windows_checked": nw,
                           "tolerance": 1e-6, "ok": bool(rel <= 1e-6 and same_iters)}}
-    prob.close(); ctx.close()
+    ctx.close()
     return out
 
 
@@ -364,12 +367,21 @@ def run_ba_large(args, rank, world, local_rank):
         tc_ = torch.tensor([S[0]["final_cost"], float(done_iters)], dtype=torch.float64, device="cuda"); cx, cn = tc_.clone(), tc_.clone()
         dist.all_reduce(cx, op=dist.ReduceOp.MAX); dist.all_reduce(cn, op=dist.ReduceOp.MIN)
         ranks_agree = bool((mx == mn).all()) and bool((cx == cn).all())
-    # e2e: host arrays in -> create (index + upload) + solve + download
-    barrier(); te = time.perf_counter()
-    prob2 = ctx.ba_problem(w["poses"], pl, ol, cl, ptl, w["K"], 1.0, rank=rank, nranks=world)
-    prob2.solve(iters); P2, X2, S2 = prob2.download()
-    barrier(); t_e2e = max_over_ranks(time.perf_counter() - te, world)
-    prob2.close()
+    # e2e: host arrays in -> create (index + upload) + solve + download + destroy, as the pipeline issues it per
+    # keyframe.  Steady state: the resident problem is closed first and one untimed call has filled the context's
+    # memory pool (the very first call of a process also pays the one-time growth of that pool).
+    prob.close()
+    e2e_reps = 2
+    S2 = None
+    t_e2e = 0.0
+    for rep in range(e2e_reps + 1):
+        barrier(); te = time.perf_counter()
+        prob2 = ctx.ba_problem(w["poses"], pl, ol, cl, ptl, w["K"], 1.0, rank=rank, nranks=world)
+        prob2.solve(iters); P2, X2, S2 = prob2.download()
+        prob2.close()
+        barrier()
+        if rep > 0:
+            t_e2e += max_over_ranks(time.perf_counter() - te, world) / e2e_reps
     out = None
     if rank == 0:
         import oracle
@@ -419,7 +431,7 @@ def run_ba_large(args, rank, world, local_rank):
                           "nccl_ranks_on_data_plane": world if world > 1 else 0},
                "e2e": {"value": S2[0]["iterations"] / t_e2e, "unit": "LM iterations/s",
                        "h2d_bytes_per_step": int(len(ol) * 28 + w["poses"].nbytes + pl.nbytes), "d2h_bytes_per_step": int(w["poses"].nbytes + pl.nbytes),
-                       "api": "pmv_ba_problem_create + solve + download (host buffers; includes indexing)"},
+                       "api": "pmv_ba_problem_create + solve + download + destroy (host buffers; includes indexing; steady state, mean of 2 calls)"},
                "gpu_launches": int(launches),
                "roofline": {"kernel": "one LM iteration (linearise + point elimination + banded Cholesky + back-substitution + candidate cost)",
                             "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
@@ -427,7 +439,6 @@ def run_ba_large(args, rank, world, local_rank):
                             "note": "whole-iteration figure; the serial banded factorisation (latency-bound, one cluster) is inside it"},
                "cpu_baseline": cpu, "clocks": clocks, "parity": parity,
                "final_cost": S[0]["final_cost"], "initial_cost": S[0]["initial_cost"], "iterations": done_iters}
-    prob.close()
     if world > 1:
         ctx.comm_destroy()
     ctx.close()

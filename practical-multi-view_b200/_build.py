@@ -15,7 +15,7 @@ LIB = HERE / "libpmv_cuda.so"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3,-fopenmp", "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
 ]
 
@@ -56,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             if log:
                 print(log, file=sys.stderr)
     if force or _stale(LIB, objs):
-        cmd = [cc, "-shared", "-o", str(LIB)] + [str(o) for o in objs] + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"]
+        cmd = [cc, "-shared", "-o", str(LIB)] + [str(o) for o in objs] + ["-lcudart_static", "-ldl", "-lpthread", "-lrt", "-lgomp"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -6,8 +6,12 @@
 // (column,row) -> observations (:45) and calls pmv_ba_solve with huber_delta 1.0 and
 // max_iters = tracker->ba_iterations (:54-61).
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <numeric>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "ba.cuh"
 #include "ba_kernels.cuh"
@@ -67,6 +71,19 @@ struct pmv_ba_problem {
 
 namespace {
 
+// host array WITHOUT value initialisation (std::vector would memset gigabytes on one core before the parallel loops
+// ever touch them)
+template <typename T>
+struct RawBuf {
+    T *p = nullptr;
+    explicit RawBuf(size_t n) : p(static_cast<T *>(malloc(std::max<size_t>(n, 1) * sizeof(T)))) {}
+    ~RawBuf() { free(p); }
+    RawBuf(const RawBuf &) = delete;
+    RawBuf &operator=(const RawBuf &) = delete;
+    T *data() const { return p; }
+    T &operator[](size_t i) const { return p[i]; }
+};
+
 template <typename T>
 int dev_alloc(pmv_ba_problem *p, T **out, size_t count)
 {
@@ -78,7 +95,9 @@ int dev_alloc(pmv_ba_problem *p, T **out, size_t count)
         if (p->arena_mode == 2) { *out = reinterpret_cast<T *>(p->arena_base + off); p->bytes += bytes; }
         return PMV_OK;
     }
-    cudaError_t e = cudaMalloc(&q, bytes);
+    // stream-ordered allocation out of the device's default pool (pmv_create keeps freed blocks cached in it): a
+    // problem created after another one was destroyed pays microseconds instead of the page-mapping cost of cudaMalloc
+    cudaError_t e = cudaMallocAsync(&q, bytes, p->ctx->stream);
     if (e != cudaSuccess) return p->ctx->fail(PMV_ERR_NOMEM, "ba problem allocation", e);
     p->allocs.push_back(q);
     p->bytes += bytes;
@@ -283,50 +302,97 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
         return nullptr;
     }
     cudaSetDevice(ctx->device);
+    // PMV_BA_TRACE=1: wall time of the phases of this function on stderr (tools / tuning)
+    const char *create_trace = getenv("PMV_BA_TRACE");
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!(create_trace && create_trace[0] == '1')) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "ba_problem_create: %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     // ---- host: order observations by (window, point), group them by (window, camera) ---------------
-    std::vector<int> win(No);
+    // (OpenMP over windows / observations / points: 136 M observations at BASELINE config 4 took 5.5 s on one core)
+    RawBuf<int> win(No);
     for (int w = 0; w < W; w++) {
         int o0 = obs_off ? obs_off[w] : 0, o1 = obs_off ? obs_off[w + 1] : No;
         if (o0 < 0 || o1 < o0 || o1 > No) { ctx->fail(PMV_ERR_INVALID, "pmv_ba_problem_create: bad obs_off"); return nullptr; }
+    }
+#pragma omp parallel for schedule(static)
+    for (int w = 0; w < W; w++) {
+        const int o0 = obs_off ? obs_off[w] : 0, o1 = obs_off ? obs_off[w + 1] : No;
         for (int i = o0; i < o1; i++) win[i] = w;
     }
-    for (int i = 0; i < No; i++)
-        if (cam_idx[i] < 0 || cam_idx[i] >= Nc || pt_idx[i] < 0 || pt_idx[i] >= Np) {
+    {
+        int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+        for (int i = 0; i < No; i++) bad |= (cam_idx[i] < 0 || cam_idx[i] >= Nc || pt_idx[i] < 0 || pt_idx[i] >= Np) ? 1 : 0;
+        if (bad) {
             ctx->fail(PMV_ERR_INVALID, "pmv_ba_problem_create: observation index out of range");
             return nullptr;
         }
+    }
     std::vector<int> pt_off((size_t)W * Np + 1, 0), cam_off((size_t)W * Nc + 1, 0);
-    for (int i = 0; i < No; i++) { pt_off[(size_t)win[i] * Np + pt_idx[i] + 1]++; cam_off[(size_t)win[i] * Nc + cam_idx[i] + 1]++; }
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < No; i++) {
+        int *pc = &pt_off[(size_t)win[i] * Np + pt_idx[i] + 1], *cc = &cam_off[(size_t)win[i] * Nc + cam_idx[i] + 1];
+#pragma omp atomic
+        (*pc)++;
+#pragma omp atomic
+        (*cc)++;
+    }
     std::partial_sum(pt_off.begin(), pt_off.end(), pt_off.begin());
     std::partial_sum(cam_off.begin(), cam_off.end(), cam_off.begin());
-    std::vector<int> perm(No), h_cam(No), h_pt(No), h_win(No), cam_obs(No);
-    std::vector<double> h_obs(2 * (size_t)No);
+    RawBuf<int> perm(No), h_cam(No), h_pt(No), h_win(No), cam_obs(No);
+    RawBuf<double> h_obs(2 * (size_t)No);
     {
+        // scatter by (window, point): slots of a point are claimed atomically, then every point orders its
+        // observations by (camera, original index) -- the result is the stable order a serial pass produces
         std::vector<int> pos(pt_off.begin(), pt_off.end() - 1);
+        RawBuf<int> orig(No);
+#pragma omp parallel for schedule(static)
         for (int i = 0; i < No; i++) {
-            int d = pos[(size_t)win[i] * Np + pt_idx[i]]++;
-            perm[i] = d; h_cam[d] = cam_idx[i]; h_pt[d] = pt_idx[i]; h_win[d] = win[i];
-            h_obs[2 * (size_t)d] = obs[2 * (size_t)i]; h_obs[2 * (size_t)d + 1] = obs[2 * (size_t)i + 1];
+            int *pp = &pos[(size_t)win[i] * Np + pt_idx[i]];
+            int d;
+#pragma omp atomic capture
+            { d = *pp; (*pp)++; }
+            orig[d] = i;
         }
-        // inside each point: observations ordered by camera (the window path indexes them by popcount)
-        std::vector<std::pair<int, int>> tmp;
-        std::vector<int> inv(No);
-        for (int i = 0; i < No; i++) inv[perm[i]] = i;
-        for (size_t q = 0; q + 1 < pt_off.size(); q++) {
-            const int a = pt_off[q], b = pt_off[q + 1];
-            if (b - a < 2) continue;
-            tmp.clear();
-            for (int d = a; d < b; d++) tmp.push_back({h_cam[d], inv[d]});
-            std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) { return x.first < y.first; });
-            for (int d = a; d < b; d++) {
-                const int src = tmp[d - a].second;
-                perm[src] = d; h_cam[d] = cam_idx[src];
-                h_obs[2 * (size_t)d] = obs[2 * (size_t)src]; h_obs[2 * (size_t)d + 1] = obs[2 * (size_t)src + 1];
+        const long long nq = (long long)pt_off.size() - 1;
+#pragma omp parallel
+        {
+            std::vector<std::pair<int, int>> tmp;
+#pragma omp for schedule(dynamic, 4096)
+            for (long long q = 0; q < nq; q++) {
+                const int a = pt_off[q], b = pt_off[q + 1];
+                if (b == a) continue;
+                tmp.clear();
+                for (int d = a; d < b; d++) tmp.push_back({cam_idx[orig[d]], orig[d]});
+                if (b - a > 1) std::sort(tmp.begin(), tmp.end());
+                const int wq = (int)(q / Np), pq = (int)(q - (long long)wq * Np);
+                for (int d = a; d < b; d++) {
+                    const int src = tmp[d - a].second;
+                    perm[src] = d; h_cam[d] = tmp[d - a].first; h_pt[d] = pq; h_win[d] = wq;
+                    h_obs[2 * (size_t)d] = obs[2 * (size_t)src]; h_obs[2 * (size_t)d + 1] = obs[2 * (size_t)src + 1];
+                }
             }
         }
+        // observations of every (window, camera) in increasing device order
         std::vector<int> cpos(cam_off.begin(), cam_off.end() - 1);
-        for (int d = 0; d < No; d++) cam_obs[cpos[(size_t)h_win[d] * Nc + h_cam[d]]++] = d;
+#pragma omp parallel for schedule(static)
+        for (int d = 0; d < No; d++) {
+            int *cp = &cpos[(size_t)h_win[d] * Nc + h_cam[d]];
+            int k;
+#pragma omp atomic capture
+            { k = *cp; (*cp)++; }
+            cam_obs[k] = d;
+        }
+        const long long nc = (long long)cam_off.size() - 1;
+#pragma omp parallel for schedule(dynamic, 64)
+        for (long long c = 0; c < nc; c++)
+            if (cam_off[c + 1] - cam_off[c] > 1) std::sort(cam_obs.data() + cam_off[c], cam_obs.data() + cam_off[c + 1]);
     }
+    lap("index observations");
     // PMV_BA_FORCE_GENERAL=1 (tests) keeps small problems on the general path so both are exercised
     const char *force_general = getenv("PMV_BA_FORCE_GENERAL");
     // The window kernels give one CTA per window: they win once a batch fills a good part of the GPU, while
@@ -340,11 +406,18 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     std::vector<unsigned> h_vis;
     if (window_ok) {
         h_vis.assign((size_t)W * Np, 0u);
-        for (int d = 0; d < No && window_ok; d++) {
-            unsigned &m = h_vis[(size_t)h_win[d] * Np + h_pt[d]];
-            if (m & (1u << h_cam[d])) window_ok = false;   // the same camera sees the point twice -> general path
-            m |= 1u << h_cam[d];
+        int twice = 0;
+        const long long nq = (long long)W * Np;
+#pragma omp parallel for schedule(static) reduction(| : twice)
+        for (long long q = 0; q < nq; q++) {       // the observations of a point are contiguous (and ordered by camera)
+            unsigned m = 0;
+            for (int d = pt_off[q]; d < pt_off[q + 1]; d++) {
+                if (m & (1u << h_cam[d])) twice = 1;   // the same camera sees the point twice -> general path
+                m |= 1u << h_cam[d];
+            }
+            h_vis[q] = m;
         }
+        if (twice) window_ok = false;
     }
     // structural envelope of the reduced camera system: camera c couples with cameras up to emax[c]
     std::vector<double> emax(Nc);
@@ -358,6 +431,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     } else {
         for (int c = 0; c < Nc; c++) emax[c] = Nc - 1;   // batched windows use the small-n kernels anyway
     }
+    lap("visibility + envelope");
     // ---- runs of points with the same camera tuple (ba_runs.cuh): one large problem whose points see <= 8 cameras.
     // PMV_BA_NO_RUNS=1 keeps the pair-list path, PMV_BA_FORCE_RUNS=1 (tests) sends small problems through the runs.
     std::vector<int> run_off, run_pt;
@@ -368,18 +442,40 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
         bool want = W == 1 && !window_ok && !transient && !(no_runs && no_runs[0] == '1') && (No >= 100000 || forced);
         std::vector<std::pair<unsigned long long, int>> keys;
         if (want) {
-            keys.reserve(Np);
-            for (int q = 0; q < Np && want; q++) {
+            keys.resize(Np);
+            int too_wide = 0;
+#pragma omp parallel for schedule(static) reduction(| : too_wide)
+            for (int q = 0; q < Np; q++) {
                 const int a = pt_off[q], b = pt_off[q + 1];
-                if (b == a) continue;
-                if (b - a > RUN_MAXK) { want = false; break; }
+                if (b - a > RUN_MAXK) too_wide = 1;
                 unsigned long long h = 1469598103934665603ull;
                 for (int d = a; d < b; d++) h = (h ^ (unsigned long long)(unsigned)h_cam[d]) * 1099511628211ull;
-                keys.push_back({((unsigned long long)(b - a) << 60) | (h >> 4), q});   // tuple size first, then the tuple
+                // tuple size first, then the tuple; unobserved points sort to the end and are cut off below
+                keys[q] = {b == a ? ~0ull : ((unsigned long long)(b - a) << 60) | (h >> 4), q};
             }
+            if (too_wide) want = false;
         }
         if (want && !keys.empty()) {
-            std::sort(keys.begin(), keys.end());
+            {   // parallel sort: sorted chunks, then pairwise merges
+                int T = 1;
+#ifdef _OPENMP
+                T = std::max(1, std::min(omp_get_max_threads(), 32));
+#endif
+                while (T & (T - 1)) T &= T - 1;   // power of two
+                const size_t nk = keys.size();
+                std::vector<size_t> cut(T + 1);
+                for (int k = 0; k <= T; k++) cut[k] = nk * k / T;
+#pragma omp parallel for schedule(static, 1)
+                for (int k = 0; k < T; k++) std::sort(keys.begin() + cut[k], keys.begin() + cut[k + 1]);
+                for (int step = 1; step < T; step *= 2) {
+#pragma omp parallel for schedule(static, 1)
+                    for (int k = 0; k < T; k += 2 * step)
+                        std::inplace_merge(keys.begin() + cut[k], keys.begin() + cut[k + step], keys.begin() + cut[std::min(T, k + 2 * step)]);
+                }
+            }
+            while (!keys.empty() && keys.back().first == ~0ull) keys.pop_back();
+        }
+        if (want && !keys.empty()) {
             auto same_tuple = [&](int qa, int qb) {
                 const int a = pt_off[qa], b = pt_off[qb], ka = pt_off[qa + 1] - a;
                 if (ka != pt_off[qb + 1] - b) return false;
@@ -407,11 +503,12 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
         }
     }
     const bool use_runs = !run_off.empty();
+    lap("runs");
     pmv_ba_problem *p = new pmv_ba_problem();
     p->ctx = ctx;
     p->sharded = sharded_nranks > 1;
     p->rank = sharded_rank;
-    p->perm = perm;
+    p->perm.assign(perm.data(), perm.data() + No);
     BADev &D = p->D;
     D.W = W; D.Nc = Nc; D.Np = Np; D.n = 6 * Nc; D.No = No;
     D.fx = K[0]; D.cx = K[2]; D.fy = K[4]; D.cy = K[5]; D.delta = huber_delta;
@@ -467,6 +564,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     D.S = d_sys; D.rhs = d_sys + (size_t)W * n * n;
     D.obs_cam = d_cam; D.obs_pt = d_pt; D.obs_win = d_win; D.obs_xy = d_obs;
     D.pt_off = d_ptoff; D.cam_off = d_camoff; D.cam_obs = d_camobs; D.cam_active = d_camact;
+    lap("allocate");
     std::vector<int> h_camact(wc);
     for (size_t q = 0; q < wc; q++) h_camact[q] = cam_off[q + 1] > cam_off[q] ? 1 : 0;
     cudaStream_t s = ctx->stream;
@@ -486,6 +584,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
         for (int k = 0; k < RUN_MAXK + 2; k++) p->run_kbegin[k] = run_kbegin[k];
     }
     if (ok && cudaStreamSynchronize(s) != cudaSuccess) ok = false;  // host vectors die at return
+    lap("upload");
     if (!ok) { ctx->fail(PMV_ERR_CUDA, "pmv_ba_problem_create: upload failed", cudaGetLastError()); pmv_ba_problem_destroy(p); return nullptr; }
     {
         // envelope per 64-row block (global over ranks when the points are sharded)
@@ -585,6 +684,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
         }
         cudaStreamSynchronize(s);
     }
+    lap("envelope exchange + split setup");
     // ---- pair list: for every co-observed camera pair (ci <= ck) the observation pairs (i, k) of the points
     // that see both, cut into segments of <= 512 entries (one warp each).  Large single problems only: below
     // ~100 k observations the per-point kernel has more parallelism than there are segments.
@@ -632,7 +732,9 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
             }
         }
     }
+    lap("pair lists");
     if (pmv_ba_problem_reset(p, nullptr, nullptr) != PMV_OK) { pmv_ba_problem_destroy(p); return nullptr; }
+    lap("reset");
     return p;
 }
 
@@ -658,7 +760,7 @@ PMV_API void pmv_ba_problem_destroy(pmv_ba_problem *p)
     if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
     if (p->split.s2) { cudaStreamSynchronize(p->split.s2); cudaStreamDestroy(p->split.s2); }
     for (auto &e : p->split.ev) if (e) cudaEventDestroy(e);
-    for (void *q : p->allocs) cudaFree(q);
+    for (void *q : p->allocs) cudaFreeAsync(q, p->ctx->stream);
     delete p;
 }
 

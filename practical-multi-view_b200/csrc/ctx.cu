@@ -22,6 +22,14 @@ PMV_API pmv_ctx *pmv_create(int device)
         return nullptr;
     }
     for (auto &e : c->ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    {   // blocks freed with cudaFreeAsync stay in the device's default pool (bundle-adjustment problems come and go)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     c->stream = c->own_stream;
     return c;
 }
