@@ -166,6 +166,43 @@ PMV_API int pmv_pnp_ransac(pmv_ctx *ctx, const float *obj_xyz, const float *img_
                            double tvec[3], int use_extrinsic_guess, int iterations, float reproj_err, double confidence,
                            uint8_t *inlier_mask, int *n_inliers);
 
+/* ------------------------------------------------------------------ two-view initialisation -- */
+/* The two OpenCV calls of OpenCVFivePointTri::triangulate (OpenCVFivePointTri.cpp:25-27), point lists as n x 2 doubles
+ * (pixel coordinates; cv::Point / Point2f / Point2d all convert exactly), K row major, E / R row major.
+ *
+ * pmv_find_essential_mat == E = cv::findEssentialMat(p1, p2, K, cv::RANSAC, prob, threshold, maxIters, mask)
+ * (the reference passes 0.99, 1 and the default 1000): Nister five-point models on cv::RNG((uint64)-1) subsets, Sampson
+ * distance against threshold / ((fx + fy) / 2), RANSACUpdateNumIters.  *n_inliers = 0 and E = 0 when no model has
+ * more than four inliers (OpenCV returns an empty matrix).  mask: n bytes (optional).  n >= 6. */
+PMV_API int pmv_find_essential_mat(pmv_ctx *ctx, const double *p1_xy, const double *p2_xy, int n, const double K[9], double prob,
+                                   double threshold, int max_iters, double E[9], uint8_t *mask, int *n_inliers);
+/* == cv::recoverPose(E, p1, p2, K, R, t, distance_thresh, mask, tri): decomposeEssentialMat, linear triangulation under
+ * the four pose candidates, cheirality vote.  mask: n bytes, in = points to consider (NULL: all), out = points in
+ * front of both cameras for the winner; tri: 4 x n homogeneous points (optional); *n_good = votes of the winner. */
+PMV_API int pmv_recover_pose(pmv_ctx *ctx, const double E[9], const double *p1_xy, const double *p2_xy, int n, const double K[9],
+                             double distance_thresh, double R[9], double t[3], uint8_t *mask, double *tri, int *n_good);
+/* Both calls in ONE launch (what OpenCVFivePointTri::triangulate does back to back): ransac_mask = findEssentialMat's
+ * mask (optional), mask = recoverPose's in/out mask.  When no model is found *n_inliers = 0 and R / t / tri are left
+ * untouched (OpenCV would throw in recoverPose). */
+PMV_API int pmv_five_point_pose(pmv_ctx *ctx, const double *p1_xy, const double *p2_xy, int n, const double K[9], double prob,
+                                double threshold, int max_iters, double distance_thresh, double E[9], double R[9], double t[3],
+                                uint8_t *ransac_mask, uint8_t *mask, double *tri, int *n_inliers, int *n_good);
+
+/* ------------------------------------------------------------------ KITTI wire formats (host only) -- */
+/* OdometryPipeline::parsePoses (OdometryPipeline.cpp:525-593): one 3x4 row-major [R|t] per line, at most `stop` lines.
+ * R: capacity x 9, t: capacity x 3 (either may be NULL); *n = poses in the file (may exceed capacity).
+ * PMV_ERR_INVALID when the file cannot be opened (the reference throws "Unable to open pose file"). */
+PMV_API int pmv_kitti_parse_poses(const char *path, int stop, double *R, double *t, int capacity, int *n);
+/* OdometryPipeline::parseCalibration (:595-653): the left 3x3 of line `num_calib` ("Pn: ...") of calib.txt into K
+ * (row major; entries the line does not reach keep their value, as in the reference). */
+PMV_API int pmv_kitti_parse_calibration(const char *path, int num_calib, double K[9]);
+/* The error report of OdometryPipeline::run (:272-300): per-frame Frobenius / L2 distances between the n estimated
+ * poses (R: n x 9, t: n x 3; index 0 = initial pose, skipped) and the ground truth, with the reference's sign flips
+ * and its gt_R[i] (not i + init_offset) quirk.  stats = {R total, min, max, std, t total, min, max, std}; text = the
+ * error_path file content (optional). */
+PMV_API int pmv_kitti_error_report(const double *R, const double *t, int n, const double *gt_R, const double *gt_t, int n_gt,
+                                   int init_offset, double runtime, double stats[8], char *text, int text_capacity);
+
 /* ------------------------------------------------------------------ corner detectors -- */
 /* Image arguments of the extractors: `base` is the PARENT image (full_rows x full_cols, row step
  * `step` bytes) and (roi_x, roi_y, roi_w, roi_h) the view the pipeline passes

@@ -23,8 +23,13 @@ _BLUR = C.CFUNCTYPE(C.c_int, _f64p, C.c_int, C.c_int, C.c_int, _f64p)
 _PNP = C.CFUNCTYPE(C.c_int, _f32p, _f32p, C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_int, C.c_float, C.c_double, _i32p, _i32p)
 
 
+_FINDE = C.CFUNCTYPE(C.c_int, _f64p, _f64p, C.c_int, _f64p, C.c_int, C.c_double, C.c_double, _f64p, _u8p)
+_RECOVER = C.CFUNCTYPE(C.c_int, _f64p, _f64p, _f64p, C.c_int, _f64p, C.c_double, _f64p, _f64p, _u8p, _f64p)
+
+
 class Hooks(C.Structure):
-    _fields_ = [("lk", _LK), ("gftt", _GFTT), ("fast", _FAST), ("blur3", _BLUR), ("pnp_ransac", _PNP)]
+    _fields_ = [("lk", _LK), ("gftt", _GFTT), ("fast", _FAST), ("blur3", _BLUR), ("pnp_ransac", _PNP), ("find_essential", _FINDE),
+                ("recover_pose", _RECOVER)]
 
 
 def _img(ptr, rows, cols, step):
@@ -108,7 +113,32 @@ def _cv2_hooks():
         except Exception:
             return 0
 
-    return Hooks(_LK(lk), _GFTT(gftt), _FAST(fast), _BLUR(blur3), _PNP(pnp))
+    def find_essential(p1, p2, n, K, method, prob, thr, E, mask):
+        try:
+            a = np.ctypeslib.as_array(p1, shape=(n, 2)).copy(); b = np.ctypeslib.as_array(p2, shape=(n, 2)).copy()
+            Km = np.ctypeslib.as_array(K, shape=(3, 3)).copy()
+            Em, m = cv2.findEssentialMat(a, b, Km, method, prob, thr)
+            np.ctypeslib.as_array(mask, shape=(n,))[:] = 0 if m is None else m.ravel()
+            if Em is None:
+                return 0
+            np.ctypeslib.as_array(E, shape=(90,))[:Em.size] = Em.ravel()
+            return Em.shape[0]
+        except Exception:
+            return -1
+
+    def recover_pose(E, p1, p2, n, K, dist, R, t, mask, tri):
+        try:
+            a = np.ctypeslib.as_array(p1, shape=(n, 2)).copy(); b = np.ctypeslib.as_array(p2, shape=(n, 2)).copy()
+            Km = np.ctypeslib.as_array(K, shape=(3, 3)).copy(); Em = np.ctypeslib.as_array(E, shape=(3, 3)).copy()
+            m = np.ctypeslib.as_array(mask, shape=(n,))
+            good, Rm, tm, m2, tr = cv2.recoverPose(Em, a, b, Km, distanceThresh=dist, mask=m.copy().reshape(n, 1))
+            np.ctypeslib.as_array(R, shape=(9,))[:] = Rm.ravel(); np.ctypeslib.as_array(t, shape=(3,))[:] = tm.ravel()
+            m[:] = m2.ravel(); np.ctypeslib.as_array(tri, shape=(4, n))[:] = tr
+            return int(good)
+        except Exception:
+            return -1
+
+    return Hooks(_LK(lk), _GFTT(gftt), _FAST(fast), _BLUR(blur3), _PNP(pnp), _FINDE(find_essential), _RECOVER(recover_pose))
 
 
 _lib = None
@@ -231,3 +261,18 @@ def pnp_solve(K, R1, t1, points, src_cr, next_cr, R_guess, t_guess, impl=0):
                                  _p(n_cr, C.c_int), _p(R, C.c_double), _p(t, C.c_double), _p(kept, C.c_int))
     _chk(min(n_next, 0))
     return R.reshape(3, 3), t, kept.astype(bool), n_next
+
+
+def triangulate(K, src_cr, next_cr, gt0, gt1, impl=0):
+    """triangulator->triangulate(src, next, R, t) on a synthetic pipeline state (impl 0: OpenCVFivePointTri compiled from
+    the reference, cv2.findEssentialMat / recoverPose behind the shim; impl 1: GpuFivePointTri).  Returns
+    (R, t, scale, f3d_index per input pair, world points of OdometryPipeline::feats3d)."""
+    K = np.ascontiguousarray(K, np.float64).ravel()
+    s_cr = np.ascontiguousarray(src_cr, np.int32).reshape(-1, 2); n_cr = np.ascontiguousarray(next_cr, np.int32).reshape(-1, 2)
+    g0 = np.ascontiguousarray(gt0, np.float64).ravel(); g1 = np.ascontiguousarray(gt1, np.float64).ravel()
+    n = len(s_cr)
+    R = np.zeros(9); t = np.zeros(3); scale = C.c_double(0); idx = np.zeros(n, np.int32); pts = np.zeros((n, 3), np.float32)
+    k = lib().ref_triangulate(impl, _p(K, C.c_double), n, _p(s_cr, C.c_int), _p(n_cr, C.c_int), _p(g0, C.c_double), _p(g1, C.c_double),
+                              _p(R, C.c_double), _p(t, C.c_double), C.byref(scale), _p(idx, C.c_int), _p(pts, C.c_float))
+    _chk(min(k, 0))
+    return R.reshape(3, 3), t, scale.value, idx, pts[:k]

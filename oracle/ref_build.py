@@ -23,7 +23,7 @@ PKG = ROOT / "practical-multi-view_b200"
 
 REF_SOURCES = ["Feature.cpp", "Feature3D.cpp", "Frame.cpp", "ShiTomasiFeatureExtractor.cpp", "ProjectionResidual.cpp",
                "CeresBundleAdjustment.cpp", "OpenCVGoodFeatureExtractor.cpp", "OpenCVFASTFeatureExtractor.cpp",
-               "OpenCVLucasKanadeFM.cpp", "OpenCVEPnPSolver.cpp"]
+               "OpenCVLucasKanadeFM.cpp", "OpenCVEPnPSolver.cpp", "OpenCVFivePointTri.cpp"]
 OWN_SOURCES = [HERE / "ref_harness.cpp", HERE / "ref_shim" / "shim_impl.cpp"]
 ORACLE_C = sorted(HERE.glob("pmv_oracle_*.c"))
 

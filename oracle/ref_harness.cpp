@@ -4,6 +4,7 @@
 // compiled unchanged from /root/reference by oracle/ref_build.py:
 //     Feature.cpp Feature3D.cpp Frame.cpp ShiTomasiFeatureExtractor.cpp ProjectionResidual.cpp
 //     CeresBundleAdjustment.cpp OpenCVGoodFeatureExtractor.cpp OpenCVFASTFeatureExtractor.cpp OpenCVLucasKanadeFM.cpp
+//     OpenCVEPnPSolver.cpp OpenCVFivePointTri.cpp
 // against the functional OpenCV / Ceres / dlib shim in oracle/ref_shim/ (third-party kernels forwarded to the real cv2
 // wheel through hooks), plus -- in the same object, against the same shim -- the product's drop-in adapters
 // (practical-multi-view_b200/host/pmv_adapters.h -> libpmv_cuda.so).  Every entry point takes `impl`:
@@ -17,6 +18,7 @@
 #include "OdometryPipeline.h"
 #include "OpenCVEPnPSolver.h"
 #include "OpenCVFASTFeatureExtractor.h"
+#include "OpenCVFivePointTri.h"
 #include "OpenCVGoodFeatureExtractor.h"
 #include "OpenCVLucasKanadeFM.h"
 #include "ProjectionResidual.h"
@@ -35,7 +37,7 @@ REF_API void ref_set_hooks(const pmv_ref_hooks* h) { if (h) g_pmv_ref_hooks = *h
 REF_API const char* ref_sources()
 {
     return "Feature.cpp Feature3D.cpp Frame.cpp ShiTomasiFeatureExtractor.cpp ProjectionResidual.cpp CeresBundleAdjustment.cpp "
-           "OpenCVGoodFeatureExtractor.cpp OpenCVFASTFeatureExtractor.cpp OpenCVLucasKanadeFM.cpp";
+           "OpenCVGoodFeatureExtractor.cpp OpenCVFASTFeatureExtractor.cpp OpenCVLucasKanadeFM.cpp OpenCVEPnPSolver.cpp OpenCVFivePointTri.cpp";
 }
 
 // Frame(cv::Mat& orig) runs cvtColor(BGR2GRAY) (Frame.cpp:38-42): feed it B = G = R = gray, which the 8-bit fixed-point
@@ -228,5 +230,54 @@ REF_API int ref_pnp_solve(int impl, const double* K, const double* R1, const dou
     for (int a = 0; a < 3; a++) { for (int b = 0; b < 3; b++) R[3 * a + b] = Rm.at<double>(a, b); t[a] = tm.at<double>(a); }
     for (int p = 0; p < n; p++) kept[p] = std::find(pipe.feats3d.begin(), pipe.feats3d.end(), all[p]) != pipe.feats3d.end();
     return (int)next.map.size();
+    REF_CATCH
+}
+
+// ---- f4: triangulator->triangulate(src, next, R, t) as OdometryPipeline::initialise calls it, on a synthetic pipeline
+// state: n tracked features (src_cr -> next_cr, integer pixels), src frame 0 at the identity pose, ground-truth
+// translations gt0 / gt1 (their distance is the scale the reference applies).  Out: R, t (scaled), scale, for every input
+// pair the index of its Feature3D in OdometryPipeline::feats3d (-1: none) and the world coordinates of those points
+// (points: capacity n x 3).  Returns the number of Feature3D created.
+REF_API int ref_triangulate(int impl, const double* K, int n, const int* src_cr, const int* next_cr, const double* gt0, const double* gt1,
+                            double* R, double* t, double* scale, int* f3d_index, float* points)
+{
+    REF_TRY
+    OdometryPipeline pipe;
+    pipe.verbose = false;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) pipe.camera.at<double>(i, j) = K[3 * i + j];
+    cv::Mat tiny(1, 1, CV_8UC3);
+    Frame src(tiny), next(tiny);
+    src.frame = 0; next.frame = 1;
+    cv::Mat I(3, 3, CV_64FC1), z(3, 1, CV_64FC1), g0(3, 1, CV_64FC1), g1(3, 1, CV_64FC1);
+    for (int a = 0; a < 3; a++) {
+        for (int b = 0; b < 3; b++) I.at<double>(a, b) = a == b ? 1.0 : 0.0;
+        z.at<double>(a) = 0.0; g0.at<double>(a) = gt0[a]; g1.at<double>(a) = gt1[a];
+    }
+    pipe.R.push_back(I); pipe.t.push_back(z);
+    pipe.gt_t.push_back(g0); pipe.gt_t.push_back(g1);
+    std::vector<std::shared_ptr<Feature>> fs(n), fn(n);
+    for (int p = 0; p < n; p++) {
+        fs[p] = std::make_shared<Feature>(Feature(src_cr[2 * p], src_cr[2 * p + 1]));
+        fn[p] = std::make_shared<Feature>(Feature(next_cr[2 * p], next_cr[2 * p + 1]));
+        src.feat_corr[fs[p]] = fn[p];
+    }
+    cv::Mat Rm, tm;
+    std::unique_ptr<BaseTriangulator> tr;
+    if (impl == 0) tr.reset(new OpenCVFivePointTri(&pipe)); else tr.reset(new GpuFivePointTri(&pipe));
+    tr->triangulate(src, next, Rm, tm);
+    for (int a = 0; a < 3; a++) { for (int b = 0; b < 3; b++) R[3 * a + b] = Rm.at<double>(a, b); t[a] = tm.at<double>(a); }
+    *scale = pipe.scale;
+    for (int p = 0; p < n; p++) {
+        f3d_index[p] = -1;
+        auto it = src.map.find(fs[p]);
+        if (it == src.map.end() || it->second.expired()) continue;
+        std::shared_ptr<Feature3D> f = it->second.lock();
+        const int k = (int)(std::find(pipe.feats3d.begin(), pipe.feats3d.end(), f) - pipe.feats3d.begin());
+        f3d_index[p] = k;
+        cv::Point3f q = f->getPoint();
+        points[3 * k] = q.x; points[3 * k + 1] = q.y; points[3 * k + 2] = q.z;
+    }
+    if (next.map.size() != src.map.size()) throw std::runtime_error("src.map / next.map sizes disagree");
+    return (int)pipe.feats3d.size();
     REF_CATCH
 }

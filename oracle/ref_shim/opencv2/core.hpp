@@ -159,6 +159,20 @@ inline Mat operator-(const Mat& a)
     for (int r = 0; r < m.rows; r++) { double* d = m.ptr<double>(r); for (int c = 0; c < n; c++) d[c] = -d[c]; }
     return m;
 }
+inline Mat operator-(const Mat& a, const Mat& b)
+{
+    if (a.type() != CV_64FC1 || b.type() != CV_64FC1 || a.rows != b.rows || a.cols != b.cols) throw std::runtime_error("shim operator-: equal-size CV_64FC1 only");
+    Mat m = a.clone();
+    for (int r = 0; r < m.rows; r++) { double* d = m.ptr<double>(r); const double* s = b.ptr<double>(r); for (int c = 0; c < m.cols; c++) d[c] -= s[c]; }
+    return m;
+}
+inline Mat operator*(double k, const Mat& a)
+{
+    if (a.type() != CV_64FC1) throw std::runtime_error("shim scalar * Mat: CV_64FC1 only");
+    Mat m = a.clone();
+    for (int r = 0; r < m.rows; r++) { double* d = m.ptr<double>(r); for (int c = 0; c < m.cols; c++) d[c] *= k; }
+    return m;
+}
 inline void transpose(const Mat& src, OutputArray dst)
 {
     if (src.type() != CV_64FC1) throw std::runtime_error("shim transpose: CV_64FC1 only");

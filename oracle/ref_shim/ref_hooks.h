@@ -22,6 +22,12 @@ typedef struct pmv_ref_hooks {
     /* cv::solvePnPRansac(obj, img, K, noArray(), rvec, tvec, useExtrinsicGuess, iters, reprojErr, confidence, inliers) */
     int (*pnp_ransac)(const float* obj, const float* img, int n, const double* K, double* rvec, double* tvec,
                       int use_guess, int iters, float reproj_err, double confidence, int* inliers, int* n_inliers);
+    /* E = cv::findEssentialMat(p1, p2, K, method, prob, threshold, mask); points n x 2 doubles; returns the number of rows of E */
+    int (*find_essential)(const double* p1, const double* p2, int n, const double* K, int method, double prob, double threshold,
+                          double* E, uint8_t* mask);
+    /* cv::recoverPose(E, p1, p2, K, R, t, distanceThresh, mask (in/out), tri (4 x n)); returns the vote count (< 0: failed) */
+    int (*recover_pose)(const double* E, const double* p1, const double* p2, int n, const double* K, double distance_thresh,
+                        double* R, double* t, uint8_t* mask, double* tri);
 } pmv_ref_hooks;
 extern pmv_ref_hooks g_pmv_ref_hooks;
 #ifdef __cplusplus

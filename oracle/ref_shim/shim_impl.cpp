@@ -213,6 +213,49 @@ bool solvePnPRansac(const std::vector<Point3f>& obj, const std::vector<Point2f>&
     inliers.assign(inl.begin(), inl.begin() + ninl);
     return ok != 0;
 }
+
+static void shim_points(const std::vector<Point>& p, std::vector<double>& out)
+{
+    out.resize(2 * p.size());
+    for (size_t i = 0; i < p.size(); i++) { out[2 * i] = p[i].x; out[2 * i + 1] = p[i].y; }
+}
+
+Mat findEssentialMat(const std::vector<Point>& p1, const std::vector<Point>& p2, const Mat& K, int method, double prob, double threshold,
+                     OutputArray mask)
+{
+    if (!g_pmv_ref_hooks.find_essential) throw std::runtime_error("shim findEssentialMat: needs the cv2 hook");
+    const int n = (int)p1.size();
+    std::vector<double> a, b; shim_points(p1, a); shim_points(p2, b);
+    double Kd[9], E[90];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Kd[3 * i + j] = K.at<double>(i, j);
+    Mat m(n, 1, CV_8UC1);
+    const int rows = g_pmv_ref_hooks.find_essential(a.data(), b.data(), n, Kd, method, prob, threshold, E, m.data);
+    if (rows < 0) throw std::runtime_error("shim findEssentialMat: cv2 failed");
+    *mask.m = m;
+    if (rows == 0) return Mat();
+    Mat Em(rows, 3, CV_64FC1);
+    for (int i = 0; i < rows; i++) for (int j = 0; j < 3; j++) Em.at<double>(i, j) = E[3 * i + j];
+    return Em;
+}
+
+int recoverPose(const Mat& E, const std::vector<Point>& p1, const std::vector<Point>& p2, const Mat& K, OutputArray R, OutputArray t,
+                double distanceThresh, OutputArray mask, OutputArray triangulatedPoints)
+{
+    if (!g_pmv_ref_hooks.recover_pose) throw std::runtime_error("shim recoverPose: needs the cv2 hook");
+    if (E.rows != 3 || E.cols != 3) throw std::runtime_error("shim recoverPose: E must be 3x3");
+    const int n = (int)p1.size();
+    std::vector<double> a, b; shim_points(p1, a); shim_points(p2, b);
+    double Kd[9], Ed[9], Rd[9], td[3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { Kd[3 * i + j] = K.at<double>(i, j); Ed[3 * i + j] = E.at<double>(i, j); }
+    Mat tri(4, n, CV_64FC1);
+    if (mask.m->empty()) { Mat m(n, 1, CV_8UC1); std::memset(m.data, 1, n); *mask.m = m; }
+    const int good = g_pmv_ref_hooks.recover_pose(Ed, a.data(), b.data(), n, Kd, distanceThresh, Rd, td, mask.m->data, tri.ptr<double>(0));
+    if (good < 0) throw std::runtime_error("shim recoverPose: cv2 failed");
+    Mat Rm(3, 3, CV_64FC1), tm(3, 1, CV_64FC1);
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) Rm.at<double>(i, j) = Rd[3 * i + j]; tm.at<double>(i) = td[i]; }
+    *R.m = Rm; *t.m = tm; *triangulatedPoints.m = tri;
+    return good;
+}
 }  // namespace cv
 
 // ---------------------------------------------------------------------------------------------- ceres::Solve

@@ -64,6 +64,12 @@ _SIGS = {
     "pmv_tracker_add_frame": (_int, [_vp, _vp, _int, _i32p, _i32p, _i32p, _vp, _vp, _int]),
     "pmv_tracker_features": (_int, [_vp, _vp, _int, _i32p]),
     "pmv_pnp_ransac": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _vp, _int, _int, C.c_float, C.c_double, _vp, _i32p]),
+    "pmv_kitti_parse_poses": (_int, [C.c_char_p, _int, _vp, _vp, _int, _i32p]),
+    "pmv_kitti_parse_calibration": (_int, [C.c_char_p, _int, _vp]),
+    "pmv_kitti_error_report": (_int, [_vp, _vp, _int, _vp, _vp, _int, _int, C.c_double, _vp, C.c_char_p, _int]),
+    "pmv_find_essential_mat": (_int, [_vp, _vp, _vp, _int, _vp, C.c_double, C.c_double, _int, _vp, _vp, _i32p]),
+    "pmv_recover_pose": (_int, [_vp, _vp, _vp, _vp, _int, _vp, C.c_double, _vp, _vp, _vp, _vp, _i32p]),
+    "pmv_five_point_pose": (_int, [_vp, _vp, _vp, _int, _vp, C.c_double, C.c_double, _int, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _i32p, _i32p]),
     "pmv_min_eigen_val_batched_dev": (_int, [_vp, _vp, _int, _sz, _int, _int, _int, _vp, _vp]),
     "pmv_shitomasi_response_batched_dev": (_int, [_vp, _vp, _int, _sz, _int, _int, _int, _int, _vp, _vp]),
     "pmv_min_eigen_val": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp]),
@@ -122,6 +128,42 @@ def _ptr(a):
     if isinstance(a, int):
         return C.c_void_p(a)
     return C.c_void_p(a.ctypes.data)
+
+
+def kitti_parse_poses(path, stop=1 << 30):
+    """OdometryPipeline::parsePoses (OdometryPipeline.cpp:525-593).  Returns (R (n,3,3), t (n,3)).  Host only."""
+    lib = load_library()
+    n = C.c_int(0)
+    rc = lib.pmv_kitti_parse_poses(str(path).encode(), int(stop), None, None, 0, C.byref(n))
+    if rc != 0:
+        raise PmvError(rc, "Unable to open pose file")
+    R = np.zeros((n.value, 9)); t = np.zeros((n.value, 3))
+    lib.pmv_kitti_parse_poses(str(path).encode(), int(stop), _ptr(R), _ptr(t), n.value, C.byref(n))
+    return R.reshape(-1, 3, 3), t
+
+
+def kitti_parse_calibration(path, num_calib=0, K=None):
+    """OdometryPipeline::parseCalibration (:595-653).  Returns K (3,3).  Host only."""
+    lib = load_library()
+    Km = np.zeros(9) if K is None else np.array(K, np.float64).reshape(9).copy()
+    rc = lib.pmv_kitti_parse_calibration(str(path).encode(), int(num_calib), _ptr(Km))
+    if rc != 0:
+        raise PmvError(rc, "Unable to open calibration file")
+    return Km.reshape(3, 3)
+
+
+def kitti_error_report(R, t, gt_R, gt_t, init_offset=0, runtime=0.0):
+    """The error report of OdometryPipeline::run (:272-300).  Returns (stats dict, text of error_path).  Host only."""
+    lib = load_library()
+    R = np.ascontiguousarray(R, np.float64).reshape(-1, 9); t = np.ascontiguousarray(t, np.float64).reshape(-1, 3)
+    gR = np.ascontiguousarray(gt_R, np.float64).reshape(-1, 9); gt = np.ascontiguousarray(gt_t, np.float64).reshape(-1, 3)
+    stats = np.zeros(8); text = C.create_string_buffer(1024)
+    rc = lib.pmv_kitti_error_report(_ptr(R), _ptr(t), len(R), _ptr(gR), _ptr(gt), len(gR), int(init_offset), float(runtime), _ptr(stats),
+                                    text, 1024)
+    if rc != 0:
+        raise PmvError(rc, "pmv_kitti_error_report: bad argument")
+    keys = ["R_total", "R_min", "R_max", "R_std", "t_total", "t_min", "t_max", "t_std"]
+    return dict(zip(keys, stats.tolist())), text.value.decode()
 
 
 class Context:
@@ -256,6 +298,46 @@ class Context:
         self._chk(self.lib.pmv_pnp_ransac(self.h, _ptr(obj), _ptr(img), n, _ptr(K), _ptr(r), _ptr(t), int(use_guess), iterations,
                                           reproj_err, confidence, _ptr(mask), C.byref(ni)))
         return ni.value > 0, r, t, np.nonzero(mask[:n])[0].astype(np.int32)
+
+    @staticmethod
+    def _pairs(p1, p2):
+        p1 = np.ascontiguousarray(p1, np.float64).reshape(-1, 2); p2 = np.ascontiguousarray(p2, np.float64).reshape(-1, 2)
+        assert len(p1) == len(p2)
+        return p1, p2
+
+    def find_essential_mat(self, p1, p2, K, prob=0.99, threshold=1.0, max_iters=1000):
+        """== cv2.findEssentialMat(p1, p2, K, cv2.RANSAC, prob, threshold, maxIters).  Returns (E (3,3) or None, mask (n,))."""
+        p1, p2 = self._pairs(p1, p2)
+        K = np.ascontiguousarray(K, np.float64).reshape(9)
+        E = np.zeros(9); mask = np.zeros(max(len(p1), 1), np.uint8); ni = C.c_int(0)
+        self._chk(self.lib.pmv_find_essential_mat(self.h, _ptr(p1), _ptr(p2), len(p1), _ptr(K), prob, threshold, max_iters, _ptr(E),
+                                                  _ptr(mask), C.byref(ni)))
+        return (E.reshape(3, 3) if ni.value > 0 else None), mask[:len(p1)]
+
+    def recover_pose(self, E, p1, p2, K, distance_thresh=float("inf"), mask=None):
+        """== cv2.recoverPose(E, p1, p2, K, distanceThresh, mask).  Returns (n_good, R, t, mask, tri (4, n))."""
+        p1, p2 = self._pairs(p1, p2)
+        n = len(p1)
+        K = np.ascontiguousarray(K, np.float64).reshape(9); E = np.ascontiguousarray(E, np.float64).reshape(9)
+        R = np.zeros(9); t = np.zeros(3); tri = np.zeros((4, n)); ng = C.c_int(0)
+        m = np.ones(n, np.uint8) if mask is None else (np.asarray(mask).reshape(-1) != 0).astype(np.uint8)
+        self._chk(self.lib.pmv_recover_pose(self.h, _ptr(E), _ptr(p1), _ptr(p2), n, _ptr(K), distance_thresh, _ptr(R), _ptr(t), _ptr(m),
+                                            _ptr(tri), C.byref(ng)))
+        return ng.value, R.reshape(3, 3), t, m, tri
+
+    def five_point_pose(self, p1, p2, K, prob=0.99, threshold=1.0, max_iters=1000, distance_thresh=float("inf")):
+        """findEssentialMat + recoverPose in one launch (OpenCVFivePointTri.cpp:25-27).
+        Returns dict(E, R, t, ransac_mask, mask, tri, n_inliers, n_good); E is None when no model was found."""
+        p1, p2 = self._pairs(p1, p2)
+        n = len(p1)
+        K = np.ascontiguousarray(K, np.float64).reshape(9)
+        E = np.zeros(9); R = np.zeros(9); t = np.zeros(3); tri = np.zeros((4, n))
+        rm = np.zeros(max(n, 1), np.uint8); m = np.zeros(max(n, 1), np.uint8); ni = C.c_int(0); ng = C.c_int(0)
+        self._chk(self.lib.pmv_five_point_pose(self.h, _ptr(p1), _ptr(p2), n, _ptr(K), prob, threshold, max_iters, distance_thresh,
+                                               _ptr(E), _ptr(R), _ptr(t), _ptr(rm), _ptr(m), _ptr(tri), C.byref(ni), C.byref(ng)))
+        ok = ni.value > 0
+        return dict(E=E.reshape(3, 3) if ok else None, R=R.reshape(3, 3), t=t, ransac_mask=rm[:n], mask=m[:n], tri=tri,
+                    n_inliers=ni.value, n_good=ng.value)
 
     def tracker(self, rows, cols, win=(32, 32), max_level=4, capacity=4096, min_tracked=400, tracked_tol=150, grid=255,
                 quality=0.01, min_dist=5.0, neighbor_dist=5):

@@ -5,7 +5,7 @@
 //     matcher   = new GpuLucasKanadeFM();             // was OpenCVLucasKanadeFM
 //     ba        = new GpuBundleAdjustment(this);      // was CeresBundleAdjustment
 //     pnpsolver = new GpuEPnPSolver(this);            // was OpenCVEPnPSolver
-//     (triangulator unchanged: the BaseTriangulator implementation stays)
+//     triangulator = new GpuFivePointTri(this);      // was OpenCVFivePointTri
 //
 // Each class mirrors the reference class it replaces -- same members, defaults, Feature fields it
 // fills, iteration order over Frame::map -- and only swaps the OpenCV / Ceres call for the C-ABI
@@ -31,6 +31,7 @@
 #include "BaseFeatureMatcher.h"
 #include "BaseOptimizer.h"
 #include "BasePnPSolver.h"
+#include "BaseTriangulator.h"
 #include "OdometryPipeline.h"
 #include "pmv_cuda.h"
 
@@ -339,6 +340,72 @@ public:
                 if (local_feats3d[i].expired()) continue;
                 std::shared_ptr<Feature3D> f3d = local_feats3d[i].lock();
                 tracker->feats3d.erase(std::find(tracker->feats3d.begin(), tracker->feats3d.end(), f3d));
+            }
+        }
+    }
+private:
+    pmv::Handle gpu;
+};
+
+// ---- BaseTriangulator ------------------------------------------------------------------------------------------------
+// Replaces OpenCVFivePointTri (OpenCVFivePointTri.cpp:5-54): findEssentialMat(RANSAC, 0.99, 1) + recoverPose in one
+// launch (pmv_five_point_pose), then the reference's own scale / Feature3D bookkeeping.
+class GpuFivePointTri : public BaseTriangulator
+{
+public:
+    OdometryPipeline* tracker;
+
+    GpuFivePointTri(OdometryPipeline* tracker) : tracker(tracker) {}
+
+    void triangulate(Frame& src, Frame& next, cv::Mat& R_out, cv::Mat& t_out)
+    {
+        int j = src.frame;
+        std::vector<double> p1, p2;
+        std::vector<std::shared_ptr<Feature>> p1_ptr, p2_ptr;
+
+        for (auto& p : src.feat_corr) {                                    // same walk as .cpp:13-23
+            if (p.first.expired() || p.second.expired()) continue;
+            std::shared_ptr<Feature> fst = p.first.lock();
+            std::shared_ptr<Feature> sec = p.second.lock();
+            cv::Point a = fst->getPoint(), b = sec->getPoint();            // integer pixel coordinates
+            p1.push_back(a.x); p1.push_back(a.y);
+            p2.push_back(b.x); p2.push_back(b.y);
+            p1_ptr.push_back(fst);
+            p2_ptr.push_back(sec);
+        }
+        const int n = (int)p1_ptr.size();
+        double K[9], E[9], R[9], t[3];
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) K[3 * r + c] = tracker->camera.at<double>(r, c);
+        std::vector<uint8_t> mask(n > 0 ? n : 1, 0);
+        std::vector<double> tri(4 * (size_t)(n > 0 ? n : 1), 0.0);
+        int n_inliers = 0, n_good = 0;
+        // findEssentialMat(p1, p2, camera, RANSAC, 0.99, 1, mask); recoverPose(E, p1, p2, camera, R, t, HUGE_VAL, mask, tri)  (.cpp:25-27)
+        gpu.check(pmv_five_point_pose(gpu.get(), p1.data(), p2.data(), n, K, 0.99, 1.0, 1000, HUGE_VAL, E, R, t, nullptr, mask.data(),
+                                      tri.data(), &n_inliers, &n_good), "pmv_five_point_pose");
+        if (n_inliers == 0) throw std::runtime_error("pmv_five_point_pose: no essential matrix (cv::recoverPose would throw)");
+        R_out.create(3, 3, CV_64FC1); t_out.create(3, 1, CV_64FC1);
+        for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) R_out.at<double>(r, c) = R[3 * r + c]; t_out.at<double>(r) = t[r]; }
+
+        cv::Mat dist = tracker->gt_t[j + tracker->init_offset + 1] - tracker->gt_t[j + tracker->init_offset];   // .cpp:29-35
+        tracker->scale = std::sqrt(
+            std::pow(dist.at<double>(0), 2) +
+            std::pow(dist.at<double>(1), 2) +
+            std::pow(dist.at<double>(2), 2));
+
+        t_out = tracker->scale * t_out;
+
+        for (int i = 0; i < n; i++) {                                      // .cpp:37-53
+            if (!mask[i]) continue;                                        // removing RANSAC outliers
+            const double w = tri[3 * (size_t)n + i];
+            std::shared_ptr<Feature3D> f3d_ptr = std::make_shared<Feature3D>(
+                tracker->scale * tri[i] / w,
+                tracker->scale * tri[(size_t)n + i] / w,
+                tracker->scale * tri[2 * (size_t)n + i] / w * -1);
+            if (f3d_ptr->getPoint().z < 0) {
+                f3d_ptr->transform(tracker->R[j], tracker->t[j]);
+                tracker->feats3d.push_back(f3d_ptr);
+                next.map[p2_ptr[i]] = std::weak_ptr<Feature3D>(f3d_ptr);
+                src.map[p1_ptr[i]] = std::weak_ptr<Feature3D>(f3d_ptr);
             }
         }
     }

@@ -88,3 +88,20 @@ def test_pnp_solver_adapter_vs_reference(seed):
     assert n0 == n1 == n
     assert np.array_equal(k0, k1) and k0.sum() >= n - len(sc["outliers"]) - 6 and not k0[sc["outliers"]].any()
     assert np.abs(R0 - R1).max() < 1e-7 and np.abs(t0 - t1).max() < 1e-6
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_triangulator_adapter_vs_reference(seed):
+    """triangulator->triangulate(src, next, R, t): OpenCVFivePointTri compiled unchanged from the reference
+    (cv2.findEssentialMat / cv2.recoverPose behind the shim) vs GpuFivePointTri, on the same Frame / OdometryPipeline state:
+    same pose and scale, the same correspondences turned into Feature3D, the same world points."""
+    from harness import twoview_scene
+    sc = twoview_scene.scene(5000 + seed)
+    gt0, gt1 = np.zeros(3), np.array([0.05, -0.02, 0.8 + 0.01 * seed])
+    out = [ref.triangulate(sc["K"], sc["p1"].astype(np.int32), sc["p2"].astype(np.int32), gt0, gt1, impl=i) for i in (0, 1)]
+    (R0, t0, s0, i0, p0), (R1, t1, s1, i1, p1) = out
+    assert s0 == s1 == pytest.approx(np.linalg.norm(gt1))
+    assert np.array_equal(i0, i1) and (i0 >= 0).sum() > 0.5 * len(i0)
+    assert np.abs(R0 - R1).max() < 1e-6 and np.abs(t0 - t1).max() < 1e-6
+    assert np.abs(p0 - p1).max() <= 1e-4 * np.abs(p0).max()                          # float32 storage of Feature3D
+    assert np.abs(R0 - sc["R"]).max() < 3e-2
