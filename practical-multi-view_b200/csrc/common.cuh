@@ -130,9 +130,6 @@ struct pmv_ctx {
     DevBuf pts[4];    // prev_xy, next_xy, status, err
     DevBuf scratch[8];
     PinBuf pin[4];
-    DevBuf mineig_tiles;                       // corners.cu: edge tiles of the last large view (list cached per view size)
-    unsigned long long mineig_tiles_sig = 0;
-    int mineig_tiles_n = 0;
 
     int last_code = 0;   // status of the last failure (entry points that return a handle report it through this)
     int fail(int code, const char *what, cudaError_t e = cudaSuccess)

@@ -87,110 +87,201 @@ __device__ __forceinline__ float mineig_from_sums(int sxx, int sxy, int syy)
     return kf * fmaf(0.5f, Pf, -r);
 }
 
-// Region of the register-resident fast kernel: a warp owns 120 columns x MF_R rows; it runs only where
-// neither the ROI's nor the parent's edge is within reach (the tile kernel covers the rest).
-constexpr int MF_W = 120, MF_R = 16;
-__host__ __device__ __forceinline__ bool mineig_fast_region(int x0, int y0, int rw, int rh)
+// the same closed form from box sums held as exact fp32 integers (Sxx + Syy rounds once, like the int -> float
+// conversion of the integer sum does)
+__device__ __forceinline__ float mineig_from_fsums(float sxx, float sxy, float syy)
 {
-    return rw >= 2 * MF_W && rh >= 2 * MF_R &&   // the host launches the fast kernel under the same condition
-           x0 >= 4 && x0 + MF_W + 4 <= rw && y0 >= 2 && y0 + MF_R + 2 <= rh;
-}
-// is the 64x32 tile of the tile kernel fully inside fast regions?
-__host__ __device__ __forceinline__ bool mineig_tile_is_fast(int tx0, int ty0, int rw, int rh)
-{
-    const int xa = (tx0 / MF_W) * MF_W, xb = ((tx0 + CT_W - 1) / MF_W) * MF_W;
-    for (int y = (ty0 / MF_R) * MF_R; y < ty0 + CT_H; y += MF_R)
-        if (!mineig_fast_region(xa, y, rw, rh) || !mineig_fast_region(xb, y, rw, rh)) return false;
-    return ty0 + CT_H <= rh && tx0 + CT_W <= rw;
+    const float kf = (float)((1.0 / 3060.0) * (1.0 / 3060.0));
+    const float Pf = __fadd_rn(sxx, syy), Qf = __fsub_rn(sxx, syy);
+    const float t = fmaf(0.25f * Qf, Qf, sxy * sxy);
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    return kf * fmaf(0.5f, Pf, -r);
 }
 
-// K4 (interior): lane L holds the 4 pixels at columns x0 - 4 + 4L of the current input row (one aligned
-// 32-bit load), the two missing neighbours come from the adjacent lanes; Sobel, products, the 3x3 box sum
-// and the closed form stay in registers while the warp walks down MF_R + 4 input rows.  Lanes 1..30 write
-// 4 responses each (16-byte stores when the map pitch allows).  HBM traffic: 1 B/px in, 4 B/px out.
-__global__ void __launch_bounds__(256)
-mineig_fast_kernel(ImgView v, float *__restrict__ eig, int *__restrict__ max_bits, size_t vstride, size_t estride)
+// Regions of the register-resident fast kernel: a warp owns 120 columns x R rows (R = 16, 32 or 64, picked per launch).
+// Regions start at column 4 / row 2 and
+// tile the view; the LAST region of a row / column of regions is shifted back so that it ends inside the view (it
+// overlaps its neighbour and writes the same values again).  What is left is a rim of 2 rows at the top and bottom,
+// 4 columns on the left and 4..7 on the right: mineig_rim_kernel.  Small or unaligned views take the tile kernel.
+constexpr int MF_W = 120;
+struct FastGrid {
+    int ok, R, nx, ny, xlast, ylast, xend;   // regions nx x ny of 120 x R outputs; output columns [4, xend), rows [2, rh - 2)
+};
+__host__ __device__ __forceinline__ FastGrid mineig_fast_grid(int rw, int rh, int word_ok, int R)
 {
-    v.ptr += (size_t)blockIdx.z * vstride; eig += (size_t)blockIdx.z * estride; max_bits += blockIdx.z;   // image of a batch
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x0 = blockIdx.x * MF_W, y0 = (blockIdx.y * 8 + warp) * MF_R;
-    if (!v.word_ok || !mineig_fast_region(x0, y0, v.rw, v.rh)) return;      // warp-uniform
-    const int cx = x0 - 4 + 4 * lane;                          // ROI column of byte 0 of this lane's word
-    const uint8_t *g = v.ptr + (ptrdiff_t)(v.ry + y0 - 2 - v.oy) * v.pitch + (v.rx + cx - v.ox);
-    int dxp[2][4], smp[2][4];                                  // horizontal diff / smooth of the two previous rows
-    int Hxx[2][4], Hxy[2][4], Hyy[2][4];                       // horizontal 3-sums of the two previous gradient rows
-    float vmax = 0.f;
-    // all MF_R + 4 input rows are requested up front: independent loads cover the HBM latency
-    unsigned win[MF_R + 4];
+    FastGrid g;
+    g.R = R;
+    g.ok = word_ok && rw >= MF_W + 8 && rh >= R + 4;
+    g.xlast = (rw - MF_W - 4) & ~3; g.ylast = rh - R - 2;
+    g.nx = g.ok ? (g.xlast - 4 + MF_W - 1) / MF_W + 1 : 0;
+    g.ny = g.ok ? (g.ylast - 2 + R - 1) / R + 1 : 0;
+    g.xend = g.xlast + MF_W;
+    return g;
+}
+// Region height: every region reads R + 4 input rows, so taller regions amortise the halo (64: 6 % extra rows, 16: 25 %),
+// as long as there are enough regions to fill the GPU four times over (24 warps per SM): on 8 x 4K, 64-row regions
+// (2.4 waves) lose more to the tail than they save (measured 104 vs 100 us).
+inline int mineig_pick_rows(int rw, int rh, int batch, int sm_count)
+{
+    static const int forced = getenv("PMV_MINEIG_ROWS") ? atoi(getenv("PMV_MINEIG_ROWS")) : 0;
+    if (forced >= 4 && forced % 4 == 0 && rh >= forced + 4) return forced;
+    for (int R = 64; R > 16; R >>= 1) {
+        if (rh < R + 4) continue;
+        const FastGrid g = mineig_fast_grid(rw, rh, 1, R);
+        if ((long long)g.nx * g.ny * batch >= 4LL * 24 * sm_count) return R;
+    }
+    return 16;
+}
+
+// byte k of w as the float 2^23 + b (one PRMT): differences of two such values are the exact pixel differences
+__device__ __forceinline__ float biased_byte(unsigned w, unsigned sel)
+{
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, sel));
+}
+
+// K4 (interior): lane L holds the 4 pixels at columns x0 - 4 + 4L of the current input row (one aligned 32-bit load),
+// the two missing neighbours come from the adjacent lanes; Sobel, products, the 3x3 box sum and the closed form stay in
+// registers while the warp walks down R + 4 input rows.  Lanes 1..30 write 4 responses each (16-byte stores when the
+// map pitch allows).  HBM traffic: 1 B/px in, 4 B/px out.
+// All of it is fp32 arithmetic on EXACT integers (|Sobel| <= 1020, products <= 2^20, box sums <= 9.4e6 < 2^24), so the
+// values are those of the integer formulation bit for bit while the adds run on the FMA pipes instead of the
+// half-rate integer ALU (which bounded the integer version: 22 ALU instructions per pixel), and products fold into
+// the horizontal sums as FFMA.  Vertical 3-sums share the pair h(t-1) + h(t) between two consecutive output rows.
+// State a lane carries from input row to input row (all exact small integers held in fp32).
+struct MfState {
+    float fb1[6], fb2[6];                                      // biased pixels of the previous row / the row before
+    float dx1[4], dx2[4];                                      // horizontal differences of those rows
+    float Hxx[2][4], Hxy[2][4], Hyy[2][4];                     // horizontal 3-sums of the two previous gradient rows
+    float Pxx[4], Pxy[4], Pyy[4];                              // h(t-1) + h(t) of the last even step
+};
+
+// One input row.  STAGE 0: rows 0, 1 of a region (pixels only); 1: rows 2, 3 (gradient row, no output yet);
+// 2: even output step (pair = h(t-1) + h(t), out = h(t-2) + pair); 3: odd output step (out = pair + h(t)).
+template <int STAGE>
+__device__ __forceinline__ void mf_row(MfState &S, unsigned w, float *__restrict__ o, bool writer, bool vec, float &vmax)
+{
+    const unsigned wl = __shfl_up_sync(0xffffffffu, w, 1), wr = __shfl_down_sync(0xffffffffu, w, 1);
+    float fb[6], dx[4];
+    fb[0] = biased_byte(wl, 0x7543); fb[1] = biased_byte(w, 0x7540); fb[2] = biased_byte(w, 0x7541);
+    fb[3] = biased_byte(w, 0x7542); fb[4] = biased_byte(w, 0x7543); fb[5] = biased_byte(wr, 0x7540);
 #pragma unroll
-    for (int it = 0; it < MF_R + 4; it++) win[it] = __ldg(reinterpret_cast<const unsigned *>(g + (ptrdiff_t)it * v.pitch));
+    for (int j = 0; j < 4; j++) dx[j] = fb[j + 2] - fb[j];
+    if (STAGE >= 1) {
+        float dv[6], sx[4], sy[4];
 #pragma unroll
-    for (int it = 0; it < MF_R + 4; it++) {
-        // input row y0 - 2 + it ; after this row: gradient row y0 - 3 + it, box-sum (output) row y0 - 4 + it
-        const unsigned w = win[it];
-        const unsigned wl = __shfl_up_sync(0xffffffffu, w, 1), wr = __shfl_down_sync(0xffffffffu, w, 1);
-        int p[6];
-        p[0] = wl >> 24; p[1] = w & 255; p[2] = (w >> 8) & 255; p[3] = (w >> 16) & 255; p[4] = w >> 24; p[5] = wr & 255;
-        int dx[4], sm[4];
+        for (int k = 0; k < 6; k++) dv[k] = fb[k] - S.fb2[k];
 #pragma unroll
-        for (int j = 0; j < 4; j++) { dx[j] = p[j + 2] - p[j]; sm[j] = p[j] + 2 * p[j + 1] + p[j + 2]; }
-        if (it >= 2) {
-            int xx[4], xy[4], yy[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int sx = dxp[0][j] + 2 * dxp[1][j] + dx[j], sy = sm[j] - smp[0][j];
-                xx[j] = sx * sx; xy[j] = sx * sy; yy[j] = sy * sy;
-            }
-            // horizontal 3-sums; the outer terms come from the neighbouring lanes
-            const int lxx = __shfl_up_sync(0xffffffffu, xx[3], 1), lxy = __shfl_up_sync(0xffffffffu, xy[3], 1),
-                      lyy = __shfl_up_sync(0xffffffffu, yy[3], 1);
-            const int rxx = __shfl_down_sync(0xffffffffu, xx[0], 1), rxy = __shfl_down_sync(0xffffffffu, xy[0], 1),
-                      ryy = __shfl_down_sync(0xffffffffu, yy[0], 1);
-            int hxx[4], hxy[4], hyy[4];
-            hxx[0] = lxx + xx[0] + xx[1]; hxx[1] = xx[0] + xx[1] + xx[2]; hxx[2] = xx[1] + xx[2] + xx[3]; hxx[3] = xx[2] + xx[3] + rxx;
-            hxy[0] = lxy + xy[0] + xy[1]; hxy[1] = xy[0] + xy[1] + xy[2]; hxy[2] = xy[1] + xy[2] + xy[3]; hxy[3] = xy[2] + xy[3] + rxy;
-            hyy[0] = lyy + yy[0] + yy[1]; hyy[1] = yy[0] + yy[1] + yy[2]; hyy[2] = yy[1] + yy[2] + yy[3]; hyy[3] = yy[2] + yy[3] + ryy;
-            if (it >= 4) {
-                const int y = y0 + it - 4;
-                float e[4];
+        for (int j = 0; j < 4; j++) {
+            sx[j] = fmaf(2.f, S.dx1[j], S.dx2[j]) + dx[j];
+            sy[j] = fmaf(2.f, dv[j + 1], dv[j]) + dv[j + 2];
+        }
+        // horizontal 3-sums of the products; the outer terms come from the neighbouring lanes
+        const float xx0 = sx[0] * sx[0], xy0 = sx[0] * sy[0], yy0 = sy[0] * sy[0];
+        const float xx3 = sx[3] * sx[3], xy3 = sx[3] * sy[3], yy3 = sy[3] * sy[3];
+        const float lxx = __shfl_up_sync(0xffffffffu, xx3, 1), lxy = __shfl_up_sync(0xffffffffu, xy3, 1),
+                    lyy = __shfl_up_sync(0xffffffffu, yy3, 1);
+        const float rxx = __shfl_down_sync(0xffffffffu, xx0, 1), rxy = __shfl_down_sync(0xffffffffu, xy0, 1),
+                    ryy = __shfl_down_sync(0xffffffffu, yy0, 1);
+        float hxx[4], hxy[4], hyy[4];
+        {
+            const float a = fmaf(sx[1], sx[1], xx0), b = fmaf(sx[2], sx[2], xx3);
+            hxx[0] = lxx + a; hxx[1] = fmaf(sx[2], sx[2], a); hxx[2] = fmaf(sx[1], sx[1], b); hxx[3] = b + rxx;
+        }
+        {
+            const float a = fmaf(sx[1], sy[1], xy0), b = fmaf(sx[2], sy[2], xy3);
+            hxy[0] = lxy + a; hxy[1] = fmaf(sx[2], sy[2], a); hxy[2] = fmaf(sx[1], sy[1], b); hxy[3] = b + rxy;
+        }
+        {
+            const float a = fmaf(sy[1], sy[1], yy0), b = fmaf(sy[2], sy[2], yy3);
+            hyy[0] = lyy + a; hyy[1] = fmaf(sy[2], sy[2], a); hyy[2] = fmaf(sy[1], sy[1], b); hyy[3] = b + ryy;
+        }
+        if (STAGE >= 2) {
+            float e[4];
+            if (STAGE == 2) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    e[j] = mineig_from_sums(Hxx[0][j] + Hxx[1][j] + hxx[j], Hxy[0][j] + Hxy[1][j] + hxy[j],
-                                            Hyy[0][j] + Hyy[1][j] + hyy[j]);
+                    S.Pxx[j] = S.Hxx[1][j] + hxx[j]; S.Pxy[j] = S.Hxy[1][j] + hxy[j]; S.Pyy[j] = S.Hyy[1][j] + hyy[j];
+                    e[j] = mineig_from_fsums(S.Hxx[0][j] + S.Pxx[j], S.Hxy[0][j] + S.Pxy[j], S.Hyy[0][j] + S.Pyy[j]);
                 }
-                if (lane >= 1 && lane <= 30) {
-                    float *o = eig + (size_t)y * v.rw + cx;
-                    if ((v.rw & 3) == 0) *reinterpret_cast<float4 *>(o) = make_float4(e[0], e[1], e[2], e[3]);
-                    else { o[0] = e[0]; o[1] = e[1]; o[2] = e[2]; o[3] = e[3]; }
-                    vmax = fmaxf(vmax, fmaxf(fmaxf(e[0], e[1]), fmaxf(e[2], e[3])));
-                }
-            }
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                Hxx[0][j] = Hxx[1][j]; Hxy[0][j] = Hxy[1][j]; Hyy[0][j] = Hyy[1][j];
-                Hxx[1][j] = hxx[j]; Hxy[1][j] = hxy[j]; Hyy[1][j] = hyy[j];
+                for (int j = 0; j < 4; j++) e[j] = mineig_from_fsums(S.Pxx[j] + hxx[j], S.Pxy[j] + hxy[j], S.Pyy[j] + hyy[j]);
+            }
+            if (writer) {
+                if (vec) *reinterpret_cast<float4 *>(o) = make_float4(e[0], e[1], e[2], e[3]);
+                else { o[0] = e[0]; o[1] = e[1]; o[2] = e[2]; o[3] = e[3]; }
+                vmax = fmaxf(vmax, fmaxf(fmaxf(e[0], e[1]), fmaxf(e[2], e[3])));
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) { dxp[0][j] = dxp[1][j]; smp[0][j] = smp[1][j]; dxp[1][j] = dx[j]; smp[1][j] = sm[j]; }
+        for (int j = 0; j < 4; j++) {
+            S.Hxx[0][j] = S.Hxx[1][j]; S.Hxy[0][j] = S.Hxy[1][j]; S.Hyy[0][j] = S.Hyy[1][j];
+            S.Hxx[1][j] = hxx[j]; S.Hxy[1][j] = hxy[j]; S.Hyy[1][j] = hyy[j];
+        }
     }
-    for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+#pragma unroll
+    for (int k = 0; k < 6; k++) { S.fb2[k] = S.fb1[k]; S.fb1[k] = fb[k]; }
+#pragma unroll
+    for (int j = 0; j < 4; j++) { S.dx2[j] = S.dx1[j]; S.dx1[j] = dx[j]; }
+}
+
+// The row loop is a ROLLED loop of four rows per trip (the state rotates with period two, so a four-row body needs no
+// register moves) with the next four input rows requested at the top of each trip: the fully unrolled form of this
+// kernel (R + 4 rows, ~18 k instructions) spent 0.85 stall cycles per issue waiting for instruction fetch.
+__global__ void __launch_bounds__(256, 3)
+mineig_fast_kernel(ImgView v, float *__restrict__ eig, int *__restrict__ max_bits, size_t vstride, size_t estride, int R)
+{
+    v.ptr += (size_t)blockIdx.z * vstride; eig += (size_t)blockIdx.z * estride; max_bits += blockIdx.z;   // image of a batch
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const FastGrid fg = mineig_fast_grid(v.rw, v.rh, v.word_ok, R);
+    const int ky = blockIdx.y * 8 + warp;
+    if (!fg.ok || ky >= fg.ny) return;                                      // warp-uniform
+    const int x0 = min(4 + (int)blockIdx.x * MF_W, fg.xlast), y0 = min(2 + ky * R, fg.ylast);
+    const int cx = x0 - 4 + 4 * lane;                          // ROI column of byte 0 of this lane's word
+    const uint8_t *g = v.ptr + (ptrdiff_t)(v.ry + y0 - 2 - v.oy) * v.pitch + (v.rx + cx - v.ox);
+    const bool writer = lane >= 1 && lane <= 30;
+    const bool vec = (v.rw & 3) == 0;
+    float *o = eig + (size_t)y0 * v.rw + cx;                   // output row y0 belongs to input row it = 4
+    MfState S;
+    float vmax = 0.f;
+    unsigned cur[4], nxt[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) cur[k] = __ldg(reinterpret_cast<const unsigned *>(g + (ptrdiff_t)k * v.pitch));
+#pragma unroll
+    for (int k = 0; k < 4; k++) nxt[k] = __ldg(reinterpret_cast<const unsigned *>(g + (ptrdiff_t)(4 + k) * v.pitch));
+    mf_row<0>(S, cur[0], o, writer, vec, vmax);
+    mf_row<0>(S, cur[1], o, writer, vec, vmax);
+    mf_row<1>(S, cur[2], o, writer, vec, vmax);
+    mf_row<1>(S, cur[3], o, writer, vec, vmax);
+#pragma unroll 1
+    for (int it = 4; it < R + 4; it += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) cur[k] = nxt[k];
+        if (it + 4 < R + 4) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) nxt[k] = __ldg(reinterpret_cast<const unsigned *>(g + (ptrdiff_t)(it + 4 + k) * v.pitch));
+        }
+        mf_row<2>(S, cur[0], o, writer, vec, vmax);
+        mf_row<3>(S, cur[1], o + v.rw, writer, vec, vmax);
+        mf_row<2>(S, cur[2], o + 2 * (size_t)v.rw, writer, vec, vmax);
+        mf_row<3>(S, cur[3], o + 3 * (size_t)v.rw, writer, vec, vmax);
+        o += 4 * (size_t)v.rw;
+    }
+    for (int o2 = 16; o2; o2 >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o2));
     if (lane == 0 && vmax > 0.f) atomicMax(max_bits, __float_as_int(vmax));
 }
 
 // K4: eig(y,x) over the ROI + global max (atomicMax on the bits of a non-negative float)
 __global__ void __launch_bounds__(256)
-mineig_kernel(ImgView v, float *__restrict__ eig, int *__restrict__ max_bits, size_t vstride, size_t estride,
-              const ushort2 *__restrict__ tiles)
+mineig_kernel(ImgView v, float *__restrict__ eig, int *__restrict__ max_bits, size_t vstride, size_t estride)
 {
     v.ptr += (size_t)blockIdx.z * vstride; eig += (size_t)blockIdx.z * estride; max_bits += blockIdx.z;
     __shared__ __align__(16) uint8_t s_px[CS_H][CS_P];
     __shared__ int s_d[CD_H][CD_W];   // Sobel (sx | sy << 16) at ROI coords (ty0-1+r, tx0-1+c)
     __shared__ float s_red[8];
     const int tid = threadIdx.x;
-    // tiles != nullptr: the launch enumerates only the tiles the register-resident kernel does not cover
-    const int tx0 = (tiles ? tiles[blockIdx.x].x : blockIdx.x) * CT_W, ty0 = (tiles ? tiles[blockIdx.x].y : blockIdx.y) * CT_H;
-    if (v.word_ok && mineig_tile_is_fast(tx0, ty0, v.rw, v.rh)) return;   // written by mineig_fast_kernel
+    const int tx0 = blockIdx.x * CT_W, ty0 = blockIdx.y * CT_H;
     stage_tile(s_px, v, tx0, ty0, tid);
     __syncthreads();
     // Sobel at halo-1 positions; positions outside the ROI take the value of their reflect-101
@@ -240,6 +331,67 @@ mineig_kernel(ImgView v, float *__restrict__ eig, int *__restrict__ max_bits, si
     }
     vmax = block_max_f(vmax, s_red);
     if (tid == 0 && vmax > 0.f) atomicMax(max_bits, __float_as_int(vmax));
+}
+
+// reflect-101 for an overshoot of at most len - 1 (no loop)
+__device__ __forceinline__ int reflect101_near(int p, int len)
+{
+    p = p < 0 ? -p : p;
+    return p >= len ? 2 * (len - 1) - p : p;
+}
+// 3-tap box weights at position q of an isolated image of `len` samples with reflect-101 borders
+__device__ __forceinline__ void rim_weights(int q, int len, int w[3])
+{
+    w[0] = w[1] = w[2] = 1;
+    if (q == 0) { w[0] = 0; w[2] = 2; }
+    if (q == len - 1) { w[2] = 0; w[0] = w[0] ? 2 : 0; }      // len >= 3 here, so both cannot apply
+}
+
+// K4 (rim of a view whose interior the register-resident kernel covers): one thread per pixel, everything from global
+// memory.  Sobel taps read the PARENT (reflect-101 at its edges only); gradient positions outside the view take the
+// value of their reflect-101 image inside it (the covariance image is isolated) -- the tile kernel's rules.
+__global__ void __launch_bounds__(256)
+mineig_rim_kernel(ImgView v, float *__restrict__ eig, int *__restrict__ max_bits, size_t vstride, size_t estride, int xend)
+{
+    v.ptr += (size_t)blockIdx.z * vstride; eig += (size_t)blockIdx.z * estride; max_bits += blockIdx.z;
+    const int wr = v.rw - xend, side = 4 + wr;                 // rim columns per interior row: 4 left + wr right
+    const int n_tb = 4 * v.rw, n = n_tb + (v.rh - 4) * side;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    float e = 0.f;
+    if (i < n) {
+        int x, y;
+        if (i < n_tb) { const int r = i / v.rw; x = i - r * v.rw; y = r < 2 ? r : v.rh - 4 + r; }
+        else { const int k = i - n_tb, r = k / side, c = k - r * side; y = 2 + r; x = c < 4 ? c : xend + c - 4; }
+        // the 5 x 5 parent neighbourhood once (25 independent loads), then the nine Sobel responses from registers
+        int p[5][5];
+#pragma unroll
+        for (int a = 0; a < 5; a++) {
+            const int py = reflect101_near(v.ry + y - 2 + a, v.full_rows) - v.oy;
+#pragma unroll
+            for (int b = 0; b < 5; b++) {
+                const int px = reflect101_near(v.rx + x - 2 + b, v.full_cols) - v.ox;
+                p[a][b] = __ldg(v.ptr + (ptrdiff_t)py * v.pitch + px);
+            }
+        }
+        // gradient positions outside the view fold back onto their reflect-101 image inside it: weights (0,1,2) / (2,1,0)
+        // on the view's first / last row or column, (1,1,1) elsewhere
+        int wr[3], wc[3];
+        rim_weights(y, v.rh, wr); rim_weights(x, v.rw, wc);
+        int sxx = 0, sxy = 0, syy = 0;
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                const int sx = (p[a][b + 2] - p[a][b]) + 2 * (p[a + 1][b + 2] - p[a + 1][b]) + (p[a + 2][b + 2] - p[a + 2][b]);
+                const int sy = (p[a + 2][b] - p[a][b]) + 2 * (p[a + 2][b + 1] - p[a][b + 1]) + (p[a + 2][b + 2] - p[a][b + 2]);
+                const int wgt = wr[a] * wc[b];
+                sxx += wgt * sx * sx; sxy += wgt * sx * sy; syy += wgt * sy * sy;
+            }
+        e = mineig_from_sums(sxx, sxy, syy);
+        eig[(size_t)y * v.rw + x] = e;
+    }
+    for (int o = 16; o; o >>= 1) e = fmaxf(e, __shfl_xor_sync(0xffffffffu, e, o));
+    if ((threadIdx.x & 31) == 0 && e > 0.f) atomicMax(max_bits, __float_as_int(e));
 }
 
 // K6a: threshold + 3x3 NMS + unordered compaction of (response bits, index) records.  A CTA sweeps a
@@ -428,6 +580,22 @@ gftt_select_kernel(const Rec128 *__restrict__ recs, int n, int rows, int cols, c
 }
 
 // ------------------------------------------------------------------ K5 reference ShiTomasi
+// min(lambda_1, lambda_2) of the blurred Harris matrix from the box sums of (2 gx)^2, (2 gx)(2 gy), (2 gy)^2 (exact
+// integers): / 4 is exact, then the reference's fp64 expression in its own order, every operation rounded to nearest
+// (ShiTomasiFeatureExtractor.cpp:62-71, Frame.cpp:119-138 blur = sum * (1/9))
+__device__ __forceinline__ double shitomasi_from_sums(double sxx, double sxy, double syy)
+{
+    const double ninth = 1.0 / 9;
+    const double Ixx = __dmul_rn(sxx * 0.25, ninth), Iyy = __dmul_rn(syy * 0.25, ninth), Ixy = __dmul_rn(sxy * 0.25, ninth);
+    const double B = __dsub_rn(-Ixx, Iyy);
+    const double C = __dsub_rn(__dmul_rn(Ixx, Iyy), __dmul_rn(Ixy, Ixy));
+    const double disc = __dsub_rn(__dmul_rn(B, B), __dmul_rn(4.0, C));
+    const double sq = __dsqrt_rn(disc);
+    const double l1 = __dmul_rn(__dadd_rn(-B, sq), 0.5);
+    const double l2 = __dmul_rn(__dsub_rn(-B, sq), 0.5);
+    return (l2 < l1) ? l2 : l1;  // std::min(l1, l2)
+}
+
 // R(y,x) in fp64 + global max (bits of a non-negative double).  The view is isolated (fresh Mats in
 // the reference): gradient zero on the rim, blur reflects at the view's own edges, last column 0.
 __global__ void __launch_bounds__(256)
@@ -473,26 +641,14 @@ shitomasi_response_kernel(ImgView v, int signed_quirk, double *__restrict__ R,
     hsum(tyb + 0, hxx[0], hxy[0], hyy[0]);
     hsum(tyb + 1, hxx[1], hxy[1], hyy[1]);
     double vmax = 0.0;
-    const double ninth = 1.0 / 9;
 #pragma unroll
     for (int r = 0; r < CT_R; r++) {
         hsum(tyb + r + 2, hxx[(r + 2) % 3], hxy[(r + 2) % 3], hyy[(r + 2) % 3]);
         const int y = ty0 + tyb + r;
         if (x < v.rw && y < v.rh) {
-            double out = 0.0;
-            if (x < v.rw - 1) {  // ShiTomasiFeatureExtractor.cpp:58 skips the last column
-                // sums of (2g)^2 are exact integers; /4 is exact; then the reference's fp64 order
-                double Ixx = __dmul_rn((double)(hxx[0] + hxx[1] + hxx[2]) * 0.25, ninth);
-                double Iyy = __dmul_rn((double)(hyy[0] + hyy[1] + hyy[2]) * 0.25, ninth);
-                double Ixy = __dmul_rn((double)(hxy[0] + hxy[1] + hxy[2]) * 0.25, ninth);
-                double B = __dsub_rn(-Ixx, Iyy);
-                double C = __dsub_rn(__dmul_rn(Ixx, Iyy), __dmul_rn(Ixy, Ixy));
-                double disc = __dsub_rn(__dmul_rn(B, B), __dmul_rn(4.0, C));
-                double sq = __dsqrt_rn(disc);
-                double l1 = __dmul_rn(__dadd_rn(-B, sq), 0.5);
-                double l2 = __dmul_rn(__dsub_rn(-B, sq), 0.5);
-                out = (l2 < l1) ? l2 : l1;  // std::min(l1, l2)
-            }
+            // ShiTomasiFeatureExtractor.cpp:58 skips the last column
+            const double out = x < v.rw - 1 ? shitomasi_from_sums((double)(hxx[0] + hxx[1] + hxx[2]), (double)(hxy[0] + hxy[1] + hxy[2]),
+                                                                   (double)(hyy[0] + hyy[1] + hyy[2])) : 0.0;
             R[(size_t)y * v.rw + x] = out;
             if (out > vmax) vmax = out;
         }
@@ -504,6 +660,170 @@ shitomasi_response_kernel(ImgView v, int signed_quirk, double *__restrict__ R,
         for (int k = 1; k < 8; k++) vmax = fmax(vmax, s_redd[k]);
         if (vmax > 0.0) atomicMax(max_bits, (unsigned long long)__double_as_longlong(vmax));
     }
+}
+
+// K5 (interior), the register-resident scheme of mineig_fast_kernel for the reference's response: central differences
+// 2 gx = right - left, 2 gy = down - up (Frame.cpp:63-84) as exact fp32 integers, products folded into the horizontal
+// 3-sums, vertical 3-sums sharing a pair between two output rows; only the closed form runs in fp64.
+struct SfState {
+    float fb1[6], fb2[6];                                      // biased pixels of the previous row / the row before
+    float Hxx[2][4], Hxy[2][4], Hyy[2][4];
+    float Pxx[4], Pxy[4], Pyy[4];
+};
+
+template <int STAGE>
+__device__ __forceinline__ void sf_row(SfState &S, unsigned w, unsigned flip, double *__restrict__ o, bool writer, bool vec, double &vmax)
+{
+    w ^= flip;                                                 // signed-char quirk: b ^ 0x80 = (signed char)b + 128
+    const unsigned wl = __shfl_up_sync(0xffffffffu, w, 1), wr = __shfl_down_sync(0xffffffffu, w, 1);
+    float fb[6];
+    fb[0] = biased_byte(wl, 0x7543); fb[1] = biased_byte(w, 0x7540); fb[2] = biased_byte(w, 0x7541);
+    fb[3] = biased_byte(w, 0x7542); fb[4] = biased_byte(w, 0x7543); fb[5] = biased_byte(wr, 0x7540);
+    if (STAGE >= 1) {
+        float gx[4], gy[4];                                    // gradient row = the previous input row
+#pragma unroll
+        for (int j = 0; j < 4; j++) { gx[j] = S.fb1[j + 2] - S.fb1[j]; gy[j] = fb[j + 1] - S.fb2[j + 1]; }
+        const float xx0 = gx[0] * gx[0], xy0 = gx[0] * gy[0], yy0 = gy[0] * gy[0];
+        const float xx3 = gx[3] * gx[3], xy3 = gx[3] * gy[3], yy3 = gy[3] * gy[3];
+        const float lxx = __shfl_up_sync(0xffffffffu, xx3, 1), lxy = __shfl_up_sync(0xffffffffu, xy3, 1),
+                    lyy = __shfl_up_sync(0xffffffffu, yy3, 1);
+        const float rxx = __shfl_down_sync(0xffffffffu, xx0, 1), rxy = __shfl_down_sync(0xffffffffu, xy0, 1),
+                    ryy = __shfl_down_sync(0xffffffffu, yy0, 1);
+        float hxx[4], hxy[4], hyy[4];
+        {
+            const float a = fmaf(gx[1], gx[1], xx0), b = fmaf(gx[2], gx[2], xx3);
+            hxx[0] = lxx + a; hxx[1] = fmaf(gx[2], gx[2], a); hxx[2] = fmaf(gx[1], gx[1], b); hxx[3] = b + rxx;
+        }
+        {
+            const float a = fmaf(gx[1], gy[1], xy0), b = fmaf(gx[2], gy[2], xy3);
+            hxy[0] = lxy + a; hxy[1] = fmaf(gx[2], gy[2], a); hxy[2] = fmaf(gx[1], gy[1], b); hxy[3] = b + rxy;
+        }
+        {
+            const float a = fmaf(gy[1], gy[1], yy0), b = fmaf(gy[2], gy[2], yy3);
+            hyy[0] = lyy + a; hyy[1] = fmaf(gy[2], gy[2], a); hyy[2] = fmaf(gy[1], gy[1], b); hyy[3] = b + ryy;
+        }
+        if (STAGE >= 2) {
+            double e[4];
+            if (STAGE == 2) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    S.Pxx[j] = S.Hxx[1][j] + hxx[j]; S.Pxy[j] = S.Hxy[1][j] + hxy[j]; S.Pyy[j] = S.Hyy[1][j] + hyy[j];
+                    e[j] = shitomasi_from_sums((double)(S.Hxx[0][j] + S.Pxx[j]), (double)(S.Hxy[0][j] + S.Pxy[j]), (double)(S.Hyy[0][j] + S.Pyy[j]));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    e[j] = shitomasi_from_sums((double)(S.Pxx[j] + hxx[j]), (double)(S.Pxy[j] + hxy[j]), (double)(S.Pyy[j] + hyy[j]));
+            }
+            if (writer) {
+                if (vec) {
+                    *reinterpret_cast<double2 *>(o) = make_double2(e[0], e[1]);
+                    *reinterpret_cast<double2 *>(o + 2) = make_double2(e[2], e[3]);
+                } else { o[0] = e[0]; o[1] = e[1]; o[2] = e[2]; o[3] = e[3]; }
+                vmax = fmax(vmax, fmax(fmax(e[0], e[1]), fmax(e[2], e[3])));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            S.Hxx[0][j] = S.Hxx[1][j]; S.Hxy[0][j] = S.Hxy[1][j]; S.Hyy[0][j] = S.Hyy[1][j];
+            S.Hxx[1][j] = hxx[j]; S.Hxy[1][j] = hxy[j]; S.Hyy[1][j] = hyy[j];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) { S.fb2[k] = S.fb1[k]; S.fb1[k] = fb[k]; }
+}
+
+__global__ void __launch_bounds__(256, 3)
+shitomasi_fast_kernel(ImgView v, int signed_quirk, double *__restrict__ Rm, unsigned long long *__restrict__ max_bits, size_t vstride,
+                      size_t rstride, int R)
+{
+    v.ptr += (size_t)blockIdx.z * vstride; Rm += (size_t)blockIdx.z * rstride; max_bits += blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const FastGrid fg = mineig_fast_grid(v.rw, v.rh, v.word_ok, R);
+    const int ky = blockIdx.y * 8 + warp;
+    if (!fg.ok || ky >= fg.ny) return;                                      // warp-uniform
+    const int x0 = min(4 + (int)blockIdx.x * MF_W, fg.xlast), y0 = min(2 + ky * R, fg.ylast);
+    const int cx = x0 - 4 + 4 * lane;
+    const uint8_t *g = v.ptr + (ptrdiff_t)(v.ry + y0 - 2 - v.oy) * v.pitch + (v.rx + cx - v.ox);
+    const bool writer = lane >= 1 && lane <= 30;
+    const bool vec = (v.rw & 1) == 0;
+    const unsigned flip = signed_quirk ? 0x80808080u : 0u;
+    double *o = Rm + (size_t)y0 * v.rw + cx;
+    SfState S;
+    double vmax = 0.0;
+    unsigned cur[4], nxt[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) cur[k] = __ldg(reinterpret_cast<const unsigned *>(g + (ptrdiff_t)k * v.pitch));
+#pragma unroll
+    for (int k = 0; k < 4; k++) nxt[k] = __ldg(reinterpret_cast<const unsigned *>(g + (ptrdiff_t)(4 + k) * v.pitch));
+    sf_row<0>(S, cur[0], flip, o, writer, vec, vmax);
+    sf_row<0>(S, cur[1], flip, o, writer, vec, vmax);
+    sf_row<1>(S, cur[2], flip, o, writer, vec, vmax);
+    sf_row<1>(S, cur[3], flip, o, writer, vec, vmax);
+#pragma unroll 1
+    for (int it = 4; it < R + 4; it += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) cur[k] = nxt[k];
+        if (it + 4 < R + 4) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) nxt[k] = __ldg(reinterpret_cast<const unsigned *>(g + (ptrdiff_t)(it + 4 + k) * v.pitch));
+        }
+        sf_row<2>(S, cur[0], flip, o, writer, vec, vmax);
+        sf_row<3>(S, cur[1], flip, o + v.rw, writer, vec, vmax);
+        sf_row<2>(S, cur[2], flip, o + 2 * (size_t)v.rw, writer, vec, vmax);
+        sf_row<3>(S, cur[3], flip, o + 3 * (size_t)v.rw, writer, vec, vmax);
+        o += 4 * (size_t)v.rw;
+    }
+    for (int o2 = 16; o2; o2 >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o2));
+    if (lane == 0 && vmax > 0.0) atomicMax(max_bits, (unsigned long long)__double_as_longlong(vmax));
+}
+
+// K5 (rim of a view whose interior shitomasi_fast_kernel covers): one thread per pixel.  The view is isolated: gradients
+// are zero on its outermost rows / columns, the blur reflects (101) at the view's own edges, the last column stays 0.
+__global__ void __launch_bounds__(256)
+shitomasi_rim_kernel(ImgView v, int signed_quirk, double *__restrict__ Rm, unsigned long long *__restrict__ max_bits, size_t vstride,
+                     size_t rstride, int xend)
+{
+    v.ptr += (size_t)blockIdx.z * vstride; Rm += (size_t)blockIdx.z * rstride; max_bits += blockIdx.z;
+    const int wr_ = v.rw - xend, side = 4 + wr_;
+    const int n_tb = 4 * v.rw, n = n_tb + (v.rh - 4) * side;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    double e = 0.0;
+    if (i < n) {
+        int x, y;
+        if (i < n_tb) { const int r = i / v.rw; x = i - r * v.rw; y = r < 2 ? r : v.rh - 4 + r; }
+        else { const int k = i - n_tb, r = k / side, c = k - r * side; y = 2 + r; x = c < 4 ? c : xend + c - 4; }
+        if (x < v.rw - 1) {
+            int p[5][5];
+#pragma unroll
+            for (int a = 0; a < 5; a++) {
+                const int py = min(max(y - 2 + a, 0), v.rh - 1) + v.ry - v.oy;     // taps of interior gradients never leave the view
+#pragma unroll
+                for (int b = 0; b < 5; b++) {
+                    const int px = min(max(x - 2 + b, 0), v.rw - 1) + v.rx - v.ox;
+                    const int q = __ldg(v.ptr + (ptrdiff_t)py * v.pitch + px);
+                    p[a][b] = signed_quirk ? (int)(signed char)q : q;
+                }
+            }
+            int wr[3], wc[3];
+            rim_weights(y, v.rh, wr); rim_weights(x, v.rw, wc);
+            int sxx = 0, sxy = 0, syy = 0;
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) {
+                    const int gy_ = y - 1 + a, gx_ = x - 1 + b;                     // gradient position (inside the view wherever its weight is not 0)
+                    const bool inner = gy_ >= 1 && gy_ < v.rh - 1 && gx_ >= 1 && gx_ < v.rw - 1;   // Frame.cpp:63-84: rim gradients stay zero
+                    const int gx2 = inner ? p[a + 1][b + 2] - p[a + 1][b] : 0, gy2 = inner ? p[a + 2][b + 1] - p[a][b + 1] : 0;
+                    const int wgt = wr[a] * wc[b];
+                    sxx += wgt * gx2 * gx2; sxy += wgt * gx2 * gy2; syy += wgt * gy2 * gy2;
+                }
+            e = shitomasi_from_sums((double)sxx, (double)sxy, (double)syy);
+        }
+        Rm[(size_t)y * v.rw + x] = e;
+    }
+    for (int o = 16; o; o >>= 1) e = fmax(e, __shfl_xor_sync(0xffffffffu, e, o));
+    if ((threadIdx.x & 31) == 0 && e > 0.0) atomicMax(max_bits, (unsigned long long)__double_as_longlong(e));
 }
 
 // K6 (reference flavour): every pixel with R > rmax*quality, no NMS
@@ -561,38 +881,65 @@ int check_roi(pmv_ctx *ctx, const void *base, int full_rows, int full_cols, int 
     return PMV_OK;
 }
 
+// fp64 response map of the reference extractor + its maximum (the caller zeroes d_max): interior by the register-resident
+// kernel, rim by one thread per pixel on the side stream; small or unaligned views by the tile kernel
+int run_shitomasi(pmv_ctx *ctx, const ImgView &v, int signed_quirk, double *d_R, unsigned long long *d_max, cudaStream_t s, int batch = 1,
+                  size_t vstride = 0, size_t rstride = 0)
+{
+    const FastGrid fg = mineig_fast_grid(v.rw, v.rh, v.word_ok, mineig_pick_rows(v.rw, v.rh, batch, ctx->sm_count));
+    if (fg.ok) {
+        const bool fork = ctx->copy_stream != nullptr && ctx->copy_stream != s && ctx->ev[2] != nullptr && ctx->ev[3] != nullptr;
+        cudaStream_t se = fork ? ctx->copy_stream : s;
+        if (fork) {
+            PMV_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
+            PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(se, ctx->ev[2], 0));
+        }
+        const int n_rim = 4 * v.rw + (v.rh - 4) * (4 + v.rw - fg.xend);
+        shitomasi_rim_kernel<<<dim3((n_rim + 255) / 256, 1, batch), 256, 0, se>>>(v, signed_quirk, d_R, d_max, vstride, rstride, fg.xend);
+        PMV_LAUNCH_CHECK(ctx, "shitomasi_rim_kernel");
+        shitomasi_fast_kernel<<<dim3(fg.nx, (fg.ny + 7) / 8, batch), 256, 0, s>>>(v, signed_quirk, d_R, d_max, vstride, rstride, fg.R);
+        PMV_LAUNCH_CHECK(ctx, "shitomasi_fast_kernel");
+        if (fork) {
+            PMV_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], se));
+            PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev[3], 0));
+        }
+    } else {
+        dim3 grid((v.rw + CT_W - 1) / CT_W, (v.rh + CT_H - 1) / CT_H, batch);
+        shitomasi_response_kernel<<<grid, 256, 0, s>>>(v, signed_quirk, d_R, d_max, vstride, rstride);
+        PMV_LAUNCH_CHECK(ctx, "shitomasi_response_kernel");
+    }
+    return PMV_OK;
+}
+
 int run_mineig(pmv_ctx *ctx, const ImgView &v, float *d_eig, int *d_max, cudaStream_t s, int batch = 1, size_t vstride = 0, size_t estride = 0)
 {
     ProfScope ps(ctx, PMV_PHASE_RESPONSE, s);
     PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_max, 0, sizeof(int) * batch, s));
-    if (v.word_ok && v.rw >= 2 * MF_W && v.rh >= 2 * MF_R) {   // an interior exists: register-resident kernel (same predicate on device)
-        dim3 gridf((v.rw + MF_W - 1) / MF_W, (v.rh + 8 * MF_R - 1) / (8 * MF_R), batch);
-        mineig_fast_kernel<<<gridf, 256, 0, s>>>(v, d_eig, d_max, vstride, estride);
-        PMV_LAUNCH_CHECK(ctx, "mineig_fast_kernel");
-    }
-    dim3 grid((v.rw + CT_W - 1) / CT_W, (v.rh + CT_H - 1) / CT_H, batch);   // edges (and small ROIs): tile kernel
-    const ushort2 *tiles = nullptr;
-    if (v.word_ok && v.rw >= 2 * MF_W && v.rh >= 2 * MF_R && grid.x * grid.y > 64) {
-        // large view: launch only the edge tiles (most of a 4K frame belongs to the register-resident kernel).  The
-        // list depends on the view size alone and is cached in the context.
-        const unsigned long long sig = ((unsigned long long)v.rw << 32) | (unsigned)v.rh;
-        if (ctx->mineig_tiles_sig != sig) {
-            std::vector<ushort2> h;
-            for (unsigned ty = 0; ty < grid.y; ty++)
-                for (unsigned tx = 0; tx < grid.x; tx++)
-                    if (!mineig_tile_is_fast(tx * CT_W, ty * CT_H, v.rw, v.rh)) h.push_back(make_ushort2((unsigned short)tx, (unsigned short)ty));
-            cudaError_t e = ctx->mineig_tiles.reserve(h.size() * sizeof(ushort2) + 16);
-            if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "edge tile list", e);
-            PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));   // the list may still be in use by an earlier launch
-            PMV_CUDA_TRY(ctx, cudaMemcpy(ctx->mineig_tiles.p, h.data(), h.size() * sizeof(ushort2), cudaMemcpyHostToDevice));
-            ctx->mineig_tiles_sig = sig;
-            ctx->mineig_tiles_n = (int)h.size();
+    const FastGrid fg = mineig_fast_grid(v.rw, v.rh, v.word_ok, mineig_pick_rows(v.rw, v.rh, batch, ctx->sm_count));
+    if (fg.ok) {
+        // rim (2 rows / 4..7 columns, one thread per pixel) on the side stream while the register-resident kernel covers
+        // the interior: disjoint pixels, both feed the atomic maximum
+        const bool fork = ctx->copy_stream != nullptr && ctx->copy_stream != s && ctx->ev[2] != nullptr && ctx->ev[3] != nullptr;
+        cudaStream_t se = fork ? ctx->copy_stream : s;
+        if (fork) {
+            PMV_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
+            PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(se, ctx->ev[2], 0));
         }
-        tiles = ctx->mineig_tiles.as<ushort2>();
-        grid = dim3(ctx->mineig_tiles_n, 1, batch);
+        const int n_rim = 4 * v.rw + (v.rh - 4) * (4 + v.rw - fg.xend);
+        mineig_rim_kernel<<<dim3((n_rim + 255) / 256, 1, batch), 256, 0, se>>>(v, d_eig, d_max, vstride, estride, fg.xend);
+        PMV_LAUNCH_CHECK(ctx, "mineig_rim_kernel");
+        dim3 gridf(fg.nx, (fg.ny + 7) / 8, batch);
+        mineig_fast_kernel<<<gridf, 256, 0, s>>>(v, d_eig, d_max, vstride, estride, fg.R);
+        PMV_LAUNCH_CHECK(ctx, "mineig_fast_kernel");
+        if (fork) {
+            PMV_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], se));
+            PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev[3], 0));
+        }
+    } else {
+        dim3 grid((v.rw + CT_W - 1) / CT_W, (v.rh + CT_H - 1) / CT_H, batch);   // small / unaligned views: tile kernel
+        mineig_kernel<<<grid, 256, 0, s>>>(v, d_eig, d_max, vstride, estride);
+        PMV_LAUNCH_CHECK(ctx, "mineig_kernel");
     }
-    if (grid.x > 0) mineig_kernel<<<grid, 256, 0, s>>>(v, d_eig, d_max, vstride, estride, tiles);
-    PMV_LAUNCH_CHECK(ctx, "mineig_kernel");
     return PMV_OK;
 }
 
@@ -721,11 +1068,7 @@ PMV_API int pmv_shitomasi_response_batched_dev(pmv_ctx *ctx, const uint8_t *d_im
     v.word_ok = (((uintptr_t)d_imgs | (uintptr_t)step | (uintptr_t)img_stride) & 3) == 0;
     ProfScope ps(ctx, PMV_PHASE_RESPONSE, s);
     PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_max, 0, sizeof(double) * batch, s));
-    dim3 grid((cols + CT_W - 1) / CT_W, (rows + CT_H - 1) / CT_H, batch);
-    shitomasi_response_kernel<<<grid, 256, 0, s>>>(v, signed_quirk, d_R, reinterpret_cast<unsigned long long *>(d_max), img_stride,
-                                                   (size_t)rows * cols);
-    PMV_LAUNCH_CHECK(ctx, "shitomasi_response_kernel");
-    return PMV_OK;
+    return run_shitomasi(ctx, v, signed_quirk, d_R, reinterpret_cast<unsigned long long *>(d_max), s, batch, img_stride, (size_t)rows * cols);
 }
 
 PMV_API int pmv_gftt(pmv_ctx *ctx, const uint8_t *base, int full_rows, int full_cols, int step,
@@ -773,10 +1116,8 @@ PMV_API int pmv_shitomasi_response(pmv_ctx *ctx, const uint8_t *img, int rows, i
     if (e == cudaSuccess) e = ctx->scratch[1].reserve(256);
     if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "shitomasi map", e);
     PMV_CUDA_TRY(ctx, cudaMemsetAsync(ctx->scratch[1].p, 0, 16, s));
-    dim3 grid((cols + CT_W - 1) / CT_W, (rows + CT_H - 1) / CT_H);
-    shitomasi_response_kernel<<<grid, 256, 0, s>>>(v, signed_quirk, ctx->scratch[0].as<double>(),
-                                                   ctx->scratch[1].as<unsigned long long>(), 0, 0);
-    PMV_LAUNCH_CHECK(ctx, "shitomasi_response_kernel");
+    rc = run_shitomasi(ctx, v, signed_quirk, ctx->scratch[0].as<double>(), ctx->scratch[1].as<unsigned long long>(), s);
+    if (rc) return rc;
     PMV_CUDA_TRY(ctx, cudaMemcpyAsync(R, ctx->scratch[0].p, n * 8, cudaMemcpyDeviceToHost, s));
     PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
     return PMV_OK;
@@ -809,9 +1150,8 @@ PMV_API int pmv_shitomasi(pmv_ctx *ctx, const uint8_t *img, int rows, int cols, 
     PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_max, 0, 16, s));
     {
         ProfScope ps(ctx, PMV_PHASE_RESPONSE, s);
-        dim3 grid((cols + CT_W - 1) / CT_W, (rows + CT_H - 1) / CT_H);
-        shitomasi_response_kernel<<<grid, 256, 0, s>>>(v, signed_quirk, d_R, d_max, 0, 0);
-        PMV_LAUNCH_CHECK(ctx, "shitomasi_response_kernel");
+        rc = run_shitomasi(ctx, v, signed_quirk, d_R, d_max, s);
+        if (rc) return rc;
     }
     ProfScope ps(ctx, PMV_PHASE_SELECT, s);
     shitomasi_candidates_kernel<<<(int)((npx + 255) / 256), 256, 0, s>>>(d_R, (int)npx, d_max, quality, d_rec, d_count, (int)npx);

@@ -46,7 +46,6 @@ PMV_API void pmv_destroy(pmv_ctx *c)
     for (auto &b : c->pts) b.release();
     for (auto &b : c->scratch) b.release();
     for (auto &b : c->pin) b.release();
-    c->mineig_tiles.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->chunk_ev) cudaEventDestroy(e);
     for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
