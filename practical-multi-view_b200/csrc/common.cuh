@@ -98,6 +98,8 @@ struct pmv_ctx {
     cudaStream_t stream = nullptr;      // stream work is enqueued on
     cudaStream_t own_stream = nullptr;  // created by pmv_create
     cudaStream_t copy_stream = nullptr; // second stream for chunked upload overlap
+    cudaStream_t d2h_stream = nullptr;  // third stream: chunked result download (created on first use)
+    cudaStream_t aux_stream = nullptr;  // second compute stream of the chunked host paths (created on first use)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> chunk_ev;  // upload/compute hand-off events of the chunked host paths
     std::string err;

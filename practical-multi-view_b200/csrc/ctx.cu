@@ -52,6 +52,8 @@ PMV_API void pmv_destroy(pmv_ctx *c)
     for (auto &e : c->prof_pool) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     delete c;
 }
 

@@ -25,6 +25,8 @@
 // ops); the limiter is the integer/LSU issue rate -- see DESIGN.md.
 #include <stdlib.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
@@ -485,15 +487,38 @@ PMV_API int pmv_lk_track_batched(pmv_ctx *ctx, const uint8_t *prev, const uint8_
     if (img_stride < (size_t)rows * step) return ctx->fail(PMV_ERR_INVALID, "lk: img_stride < rows*step");
     cudaSetDevice(ctx->device);
 
-    // Chunked pipeline: raw image bytes go up on the copy stream (one contiguous transfer per chunk and
-    // image set), the compute stream imports / builds pyramids / tracks chunk c while chunk c+1 is in flight.
+    // Chunked pipeline: raw image bytes go up on the copy stream (one contiguous transfer per chunk and image set);
+    // chunks alternate between TWO compute streams, each with its own pyramid / derivative slot, so that the pyramid
+    // build of chunk c+1 and the tail of chunk c's tracking kernel (a few long-running features on a mostly idle GPU)
+    // overlap; results go back per chunk on a fourth stream (uploads and downloads use different copy engines).
+    // The first chunk is small (nothing overlaps its upload), the following ones grow to CH.
     const char *ch_env = getenv("PMV_LK_CHUNK");   // tuning knob (tools/): images per upload chunk
     const int CH = batch <= 8 ? batch : (ch_env && atoi(ch_env) > 0 ? atoi(ch_env) : 32);
-    const int nchunks = (batch + CH - 1) / CH;
-    PyrSet sp, sn;
-    DerivSet dv;
-    rc = lk_plan(ctx, CH, rows, cols, win_w, win_h, max_level, &sp, &sn, &dv, ctx->stream);
+    std::vector<int> chunk_begin;
+    for (int b0 = 0, sz = CH < 8 ? CH : 8; b0 < batch;) {
+        chunk_begin.push_back(b0);
+        b0 += sz < batch - b0 ? sz : batch - b0;
+        sz = 2 * sz < CH ? 2 * sz : CH;
+    }
+    chunk_begin.push_back(batch);
+    const int nchunks = (int)chunk_begin.size() - 1;
+    const int nslots = nchunks > 1 && !getenv("PMV_LK_ONE_STREAM") ? 2 : 1;
+    cudaStream_t s = ctx->stream;
+    // slot k: prev images [2k CH, (2k+1) CH), next images [(2k+1) CH, (2k+2) CH) of one pyramid plan; derivatives likewise
+    PyrSet all, sp[2], sn[2];
+    DerivSet dall, dv[2];
+    rc = pmv_internal_pyr_plan(ctx, 0, 2 * nslots * CH, rows, cols, pmv_internal_lk_border(win_w, win_h), win_w, win_h, max_level, &all);
     if (rc) return rc;
+    rc = pmv_internal_deriv_plan(ctx, all, nslots * CH, &dall, s);
+    if (rc) return rc;
+    for (int k = 0; k < nslots; k++) {
+        sp[k] = all; sn[k] = all; dv[k] = dall;
+        for (int l = 0; l <= all.top; l++) {
+            sp[k].lv[l].ptr = all.lv[l].ptr + (size_t)(2 * k) * CH * all.lv[l].img_stride;
+            sn[k].lv[l].ptr = all.lv[l].ptr + (size_t)(2 * k + 1) * CH * all.lv[l].img_stride;
+            dv[k].lv[l].ptr = dall.lv[l].ptr + (size_t)k * CH * dall.lv[l].img_stride;
+        }
+    }
     const size_t raw_bytes = (size_t)batch * img_stride;
     cudaError_t e = ctx->pts[0].reserve((size_t)batch * n * 8 + 8);
     if (e == cudaSuccess) e = ctx->pts[1].reserve((size_t)batch * n * 8 + 8);
@@ -506,19 +531,29 @@ PMV_API int pmv_lk_track_batched(pmv_ctx *ctx, const uint8_t *prev, const uint8_
     uint8_t *dst = ctx->pts[2].as<uint8_t>();
     float *der = ctx->pts[3].as<float>();
     uint8_t *rawP = ctx->img[0].as<uint8_t>(), *rawN = ctx->img[1].as<uint8_t>();
-    cudaStream_t s = ctx->stream, cs = nchunks > 1 ? ctx->copy_stream : ctx->stream;
-    while ((int)ctx->chunk_ev.size() < nchunks) {
+    cudaStream_t cs = nchunks > 1 ? ctx->copy_stream : s;
+    if (nchunks > 1 && !ctx->d2h_stream) PMV_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    if (nslots > 1 && !ctx->aux_stream) PMV_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    cudaStream_t ds = nchunks > 1 ? ctx->d2h_stream : s;
+    cudaStream_t comp[2] = {s, nslots > 1 ? ctx->aux_stream : s};
+    while ((int)ctx->chunk_ev.size() < 2 * nchunks + 2) {
         cudaEvent_t ev = nullptr;
         PMV_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         ctx->chunk_ev.push_back(ev);
     }
+    cudaEvent_t ev_start = ctx->chunk_ev[2 * nchunks], ev_join = ctx->chunk_ev[2 * nchunks + 1];
     if (n > 0) {
         PMV_CUDA_TRY(ctx, cudaMemcpyAsync(dpx, prev_xy, (size_t)batch * n * 8, cudaMemcpyHostToDevice, s));
         if (flags & PMV_LK_USE_INITIAL_FLOW)
             PMV_CUDA_TRY(ctx, cudaMemcpyAsync(dnx, next_xy, (size_t)batch * n * 8, cudaMemcpyHostToDevice, s));
     }
+    if (nchunks > 1) {   // the side streams start behind what the caller's stream holds (points, zeroed derivative borders)
+        PMV_CUDA_TRY(ctx, cudaEventRecord(ev_start, s));
+        PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ev_start, 0));
+        if (nslots > 1) PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(comp[1], ev_start, 0));
+    }
     for (int c = 0; c < nchunks; c++) {
-        const int b0 = c * CH, nb = (batch - b0 < CH) ? batch - b0 : CH;
+        const int b0 = chunk_begin[c], nb = chunk_begin[c + 1] - b0, k = c % nslots;
         const size_t off = (size_t)b0 * img_stride;
         // the last image of the batch may be shorter than img_stride in the caller's buffer
         const size_t bytes = (size_t)(nb - 1) * img_stride + (size_t)(rows - 1) * step + cols;
@@ -526,17 +561,30 @@ PMV_API int pmv_lk_track_batched(pmv_ctx *ctx, const uint8_t *prev, const uint8_
         PMV_CUDA_TRY(ctx, cudaMemcpyAsync(rawN + off, next + off, bytes, cudaMemcpyHostToDevice, cs));
         if (nchunks > 1) {
             PMV_CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[c], cs));
-            PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->chunk_ev[c], 0));
+            PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(comp[k], ctx->chunk_ev[c], 0));
         }
-        rc = lk_enqueue(ctx, sp, sn, dv, rawP + off, rawN + off, nb, img_stride, step, dpx + (size_t)b0 * n * 2, n, win_w,
+        rc = lk_enqueue(ctx, sp[k], sn[k], dv[k], rawP + off, rawN + off, nb, img_stride, step, dpx + (size_t)b0 * n * 2, n, win_w,
                         win_h, max_count, eps, flags, min_eig_thr, dnx + (size_t)b0 * n * 2, dst + (size_t)b0 * n,
-                        der + (size_t)b0 * n, s);
+                        der + (size_t)b0 * n, comp[k]);
         if (rc) return rc;
+        if (n > 0) {
+            if (nchunks > 1) {
+                PMV_CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[nchunks + c], comp[k]));
+                PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(ds, ctx->chunk_ev[nchunks + c], 0));
+            }
+            const size_t o = (size_t)b0 * n, cnt = (size_t)nb * n;
+            PMV_CUDA_TRY(ctx, cudaMemcpyAsync(next_xy + 2 * o, dnx + 2 * o, cnt * 8, cudaMemcpyDeviceToHost, ds));
+            PMV_CUDA_TRY(ctx, cudaMemcpyAsync(status + o, dst + o, cnt, cudaMemcpyDeviceToHost, ds));
+            PMV_CUDA_TRY(ctx, cudaMemcpyAsync(err + o, der + o, cnt * 4, cudaMemcpyDeviceToHost, ds));
+        }
     }
-    if (n > 0) {
-        PMV_CUDA_TRY(ctx, cudaMemcpyAsync(next_xy, dnx, (size_t)batch * n * 8, cudaMemcpyDeviceToHost, s));
-        PMV_CUDA_TRY(ctx, cudaMemcpyAsync(status, dst, (size_t)batch * n, cudaMemcpyDeviceToHost, s));
-        PMV_CUDA_TRY(ctx, cudaMemcpyAsync(err, der, (size_t)batch * n * 4, cudaMemcpyDeviceToHost, s));
+    if (nchunks > 1) {   // join: the caller's stream is complete when the last download and both compute streams are
+        PMV_CUDA_TRY(ctx, cudaEventRecord(ev_join, ds));
+        PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(s, ev_join, 0));
+        if (nslots > 1) {
+            PMV_CUDA_TRY(ctx, cudaEventRecord(ev_start, comp[1]));
+            PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(s, ev_start, 0));
+        }
     }
     PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
     return PMV_OK;
