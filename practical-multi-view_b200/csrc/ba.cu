@@ -17,7 +17,8 @@
 #include "ba_kernels.cuh"
 #include "ba_runs.cuh"
 
-int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_host, const BASplit *split, cudaStream_t s);  // ba_chol.cu
+int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_host, const BASplit *split, const BAPart *part,
+                                   cudaStream_t s);  // ba_chol.cu
 int pmv_internal_ba_cholesky_band_T(int n, const int *lim_host);                                    // ba_chol_band.cu
 int pmv_internal_ba_allreduce(pmv_ctx *ctx, const double *send, double *recv, size_t count, int op_max,
                               cudaStream_t s);                                      // ba_nccl.cu
@@ -63,6 +64,9 @@ struct pmv_ba_problem {
     // two-sided solve of the banded reduced camera system (BASplit, ba.cuh)
     BASplit split;
     std::vector<int> split_lim[3];
+    // partitioned solve (BAPart, ba.cuh): P segments, P - 1 separators
+    BAPart part;
+    std::vector<int> part_lim[PMV_PART_MAX + 1];
     // window-batched path (ba_window.cu): Nc <= 22, every (point, camera) pair observed at most once
     int use_window = 0;
     unsigned *d_vis = nullptr;
@@ -254,7 +258,7 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
         ba_cholesky_small_kernel<<<W, 256, smem, s>>>(D);
         PMV_LAUNCH_CHECK(ctx, "ba_cholesky_small_kernel");
     } else {
-        int rc = pmv_internal_ba_cholesky_large(ctx, D, p->chol_lim.empty() ? nullptr : p->chol_lim.data(), &p->split, s);
+        int rc = pmv_internal_ba_cholesky_large(ctx, D, p->chol_lim.empty() ? nullptr : p->chol_lim.data(), &p->split, &p->part, s);
         if (rc) return rc;
     }
     ba_cam_candidate_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D, p->sharded ? (p->rank == 0) : 1);
@@ -670,6 +674,71 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
                 }
             }
         }
+        // ---- partitioned solve: P segments separated by P - 1 separators of w columns (BAPart).  OPT-IN (PMV_CHOL_PARTS >= 3):
+        //      measured on config 5 it does not beat the two-sided solve (2.39 vs 2.31 ms per iteration at P = 4; the spikes and the
+        //      sequential separator chain cost what the shorter segment chains save), so the two-sided solve stays the default
+        {
+            const char *parts_env = getenv("PMV_CHOL_PARTS");
+            const int NBk = PMV_CHOL_NB, nn = (int)n;
+            int maxw = 0;
+            for (int kb = 0; kb < nblk; kb++) maxw = std::max(maxw, p->chol_lim[kb] - kb * NBk);
+            const int w = (maxw + NBk - 1) / NBk * NBk;
+            int P = parts_env ? atoi(parts_env) : 0;
+            while (P >= 3 && ((nn - (P - 1) * w) / P) / NBk * NBk < 2 * w) P--;
+            const bool want = p->split.enabled && P >= 3 && P <= PMV_PART_MAX && w > 0;
+            if (want) {
+                BAPart &Q = p->part;
+                Q.P = P; Q.w = w; Q.nR = (P - 1) * w;
+                const int ns = ((nn - (P - 1) * w) / P) / NBk * NBk;
+                bool elig = true;
+                for (int i = 0; i < P; i++) {
+                    Q.a[i] = i * (ns + w);
+                    Q.ns[i] = i < P - 1 ? ns : nn - Q.a[i];
+                    Q.nx[i] = i < P - 1 ? ns + w : Q.ns[i];
+                    std::vector<int> &l = p->part_lim[i];
+                    const int nbx = (Q.nx[i] + NBk - 1) / NBk, kb0 = Q.a[i] / NBk;
+                    l.resize(nbx);
+                    for (int kb = 0; kb < nbx; kb++) {
+                        l[kb] = std::min(p->chol_lim[kb0 + kb], Q.a[i] + Q.nx[i]) - Q.a[i];
+                        elig = elig && (l[kb] - kb * NBk + NBk - 1) / NBk <= 11;           // part_spike_kernel: diagonal + 10 tiles per block row
+                    }
+                    elig = elig && pmv_internal_ba_cholesky_band_T(Q.nx[i], l.data()) > 0;
+                    // the separator right of segment i must not reach beyond segment i + 1
+                    if (i < P - 1) elig = elig && p->chol_lim[(Q.a[i] + Q.nx[i] - 1) / NBk] <= Q.a[i] + Q.nx[i] + (i + 1 < P - 1 ? ns : nn);
+                }
+                std::vector<int> &lr = p->part_lim[PMV_PART_MAX];            // dense envelope of one separator block
+                const int nbr = w / NBk;
+                lr.assign(nbr, w);
+                elig = elig && pmv_internal_ba_cholesky_band_T(w, lr.data()) > 0 && w <= 320;   // 320: staged back-substitution
+                if (getenv("PMV_BA_TRACE")) fprintf(stderr, "[pmv] part solve: n %d w %d P %d ns %d nR %d eligible %d\n", nn, w, P, ns, Q.nR, (int)elig);
+                if (elig) {
+                    int rc2 = 0;
+                    for (int i = 0; i < P; i++) {
+                        rc2 |= dev_alloc(p, &Q.limX[i], p->part_lim[i].size());
+                        if (i > 0) rc2 |= dev_alloc(p, &Q.G[i], (size_t)Q.nx[i] * w);
+                    }
+                    const size_t ww = (size_t)w * w;
+                    rc2 |= dev_alloc(p, &Q.Dsep, (P - 1) * ww); rc2 |= dev_alloc(p, &Q.E, (P - 1) * ww); rc2 |= dev_alloc(p, &Q.F, (P - 1) * ww);
+                    rc2 |= dev_alloc(p, &Q.bR, (size_t)Q.nR); rc2 |= dev_alloc(p, &Q.yR, (size_t)Q.nR);
+                    rc2 |= dev_alloc(p, &Q.limD, nbr); rc2 |= dev_alloc(p, &Q.stp, 2 * P - 1);
+                    if (rc2) { pmv_ba_problem_destroy(p); return nullptr; }
+                    for (int i = 0; i < P; i++) {
+                        cudaMemcpyAsync(Q.limX[i], p->part_lim[i].data(), sizeof(int) * p->part_lim[i].size(), cudaMemcpyHostToDevice, s);
+                        Q.limX_h[i] = p->part_lim[i].data();
+                    }
+                    cudaMemcpyAsync(Q.limD, lr.data(), sizeof(int) * nbr, cudaMemcpyHostToDevice, s);
+                    cudaMemsetAsync(Q.Dsep, 0, sizeof(double) * (P - 1) * ww, s);   // tiles below the diagonal are never written
+                    Q.limD_h = lr.data();
+                    bool okc = true;
+                    for (int i = 1; i < P; i++) okc = okc && cudaStreamCreateWithFlags(&Q.str[i], cudaStreamNonBlocking) == cudaSuccess;
+                    for (auto &e : Q.ev_fork) okc = okc && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+                    for (int k = 0; k < 2; k++)
+                        for (int i = 1; i < P; i++) okc = okc && cudaEventCreateWithFlags(&Q.ev_join[k][i], cudaEventDisableTiming) == cudaSuccess;
+                    if (!okc) { ctx->fail(PMV_ERR_CUDA, "part solve: streams / events"); pmv_ba_problem_destroy(p); return nullptr; }
+                    Q.enabled = 1;
+                }
+            }
+        }
         if (p->sharded) {
             std::vector<long long> off(n + 1);
             long long acc = 0;
@@ -760,6 +829,9 @@ PMV_API void pmv_ba_problem_destroy(pmv_ba_problem *p)
     if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
     if (p->split.s2) { cudaStreamSynchronize(p->split.s2); cudaStreamDestroy(p->split.s2); }
     for (auto &e : p->split.ev) if (e) cudaEventDestroy(e);
+    for (auto &st : p->part.str) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (auto &e : p->part.ev_fork) if (e) cudaEventDestroy(e);
+    for (auto &row : p->part.ev_join) for (auto &e : row) if (e) cudaEventDestroy(e);
     for (void *q : p->allocs) cudaFreeAsync(q, p->ctx->stream);
     delete p;
 }

@@ -74,3 +74,33 @@ struct BASplit {
     cudaStream_t s2 = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
+
+// Partitioned elimination of a long banded reduced camera system (ba_chol.cu: part solve) -- nested dissection with P
+// segments.  The band is cut by P - 1 separators M_j of w columns (w >= the envelope width, so neighbouring segments
+// do not couple): seg_1 M_1 seg_2 M_2 ... M_{P-1} seg_P.  The extended systems X_i = [seg_i | M_i] (X_P = seg_P) are
+// factorised IN PLACE in S, concurrently, each by its own cluster; a segment's coupling to the separator on its LEFT is
+// carried as w extra right-hand sides through that factor (the "spike" G_i = U_{X_i}^-T B_i, part_spike_kernel); the
+// separators' Schur complement -- block tridiagonal, D_j = U_M(j)^T U_M(j) - G_s(j+1)^T G_s(j+1),
+// E_j = H(j+1)^T U_M(j+1), r_j = U_M(j)^T z_M(j) - G_s(j+1)^T z_s(j+1) with G = [G_s; H] split at the segment / separator
+// boundary -- is assembled without atomics (every rank of a sharded solve must produce the same bits) and eliminated
+// separator by separator (dense w x w factorisations by the same cluster kernel, F_j = U_j^-T E_j by the spike kernel,
+// D_{j+1} -= F_j^T F_j), and the segments are back-substituted concurrently.  Chain of dependent 32-row block steps:
+// n / 32 -> (n / P + w) / 32 + (P - 1) w / 32.
+constexpr int PMV_PART_MAX = 12;
+struct BAPart {
+    int enabled = 0;
+    int P = 0, w = 0, nR = 0;                    // segments, separator width, order of the separator system (P - 1) w
+    int a[PMV_PART_MAX] = {0};                   // first row of segment i
+    int ns[PMV_PART_MAX] = {0};                  // rows of segment i (without its separator)
+    int nx[PMV_PART_MAX] = {0};                  // rows of the extended system X_i
+    int *limX[PMV_PART_MAX] = {nullptr};         // envelopes of the extended systems, relative (device)
+    int *limX_h[PMV_PART_MAX] = {nullptr};       // host copies (owned by the problem)
+    double *G[PMV_PART_MAX] = {nullptr};         // spikes, nx[i] x w row major (i >= 1)
+    // separator system (block tridiagonal): diagonal blocks D_j, couplings E_j, F_j = U_j^-T E_j, each w x w (ld = w)
+    double *Dsep = nullptr, *E = nullptr, *F = nullptr, *bR = nullptr, *yR = nullptr;
+    int *limD = nullptr, *limD_h = nullptr;      // dense envelope of one separator block (w in every entry)
+    BAState *stp = nullptr;                      // [2 P - 1]: private status of the P segment and P - 1 separator factorisations
+    cudaStream_t str[PMV_PART_MAX] = {nullptr};  // streams of segments 1 .. P-1 (segment 0 runs on the caller's)
+    cudaEvent_t ev_fork[2] = {nullptr, nullptr};
+    cudaEvent_t ev_join[2][PMV_PART_MAX] = {{nullptr}, {nullptr}};
+};

@@ -424,6 +424,355 @@ __global__ void __launch_bounds__(256) split_finish_kernel(double *__restrict__ 
     if (blockIdx.x == 0 && threadIdx.x == 0) st->chol_ok = P.st3[0].chol_ok && P.st3[1].chol_ok && P.st3[2].chol_ok;
 }
 
+// ---- part solve (BAPart): kernels around the P concurrent segment factorisations ----------------------------------
+// 0. private status blocks
+__global__ void part_prepare_kernel(BAPart Q, const BAState *st)
+{
+    if (threadIdx.x < 2 * Q.P - 1) {
+        BAState t = *st;
+        t.chol_ok = 0;
+        Q.stp[threadIdx.x] = t;
+    }
+}
+
+// 1. spike of segment i >= 1: G = U_X^-T B, forward substitution of w right-hand sides through the factor of the
+//    extended system X_i (in place in S at (a_i, a_i)).  B[r][c] = S[mprev + c][a_i + r] inside the envelope of the
+//    separator rows mprev + c (non-zero only in the first < w rows).  One CTA per 32 right-hand sides: the current and the
+//    next PS_T block rows of the right-hand side live in a shared-memory ring; per block row warp 0 solves the 32 x 32
+//    triangle (lane = column of the right-hand side, the column in registers) while warp j stages the factor's tile
+//    U_{k,k+j}, then warp j applies U_{k,k+j}^T Y to the j-th tile below.  The NEXT diagonal tile arrives by cp.async.
+constexpr int PS_T = 10;                 // off-diagonal tiles per block row of the factor (envelope up to 11 tiles of 32 columns)
+constexpr int PS_WARPS = PS_T + 1;       // warp 0: triangle; warp j = 1 .. PS_T: the tile j below
+constexpr size_t PS_SMEM = sizeof(double) * ((size_t)(2 + PS_T) * NB * NB + (size_t)(PS_T + 2) * NB * 16);   // U_kk x 2 | U_{k,k+j} | ring | Y
+
+__device__ __forceinline__ void ps_cp_async_16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+struct SpikeArgs {
+    const double *Sx;        // factor (upper triangular rows inside the envelope), element (r, c) at Sx[r * ld + c]
+    size_t ld;
+    int nx;                  // order of the system
+    const int *lim;          // its envelope per 32-row block, relative (device)
+    int w;                   // right-hand sides
+    // right-hand sides: mode 0 -- B[row][col] = Bsrc[col * bld + row] where row < blim[(brow0 + col) / 32] - bcol0 (rows of a
+    // banded matrix read as columns); mode 1 -- B[row][col] = Bsrc[row * bld + col], row < nx
+    int bmode;
+    const double *Bsrc;
+    size_t bld;
+    const int *blim;
+    int brow0, bcol0;
+    double *G;               // out: nx x w, row major
+    const BAState *st;       // status of the factorisation the factor comes from
+};
+
+// One CTA per PS_CC = 16 right-hand sides; lane = (column c = lane & 15, half h = lane >> 4): a lane owns rows
+// h, h + 2, h + 4, ... of its column (interleaved, so both halves stay busy down the triangle).
+constexpr int PS_CC = 16;
+
+__global__ void __launch_bounds__(PS_WARPS * 32)
+part_spike_kernel(const SpikeArgs A)
+{
+    const BAState *st = A.st;
+    if (st->done || !st->chol_ok) return;
+    extern __shared__ __align__(16) double psm[];
+    double *Ukk = psm;                                   // [2][NB][NB]  diagonal tile of the current / next block row
+    double *Uoff = psm + 2 * NB * NB;                    // [PS_T][NB][NB] tile j of the current block row, staged by warp j
+    double *Bring = Uoff + PS_T * NB * NB;               // [PS_T + 1][NB][PS_CC] right-hand-side rows kb*32 .., slot = block row % (PS_T + 1)
+    double *Ys = Bring + (PS_T + 1) * NB * PS_CC;        // [NB][PS_CC]
+    __shared__ double rdiag[NB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = lane & 15, h = lane >> 4;
+    const int nx = A.nx, w = A.w;
+    const int *lim = A.lim;
+    const size_t ld = A.ld;
+    const int nblk = (nx + NB - 1) / NB;
+    const int c0 = blockIdx.x * PS_CC;                      // first right-hand-side column of this CTA
+    double *G = A.G;
+    const double *Sx = A.Sx;
+    const bool even = (ld & 1) == 0 && ((size_t)Sx & 15) == 0;   // tile rows start on 16-byte boundaries
+    auto tiles_of = [&](int kb) { return min(PS_T + 1, (min(nx, lim[kb]) - kb * NB + NB - 1) / NB); };   // diagonal tile included
+    // one tile of the factor, rows k0 .. k0 + 32, columns cb .. cb + 32 of X, into dst[NB][NB] by ONE warp (zero beyond X)
+    auto load_tile = [&](double *dst, int k0, int cb, bool async) {
+        for (int i = lane; i < NB * (NB / 2); i += 32) {
+            const int r = i / (NB / 2), p2 = i - r * (NB / 2), row = k0 + r, col = cb + 2 * p2;
+            double *d = dst + r * NB + 2 * p2;
+            if (row < nx && col + 1 < nx && even) {
+                const double *g = Sx + (size_t)row * ld + col;
+                if (async) ps_cp_async_16(d, g); else *reinterpret_cast<double2 *>(d) = *reinterpret_cast<const double2 *>(g);
+            } else {
+                d[0] = (row < nx && col < nx) ? Sx[(size_t)row * ld + col] : 0.0;
+                d[1] = (row < nx && col + 1 < nx) ? Sx[(size_t)row * ld + col + 1] : 0.0;
+            }
+        }
+    };
+    // right-hand-side tile jb enters the ring: rows jb*32 .. of B (zero beyond the reach of the separator rows)
+    auto enter = [&](int jb) {
+        double *dst = Bring + (size_t)(jb % (PS_T + 1)) * NB * PS_CC;
+        for (int i = tid; i < NB * PS_CC; i += PS_WARPS * 32) {
+            int r, cc;
+            if (A.bmode == 0) { cc = i / NB; r = i - cc * NB; } else { r = i / PS_CC; cc = i - r * PS_CC; }   // consecutive threads along the source rows
+            const int row = jb * NB + r, col = c0 + cc;
+            double v = 0.0;
+            if (row < nx && col < w) {
+                if (A.bmode == 0) { if (row < A.blim[(A.brow0 + col) / NB] - A.bcol0) v = A.Bsrc[(size_t)col * A.bld + row]; }
+                else v = A.Bsrc[(size_t)row * A.bld + col];
+            }
+            dst[r * PS_CC + cc] = v;
+        }
+    };
+    for (int jb = 0; jb < min(nblk, PS_T + 1); jb++) enter(jb);
+    if (warp == 0) load_tile(Ukk, 0, 0, false);
+    __syncthreads();
+    for (int kb = 0; kb < nblk; kb++) {
+        const int k0 = kb * NB, rows = min(NB, nx - k0), nt = tiles_of(kb);
+        const double *Uk = Ukk + (size_t)(kb & 1) * NB * NB;
+        double *Bk = Bring + (size_t)(kb % (PS_T + 1)) * NB * PS_CC;
+        if (warp == 0) {
+            if (kb + 1 < nblk) load_tile(Ukk + (size_t)((kb + 1) & 1) * NB * NB, k0 + NB, k0 + NB, true);   // next diagonal tile, asynchronously
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            rdiag[lane] = lane < rows ? 1.0 / Uk[lane * NB + lane] : 0.0;
+            __syncwarp();
+            // U_kk^T Y = B_k: lane (c, h) keeps rows h, h + 2, ... of column c; the row being solved is broadcast by its owner
+            double col[NB / 2];
+#pragma unroll
+            for (int i = 0; i < NB / 2; i++) col[i] = Bk[(2 * i + h) * PS_CC + c];
+#pragma unroll
+            for (int r = 0; r < NB; r++) {
+                const double mine = col[r >> 1] * rdiag[r];
+                const double y = __shfl_sync(0xffffffffu, mine, c + 16 * (r & 1));
+                if (h == (r & 1)) col[r >> 1] = y;
+#pragma unroll
+                for (int i = (r >> 1); i < NB / 2; i++) {
+                    const int q = 2 * i + h;               // rows below r only (q > r); the compare folds away for most i
+                    if (q > r) col[i] = fma(-Uk[r * NB + q], y, col[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NB / 2; i++) {
+                const int r = 2 * i + h;
+                Ys[r * PS_CC + c] = col[i];
+                if (r < rows && c0 + c < w) G[(size_t)(k0 + r) * w + c0 + c] = col[i];
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else if (warp < nt) {
+            load_tile(Uoff + (size_t)(warp - 1) * NB * NB, k0, k0 + warp * NB, false);   // overlaps with warp 0's triangle
+        }
+        __syncthreads();
+        if (warp >= 1 && warp < nt) {
+            // B_{k+j} -= U_{k,k+j}^T Y, j = warp: lane (c, h) updates rows 16 h .. 16 h + 15 of column c
+            const double *Uj = Uoff + (size_t)(warp - 1) * NB * NB + 16 * h;
+            double *Bj = Bring + (size_t)((kb + warp) % (PS_T + 1)) * NB * PS_CC + (16 * h) * PS_CC + c;
+            double acc[16];
+#pragma unroll
+            for (int r = 0; r < 16; r++) acc[r] = Bj[r * PS_CC];
+#pragma unroll 4
+            for (int k = 0; k < NB; k++) {
+                const double y = Ys[k * PS_CC + c];
+#pragma unroll
+                for (int r = 0; r < 16; r += 2) {
+                    const double2 u = *reinterpret_cast<const double2 *>(Uj + k * NB + r);
+                    acc[r] = fma(-u.x, y, acc[r]); acc[r + 1] = fma(-u.y, y, acc[r + 1]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 16; r++) Bj[r * PS_CC] = acc[r];
+        }
+        __syncthreads();
+        if (kb + PS_T + 1 < nblk) enter(kb + PS_T + 1);   // the slot of block row kb is free again (read next after a barrier)
+    }
+}
+
+// 2. separator system (block tridiagonal, upper part): one CTA per 32 x 32 tile, no atomics.
+//    blockIdx.y = separator j; blockIdx.x enumerates: D tiles (ti <= tj), E tiles (all, only j < P - 2), then one CTA for r_j.
+//    D_j goes to Dsep + j w^2, E_j to E + j w^2 (both w x w, ld = w), r_j to bR + j w.
+__global__ void __launch_bounds__(256)
+part_reduce_kernel(const double *__restrict__ S, const double *__restrict__ z, size_t ld, BAPart Q)
+{
+    if (Q.stp[0].done) return;
+    for (int i = 0; i < Q.P; i++) if (!Q.stp[i].chol_ok) return;
+    __shared__ double As[NB][NB + 1], Bs[NB][NB + 1];
+    const int w = Q.w, wt = w / NB, j = blockIdx.y;
+    const int nD = wt * (wt + 1) / 2, nE = wt * wt;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;       // thread computes rows ty, ty+8, ty+16, ty+24 of column tx
+    const int mj = Q.a[j] + Q.ns[j];                                 // first row of separator j
+    const double *Gn = Q.G[j + 1];                                   // spike of the segment right of separator j
+    const int nsn = Q.ns[j + 1];
+    int id = blockIdx.x;
+    if (id < nD) {
+        // D_j tile (ti, tj): U_M^T U_M - G_s^T G_s
+        int ti = 0;
+        while (id >= wt - ti) { id -= wt - ti; ti++; }
+        const int tj = ti + id;
+        double acc[4] = {0, 0, 0, 0};
+        // U_M(j): rows k <= column; k runs over block rows 0 .. tj (entries above the diagonal block of column tile ti vanish for k > ti*32+31)
+        for (int kb = 0; kb <= ti; kb++) {
+            for (int q = ty; q < NB; q += 8) {
+                const int k = kb * NB + q;
+                As[q][tx] = (k <= ti * NB + tx) ? S[(size_t)(mj + k) * ld + mj + ti * NB + tx] : 0.0;
+                Bs[q][tx] = (k <= tj * NB + tx) ? S[(size_t)(mj + k) * ld + mj + tj * NB + tx] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int q = 0; q < NB; q++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) acc[e] = fma(As[q][ty + 8 * e], Bs[q][tx], acc[e]);
+            __syncthreads();
+        }
+        double sub[4] = {0, 0, 0, 0};
+        for (int r0 = 0; r0 < nsn; r0 += NB) {
+            for (int q = ty; q < NB; q += 8) {
+                const int r = r0 + q;
+                As[q][tx] = r < nsn ? Gn[(size_t)r * w + ti * NB + tx] : 0.0;
+                Bs[q][tx] = r < nsn ? Gn[(size_t)r * w + tj * NB + tx] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int q = 0; q < NB; q++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) sub[e] = fma(As[q][ty + 8 * e], Bs[q][tx], sub[e]);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int i = ti * NB + ty + 8 * e, c = tj * NB + tx;
+            Q.Dsep[(size_t)j * w * w + (size_t)i * w + c] = c >= i ? acc[e] - sub[e] : 0.0;
+        }
+    } else if (id < nD + nE) {
+        if (j + 2 >= Q.P) return;                                     // the last separator has no neighbour on its right
+        // E_j tile (ti, tj) = H^T U_M(j+1): H = rows ns .. ns + w of G(j+1), U_M(j+1) upper triangular
+        id -= nD;
+        const int ti = id / wt, tj = id - ti * wt;
+        const int mn = Q.a[j + 1] + Q.ns[j + 1];                      // first row of separator j + 1
+        double acc[4] = {0, 0, 0, 0};
+        for (int kb = 0; kb <= tj; kb++) {
+            for (int q = ty; q < NB; q += 8) {
+                const int k = kb * NB + q;
+                As[q][tx] = Gn[(size_t)(nsn + k) * w + ti * NB + tx];
+                Bs[q][tx] = (k <= tj * NB + tx) ? S[(size_t)(mn + k) * ld + mn + tj * NB + tx] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int q = 0; q < NB; q++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) acc[e] = fma(As[q][ty + 8 * e], Bs[q][tx], acc[e]);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            Q.E[(size_t)j * w * w + (size_t)(ti * NB + ty + 8 * e) * w + tj * NB + tx] = acc[e];
+    } else {
+        // r_j = U_M(j)^T z_M(j) - G_s(j+1)^T z_s(j+1): thread i of the first w
+        const int an = Q.a[j + 1];
+        for (int i = tid; i < w; i += 256) {
+            double v = 0.0;
+            for (int k = 0; k <= i; k++) v = fma(S[(size_t)(mj + k) * ld + mj + i], z[mj + k], v);
+            double u = 0.0;
+            for (int r = 0; r < nsn; r++) u = fma(Gn[(size_t)r * w + i], z[an + r], u);
+            Q.bR[j * w + i] = v - u;
+        }
+    }
+}
+
+// 2b. separator chain, forward: D_j -= F_{j-1}^T F_{j-1} (upper tiles), r_j -= F_{j-1}^T z_{j-1} (z_{j-1}: the forward-substituted
+//     right-hand side of separator j - 1, in place in bR).  One CTA per tile + one for the right-hand side.
+__global__ void __launch_bounds__(256)
+part_sep_update_kernel(BAPart Q, int j)
+{
+    const BAState *stq = Q.stp + Q.P + j - 1;
+    if (stq->done || !stq->chol_ok) return;
+    __shared__ double As[NB][NB + 1], Bs[NB][NB + 1];
+    const int w = Q.w, wt = w / NB, nD = wt * (wt + 1) / 2;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const double *F = Q.F + (size_t)(j - 1) * w * w;
+    double *D = Q.Dsep + (size_t)j * w * w;
+    int id = blockIdx.x;
+    if (id < nD) {
+        int ti = 0;
+        while (id >= wt - ti) { id -= wt - ti; ti++; }
+        const int tj = ti + id;
+        double sub[4] = {0, 0, 0, 0};
+        for (int r0 = 0; r0 < w; r0 += NB) {
+            for (int q = ty; q < NB; q += 8) {
+                As[q][tx] = F[(size_t)(r0 + q) * w + ti * NB + tx];
+                Bs[q][tx] = F[(size_t)(r0 + q) * w + tj * NB + tx];
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int q = 0; q < NB; q++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) sub[e] = fma(As[q][ty + 8 * e], Bs[q][tx], sub[e]);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int i = ti * NB + ty + 8 * e, c = tj * NB + tx;
+            if (c >= i) D[(size_t)i * w + c] -= sub[e];
+        }
+    } else {
+        const double *zp = Q.bR + (size_t)(j - 1) * w;
+        for (int i = tid; i < w; i += 256) {
+            double u = 0.0;
+            for (int r = 0; r < w; r++) u = fma(F[(size_t)r * w + i], zp[r], u);
+            Q.bR[(size_t)j * w + i] -= u;
+        }
+    }
+}
+
+// 2c. separator chain, backward: z_j -= F_j x_{j+1} before the back-substitution of separator j (one warp per row)
+__global__ void __launch_bounds__(256)
+part_sep_back_kernel(BAPart Q, int j)
+{
+    const BAState *stq = Q.stp + Q.P + j;
+    if (stq->done || !stq->chol_ok) return;
+    const int w = Q.w, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double *F = Q.F + (size_t)j * w * w, *x = Q.yR + (size_t)(j + 1) * w;
+    for (int r = blockIdx.x * 8 + warp; r < w; r += gridDim.x * 8) {
+        double v = 0.0;
+        for (int c = lane; c < w; c += 32) v = fma(F[(size_t)r * w + c], x[c], v);
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) Q.bR[(size_t)j * w + r] -= v;
+    }
+}
+
+// 3. with the separators solved (yR): right-hand sides of the segments' back-substitutions.
+//    z_s(i) -= G_s(i) x_M(i-1) (i >= 1); separator rows of X_i (i < P - 1) become U_M(i) x_M(i) so that the ordinary
+//    back-substitution of the extended system reproduces x_M(i) and continues upwards from it.
+__global__ void __launch_bounds__(256)
+part_fix_kernel(const double *__restrict__ S, double *__restrict__ z, size_t ld, BAPart Q)
+{
+    if (Q.stp[0].done) return;
+    for (int i = Q.P; i < 2 * Q.P - 1; i++) if (!Q.stp[i].chol_ok) return;
+    const int w = Q.w, seg = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int a = Q.a[seg], ns = Q.ns[seg];
+    for (int r = blockIdx.x * 8 + warp; r < Q.nx[seg]; r += gridDim.x * 8) {
+        double v = 0.0;
+        if (r < ns) {
+            if (seg == 0) continue;
+            const double *g = Q.G[seg] + (size_t)r * w, *x = Q.yR + (seg - 1) * w;
+            for (int c = lane; c < w; c += 32) v = fma(g[c], x[c], v);
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) z[a + r] -= v;
+        } else {
+            const int k = r - ns, m = a + ns;
+            const double *x = Q.yR + seg * w;
+            for (int c = k + lane; c < w; c += 32) v = fma(S[(size_t)(m + k) * ld + m + c], x[c], v);
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) z[a + r] = v;
+        }
+    }
+}
+
+// 4. overall status
+__global__ void part_finish_kernel(BAPart Q, BAState *st)
+{
+    if (st->done) return;
+    int ok = 1;
+    for (int i = 0; i < 2 * Q.P - 1; i++) ok = ok && Q.stp[i].chol_ok;
+    st->chol_ok = ok;
+}
+
 }  // namespace
 
 int pmv_internal_ba_cholesky_band(pmv_ctx *ctx, double *S, double *b, int n, size_t ld, const int *lim_host, const int *lim_dev,
@@ -485,9 +834,91 @@ static int split_solve(pmv_ctx *ctx, const BADev &D, const BASplit &P, cudaStrea
     return 1;
 }
 
-int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_host, const BASplit *split, cudaStream_t s)
+// Partitioned solve of a banded system (BAPart, ba.cuh).  Returns 1 when done, < 0 on error.
+static int part_solve(pmv_ctx *ctx, const BADev &D, const BAPart &Q, cudaStream_t s)
+{
+    const int n = D.n, P = Q.P, w = Q.w, wt = w / NB;
+    double *S = D.S, *b = D.rhs, *y = D.yc;
+    const size_t ld = (size_t)n, ww = (size_t)w * w;
+    part_prepare_kernel<<<1, 32, 0, s>>>(Q, D.st);
+    PMV_LAUNCH_CHECK(ctx, "part_prepare_kernel");
+    if (ctx->attr_first(PMV_ATTR_CHOL_SPIKE))
+        cudaFuncSetAttribute(part_spike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_SMEM);
+    // fork: extended system i on its own stream (i = 0 on s): factorisation (+ forward substitution of b), then the spike
+    PMV_CUDA_TRY(ctx, cudaEventRecord(Q.ev_fork[0], s));
+    for (int i = 0; i < P; i++) {
+        cudaStream_t si = i == 0 ? s : Q.str[i];
+        if (i > 0) PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(si, Q.ev_fork[0], 0));
+        const int r = pmv_internal_ba_cholesky_band(ctx, S + (size_t)Q.a[i] * ld + Q.a[i], b + Q.a[i], Q.nx[i], ld, Q.limX_h[i], Q.limX[i], Q.stp + i, si);
+        if (r < 0) return r;
+        if (r == 0) return ctx->fail(PMV_ERR_UNSUPPORTED, "part solve: segment not eligible for the cluster kernel");
+        if (i > 0) {
+            SpikeArgs A;
+            A.Sx = S + (size_t)Q.a[i] * ld + Q.a[i]; A.ld = ld; A.nx = Q.nx[i]; A.lim = Q.limX[i]; A.w = w;
+            A.bmode = 0; A.Bsrc = S + (size_t)(Q.a[i] - w) * ld + Q.a[i]; A.bld = ld; A.blim = D.chol_lim; A.brow0 = Q.a[i] - w; A.bcol0 = Q.a[i];
+            A.G = Q.G[i]; A.st = Q.stp + i;
+            part_spike_kernel<<<w / PS_CC, PS_WARPS * 32, PS_SMEM, si>>>(A);
+            PMV_LAUNCH_CHECK(ctx, "part_spike_kernel");
+            PMV_CUDA_TRY(ctx, cudaEventRecord(Q.ev_join[0][i], si));
+            PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(s, Q.ev_join[0][i], 0));
+        }
+    }
+    part_reduce_kernel<<<dim3(wt * (wt + 1) / 2 + wt * wt + 1, P - 1), 256, 0, s>>>(S, b, ld, Q);
+    PMV_LAUNCH_CHECK(ctx, "part_reduce_kernel");
+    // separator chain, forward
+    for (int j = 0; j < P - 1; j++) {
+        if (j > 0) {
+            part_sep_update_kernel<<<wt * (wt + 1) / 2 + 1, 256, 0, s>>>(Q, j);
+            PMV_LAUNCH_CHECK(ctx, "part_sep_update_kernel");
+        }
+        const int r = pmv_internal_ba_cholesky_band(ctx, Q.Dsep + j * ww, Q.bR + (size_t)j * w, w, (size_t)w, Q.limD_h, Q.limD, Q.stp + P + j, s);
+        if (r <= 0) return r < 0 ? r : ctx->fail(PMV_ERR_UNSUPPORTED, "part solve: separator block not eligible for the cluster kernel");
+        if (j < P - 2) {
+            SpikeArgs A;
+            A.Sx = Q.Dsep + j * ww; A.ld = (size_t)w; A.nx = w; A.lim = Q.limD; A.w = w;
+            A.bmode = 1; A.Bsrc = Q.E + j * ww; A.bld = (size_t)w; A.blim = nullptr; A.brow0 = 0; A.bcol0 = 0;
+            A.G = Q.F + j * ww; A.st = Q.stp + P + j;
+            part_spike_kernel<<<w / PS_CC, PS_WARPS * 32, PS_SMEM, s>>>(A);
+            PMV_LAUNCH_CHECK(ctx, "part_spike_kernel");
+        }
+    }
+    // separator chain, backward
+    for (int j = P - 2; j >= 0; j--) {
+        if (j < P - 2) {
+            part_sep_back_kernel<<<8, 256, 0, s>>>(Q, j);
+            PMV_LAUNCH_CHECK(ctx, "part_sep_back_kernel");
+        }
+        int rc = launch_backsub(ctx, Q.Dsep + j * ww, Q.bR + (size_t)j * w, Q.yR + (size_t)j * w, w, (size_t)w, Q.limD_h, Q.limD, Q.stp + P + j, s);
+        if (rc) return rc;
+    }
+    part_fix_kernel<<<dim3(32, P), 256, 0, s>>>(S, b, ld, Q);
+    PMV_LAUNCH_CHECK(ctx, "part_fix_kernel");
+    PMV_CUDA_TRY(ctx, cudaEventRecord(Q.ev_fork[1], s));
+    for (int i = 0; i < P; i++) {
+        cudaStream_t si = i == 0 ? s : Q.str[i];
+        if (i > 0) PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(si, Q.ev_fork[1], 0));
+        int rc = launch_backsub(ctx, S + (size_t)Q.a[i] * ld + Q.a[i], b + Q.a[i], y + Q.a[i], Q.nx[i], ld, Q.limX_h[i], Q.limX[i], Q.stp + i, si);
+        if (rc) return rc;
+        if (i > 0) {
+            PMV_CUDA_TRY(ctx, cudaEventRecord(Q.ev_join[1][i], si));
+            PMV_CUDA_TRY(ctx, cudaStreamWaitEvent(s, Q.ev_join[1][i], 0));
+        }
+    }
+    part_finish_kernel<<<1, 1, 0, s>>>(Q, D.st);
+    PMV_LAUNCH_CHECK(ctx, "part_finish_kernel");
+    return 1;
+}
+
+int pmv_internal_ba_cholesky_large(pmv_ctx *ctx, const BADev &D, const int *lim_host, const BASplit *split, const BAPart *part,
+                                   cudaStream_t s)
 {
     const int n = D.n;
+    if (part && part->enabled && D.W == 1) {
+        chol_gradient_check_kernel<<<1, 1, 0, s>>>(D.st);
+        PMV_LAUNCH_CHECK(ctx, "chol_gradient_check_kernel");
+        const int r = part_solve(ctx, D, *part, s);
+        return r < 0 ? r : PMV_OK;
+    }
     if (split && split->enabled && D.W == 1) {
         chol_gradient_check_kernel<<<1, 1, 0, s>>>(D.st);
         PMV_LAUNCH_CHECK(ctx, "chol_gradient_check_kernel");

@@ -228,32 +228,40 @@ def test_run_organised_rejected_steps(ctx, synth, monkeypatch):
     assert abs(s[0]["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]
 
 
-@pytest.mark.parametrize("nposes,npts,span", [(400, 20000, 20), (250, 12000, 30)])
-def test_two_sided_band_solve_matches_one_sided_and_oracle(ctx, pmv, synth, monkeypatch, ba_path, nposes, npts, span):
-    """Long banded reduced camera systems are cut at a separator in the middle: the leading system and the
-    index-reversed trailing system are factorised concurrently by two clusters, the separator's Schur complement is
-    solved last (BASplit).  Same iterates as the one-sided factorisation and as the oracle."""
+@pytest.mark.parametrize("nposes,npts,span", [(400, 20000, 20), (250, 12000, 30), (700, 30000, 24)])
+def test_partitioned_and_two_sided_band_solves_match_one_sided_and_oracle(ctx, pmv, synth, monkeypatch, ba_path, nposes, npts, span):
+    """Long banded reduced camera systems are not factorised as one chain of block steps: by default the band is cut once
+    in the middle and the leading and the index-reversed trailing system are factorised by two clusters (BASplit); with
+    PMV_CHOL_PARTS=P >= 3 (opt-in) P segments separated by P - 1 separators are eliminated concurrently (spikes for the
+    left couplings, block-tridiagonal separator system: BAPart).  Same iterates as the one-sided factorisation and as
+    the oracle."""
     if ba_path == "window":
         pytest.skip("general path only")
     w = synth.ba_large(31, n_poses=nposes, n_points=npts, views=5, span=span)
     po, xo, so = oracle.ba_solve(*_args(w), 1.0, 3)
     res = {}
-    for mode in ("split", "one_sided"):
-        if mode == "split":
-            monkeypatch.delenv("PMV_CHOL_NO_SPLIT", raising=False)
-        else:
+    for mode in ("part", "part3", "split", "one_sided"):
+        monkeypatch.delenv("PMV_CHOL_NO_SPLIT", raising=False)
+        monkeypatch.delenv("PMV_CHOL_PARTS", raising=False)
+        if mode == "part3":
+            monkeypatch.setenv("PMV_CHOL_PARTS", "3")
+        elif mode == "part":
+            monkeypatch.setenv("PMV_CHOL_PARTS", "4")
+        elif mode == "one_sided":
             monkeypatch.setenv("PMV_CHOL_NO_SPLIT", "1")
         prob = ctx.ba_problem(*_args(w), 1.0)
         prob.solve(3)
         p, x, s = prob.download()
         prob.close()
         res[mode] = (p, s[0])
-        assert s[0]["iterations"] == so["iterations"] and s[0]["successful_steps"] == so["successful_steps"]
-        assert abs(s[0]["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]
-        assert np.abs(p[0] - po).max() < 1e-5
+        assert s[0]["iterations"] == so["iterations"] and s[0]["successful_steps"] == so["successful_steps"], mode
+        assert abs(s[0]["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"], mode
+        assert np.abs(p[0] - po).max() < 1e-5, mode
     monkeypatch.delenv("PMV_CHOL_NO_SPLIT", raising=False)
-    assert np.abs(res["split"][0] - res["one_sided"][0]).max() < 1e-8
-    assert abs(res["split"][1]["final_cost"] - res["one_sided"][1]["final_cost"]) <= 1e-10 * so["final_cost"]
+    monkeypatch.delenv("PMV_CHOL_PARTS", raising=False)
+    for mode in ("part", "part3", "split"):
+        assert np.abs(res[mode][0] - res["one_sided"][0]).max() < 1e-8, mode
+        assert abs(res[mode][1]["final_cost"] - res["one_sided"][1]["final_cost"]) <= 1e-10 * so["final_cost"], mode
 
 
 def test_resident_problem_reset_and_errors(ctx, pmv, synth):
