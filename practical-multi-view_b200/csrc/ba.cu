@@ -58,8 +58,10 @@ struct pmv_ba_problem {
     int2 *d_entries = nullptr;
     int nsegs = 0;
     // run-organised path of one large problem (ba_runs.cuh): points sorted by camera tuple, runs of equal tuples
-    int *d_run_off = nullptr, *d_run_pt = nullptr;
+    int *d_run_off = nullptr;
+    int2 *d_run_pt = nullptr;                           // (point, first observation of the point) per run position
     int nruns = 0;
+    RunSide run_side[2];                                // side stream + fork / join events of the elimination / the back-substitution
     int run_kbegin[RUN_MAXK + 2] = {};                  // runs are ordered by tuple size: [kbegin[k], kbegin[k+1]) have k observations
     // two-sided solve of the banded reduced camera system (BASplit, ba.cuh)
     BASplit split;
@@ -185,7 +187,11 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
     if (p->nruns > 0) {
         // runs of equal camera tuples: cost + raw camera blocks straight from the observations (nothing materialised)
         PMV_CUDA_TRY(ctx, cudaMemsetAsync(p->d_Uraw, 0, sizeof(double) * 27 * (size_t)wc, s));
-        ba_run_cam_kernel<<<(p->nruns + 3) / 4, 128, 0, s>>>(D, p->d_run_off, p->d_run_pt, p->nruns, p->d_Uraw);
+        ba_cam_trig_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D.poses, D.trig, wc, D.st, 0);
+        PMV_LAUNCH_CHECK(ctx, "ba_cam_trig_kernel");
+        if (run_minb(1) >= 4) ba_run_cam_kernel<4><<<(p->nruns + 3) / 4, 128, 0, s>>>(D, p->d_run_off, p->d_run_pt, p->nruns, p->d_Uraw);
+        else if (run_minb(1) == 3) ba_run_cam_kernel<3><<<(p->nruns + 3) / 4, 128, 0, s>>>(D, p->d_run_off, p->d_run_pt, p->nruns, p->d_Uraw);
+        else ba_run_cam_kernel<2><<<(p->nruns + 3) / 4, 128, 0, s>>>(D, p->d_run_off, p->d_run_pt, p->nruns, p->d_Uraw);
         PMV_LAUNCH_CHECK(ctx, "ba_run_cam_kernel");
     } else if (D.No > 0) {
         ba_linearize_kernel<<<(D.No + 127) / 128, 128, 0, s>>>(D);
@@ -220,7 +226,7 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
         PMV_LAUNCH_CHECK(ctx, "ba_clear_system_kernel");
     }
     if (wp > 0 && p->nruns > 0) {
-        int rc = launch_run_schur_all(ctx, D, p->d_run_off, p->d_run_pt, p->run_kbegin, s);
+        int rc = launch_run_schur_all(ctx, D, p->d_run_off, p->d_run_pt, p->run_kbegin, s, p->run_side[0]);
         if (rc) return rc;
     } else if (wp > 0) {
         const int by_pairs = p->nsegs > 0;
@@ -263,9 +269,16 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
     }
     ba_cam_candidate_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D, p->sharded ? (p->rank == 0) : 1);
     PMV_LAUNCH_CHECK(ctx, "ba_cam_candidate_kernel");
-    if (wp > 0) {
-        if (p->nruns > 0 || (W == 1 && (D.No >= 100000 || p->nsegs > 0) && D.No <= 8 * (long long)D.Np)) {
-            ba_backsub_w1_kernel<8><<<std::min((wp + 15) / 16, 148 * 32), 128, 0, s>>>(D);
+    if (D.cand_trig) {
+        ba_cam_trig_kernel<<<(wc + 127) / 128, 128, 0, s>>>(D.cand_poses, D.cand_trig, wc, D.st, 1);
+        PMV_LAUNCH_CHECK(ctx, "ba_cam_trig_kernel");
+    }
+    if (wp > 0 && p->nruns > 0) {
+        int rc = launch_run_backsub_all(ctx, D, p->d_run_off, p->d_run_pt, p->run_kbegin, s, p->run_side[1]);
+        if (rc) return rc;
+    } else if (wp > 0) {
+        if ((W == 1 && (D.No >= 100000 || p->nsegs > 0) && D.No <= 8 * (long long)D.Np)) {
+            ba_backsub_w1_kernel<8, 3><<<std::min((wp + 15) / 16, 148 * 32), 128, 0, s>>>(D);
             PMV_LAUNCH_CHECK(ctx, "ba_backsub_w1_kernel");
         } else {
             ba_backsub_kernel<<<std::min((wp + 3) / 4, 148 * 32), 128, 0, s>>>(D);
@@ -438,7 +451,8 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     lap("visibility + envelope");
     // ---- runs of points with the same camera tuple (ba_runs.cuh): one large problem whose points see <= 8 cameras.
     // PMV_BA_NO_RUNS=1 keeps the pair-list path, PMV_BA_FORCE_RUNS=1 (tests) sends small problems through the runs.
-    std::vector<int> run_off, run_pt;
+    std::vector<int> run_off;
+    std::vector<int2> run_pt;
     int run_kbegin[RUN_MAXK + 2] = {};
     {
         const char *no_runs = getenv("PMV_BA_NO_RUNS"), *force_runs = getenv("PMV_BA_FORCE_RUNS");
@@ -488,7 +502,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
             };
             run_pt.resize(keys.size());
             for (size_t i = 0; i < keys.size(); i++) {
-                run_pt[i] = keys[i].second;
+                run_pt[i] = make_int2(keys[i].second, pt_off[keys[i].second]);
                 const bool brk = i == 0 || keys[i].first != keys[i - 1].first || (int)i - run_off.back() >= RUN_MAXLEN ||
                                  !same_tuple(keys[i].second, keys[i - 1].second);
                 if (brk) run_off.push_back((int)i);
@@ -533,6 +547,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     rc |= dev_alloc(p, &p->d_init_poses, wc * 6); rc |= dev_alloc(p, &p->d_init_points, wp * 3);
     if (use_runs) {     // residuals and Jacobians are recomputed where they are used: no linearisation buffers
         rc |= dev_alloc(p, &p->d_run_off, run_off.size()); rc |= dev_alloc(p, &p->d_run_pt, run_pt.size());
+        rc |= dev_alloc(p, &D.trig, wc * 8); rc |= dev_alloc(p, &D.cand_trig, wc * 8);
     } else if (!window_ok) {   // the window path never materialises the linearisation
         rc |= dev_alloc(p, &D.Lr, 2 * (size_t)No); rc |= dev_alloc(p, &D.Ljc, 12 * (size_t)No); rc |= dev_alloc(p, &D.Ljp, 6 * (size_t)No);
     } else {
@@ -583,9 +598,19 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     up(p->d_init_poses, poses, sizeof(double) * wc * 6); up(p->d_init_points, points, sizeof(double) * wp * 3);
     if (window_ok) up(p->d_vis, h_vis.data(), sizeof(unsigned) * wp);
     if (use_runs) {
-        up(p->d_run_off, run_off.data(), sizeof(int) * run_off.size()); up(p->d_run_pt, run_pt.data(), sizeof(int) * run_pt.size());
+        up(p->d_run_off, run_off.data(), sizeof(int) * run_off.size()); up(p->d_run_pt, run_pt.data(), sizeof(int2) * run_pt.size());
         p->nruns = (int)run_off.size() - 1;
         for (int k = 0; k < RUN_MAXK + 2; k++) p->run_kbegin[k] = run_kbegin[k];
+        if (!getenv("PMV_RUN_NO_SIDE")) {
+            cudaStream_t s2 = nullptr;
+            bool okc = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking) == cudaSuccess;
+            for (auto &rs : p->run_side) {
+                rs.s2 = s2;
+                okc = okc && cudaEventCreateWithFlags(&rs.fork, cudaEventDisableTiming) == cudaSuccess &&
+                      cudaEventCreateWithFlags(&rs.join, cudaEventDisableTiming) == cudaSuccess;
+            }
+            if (!okc) ok = false;
+        }
     }
     if (ok && cudaStreamSynchronize(s) != cudaSuccess) ok = false;  // host vectors die at return
     lap("upload");
@@ -829,6 +854,8 @@ PMV_API void pmv_ba_problem_destroy(pmv_ba_problem *p)
     if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
     if (p->split.s2) { cudaStreamSynchronize(p->split.s2); cudaStreamDestroy(p->split.s2); }
     for (auto &e : p->split.ev) if (e) cudaEventDestroy(e);
+    if (p->run_side[0].s2) { cudaStreamSynchronize(p->run_side[0].s2); cudaStreamDestroy(p->run_side[0].s2); }
+    for (auto &rs : p->run_side) { if (rs.fork) cudaEventDestroy(rs.fork); if (rs.join) cudaEventDestroy(rs.join); }
     for (auto &st : p->part.str) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     for (auto &e : p->part.ev_fork) if (e) cudaEventDestroy(e);
     for (auto &row : p->part.ev_join) for (auto &e : row) if (e) cudaEventDestroy(e);
@@ -848,6 +875,8 @@ PMV_API int pmv_ba_problem_reset(pmv_ba_problem *p, const double *poses, const d
     if (points) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(p->d_init_points, points, pp, cudaMemcpyHostToDevice, s));
     PMV_CUDA_TRY(ctx, cudaMemcpyAsync(D.poses, p->d_init_poses, pc, cudaMemcpyDeviceToDevice, s));
     PMV_CUDA_TRY(ctx, cudaMemcpyAsync(D.points, p->d_init_points, pp, cudaMemcpyDeviceToDevice, s));
+    // the run-organised back-substitution writes the candidates of observed points only: the others keep x
+    if (p->nruns > 0) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(D.cand_points, p->d_init_points, pp, cudaMemcpyDeviceToDevice, s));
     ba_state_init_kernel<<<(D.W + 127) / 128, 128, 0, s>>>(D.st, D.W);
     PMV_LAUNCH_CHECK(ctx, "ba_state_init_kernel");
     if (poses || points) PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));

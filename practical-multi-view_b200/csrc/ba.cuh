@@ -50,6 +50,7 @@ struct BADev {
     double *U, *gc;              // per camera: scaled J_c^T J_c (36) and J_c^T r (6)
     double *S, *rhs, *yc;        // reduced camera system per window (n x n, upper blocks valid), solution
     double *Vinv, *gp;           // per point: (V + D^2)^-1 (6 unique) and J_p^T r (3)
+    double *trig, *cand_trig;    // run-organised path: per-camera CamTrig table (8 doubles) of poses / cand_poses, else nullptr
     BAState *st;
     const int *chol_lim;         // per PMV_CHOL_NB-row block of S: end column of its envelope (blocked Cholesky)
     int max_iters;

@@ -15,15 +15,50 @@
 namespace {
 
 // ---- ProjectionResidual: residual + analytic 2x6 / 2x3 Jacobians (== what Jets produce) ------------
-__device__ __forceinline__ void ba_project(const double *pose, const double *X, double p[3], double R[9],
-                                           double dpa[9] /* dpa[3*k+i] = d p_i / d a_k */, bool want_jac)
+// The angle-axis terms of a pose that do not depend on the point: cos / sin of the angle, its reciprocal, the unit axis.
+// ba_project() derives them in place; the kernels of one LARGE problem read them from a per-camera table that
+// ba_cam_trig_kernel fills once per iteration (5 observations per point and ~5 000 per camera: the square root, the
+// sine / cosine pair and the division were ~40 % of the instructions of every kernel that recomputes a Jacobian).
+// Same expressions either way, so both routes give the same bits.
+struct CamTrig {
+    double ct, st, ti, w0, w1, w2;   // small: w0..w2 hold the raw angle-axis vector (first-order rotation)
+    bool small;
+};
+
+__device__ __forceinline__ CamTrig ba_cam_trig(const double *pose)
 {
+    CamTrig T;
     const double a0 = pose[0], a1 = pose[1], a2 = pose[2];
-    const double q0 = X[0] + pose[3], q1 = X[1] + pose[4], q2 = X[2] + pose[5];
     const double th2 = a0 * a0 + a1 * a1 + a2 * a2;
-    if (th2 > DBL_EPSILON) {
-        const double th = sqrt(th2), ct = cos(th), st = sin(th), ti = 1.0 / th;
-        const double w0 = a0 * ti, w1 = a1 * ti, w2 = a2 * ti;
+    T.small = !(th2 > DBL_EPSILON);
+    if (!T.small) {
+        const double th = sqrt(th2);
+        T.ct = cos(th); T.st = sin(th); T.ti = 1.0 / th;
+        T.w0 = a0 * T.ti; T.w1 = a1 * T.ti; T.w2 = a2 * T.ti;
+    } else {
+        T.ct = 1.0; T.st = 0.0; T.ti = 0.0; T.w0 = a0; T.w1 = a1; T.w2 = a2;
+    }
+    return T;
+}
+
+// table layout: 8 doubles per camera {ct, st, ti, w0, w1, w2, small ? 1 : 0, 0}
+__device__ __forceinline__ CamTrig ba_cam_trig_load(const double *__restrict__ t)
+{
+    const double2 a = *reinterpret_cast<const double2 *>(t), b = *reinterpret_cast<const double2 *>(t + 2),
+                  c = *reinterpret_cast<const double2 *>(t + 4);
+    CamTrig T;
+    T.ct = a.x; T.st = a.y; T.ti = b.x; T.w0 = b.y; T.w1 = c.x; T.w2 = c.y;
+    T.small = t[6] != 0.0;
+    return T;
+}
+
+__device__ __forceinline__ void ba_project_t(const CamTrig &T, const double *tr /* pose + 3 */, const double *X, double p[3], double R[9],
+                                             double dpa[9] /* dpa[3*k+i] = d p_i / d a_k */, bool want_jac)
+{
+    const double q0 = X[0] + tr[0], q1 = X[1] + tr[1], q2 = X[2] + tr[2];
+    if (!T.small) {
+        const double ct = T.ct, st = T.st, ti = T.ti;
+        const double w0 = T.w0, w1 = T.w1, w2 = T.w2;
         const double x0 = w1 * q2 - w2 * q1, x1 = w2 * q0 - w0 * q2, x2 = w0 * q1 - w1 * q0;  // w x q
         const double d = w0 * q0 + w1 * q1 + w2 * q2, omc = 1.0 - ct;
         const double tmp = d * omc;
@@ -51,6 +86,7 @@ __device__ __forceinline__ void ba_project(const double *pose, const double *X, 
             }
         }
     } else {
+        const double a0 = T.w0, a1 = T.w1, a2 = T.w2;
         p[0] = q0 + (a1 * q2 - a2 * q1);
         p[1] = q1 + (a2 * q0 - a0 * q2);
         p[2] = q2 + (a0 * q1 - a1 * q0);
@@ -62,6 +98,32 @@ __device__ __forceinline__ void ba_project(const double *pose, const double *X, 
             dpa[6] = -q1; dpa[7] = q0; dpa[8] = 0;
         }
     }
+}
+
+__device__ __forceinline__ void ba_project(const double *pose, const double *X, double p[3], double R[9],
+                                           double dpa[9] /* dpa[3*k+i] = d p_i / d a_k */, bool want_jac)
+{
+    ba_project_t(ba_cam_trig(pose), pose + 3, X, p, R, dpa, want_jac);
+}
+
+// ---- fp64 reciprocal / reciprocal square root for the kernels of one large problem -------------------------------------
+// The hardware seed (MUFU.RCP64H / RSQ64H on the high word, measured relative error 1e-6 = 2^-20) refined by one cubic
+// step: relative error 1 - 2 ulp for normal arguments (tools/approx_probe.cu measures seed and result), without the special-case
+// branches and the correctly-rounded last step of x / y and sqrt() -- a third of the instructions and of the dependent
+// latency.  Used where the oracle's value is reproduced to ~1 ulp anyway (depth division, V^-1).
+__device__ __forceinline__ double ba_rcp_fast(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);     // error e -> e^3: the 2^-20 seed becomes 2^-60, below the rounding of the last fma
+}
+__device__ __forceinline__ double ba_rsqrt_fast(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, y, 1.0);           // 1 - x y^2
+    return fma(y, e * fma(0.375, e, 0.5), y);       // y (1 + e / 2 + 3 e^2 / 8): error -> O(e^3)
 }
 
 __device__ __forceinline__ void ba_residual_jac(const double *pose, const double *X, double ox, double oy,
@@ -84,6 +146,52 @@ __device__ __forceinline__ void ba_residual_jac(const double *pose, const double
         Jc[3 + k] = j0; Jc[9 + k] = j1;
         Jp[k] = j0; Jp[3 + k] = j1;
     }
+}
+
+// the same residual / Jacobians from the per-camera table, one refined reciprocal instead of three divisions
+__device__ __forceinline__ void ba_residual_jac_t(const CamTrig &T, const double *tr, const double *X, double ox, double oy,
+                                                  double fx, double cx, double fy, double cy,
+                                                  double r[2], double Jc[12], double Jp[6])
+{
+    double p[3], R[9], dpa[9];
+    ba_project_t(T, tr, X, p, R, dpa, true);
+    const double iz = ba_rcp_fast(p[2]);
+    r[0] = ox - (-(p[0] * iz) * fx + cx);
+    r[1] = oy - (-(p[1] * iz) * fy + cy);
+    const double a0 = fx * iz, a2 = -fx * p[0] * iz * iz;   // d r0 / d p0, d r0 / d p2
+    const double b1 = fy * iz, b2 = -fy * p[1] * iz * iz;   // d r1 / d p1, d r1 / d p2
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        Jc[k] = a0 * dpa[3 * k] + a2 * dpa[3 * k + 2];
+        Jc[6 + k] = b1 * dpa[3 * k + 1] + b2 * dpa[3 * k + 2];
+        const double j0 = a0 * R[k] + a2 * R[6 + k], j1 = b1 * R[3 + k] + b2 * R[6 + k];
+        Jc[3 + k] = j0; Jc[9 + k] = j1;
+        Jp[k] = j0; Jp[3 + k] = j1;
+    }
+}
+
+__device__ __forceinline__ void ba_residual_only_t(const CamTrig &T, const double *tr, const double *X, double ox, double oy,
+                                                   double fx, double cx, double fy, double cy, double r[2])
+{
+    double p[3];
+    ba_project_t(T, tr, X, p, nullptr, nullptr, false);
+    const double iz = ba_rcp_fast(p[2]);
+    r[0] = ox - (-(p[0] * iz) * fx + cx);
+    r[1] = oy - (-(p[1] * iz) * fy + cy);
+}
+
+// Corrector scale sqrt(rho') -- 1 for every inlier (rho' == 1 exactly): the square root only runs for outliers
+__device__ __forceinline__ double ba_sqrt_rho1(double rho1) { return rho1 == 1.0 ? 1.0 : sqrt(rho1); }
+
+// per-camera table of the kernels of one large problem (see CamTrig)
+__global__ void __launch_bounds__(128) ba_cam_trig_kernel(const double *__restrict__ poses, double *__restrict__ trig, int ncam,
+                                                          const BAState *st, int need_chol)
+{
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= ncam || st->done || (need_chol && !st->chol_ok)) return;
+    const CamTrig T = ba_cam_trig(poses + 6 * (size_t)c);
+    double *t = trig + 8 * (size_t)c;
+    t[0] = T.ct; t[1] = T.st; t[2] = T.ti; t[3] = T.w0; t[4] = T.w1; t[5] = T.w2; t[6] = T.small ? 1.0 : 0.0; t[7] = 0.0;
 }
 
 __device__ __forceinline__ void ba_residual_only(const double *pose, const double *X, double ox, double oy,
@@ -819,10 +927,11 @@ __device__ __forceinline__ void backsub_fetch(const BADev &D, int i, int ci, con
 #pragma unroll
         for (int k = 0; k < 6; k++) jp[k] = D.Ljp[6 * (size_t)i + k];
     } else {
-        ba_residual_jac(D.poses + 6 * (size_t)ci, X, D.obs_xy[2 * (size_t)i], D.obs_xy[2 * (size_t)i + 1], D.fx, D.cx, D.fy, D.cy, r, jc, jp);
+        const double2 o = *reinterpret_cast<const double2 *>(D.obs_xy + 2 * (size_t)i);
+        ba_residual_jac_t(ba_cam_trig_load(D.trig + 8 * (size_t)ci), D.poses + 6 * (size_t)ci + 3, X, o.x, o.y, D.fx, D.cx, D.fy, D.cy, r, jc, jp);
         double rho0, rho1;
         ba_huber(D.delta, r[0] * r[0] + r[1] * r[1], rho0, rho1);
-        const double sr = sqrt(rho1);
+        const double sr = ba_sqrt_rho1(rho1);
         r[0] = r[0] * sr; r[1] = r[1] * sr;
 #pragma unroll
         for (int k = 0; k < 12; k++) jc[k] = jc[k] * sr;
@@ -831,8 +940,8 @@ __device__ __forceinline__ void backsub_fetch(const BADev &D, int i, int ci, con
     }
 }
 
-template <int G>
-__global__ void __launch_bounds__(128) ba_backsub_w1_kernel(const BADev D)
+template <int G, int MINB>
+__global__ void __launch_bounds__(128, MINB) ba_backsub_w1_kernel(const BADev D)
 {
     BAState *st = &D.st[0];
     if (st->done || !st->chol_ok) return;
@@ -900,8 +1009,12 @@ __global__ void __launch_bounds__(128) ba_backsub_w1_kernel(const BADev D)
             }
             mc -= m0 * (Lr[0] + m0 / 2.0) + m1 * (Lr[1] + m1 / 2.0);
             double r[2];
-            ba_residual_only(D.cand_poses + 6 * (size_t)ci, cand, D.obs_xy[2 * (size_t)i], D.obs_xy[2 * (size_t)i + 1],
-                             D.fx, D.cx, D.fy, D.cy, r);
+            if (D.cand_trig)
+                ba_residual_only_t(ba_cam_trig_load(D.cand_trig + 8 * (size_t)ci), D.cand_poses + 6 * (size_t)ci + 3, cand,
+                                   D.obs_xy[2 * (size_t)i], D.obs_xy[2 * (size_t)i + 1], D.fx, D.cx, D.fy, D.cy, r);
+            else
+                ba_residual_only(D.cand_poses + 6 * (size_t)ci, cand, D.obs_xy[2 * (size_t)i], D.obs_xy[2 * (size_t)i + 1],
+                                 D.fx, D.cx, D.fy, D.cy, r);
             double rho0, rho1;
             ba_huber(D.delta, r[0] * r[0] + r[1] * r[1], rho0, rho1);
             cc += 0.5 * rho0;
