@@ -81,10 +81,9 @@ __device__ __forceinline__ void win_residual_jac(const double *M /* 36, shared *
 #pragma unroll
         for (int i = 0; i < 3; i++)
             dp[3 * k + i] = M[9 + 9 * k + 3 * i] * q0 + M[9 + 9 * k + 3 * i + 1] * q1 + M[9 + 9 * k + 3 * i + 2] * q2;
-    const double pz = p[2] * -1.0;
-    r[0] = ox - (p[0] / pz * fx + cx);
-    r[1] = oy - (p[1] / pz * fy + cy);
-    const double iz = 1.0 / p[2];
+    const double iz = ba_rcp_fast(p[2]);   // one refined reciprocal instead of three divisions (ba_kernels.cuh)
+    r[0] = ox - (-(p[0] * iz) * fx + cx);
+    r[1] = oy - (-(p[1] * iz) * fy + cy);
     const double a0 = fx * iz, a2 = -fx * p[0] * iz * iz, b1 = fy * iz, b2 = -fy * p[1] * iz * iz;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -192,7 +191,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D,
     if (tid < 8) sScal[tid] = 0.0;
     for (size_t i = tid; i < 4 * bufsz; i += WS_THREADS) sYW[i] = 0.0;   // padding rows / columns stay zero
     __syncthreads();
-    const double radius = st->radius;
+    const double radius = st->radius, inv_radius = 1.0 / radius;
     const int nchunks = (D.Np + P - 1) / P;
     const bool is_producer = tid >= 256;
 
@@ -238,7 +237,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D,
                             double rho0, rho1;
                             ba_huber(D.delta, r[0] * r[0] + r[1] * r[1], rho0, rho1);
                             cost += 0.5 * rho0;
-                            const double sr = sqrt(rho1);
+                            const double sr = ba_sqrt_rho1(rho1);
                             const double *sp = D.scale_p + 3 * wp;
 #pragma unroll
                             for (int k = 0; k < 3; k++) { const double sc = sr * sp[k]; it[k] = jp[k] * sc; it[3 + k] = jp[3 + k] * sc; }
@@ -286,12 +285,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D,
                             const double *sp = D.scale_p + 3 * wpp;
                             gmax = fmax(gmax, fmax(fabs(g[0] / sp[0]), fmax(fabs(g[1] / sp[1]), fabs(g[2] / sp[2]))));
                         }
-                        // D^2 = (sqrt(diag / radius))^2, like the LM strategy
-                        const double d0 = sqrt(D.diag_p[3 * wpp] / radius), d1 = sqrt(D.diag_p[3 * wpp + 1] / radius),
-                                     d2 = sqrt(D.diag_p[3 * wpp + 2] / radius);
-                        const double a = V[0] + d0 * d0, b2 = V[1], c = V[2], d = V[3] + d1 * d1, e = V[4], f = V[5] + d2 * d2;
+                        // D^2 = diag / radius (the LM strategy forms sqrt(diag / radius) and squares it again: the same to an ulp)
+                        const double a = fma(D.diag_p[3 * wpp], inv_radius, V[0]), b2 = V[1], c = V[2],
+                                     d = fma(D.diag_p[3 * wpp + 1], inv_radius, V[3]), e = V[4], f = fma(D.diag_p[3 * wpp + 2], inv_radius, V[5]);
                         const double A0 = d * f - e * e, A1 = c * e - b2 * f, A2 = b2 * e - c * d;
-                        const double idet = 1.0 / (a * A0 + b2 * A1 + c * A2);
+                        const double idet = ba_rcp_fast(a * A0 + b2 * A1 + c * A2);
                         pt[0] = A0 * idet; pt[1] = A1 * idet; pt[2] = A2 * idet;
                         pt[3] = (a * f - c * c) * idet; pt[4] = (b2 * c - a * e) * idet; pt[5] = (a * d - b2 * b2) * idet;
                         pt[6] = g[0]; pt[7] = g[1]; pt[8] = g[2];
