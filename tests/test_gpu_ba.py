@@ -264,6 +264,33 @@ def test_partitioned_and_two_sided_band_solves_match_one_sided_and_oracle(ctx, p
         assert abs(res[mode][1]["final_cost"] - res["one_sided"][1]["final_cost"]) <= 1e-10 * so["final_cost"], mode
 
 
+@pytest.mark.parametrize("runs", [False, True])
+def test_observation_order_does_not_matter(ctx, synth, monkeypatch, ba_path, runs):
+    """Problem creation takes the caller's list as it is when it is already sorted by (point, camera) -- the order
+    exporters and the generators here produce -- and sorts it otherwise: a shuffled list must give the same solve."""
+    if runs:
+        if ba_path == "window":
+            pytest.skip("general path only")
+        monkeypatch.setenv("PMV_BA_FORCE_RUNS", "1")
+        w = synth.ba_large(5, n_poses=30, n_points=2500, views=5, span=16)
+    else:
+        w = synth.ba_window(9, n_poses=6, n_points=300)
+    rng = np.random.default_rng(3)
+    order = rng.permutation(len(w["cam_idx"]))
+    out = []
+    for obs, cam, pt in ((w["obs"], w["cam_idx"], w["pt_idx"]), (w["obs"][order], w["cam_idx"][order], w["pt_idx"][order])):
+        prob = ctx.ba_problem(w["poses"], w["points"], np.ascontiguousarray(obs), np.ascontiguousarray(cam), np.ascontiguousarray(pt), w["K"], 1.0)
+        prob.solve(4)
+        p, x, s = prob.download()
+        prob.close()
+        out.append((p[0], x[0], s[0]))
+    (p0, x0, s0), (p1, x1, s1) = out
+    assert s0["iterations"] == s1["iterations"] and s0["successful_steps"] == s1["successful_steps"]
+    assert abs(s0["final_cost"] - s1["final_cost"]) <= 1e-10 * s0["final_cost"]
+    assert np.abs(p0 - p1).max() < 1e-8 and np.abs(x0 - x1).max() < 1e-5   # fp64 atomics reorder the sums of weakly constrained points
+    monkeypatch.delenv("PMV_BA_FORCE_RUNS", raising=False)
+
+
 def test_resident_problem_reset_and_errors(ctx, pmv, synth):
     w = synth.ba_window(9, n_poses=5, n_points=100)
     prob = ctx.ba_problem(*_args(w))
