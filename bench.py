@@ -457,13 +457,31 @@ def run_extract(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     Hh, Ww, NF = 2160, 3840, 10000
     steps = args.steps
-    f0, f1 = synth.frame_pair(500 + rank, h=Hh, w=Ww)
+    NPAIR = 8          # ring of resident frame pairs: 16 x 8.3 MB = 133 MB > the 126 MB L2
+    pairs = [synth.frame_pair(500 + 10 * rank + i, h=Hh, w=Ww) for i in range(NPAIR)]
+    # host side: pinned buffers (the e2e leg copies from them every step)
+    hpin = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in pairs]
+    f0, f1 = hpin[0][0].numpy(), hpin[0][1].numpy()
     ctx = pmv_b200.Context(local_rank)
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
+    dpairs = [(a.cuda(), b.cuda()) for a, b in hpin]
+    d_xy = torch.zeros(NF, 2, dtype=torch.float32, device="cuda"); d_nx = torch.zeros(NF, 2, dtype=torch.float32, device="cuda")
+    d_st = torch.zeros(NF, dtype=torch.uint8, device="cuda"); d_er = torch.zeros(NF, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
 
-    def step():
-        xy, sc = ctx.gftt(f0, NF, 0.01, 5)
-        return xy, ctx.lk_track(f0, f1, xy, WIN, MAX_LEVEL)
+    def step(i=0):
+        """host buffers in, host results out: pmv_gftt + pmv_lk_track"""
+        a, b = hpin[i % NPAIR][0].numpy(), hpin[i % NPAIR][1].numpy()
+        xy, sc = ctx.gftt(a, NF, 0.01, 5)
+        return xy, ctx.lk_track(a, b, xy, WIN, MAX_LEVEL)
+
+    def step_dev(i=0):
+        """everything resident in HBM: pmv_gftt_dev + pmv_lk_track_batched_dev (batch of one pair)"""
+        a, b = dpairs[i % NPAIR]
+        n = ctx.gftt_dev(a.data_ptr(), Hh, Ww, Ww, NF, d_xy.data_ptr())
+        ctx.lk_track_batched_dev(a.data_ptr(), b.data_ptr(), 1, Hh * Ww, Hh, Ww, Ww, d_xy.data_ptr(), n,
+                                 d_nx.data_ptr(), d_st.data_ptr(), d_er.data_ptr(), WIN, MAX_LEVEL)
+        return n
 
     def barrier():
         if world > 1:
@@ -471,18 +489,33 @@ def run_extract(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     warmup = max(args.warmup, 3)
-    for _ in range(warmup):
-        xy, (nx, st, err) = step()
+    for k in range(warmup):
+        xy, (nx, st, err) = step(0)
+        step_dev(k)
         ctx.shitomasi(f0, NF); ctx.fast(f0, 10, True, NF)
+    # the resident path must give what the host-buffer path gives
+    n_dev = step_dev(0); torch.cuda.synchronize()
+    dev_equal = bool(n_dev == len(xy) and np.array_equal(d_xy[:n_dev].cpu().numpy(), xy) and
+                     np.array_equal(d_st[:n_dev].cpu().numpy(), st) and np.array_equal(d_nx[:n_dev].cpu().numpy()[st == 1], nx[st == 1]))
     barrier()
     sampler = ClockSampler(local_rank); ctx.profile(True); ctx.profile_collect(); l0 = ctx.launches
     barrier(); sampler.start()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record(stream)
+    for k in range(steps):
+        step_dev(k)
+    eb.record(stream)
+    barrier()
+    dt_dev = ea.elapsed_time(eb) * 1e-3
+    clocks = sampler.stop(); launches = ctx.launches - l0
+    ctx.profile_collect()
+    barrier()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        xy, (nx, st, err) = step()
+    for k in range(steps):
+        step(k)
     barrier()
     dt = time.perf_counter() - t0
-    clocks = sampler.stop(); launches = ctx.launches - l0
+    xy, (nx, st, err) = step(0)
     prof = ctx.profile_collect()
     for _ in range(steps):
         ctx.shitomasi(f0, NF)
@@ -512,11 +545,14 @@ def run_extract(args, rank, world, local_rank):
     ms_eig8 = timed8(lambda: ctx.min_eigen_val_batched_dev(d8.data_ptr(), NB8, Hh * pitch8, Hh, Ww, pitch8, eig8.data_ptr(), emax8.data_ptr()))
     ms_shi8 = timed8(lambda: ctx.shitomasi_response_batched_dev(d8.data_ptr(), NB8, Hh * pitch8, Hh, Ww, pitch8, R8.data_ptr(), rmax8.data_ptr()))
     dt_max = max_over_ranks(dt, world)
-    value = world * steps / dt_max
+    dt_dev_max = max_over_ranks(dt_dev, world)
+    value = world * steps / dt_dev_max
+    e2e_value = world * steps / dt_max
     out = None
     if rank == 0:
         import cv2
         cv2.setNumThreads(os.cpu_count() or 1)
+        f0, f1 = pairs[0]
         tc = time.perf_counter()
         reps = 2
         for _ in range(reps):
@@ -535,8 +571,9 @@ def run_extract(args, rank, world, local_rank):
                     "lk_4k_status_equal_to_cv2": bool(np.array_equal(st, cst.ravel())),
                     "lk_4k_max_abs_dpos_px": float(np.abs(nx[okm] - c1.reshape(-1, 2)[okm]).max()) if okm.any() else None,
                     "tracked": int(st.sum())})
+        par["resident_path_identical_to_host_path"] = dev_equal
         par["ok"] = bool(par["set_equal"] and par["swaps_within_tie"] and ok_ties and par["lk_4k_status_equal_to_cv2"]
-                         and (par["lk_4k_max_abs_dpos_px"] or 0) < 0.01)
+                         and (par["lk_4k_max_abs_dpos_px"] or 0) < 0.01 and dev_equal)
         peak, peak_src = hbm_peak()
         npx = Hh * Ww
 
@@ -556,14 +593,15 @@ def run_extract(args, rank, world, local_rank):
         kern["shitomasi_response_kernel, 8 resident 4K frames per launch (1 B/px in + 8 B/px out; 597 MB > L2)"] = frac((ms_shi8, 1), NB8 * npx * 9)
         main_k = kern["mineig kernels, 8 resident 4K frames per launch (1 B/px in + 4 B/px out; inputs + outputs 332 MB > L2)"]
         out = {"metric": "frames_per_s_extract_plus_lk", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps,
-               "warmup": warmup, "ms_per_step": 1e3 * dt_max / steps, "higher_is_better": True, "scaling": "weak",
+               "warmup": warmup, "ms_per_step": 1e3 * dt_dev_max / steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "u8/int32+fp32", "data": "synthetic",
                "config": {"workload": "BASELINE config 3: Shi-Tomasi (goodFeaturesToTrack 10000, .01, 5) + pyramidal LK 21x21/maxLevel 3 on "
-                                      "3840x2160 frames, one stream per GPU, host buffers every step", "image": [Hh, Ww], "features": NF,
-                          "l2_policy": "one 8.3 MB frame pair per step fits L2; images arrive from the host every step (PCIe), kernels timed with CUDA events",
+                                      "3840x2160 frames, one stream per GPU; value: frames resident in HBM (pmv_gftt_dev + pmv_lk_track_batched_dev), "
+                                      "e2e: pinned host buffers every step", "image": [Hh, Ww], "features": NF,
+                          "l2_policy": f"ring of {NPAIR} resident frame pairs ({2 * NPAIR * npx // 1000000} MB) larger than the 126 MB L2, one pair per step; CUDA events on the launch stream",
                           "parallelism": "independent streams, no collective"},
-               "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": int(3 * npx), "d2h_bytes_per_step": int(NF * 12 + NF * 13),
-                       "api": "pmv_gftt + pmv_lk_track (host buffers)"},
+               "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(3 * npx), "d2h_bytes_per_step": int(NF * 12 + NF * 13),
+                       "ms_per_step": 1e3 * dt_max / steps, "api": "pmv_gftt + pmv_lk_track (pinned host buffers; the frame pair crosses PCIe every step)"},
                "gpu_launches": int(launches),
                "roofline": {"kernel": "mineig_fast_kernel + mineig_kernel (edges), batch of 8 resident 4K frames", "bound": "hbm", "achieved": main_k["achieved_GBps"] if main_k else None, "peak": peak,
                             "unit": "GB/s", "frac": main_k["frac_of_hbm_peak"] if main_k else None, "traffic": None, "peak_source": peak_src, "kernels": kern},
@@ -784,6 +822,12 @@ def run_lk(args, rank, world, local_rank):
     py_avg = py_ms / max(py_n, 1)
     py_bytes = (ALG_BYTES_PER_IMAGE_PYR * 2 + ALG_BYTES_PER_PREV_IMAGE_DERIV) * batch
     py_ach = py_bytes / (py_avg * 1e-3) / 1e9 if py_avg else None
+    # the level-0 launch of the group (two thirds of its time): reads W*H, writes level 1 and, for the prev images,
+    # the 4 B/px Scharr plane (+ 1 B/px read, SURVEY's K2 accounting); its bordered level-0 copy is not counted
+    p0_ms, p0_n = prof.get("pyr_l0", (0.0, 0))
+    p0_avg = p0_ms / max(p0_n, 1)
+    p0_bytes = ((H * W + 188 * 621) * 2 + 5 * H * W) * batch
+    p0_ach = p0_bytes / (p0_avg * 1e-3) / 1e9 if p0_avg else None
     # LK is bounded by instruction issue, not by HBM (SURVEY 8d asks for both figures): warp instructions per
     # feature and DRAM bytes per pair come from the ncu --set full capture of this kernel committed as
     # profiles/r2_lk_ncu_summary.txt (smsp__inst_executed.sum / 512 000 features); DRAM bytes per pair from the cold-cache
@@ -807,7 +851,12 @@ def run_lk(args, rank, world, local_rank):
                 "other_kernels": {"pyramid group (pyr_fused_kernel x4 per step: TMA tile -> level-0 copy + borders + Scharr planes + next level)": {
                     "bound": "hbm", "achieved": py_ach, "peak": peak, "unit": "GB/s",
                     "frac": (py_ach / peak) if py_ach else None, "avg_group_ms": py_avg,
-                    "algorithmic_bytes_per_group": py_bytes, "share_of_step": py_ms / ms if ms else None}}}
+                    "algorithmic_bytes_per_group": py_bytes, "share_of_step": py_ms / ms if ms else None},
+                    "pyr_fused_kernel<true>, level-0 launch of that group (dominant image kernel of the step)": {
+                    "bound": "hbm", "achieved": p0_ach, "peak": peak, "unit": "GB/s",
+                    "frac": (p0_ach / peak) if p0_ach else None, "avg_launch_ms": p0_avg,
+                    "algorithmic_bytes_per_launch": p0_bytes,
+                    "traffic": 1042363392.0, "traffic_source": "dram__bytes_read + dram__bytes_write, profiles/r2_pyr_fused_ncu_summary.txt"}}}
 
     out = None
     if rank == 0:

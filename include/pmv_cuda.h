@@ -75,6 +75,7 @@ PMV_API const char *pmv_version(void);
 #define PMV_PHASE_SELECT 3
 #define PMV_PHASE_FAST 4
 #define PMV_PHASE_BA 5
+#define PMV_PHASE_PYR_L0 6   /* the level-0 launch of the pyramid group (inside PMV_PHASE_PYRAMID) */
 #define PMV_PHASE_COUNT 8
 PMV_API int pmv_profile_enable(pmv_ctx *ctx, int on);
 PMV_API int pmv_profile_collect(pmv_ctx *ctx, int n_phases, double *ms_sum, int *count);
@@ -233,6 +234,15 @@ PMV_API int pmv_shitomasi_response_batched_dev(pmv_ctx *ctx, const uint8_t *d_im
 PMV_API int pmv_gftt(pmv_ctx *ctx, const uint8_t *base, int full_rows, int full_cols, int step,
                      int roi_x, int roi_y, int roi_w, int roi_h, int max_corners, double quality,
                      double min_dist, int block_size, int ksize, float *xy, float *score, int *n_out);
+
+/* pmv_gftt on an image that is already RESIDENT in HBM (device pointer, read in place; the fast response kernels need
+ * base, step and roi_x 4-byte aligned, otherwise the tile kernels run).  The corner list stays on the device:
+ * d_xy (max_corners x 2 floats), d_score (max_corners floats, may be NULL); *n_out on the host -- the call
+ * synchronises on the two counts goodFeaturesToTrack's control flow needs (candidates, corners), nothing else crosses
+ * PCIe.  max_corners > 0, block_size 3 / ksize 3. */
+PMV_API int pmv_gftt_dev(pmv_ctx *ctx, const uint8_t *d_base, int full_rows, int full_cols, int step,
+                         int roi_x, int roi_y, int roi_w, int roi_h, int max_corners, double quality,
+                         double min_dist, float *d_xy, float *d_score, int *n_out);
 
 /* ShiTomasiFeatureExtractor::computeShiTomasiResponse (ShiTomasiFeatureExtractor.cpp:49-75) on
  * Frame::getHarrisMatrix() (Frame.cpp:58-86, 119-138): fp64 response map, rows x cols doubles.

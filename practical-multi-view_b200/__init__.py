@@ -75,6 +75,7 @@ _SIGS = {
     "pmv_min_eigen_val": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp]),
     "pmv_gftt": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _dbl, _dbl, _int, _int,
                         _vp, _vp, _i32p]),
+    "pmv_gftt_dev": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _dbl, _dbl, _vp, _vp, _i32p]),
     "pmv_shitomasi_response": (_int, [_vp, _vp, _int, _int, _int, _int, _vp]),
     "pmv_shitomasi": (_int, [_vp, _vp, _int, _int, _int, _int, _dbl, _int, _vp, _vp, _vp, _i32p]),
     "pmv_fast": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _i32p, _i32p]),
@@ -202,7 +203,7 @@ class Context:
     def launches(self) -> int:
         return int(self.lib.pmv_launch_count(self.h))
 
-    PHASES = ("pyramid", "lk", "response", "select", "fast", "ba", "p6", "p7")
+    PHASES = ("pyramid", "lk", "response", "select", "fast", "ba", "pyr_l0", "p7")
 
     def profile(self, on: bool):
         self._chk(self.lib.pmv_profile_enable(self.h, int(on)))
@@ -375,6 +376,14 @@ class Context:
         self._chk(self.lib.pmv_gftt(self.h, _ptr(img), img.shape[0], img.shape[1], img.strides[0], x, y, w, h,
                                     max_corners, quality, min_dist, block_size, ksize, _ptr(xy), _ptr(sc), C.byref(n)))
         return xy[:n.value], sc[:n.value]
+
+    def gftt_dev(self, d_img: int, rows, cols, step, max_corners, d_xy: int, d_score: int = 0, quality=0.01, min_dist=5.0, roi=None):
+        """pmv_gftt_dev: resident image (device pointer as int) in, corner list to device buffers; returns the count."""
+        x, y, w, h = roi if roi is not None else (0, 0, cols, rows)
+        n = C.c_int(0)
+        self._chk(self.lib.pmv_gftt_dev(self.h, _ptr(d_img), rows, cols, step, x, y, w, h, max_corners, quality, min_dist,
+                                        _ptr(d_xy), _ptr(d_score), C.byref(n)))
+        return n.value
 
     def shitomasi_response(self, img, signed_quirk=True):
         assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1

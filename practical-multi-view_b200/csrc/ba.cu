@@ -41,7 +41,6 @@ struct pmv_ba_problem {
     double *d_init_poses = nullptr, *d_init_points = nullptr;
     double *d_Uraw = nullptr, *d_Uraw_red = nullptr;   // 27 doubles per camera (+ W cost slots at the end)
     double *d_scal = nullptr, *d_scal_red = nullptr;   // per window: model_change, cand_cost, step_norm2, x_norm2
-    std::vector<int> perm;                               // caller observation order -> device order
     std::vector<int> chol_lim;                           // envelope of S per PMV_CHOL_NB-row block (host copy)
     // one LM iteration is a fixed launch sequence (all decisions live in BAState on the device), so it is
     // captured once into a CUDA graph and replayed: removes the launch gaps of the ~600 dependent launches
@@ -351,22 +350,9 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
             return nullptr;
         }
     }
-    std::vector<int> pt_off((size_t)W * Np + 1, 0), cam_off((size_t)W * Nc + 1, 0);
-#pragma omp parallel for schedule(static)
-    for (int i = 0; i < No; i++) {
-        int *pc = &pt_off[(size_t)win[i] * Np + pt_idx[i] + 1], *cc = &cam_off[(size_t)win[i] * Nc + cam_idx[i] + 1];
-#pragma omp atomic
-        (*pc)++;
-#pragma omp atomic
-        (*cc)++;
-    }
-    std::partial_sum(pt_off.begin(), pt_off.end(), pt_off.begin());
-    std::partial_sum(cam_off.begin(), cam_off.end(), cam_off.begin());
-    RawBuf<int> perm(No), h_cam(No), h_pt(No), h_win(No), cam_obs;
-    RawBuf<double> h_obs(2 * (size_t)No);
     // Fast path: the caller's list is already in device order -- sorted by (window, point, camera), which is how
-    // structure-from-motion exports (and BAL files) come.  Then the permutation is the identity and the per-point sorts
-    // below are not needed (5 M observations: 92 -> ~15 ms).
+    // structure-from-motion exports (and BAL files) come.  Then the permutation is the identity, the point offsets are
+    // the boundaries of the list and nothing has to be sorted (5 M observations: 92 -> ~15 ms).
     int in_order = 1;
 #pragma omp parallel for schedule(static) reduction(& : in_order)
     for (int i = 1; i < No; i++) {
@@ -374,13 +360,62 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
                         (pt_idx[i - 1] == pt_idx[i] && cam_idx[i - 1] <= cam_idx[i])));
         in_order &= le ? 1 : 0;
     }
+    std::vector<int> pt_off((size_t)W * Np + 1, 0), cam_off((size_t)W * Nc + 1, 0);
     if (in_order) {
+        const long long nq = (long long)W * Np;
+        auto key = [&](int i) { return (long long)win[i] * Np + pt_idx[i]; };
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < No; i++) {            // pt_off[q] = first observation whose key is >= q
+            const long long k = key(i), kp = i ? key(i - 1) : -1;
+            for (long long q = kp + 1; q <= k; q++) pt_off[q] = i;
+        }
+        const long long last = No ? key(No - 1) : -1;
+#pragma omp parallel for schedule(static)
+        for (long long q = last + 1; q <= nq; q++) pt_off[q] = No;
+        // per-camera counts from thread-private histograms
+        int T = 1;
+#ifdef _OPENMP
+        T = std::max(1, omp_get_max_threads());
+#endif
+        const size_t bins = (size_t)W * Nc;
+        std::vector<int> hist((size_t)T * bins, 0);
+#pragma omp parallel num_threads(T)
+        {
+            int t = 0;
+#ifdef _OPENMP
+            t = omp_get_thread_num();
+#endif
+            int *hcnt = hist.data() + (size_t)t * bins;
+#pragma omp for schedule(static)
+            for (int i = 0; i < No; i++) hcnt[(size_t)win[i] * Nc + cam_idx[i]]++;
+        }
+#pragma omp parallel for schedule(static)
+        for (long long b = 0; b < (long long)bins; b++) {
+            int c = 0;
+            for (int t = 0; t < T; t++) c += hist[(size_t)t * bins + b];
+            cam_off[b + 1] = c;
+        }
+        std::partial_sum(cam_off.begin(), cam_off.end(), cam_off.begin());
+    } else {
 #pragma omp parallel for schedule(static)
         for (int i = 0; i < No; i++) {
-            perm[i] = i; h_cam[i] = cam_idx[i]; h_pt[i] = pt_idx[i]; h_win[i] = win[i];
-            h_obs[2 * (size_t)i] = obs[2 * (size_t)i]; h_obs[2 * (size_t)i + 1] = obs[2 * (size_t)i + 1];
+            int *pc = &pt_off[(size_t)win[i] * Np + pt_idx[i] + 1], *cc = &cam_off[(size_t)win[i] * Nc + cam_idx[i] + 1];
+#pragma omp atomic
+            (*pc)++;
+#pragma omp atomic
+            (*cc)++;
         }
-    } else {
+        std::partial_sum(pt_off.begin(), pt_off.end(), pt_off.begin());
+        std::partial_sum(cam_off.begin(), cam_off.end(), cam_off.begin());
+    }
+    // device-order arrays: the caller's own when the list is in order (no copies: 4 GB at BASELINE config 4), else sorted copies
+    RawBuf<int> h_cam, h_pt, h_win, cam_obs;
+    RawBuf<double> h_obs;
+    const int32_t *Hcam = cam_idx, *Hpt = pt_idx, *Hwin = win.data();
+    const double *Hobs = obs;
+    if (!in_order) {
+        h_cam.alloc(No); h_pt.alloc(No); h_win.alloc(No); h_obs.alloc(2 * (size_t)No);
+        Hcam = h_cam.data(); Hpt = h_pt.data(); Hwin = h_win.data(); Hobs = h_obs.data();
         // scatter by (window, point): slots of a point are claimed atomically, then every point orders its
         // observations by (camera, original index) -- the result is the stable order a serial pass produces
         std::vector<int> pos(pt_off.begin(), pt_off.end() - 1);
@@ -407,7 +442,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
                 const int wq = (int)(q / Np), pq = (int)(q - (long long)wq * Np);
                 for (int d = a; d < b; d++) {
                     const int src = tmp[d - a].second;
-                    perm[src] = d; h_cam[d] = tmp[d - a].first; h_pt[d] = pq; h_win[d] = wq;
+                    h_cam[d] = tmp[d - a].first; h_pt[d] = pq; h_win[d] = wq;
                     h_obs[2 * (size_t)d] = obs[2 * (size_t)src]; h_obs[2 * (size_t)d + 1] = obs[2 * (size_t)src + 1];
                 }
             }
@@ -420,7 +455,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
         std::vector<int> cpos(cam_off.begin(), cam_off.end() - 1);
 #pragma omp parallel for schedule(static)
         for (int d = 0; d < No; d++) {
-            int *cp = &cpos[(size_t)h_win[d] * Nc + h_cam[d]];
+            int *cp = &cpos[(size_t)Hwin[d] * Nc + Hcam[d]];
             int k;
 #pragma omp atomic capture
             { k = *cp; (*cp)++; }
@@ -451,8 +486,8 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
         for (long long q = 0; q < nq; q++) {       // the observations of a point are contiguous (and ordered by camera)
             unsigned m = 0;
             for (int d = pt_off[q]; d < pt_off[q + 1]; d++) {
-                if (m & (1u << h_cam[d])) twice = 1;   // the same camera sees the point twice -> general path
-                m |= 1u << h_cam[d];
+                if (m & (1u << Hcam[d])) twice = 1;   // the same camera sees the point twice -> general path
+                m |= 1u << Hcam[d];
             }
             h_vis[q] = m;
         }
@@ -464,8 +499,8 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     if (W == 1) {
         for (size_t q = 0; q + 1 < pt_off.size(); q++) {
             int cm = -1;
-            for (int d = pt_off[q]; d < pt_off[q + 1]; d++) cm = std::max(cm, h_cam[d]);
-            for (int d = pt_off[q]; d < pt_off[q + 1]; d++) emax[h_cam[d]] = std::max(emax[h_cam[d]], (double)cm);
+            for (int d = pt_off[q]; d < pt_off[q + 1]; d++) cm = std::max(cm, Hcam[d]);
+            for (int d = pt_off[q]; d < pt_off[q + 1]; d++) emax[Hcam[d]] = std::max(emax[Hcam[d]], (double)cm);
         }
     } else {
         for (int c = 0; c < Nc; c++) emax[c] = Nc - 1;   // batched windows use the small-n kernels anyway
@@ -489,7 +524,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
                 const int a = pt_off[q], b = pt_off[q + 1];
                 if (b - a > RUN_MAXK) too_wide = 1;
                 unsigned long long h = 1469598103934665603ull;
-                for (int d = a; d < b; d++) h = (h ^ (unsigned long long)(unsigned)h_cam[d]) * 1099511628211ull;
+                for (int d = a; d < b; d++) h = (h ^ (unsigned long long)(unsigned)Hcam[d]) * 1099511628211ull;
                 // tuple size first, then the tuple; unobserved points sort to the end and are cut off below
                 keys[q] = {b == a ? ~0ull : ((unsigned long long)(b - a) << 60) | (h >> 4), q};
             }
@@ -519,16 +554,18 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
             auto same_tuple = [&](int qa, int qb) {
                 const int a = pt_off[qa], b = pt_off[qb], ka = pt_off[qa + 1] - a;
                 if (ka != pt_off[qb + 1] - b) return false;
-                for (int d = 0; d < ka; d++) if (h_cam[a + d] != h_cam[b + d]) return false;
+                for (int d = 0; d < ka; d++) if (Hcam[a + d] != Hcam[b + d]) return false;
                 return true;
             };
             run_pt.resize(keys.size());
-            for (size_t i = 0; i < keys.size(); i++) {
+            std::vector<char> new_tuple(keys.size());
+#pragma omp parallel for schedule(static)
+            for (long long i = 0; i < (long long)keys.size(); i++) {
                 run_pt[i] = make_int2(keys[i].second, pt_off[keys[i].second]);
-                const bool brk = i == 0 || keys[i].first != keys[i - 1].first || (int)i - run_off.back() >= RUN_MAXLEN ||
-                                 !same_tuple(keys[i].second, keys[i - 1].second);
-                if (brk) run_off.push_back((int)i);
+                new_tuple[i] = i == 0 || keys[i].first != keys[i - 1].first || !same_tuple(keys[i].second, keys[i - 1].second);
             }
+            for (size_t i = 0; i < keys.size(); i++)     // a tuple's points in runs of at most RUN_MAXLEN
+                if (new_tuple[i] || (int)i - run_off.back() >= RUN_MAXLEN) run_off.push_back((int)i);
             run_off.push_back((int)keys.size());
             {   // first run of every tuple size
                 int r = 0;
@@ -550,7 +587,6 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     p->ctx = ctx;
     p->sharded = sharded_nranks > 1;
     p->rank = sharded_rank;
-    p->perm.assign(perm.data(), perm.data() + No);
     BADev &D = p->D;
     D.W = W; D.Nc = Nc; D.Np = Np; D.n = 6 * Nc; D.No = No;
     D.fx = K[0]; D.cx = K[2]; D.fy = K[4]; D.cy = K[5]; D.delta = huber_delta;
@@ -612,11 +648,40 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     for (size_t q = 0; q < wc; q++) h_camact[q] = cam_off[q + 1] > cam_off[q] ? 1 : 0;
     cudaStream_t s = ctx->stream;
     bool ok = true;
+    // Large host arrays travel through two pinned staging buffers of the context: OpenMP threads fill one while the
+    // other is on the link (a cudaMemcpyAsync from pageable memory moves ~10 GB/s through the driver's own staging).
+    constexpr size_t STAGE = (size_t)32 << 20;
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    bool stage_busy[2] = {false, false};
+    int stage_k = 0;
+    const bool stage_ok = !getenv("PMV_BA_NO_STAGING") && ctx->pin[2].reserve(STAGE) == cudaSuccess && ctx->pin[3].reserve(STAGE) == cudaSuccess &&
+                          cudaEventCreateWithFlags(&stage_ev[0], cudaEventDisableTiming) == cudaSuccess &&
+                          cudaEventCreateWithFlags(&stage_ev[1], cudaEventDisableTiming) == cudaSuccess;
     auto up = [&](void *dst, const void *src, size_t bytes) {
-        if (bytes && cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) ok = false;
+        if (!bytes) return;
+        if (!stage_ok || bytes < ((size_t)4 << 20)) {
+            if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) ok = false;
+            return;
+        }
+        for (size_t off = 0; off < bytes; off += STAGE, stage_k++) {
+            const int b = stage_k & 1;
+            const size_t nb = std::min(STAGE, bytes - off);
+            char *pin = ctx->pin[2 + b].as<char>();
+            if (stage_busy[b] && cudaEventSynchronize(stage_ev[b]) != cudaSuccess) ok = false;
+            const char *from = static_cast<const char *>(src) + off;
+            const long long pieces = (long long)((nb + ((size_t)1 << 20) - 1) >> 20);
+#pragma omp parallel for schedule(static)
+            for (long long q = 0; q < pieces; q++) {
+                const size_t a = (size_t)q << 20, len = std::min((size_t)1 << 20, nb - a);
+                memcpy(pin + a, from + a, len);
+            }
+            if (cudaMemcpyAsync(static_cast<char *>(dst) + off, pin, nb, cudaMemcpyHostToDevice, s) != cudaSuccess) ok = false;
+            if (cudaEventRecord(stage_ev[b], s) != cudaSuccess) ok = false;
+            stage_busy[b] = true;
+        }
     };
-    up(d_cam, h_cam.data(), sizeof(int) * No); up(d_pt, h_pt.data(), sizeof(int) * No); up(d_win, h_win.data(), sizeof(int) * No);
-    up(d_obs, h_obs.data(), sizeof(double) * 2 * No); up(d_ptoff, pt_off.data(), sizeof(int) * (wp + 1));
+    up(d_cam, Hcam, sizeof(int) * No); up(d_pt, Hpt, sizeof(int) * No); up(d_win, Hwin, sizeof(int) * No);
+    up(d_obs, Hobs, sizeof(double) * 2 * No); up(d_ptoff, pt_off.data(), sizeof(int) * (wp + 1));
     up(d_camoff, cam_off.data(), sizeof(int) * (wc + 1));
     if (need_cam_obs) up(d_camobs, cam_obs.data(), sizeof(int) * No);
     up(d_camact, h_camact.data(), sizeof(int) * wc);
@@ -638,6 +703,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
         }
     }
     if (ok && cudaStreamSynchronize(s) != cudaSuccess) ok = false;  // host vectors die at return
+    for (auto &e : stage_ev) if (e) cudaEventDestroy(e);
     lap("upload");
     if (!ok) { ctx->fail(PMV_ERR_CUDA, "pmv_ba_problem_create: upload failed", cudaGetLastError()); pmv_ba_problem_destroy(p); return nullptr; }
     {
@@ -666,6 +732,8 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
         }
         cudaMemcpyAsync(d_lim, p->chol_lim.data(), sizeof(int) * nblk, cudaMemcpyHostToDevice, s);
         D.chol_lim = d_lim;
+        // ba_clear_system_kernel clears only the envelope of one large system per iteration: everything else is zeroed here, once
+        if (W == 1 && n > 160 && !window_ok) cudaMemsetAsync(D.S, 0, sizeof(double) * n * n, s);
         // ---- two-sided solve: separator of w columns in the middle of a long banded system
         {
             const char *no_split = getenv("PMV_CHOL_NO_SPLIT");
@@ -817,7 +885,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
             for (size_t q = 0; q + 1 < pt_off.size(); q++)
                 for (int i = pt_off[q]; i < pt_off[q + 1]; i++)
                     for (int k = pt_off[q]; k < pt_off[q + 1]; k++)
-                        if (h_cam[i] <= h_cam[k]) pcnt[(size_t)h_cam[i] * Nc + h_cam[k] + 1]++;
+                        if (Hcam[i] <= Hcam[k]) pcnt[(size_t)Hcam[i] * Nc + Hcam[k] + 1]++;
             unsigned long long total = 0;
             for (size_t a = 1; a < pcnt.size(); a++) total += pcnt[a];
             if (total > 0 && total < (1ull << 31)) {
@@ -835,7 +903,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
                 for (size_t q = 0; q + 1 < pt_off.size(); q++)
                     for (int i = pt_off[q]; i < pt_off[q + 1]; i++)
                         for (int k = pt_off[q]; k < pt_off[q + 1]; k++)
-                            if (h_cam[i] <= h_cam[k]) ent[cur[(size_t)h_cam[i] * Nc + h_cam[k]]++] = make_int2(i, k);
+                            if (Hcam[i] <= Hcam[k]) ent[cur[(size_t)Hcam[i] * Nc + Hcam[k]]++] = make_int2(i, k);
                 if (dev_alloc(p, &p->d_segs, segs.size()) != PMV_OK || dev_alloc(p, &p->d_entries, ent.size()) != PMV_OK) {
                     pmv_ba_problem_destroy(p);
                     return nullptr;

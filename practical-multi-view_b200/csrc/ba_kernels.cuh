@@ -404,7 +404,20 @@ __global__ void __launch_bounds__(256) ba_clear_system_kernel(const BADev D)
     BAState *st = &D.st[w];
     if (st->done) return;
     const size_t nn = (size_t)D.n * D.n;
-    for (size_t i = blockIdx.x * 256 + threadIdx.x; i < nn; i += (size_t)gridDim.x * 256) D.S[(size_t)w * nn + i] = 0.0;
+    if (D.W == 1 && D.chol_lim != nullptr && D.n > 160) {
+        // One large problem with a known envelope: S was zeroed once at creation and nothing ever writes outside the
+        // envelope, so only that part is cleared (12 MB instead of 288 MB at BASELINE config 5).  Row r: from the first
+        // column of its camera's diagonal block to the end of the envelope rounded up to the factorisation's tiles + one.
+        const int n = D.n;
+        for (int r = blockIdx.x; r < n; r += gridDim.x) {
+            const int c0 = r / 6 * 6;
+            int c1 = (D.chol_lim[r / PMV_CHOL_NB] + PMV_CHOL_NB - 1) / PMV_CHOL_NB * PMV_CHOL_NB + PMV_CHOL_NB;
+            c1 = c1 < n ? c1 : n;
+            for (int c = c0 + threadIdx.x; c < c1; c += 256) D.S[(size_t)r * n + c] = 0.0;
+        }
+    } else {
+        for (size_t i = blockIdx.x * 256 + threadIdx.x; i < nn; i += (size_t)gridDim.x * 256) D.S[(size_t)w * nn + i] = 0.0;
+    }
     if (blockIdx.x == 0) {
         for (int i = threadIdx.x; i < D.n; i += 256) D.rhs[(size_t)w * D.n + i] = 0.0;
     }

@@ -165,7 +165,7 @@ struct ProfScope {
     pmv_ctx *c; cudaStream_t s; int phase; cudaEvent_t a = nullptr;
     ProfScope(pmv_ctx *c_, int phase_, cudaStream_t s_) : c(c_), s(s_), phase(phase_)
     {
-        if (c->prof_on) { a = c->prof_event(); cudaEventRecord(a, s); }
+        if (c && c->prof_on) { a = c->prof_event(); cudaEventRecord(a, s); }
     }
     ~ProfScope()
     {

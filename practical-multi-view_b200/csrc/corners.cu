@@ -1099,6 +1099,31 @@ PMV_API int pmv_gftt(pmv_ctx *ctx, const uint8_t *base, int full_rows, int full_
     return PMV_OK;
 }
 
+PMV_API int pmv_gftt_dev(pmv_ctx *ctx, const uint8_t *d_base, int full_rows, int full_cols, int step,
+                         int roi_x, int roi_y, int roi_w, int roi_h, int max_corners, double quality,
+                         double min_dist, float *d_xy_out, float *d_score_out, int *n_out)
+{
+    if (!ctx) return PMV_ERR_INVALID;
+    int rc = check_roi(ctx, d_base, full_rows, full_cols, step, roi_x, roi_y, roi_w, roi_h);
+    if (rc) return rc;
+    if (!n_out || quality <= 0 || min_dist < 0 || max_corners <= 0) return ctx->fail(PMV_ERR_INVALID, "pmv_gftt_dev: bad argument");
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    // the resident image is read in place: the view starts at parent pixel (0, 0)
+    ImgView v{d_base, step, 0, 0, full_rows, full_cols, roi_x, roi_y, roi_w, roi_h};
+    v.word_ok = (((uintptr_t)d_base | (uintptr_t)step | (uintptr_t)roi_x) & 3) == 0;
+    float *d_xy = nullptr, *d_sc = nullptr;
+    int n = 0;
+    rc = gftt_run(ctx, v, max_corners, quality, min_dist, &d_xy, &d_sc, &n);
+    if (rc) return rc;
+    if (n > 0) {
+        if (d_xy_out) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(d_xy_out, d_xy, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+        if (d_score_out) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(d_score_out, d_sc, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    *n_out = n;
+    return PMV_OK;
+}
+
 PMV_API int pmv_shitomasi_response(pmv_ctx *ctx, const uint8_t *img, int rows, int cols, int step,
                                    int signed_quirk, double *R)
 {

@@ -18,16 +18,29 @@ constexpr int FT_W = 64, FT_H = 16;
 constexpr int FS_W = FT_W + 8, FS_H = FT_H + 8, FS_P = 72;
 constexpr int FC_W = FT_W + 2, FC_H = FT_H + 2;
 
-__constant__ int c_fdx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-__constant__ int c_fdy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+// radius-3 Bresenham circle; constexpr so that the staged-tile offsets fold into the load instructions
+__host__ __device__ constexpr int fast_off(int k)
+{
+    const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+    return dy[k] * FS_P + dx[k];
+}
 
 __device__ __forceinline__ int fast_score_at(const uint8_t *p, int threshold)
 {
     // offsets relative to p in the staged tile (pitch FS_P)
-    int v = p[0];
+    const int v = p[0];
+    {
+        // An arc of 9 of the 16 circle pixels contains one pixel of every antipodal pair: two pairs reject most
+        // pixels after four loads (the same necessary condition cv::FAST tests first).
+        const int e0 = v - p[fast_off(0)], e8 = v - p[fast_off(8)], e4 = v - p[fast_off(4)], e12 = v - p[fast_off(12)];
+        const bool bright = (e0 < -threshold || e8 < -threshold) && (e4 < -threshold || e12 < -threshold);
+        const bool dark = (e0 > threshold || e8 > threshold) && (e4 > threshold || e12 > threshold);
+        if (!bright && !dark) return 0;
+    }
     int d[25];
 #pragma unroll
-    for (int k = 0; k < 16; k++) d[k] = v - p[c_fdy[k] * FS_P + c_fdx[k]];
+    for (int k = 0; k < 16; k++) d[k] = v - p[fast_off(k)];
 #pragma unroll
     for (int k = 16; k < 25; k++) d[k] = d[k - 16];
     // segment test: >= 9 contiguous brighter (d < -t) or darker (d > t)

@@ -512,8 +512,11 @@ int pmv_internal_pyr_run(pmv_ctx *ctx, const PyrSet &set, int batch, const uint8
             A.down = const_cast<uint8_t *>(d.ptr); A.drows = d.rows; A.dcols = d.cols; A.wpitch = d.pitch; A.wstride = d.img_stride;
         }
         dim3 grid((a.cols + FT_W - 1) / FT_W, (a.rows + FT_NT * FT_H - 1) / (FT_NT * FT_H), nz);
-        if (copy) pyr_fused_kernel<true><<<grid, 256, 0, s>>>(mA, mB, A);
-        else pyr_fused_kernel<false><<<grid, 256, 0, s>>>(mA, mB, A);
+        {
+            ProfScope p0(l == 0 ? ctx : nullptr, PMV_PHASE_PYR_L0, s);   // the dominant launch of the group, timed on its own
+            if (copy) pyr_fused_kernel<true><<<grid, 256, 0, s>>>(mA, mB, A);
+            else pyr_fused_kernel<false><<<grid, 256, 0, s>>>(mA, mB, A);
+        }
         PMV_LAUNCH_CHECK(ctx, "pyr_fused_kernel");
     }
     return PMV_OK;

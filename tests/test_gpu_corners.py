@@ -168,3 +168,25 @@ def test_batched_resident_responses_match_single_image_calls(ctx, synth, shape):
         assert np.array_equal(eig[b].cpu().numpy(), e1)
         assert np.array_equal(R[b].cpu().numpy(), r1)
         assert float(emax[b]) == float(e1.max()) and float(rmax[b]) == float(r1.max())
+
+
+@pytest.mark.parametrize("shape,roi,pitch_pad", [((376, 1241), None, 7), ((376, 1241), (256, 60, 255, 255), 7), ((376, 1241), (255, 61, 250, 200), 0),
+                                                 ((720, 1280), None, 0)])
+def test_gftt_on_resident_image_matches_host_call(ctx, synth, shape, roi, pitch_pad):
+    """pmv_gftt_dev reads an image that is already in HBM in place (parent borders included) and leaves the corner
+    list on the device: same ordered list and scores as pmv_gftt on the host copy, for whole images and for ROI views,
+    with word-aligned and unaligned pitches / ROI origins (fast kernels vs tile kernels)."""
+    import torch
+    h, w = shape
+    img = synth.frame_pair(77, h=h, w=w)[0]
+    pitch = w + pitch_pad
+    d = torch.zeros(h, pitch, dtype=torch.uint8, device="cuda")
+    d[:, :w] = torch.from_numpy(img).cuda()
+    nmax = 700
+    d_xy = torch.zeros(nmax, 2, dtype=torch.float32, device="cuda"); d_sc = torch.zeros(nmax, dtype=torch.float32, device="cuda")
+    n = ctx.gftt_dev(d.data_ptr(), h, w, pitch, nmax, d_xy.data_ptr(), d_sc.data_ptr(), 0.01, 5.0, roi=roi)
+    ctx.sync()
+    xy, sc = ctx.gftt(img, nmax, 0.01, 5.0, roi=roi)
+    assert n == len(xy) and n > 50
+    assert np.array_equal(d_xy[:n].cpu().numpy(), xy)
+    assert np.array_equal(d_sc[:n].cpu().numpy(), sc)
