@@ -401,7 +401,8 @@ constexpr int GC_ROWS = 64;
 
 __global__ void __launch_bounds__(256)
 gftt_candidates_kernel(const float *__restrict__ eig, int rows, int cols, const int *__restrict__ max_bits,
-                       double quality, Rec128 *__restrict__ out, int *__restrict__ count, int cap)
+                       double quality, Rec128 *__restrict__ out, int *__restrict__ count, int cap, int *__restrict__ hist,
+                       int *__restrict__ hist_overflow)
 {
     __shared__ Rec128 s_rec[32 * GC_ROWS];   // every pixel of the tile may qualify (plateaus)
     __shared__ int s_n, s_base;
@@ -420,6 +421,12 @@ gftt_candidates_kernel(const float *__restrict__ eig, int rows, int cols, const 
         if (val < m) continue;  // val == dilate(thresholded) <=> val >= every neighbour
         const int slot = atomicAdd(&s_n, 1);
         s_rec[slot] = Rec128{(unsigned long long)__float_as_uint(val), (unsigned long long)(y * cols + x)};
+        // response histogram for the bucket sort (sort.cuh)
+        if (hist) {
+            const int b = bs_bucket(__float_as_uint(val), (unsigned)*max_bits);
+            if (b >= 0 && b < BS_BINS) atomicAdd(&hist[b], 1);
+            else *hist_overflow = 0x7fffffff;
+        }
     }
     __syncthreads();
     const int n = s_n;
@@ -953,7 +960,7 @@ int gftt_run(pmv_ctx *ctx, const ImgView &v, int max_corners, double quality, do
     const int cap = (int)npx;  // plateaus of equal responses can make every pixel a candidate
     const int cap2 = sort_capacity(cap);
     cudaError_t e = ctx->scratch[0].reserve(npx * 4);                 // eig map
-    if (e == cudaSuccess) e = ctx->scratch[1].reserve(256);          // max bits, count, n_out
+    if (e == cudaSuccess) e = ctx->scratch[1].reserve(256 + 3 * (size_t)BS_BINS * 4);   // max bits, count, n_out, largest bucket | histogram, starts, cursors
     if (e == cudaSuccess) e = ctx->scratch[2].reserve((size_t)cap2 * sizeof(Rec128));
     if (e == cudaSuccess) e = ctx->scratch[3].reserve(npx * 4);      // rank map
     if (e == cudaSuccess) e = ctx->scratch[4].reserve(2 * (size_t)cap + 64);   // status | neighbour counts
@@ -973,15 +980,34 @@ int gftt_run(pmv_ctx *ctx, const ImgView &v, int max_corners, double quality, do
     {
         ProfScope ps(ctx, PMV_PHASE_SELECT, s);
         dim3 grid((v.rw + 31) / 32, (v.rh + GC_ROWS - 1) / GC_ROWS);
-        gftt_candidates_kernel<<<grid, 256, 0, s>>>(d_eig, v.rh, v.rw, d_misc, quality, d_rec, d_misc + 1, cap);
+        int *d_hist = d_misc + 64, *d_start = d_hist + BS_BINS, *d_cursor = d_start + BS_BINS;
+        const bool big = npx >= (size_t)1 << 19;    // small views: a few thousand candidates, the bitonic network is two launches
+        if (big) PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_hist, 0, sizeof(int) * 3 * (size_t)BS_BINS, s));
+        gftt_candidates_kernel<<<grid, 256, 0, s>>>(d_eig, v.rh, v.rw, d_misc, quality, d_rec, d_misc + 1, cap, big ? d_hist : nullptr, d_misc + 3);
         PMV_LAUNCH_CHECK(ctx, "gftt_candidates_kernel");
+        if (big) {
+            if (ctx->attr_first(PMV_ATTR_BS_SCAN)) cudaFuncSetAttribute(bs_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SCAN_SMEM);
+            bs_scan_kernel<<<1, 1024, BS_SCAN_SMEM, s>>>(d_hist, d_start, d_misc + 3);
+            PMV_LAUNCH_CHECK(ctx, "bs_scan_kernel");
+        }
         PMV_CUDA_TRY(ctx, cudaMemcpyAsync(h_misc, d_misc, 16, cudaMemcpyDeviceToHost, s));
         PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
         n_cand = h_misc[1] < cap ? h_misc[1] : cap;
         const int want = max_corners > 0 ? max_corners : n_cand;
         if (n_cand > 0) {
-            rc = sort_desc_128(ctx, d_rec, n_cand, s);
-            if (rc) return rc;
+            if (big && n_cand >= 4 * SORT_CHUNK && h_misc[1] <= cap && h_misc[3] <= BS_MAXBUCKET) {
+                // bucket sort: scatter by the top bits of the response, then rank inside the buckets (sort.cuh)
+                e = ctx->scratch[6].reserve((size_t)n_cand * GF_NBMAX * 4 + 16);   // >= 16 B per record; reused for the neighbour lists below
+                if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "gftt sort workspace", e);
+                Rec128 *d_tmp = ctx->scratch[6].as<Rec128>();
+                bs_scatter_kernel<<<(n_cand + 255) / 256, 256, 0, s>>>(d_rec, n_cand, d_misc, d_start, d_cursor, d_tmp);
+                PMV_LAUNCH_CHECK(ctx, "bs_scatter_kernel");
+                bs_rank_kernel<<<(n_cand + 255) / 256, 256, 0, s>>>(d_tmp, n_cand, d_misc, d_start, d_hist, d_rec);
+                PMV_LAUNCH_CHECK(ctx, "bs_rank_kernel");
+            } else {
+                rc = sort_desc_128(ctx, d_rec, n_cand, s);
+                if (rc) return rc;
+            }
             PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_rank, 0xff, npx * 4, s));
             PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_status, 0, n_cand, s));
             rank_scatter_kernel<<<(n_cand + 255) / 256, 256, 0, s>>>(d_rec, n_cand, d_rank);

@@ -110,4 +110,82 @@ static inline int sort_desc_128(pmv_ctx *ctx, Rec128 *d, int n, cudaStream_t s)
     return PMV_OK;
 }
 
+// ---- bucket sort for large candidate lists whose primary key is a non-negative float (GFTT at 4K: ~220 k records) -----
+// The bitonic network above costs 36 launches (190 us) at 2^18 records, most of them latency.  When `hi` holds the bit
+// pattern of a float in [q * max, max], its top bits split the list into a few thousand buckets that are already in
+// order among themselves: histogram (by the producer kernel), exclusive scan, scatter into buckets, and a final pass in
+// which every record counts the records of ITS bucket that precede it -- the exact descending (hi, lo) order in four
+// small launches.  Buckets stay small because the response histogram of an image is smooth; the host falls back to the
+// bitonic network when the largest bucket says otherwise (plateaus of equal responses).
+constexpr int BS_SHIFT = 14;          // bucket = (max_bits >> 14) - (bits >> 14): 512 buckets per octave of response
+constexpr int BS_BINS = 1 << 14;      // 32 octaves below the maximum; a wider range falls back to the bitonic network
+constexpr int BS_MAXBUCKET = 2048;    // above this the quadratic last pass is no longer cheap
+
+__device__ __forceinline__ int bs_bucket(unsigned bits, unsigned max_bits)
+{
+    return (int)(max_bits >> BS_SHIFT) - (int)(bits >> BS_SHIFT);
+}
+
+// exclusive scan of the histogram (one CTA, the histogram staged in 64 KB of dynamic shared memory with coalesced
+// loads; slot i of the staging array is skewed by i / 16 so that the 16 bins a thread scans do not collide in one bank),
+// largest bucket -> *max_count
+constexpr size_t BS_SCAN_SMEM = sizeof(int) * (BS_BINS + BS_BINS / 16);
+__global__ void __launch_bounds__(1024) bs_scan_kernel(const int *__restrict__ hist, int *__restrict__ start, int *__restrict__ max_count)
+{
+    extern __shared__ int s_h[];
+    __shared__ int s_sum[1024];
+    __shared__ int s_max[32];
+    constexpr int PER = BS_BINS / 1024;   // 16
+    const int t = threadIdx.x;
+    for (int i = t; i < BS_BINS; i += 1024) s_h[i + i / 16] = hist[i];
+    __syncthreads();
+    int local = 0, mx = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { const int c = s_h[t * PER + k + t]; local += c; mx = c > mx ? c : mx; }
+    s_sum[t] = local;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {        // Hillis-Steele inclusive scan of the per-thread sums
+        const int v = t >= o ? s_sum[t - o] : 0;
+        __syncthreads();
+        s_sum[t] += v;
+        __syncthreads();
+    }
+    int run = s_sum[t] - local;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { const int c = s_h[t * PER + k + t]; s_h[t * PER + k + t] = run; run += c; }
+    __syncthreads();
+    for (int i = t; i < BS_BINS; i += 1024) start[i] = s_h[i + i / 16];
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((t & 31) == 0) s_max[t >> 5] = mx;
+    __syncthreads();
+    if (t < 32) {
+        mx = s_max[t];
+        for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (t == 0) atomicMax(max_count, mx);
+    }
+}
+
+__global__ void __launch_bounds__(256) bs_scatter_kernel(const Rec128 *__restrict__ in, int n, const int *__restrict__ max_bits,
+                                                         const int *__restrict__ start, int *__restrict__ cursor, Rec128 *__restrict__ tmp)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const Rec128 r = in[i];
+    const int b = bs_bucket((unsigned)r.hi, (unsigned)*max_bits);
+    tmp[start[b] + atomicAdd(&cursor[b], 1)] = r;
+}
+
+__global__ void __launch_bounds__(256) bs_rank_kernel(const Rec128 *__restrict__ tmp, int n, const int *__restrict__ max_bits,
+                                                      const int *__restrict__ start, const int *__restrict__ hist, Rec128 *__restrict__ out)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const Rec128 r = tmp[i];
+    const int b = bs_bucket((unsigned)r.hi, (unsigned)*max_bits);
+    const int s0 = start[b], c = hist[b];
+    int before = 0;
+    for (int k = 0; k < c; k++) before += rec_greater(tmp[s0 + k], r) ? 1 : 0;
+    out[s0 + before] = r;
+}
+
 }  // namespace
