@@ -30,6 +30,11 @@ import threading
 import time
 from pathlib import Path
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the host side of the BA legs (problem indexing in libpmv_cuda.so, the
+# CPU baselines) is OpenMP code, so each rank takes its share of the host cores instead -- before any OpenMP runtime loads.
+if "LOCAL_RANK" in os.environ and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))))
+
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent

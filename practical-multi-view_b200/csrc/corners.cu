@@ -410,12 +410,21 @@ gftt_candidates_kernel(const float *__restrict__ eig, int rows, int cols, const 
     __syncthreads();
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const float thr = (float)((double)__int_as_float(*max_bits) * quality);
-    for (int ys = 0; ys < GC_ROWS; ys += 8) {
-        const int y = blockIdx.y * GC_ROWS + ys + (threadIdx.x >> 5);
-        if (x < 1 || y < 1 || x >= cols - 1 || y >= rows - 1) continue;
+    // the eight responses of this thread's column are requested together (few of them pass the threshold: the kernel is one
+    // streaming read of the map, and eight dependent load -> test -> branch rounds left it latency-bound)
+    float vals[GC_ROWS / 8];
+#pragma unroll
+    for (int k = 0; k < GC_ROWS / 8; k++) {
+        const int y = blockIdx.y * GC_ROWS + 8 * k + (threadIdx.x >> 5);
+        const bool in = x >= 1 && y >= 1 && x < cols - 1 && y < rows - 1;
+        vals[k] = in ? __ldg(eig + (size_t)y * cols + x) : -1.f;
+    }
+#pragma unroll
+    for (int k = 0; k < GC_ROWS / 8; k++) {
+        const int y = blockIdx.y * GC_ROWS + 8 * k + (threadIdx.x >> 5);
+        const float val = vals[k];
+        if (!(val > thr)) continue;       // also skips the positions outside the interior (-1; thr >= 0)
         const float *p = eig + (size_t)y * cols + x;
-        const float val = p[0];
-        if (!(val > thr)) continue;
         float m = fmaxf(fmaxf(p[-cols - 1], p[-cols]), fmaxf(p[-cols + 1], p[-1]));
         m = fmaxf(m, fmaxf(fmaxf(p[1], p[cols - 1]), fmaxf(p[cols], p[cols + 1])));
         if (val < m) continue;  // val == dilate(thresholded) <=> val >= every neighbour
