@@ -298,7 +298,8 @@ PMV_API int pmv_ba_solve(pmv_ctx *ctx, double *poses, double *points, const doub
                          int max_iters, pmv_ba_summary *summary);
 
 /* W independent windows in one call (BASELINE config 4): window w owns poses[w*Nc..], points[w*Np..]
- * and the observation slice [obs_off[w], obs_off[w+1]) whose cam_idx / pt_idx are window-local. */
+ * and the observation slice [obs_off[w], obs_off[w+1]) whose cam_idx / pt_idx are window-local (obs_off[0] == 0,
+ * obs_off[W] == No). */
 PMV_API int pmv_ba_solve_batched(pmv_ctx *ctx, double *poses, double *points, const double *obs,
                                  const int32_t *cam_idx, const int32_t *pt_idx, const int32_t *obs_off, int W,
                                  int Nc, int Np, int No, const double K[9], double huber_delta, int max_iters,

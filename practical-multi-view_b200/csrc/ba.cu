@@ -331,89 +331,158 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     };
     // ---- host: order observations by (window, point), group them by (window, camera) ---------------
     // (OpenMP over windows / observations / points: 136 M observations at BASELINE config 4 took 5.5 s on one core)
+    // window of every observation: only the unordered path and the general path's kernels need the array, so it is
+    // filled on demand (touching 572 MB of fresh pages cost more than the whole indexing pass at BASELINE config 4)
     RawBuf<int> win(No);
+    bool win_filled = false;
+    auto fill_win = [&]() {
+        if (win_filled) return;
+        win_filled = true;
+#pragma omp parallel for schedule(static)
+        for (int w = 0; w < W; w++) {
+            const int o0 = obs_off ? obs_off[w] : 0, o1 = obs_off ? obs_off[w + 1] : No;
+            for (int i = o0; i < o1; i++) win[i] = w;
+        }
+    };
     for (int w = 0; w < W; w++) {
         int o0 = obs_off ? obs_off[w] : 0, o1 = obs_off ? obs_off[w + 1] : No;
         if (o0 < 0 || o1 < o0 || o1 > No) { ctx->fail(PMV_ERR_INVALID, "pmv_ba_problem_create: bad obs_off"); return nullptr; }
     }
-#pragma omp parallel for schedule(static)
-    for (int w = 0; w < W; w++) {
-        const int o0 = obs_off ? obs_off[w] : 0, o1 = obs_off ? obs_off[w + 1] : No;
-        for (int i = o0; i < o1; i++) win[i] = w;
+    if (obs_off && (obs_off[0] != 0 || obs_off[W] != No)) {
+        ctx->fail(PMV_ERR_INVALID, "pmv_ba_problem_create: obs_off must cover the observation list (obs_off[0] == 0, obs_off[W] == No)");
+        return nullptr;
     }
-    {
-        int bad = 0;
-#pragma omp parallel for schedule(static) reduction(| : bad)
-        for (int i = 0; i < No; i++) bad |= (cam_idx[i] < 0 || cam_idx[i] >= Nc || pt_idx[i] < 0 || pt_idx[i] >= Np) ? 1 : 0;
-        if (bad) {
-            ctx->fail(PMV_ERR_INVALID, "pmv_ba_problem_create: observation index out of range");
-            return nullptr;
-        }
-    }
-    // Fast path: the caller's list is already in device order -- sorted by (window, point, camera), which is how
-    // structure-from-motion exports (and BAL files) come.  Then the permutation is the identity, the point offsets are
-    // the boundaries of the list and nothing has to be sorted (5 M observations: 92 -> ~15 ms).
-    int in_order = 1;
-#pragma omp parallel for schedule(static) reduction(& : in_order)
-    for (int i = 1; i < No; i++) {
-        const bool le = win[i - 1] < win[i] || (win[i - 1] == win[i] && (pt_idx[i - 1] < pt_idx[i] ||
-                        (pt_idx[i - 1] == pt_idx[i] && cam_idx[i - 1] <= cam_idx[i])));
-        in_order &= le ? 1 : 0;
-    }
+    // ONE streaming pass over the caller's list (143.7 M observations at BASELINE config 4: five separate passes took 0.38 s):
+    // window of every observation, range check, "already in device order?" -- sorted by (window, point, camera), which is
+    // how structure-from-motion exports (and BAL files) come --, and, optimistically for that case, the point offsets
+    // (boundaries of the list) and thread-private per-camera histograms.  In order: the permutation is the identity and
+    // nothing has to be sorted or copied.  Otherwise the offsets are recounted below and the list is sorted.
     std::vector<int> pt_off((size_t)W * Np + 1, 0), cam_off((size_t)W * Nc + 1, 0);
-    if (in_order) {
+    int in_order = 1;
+    bool sorted_per_window = false;     // unordered list of many windows: every window was sorted on its own (below)
+    // device-order arrays: the caller's own when the list is in order (no copies: 4 GB at BASELINE config 4), else sorted copies
+    RawBuf<int> h_cam, h_pt, h_win, cam_obs;
+    RawBuf<double> h_obs;
+    {
         const long long nq = (long long)W * Np;
-        auto key = [&](int i) { return (long long)win[i] * Np + pt_idx[i]; };
-#pragma omp parallel for schedule(static)
-        for (int i = 0; i < No; i++) {            // pt_off[q] = first observation whose key is >= q
-            const long long k = key(i), kp = i ? key(i - 1) : -1;
-            for (long long q = kp + 1; q <= k; q++) pt_off[q] = i;
-        }
-        const long long last = No ? key(No - 1) : -1;
-#pragma omp parallel for schedule(static)
-        for (long long q = last + 1; q <= nq; q++) pt_off[q] = No;
-        // per-camera counts from thread-private histograms
+        const size_t bins = (size_t)W * Nc;
         int T = 1;
 #ifdef _OPENMP
         T = std::max(1, omp_get_max_threads());
 #endif
-        const size_t bins = (size_t)W * Nc;
         std::vector<int> hist((size_t)T * bins, 0);
-#pragma omp parallel num_threads(T)
+        int bad = 0, nthreads_used = 1;
+#pragma omp parallel num_threads(T) reduction(| : bad) reduction(& : in_order)
         {
-            int t = 0;
+            int t = 0, nt = 1;
 #ifdef _OPENMP
-            t = omp_get_thread_num();
+            t = omp_get_thread_num(); nt = omp_get_num_threads();
 #endif
+            if (t == 0) nthreads_used = nt;
             int *hcnt = hist.data() + (size_t)t * bins;
-#pragma omp for schedule(static)
-            for (int i = 0; i < No; i++) hcnt[(size_t)win[i] * Nc + cam_idx[i]]++;
+            const int i0 = (int)((long long)No * t / nt), i1 = (int)((long long)No * (t + 1) / nt);
+            int w = 0;
+            if (obs_off && i0 < i1) w = (int)(std::upper_bound(obs_off, obs_off + W + 1, i0) - obs_off) - 1;
+            long long kp = -1;          // key of the previous observation (the chunk's predecessor for its first one)
+            int cprev = -1;
+            if (i0 > 0 && i0 < i1) {
+                int wq = 0;
+                if (obs_off) wq = (int)(std::upper_bound(obs_off, obs_off + W + 1, i0 - 1) - obs_off) - 1;
+                kp = (long long)wq * Np + pt_idx[i0 - 1]; cprev = cam_idx[i0 - 1];
+            }
+            for (int i = i0; i < i1; i++) {
+                if (obs_off) while (i >= obs_off[w + 1]) w++;
+                const int c = cam_idx[i], q = pt_idx[i];
+                if (c < 0 || c >= Nc || q < 0 || q >= Np) { bad = 1; kp = nq; continue; }
+                hcnt[(size_t)w * Nc + c]++;
+                const long long k = (long long)w * Np + q;
+                if (!(kp < k || (kp == k && cprev <= c))) in_order = 0;
+                for (long long u = std::max(kp + 1, 0ll); u <= k; u++) pt_off[u] = i;    // pt_off[u] = first observation whose key is >= u
+                kp = k; cprev = c;
+            }
         }
+        if (bad) {
+            ctx->fail(PMV_ERR_INVALID, "pmv_ba_problem_create: observation index out of range");
+            return nullptr;
+        }
+        if (in_order) {
+            long long last = -1;
+            if (No) {
+                const int wl = obs_off ? (int)(std::upper_bound(obs_off, obs_off + W + 1, No - 1) - obs_off) - 1 : 0;
+                last = (long long)wl * Np + pt_idx[No - 1];
+            }
 #pragma omp parallel for schedule(static)
-        for (long long b = 0; b < (long long)bins; b++) {
-            int c = 0;
-            for (int t = 0; t < T; t++) c += hist[(size_t)t * bins + b];
-            cam_off[b + 1] = c;
-        }
-        std::partial_sum(cam_off.begin(), cam_off.end(), cam_off.begin());
-    } else {
+            for (long long u = last + 1; u <= nq; u++) pt_off[u] = No;
 #pragma omp parallel for schedule(static)
-        for (int i = 0; i < No; i++) {
-            int *pc = &pt_off[(size_t)win[i] * Np + pt_idx[i] + 1], *cc = &cam_off[(size_t)win[i] * Nc + cam_idx[i] + 1];
+            for (long long b = 0; b < (long long)bins; b++) {
+                int c = 0;
+                for (int t = 0; t < nthreads_used; t++) c += hist[(size_t)t * bins + b];
+                cam_off[b + 1] = c;
+            }
+            std::partial_sum(cam_off.begin(), cam_off.end(), cam_off.begin());
+        } else if (W >= 64) {
+            // Unordered list of many windows -- e.g. camera-major, the order CeresBundleAdjustment::apply adds its residual
+            // blocks in (frame by frame, CeresBundleAdjustment.cpp:27-52): a window's observations are contiguous in both
+            // orders, so every window is sorted on its own by one thread with a stable counting sort by point (original
+            // order inside a point = ascending camera for camera-major input; a point whose cameras do not come out
+            // ascending is insertion-sorted).  No atomics, no per-point std::sort: 0.4 -> 0.15 s at 143.7 M observations.
+            sorted_per_window = true;
+            h_cam.alloc(No); h_pt.alloc(No); h_win.alloc(No); h_obs.alloc(2 * (size_t)No);
+#pragma omp parallel
+            {
+                std::vector<int> pos(Np + 1);
+#pragma omp for schedule(dynamic, 4)
+                for (int w = 0; w < W; w++) {
+                    const int o0 = obs_off[w], o1 = obs_off[w + 1];
+                    std::fill(pos.begin(), pos.end(), 0);
+                    int *ccnt = &cam_off[(size_t)w * Nc + 1];
+                    for (int i = o0; i < o1; i++) { pos[pt_idx[i] + 1]++; ccnt[cam_idx[i]]++; }
+                    for (int q = 0; q < Np; q++) pos[q + 1] += pos[q];
+                    int *po = &pt_off[(size_t)w * Np];
+                    for (int q = 0; q < Np; q++) po[q] = o0 + pos[q];
+                    for (int i = o0; i < o1; i++) {
+                        const int q = pt_idx[i], d = o0 + pos[q]++;
+                        h_cam[d] = cam_idx[i]; h_pt[d] = q; h_win[d] = w;
+                        h_obs[2 * (size_t)d] = obs[2 * (size_t)i]; h_obs[2 * (size_t)d + 1] = obs[2 * (size_t)i + 1];
+                    }
+                    for (int q = 0; q < Np; q++) {          // cameras of a point ascending (stable): already so for camera-major input
+                        const int a = po[q], b = o0 + pos[q];
+                        for (int d = a + 1; d < b; d++) {
+                            if (h_cam[d - 1] <= h_cam[d]) continue;
+                            const int c = h_cam[d];
+                            const double ox = h_obs[2 * (size_t)d], oy = h_obs[2 * (size_t)d + 1];
+                            int e = d;
+                            while (e > a && h_cam[e - 1] > c) {
+                                h_cam[e] = h_cam[e - 1]; h_obs[2 * (size_t)e] = h_obs[2 * (size_t)e - 2]; h_obs[2 * (size_t)e + 1] = h_obs[2 * (size_t)e - 1];
+                                e--;
+                            }
+                            h_cam[e] = c; h_obs[2 * (size_t)e] = ox; h_obs[2 * (size_t)e + 1] = oy;
+                        }
+                    }
+                }
+            }
+            pt_off[(size_t)W * Np] = No;
+            std::partial_sum(cam_off.begin(), cam_off.end(), cam_off.begin());
+        } else {
+            std::fill(pt_off.begin(), pt_off.end(), 0);
+            fill_win();
+#pragma omp parallel for schedule(static)
+            for (int i = 0; i < No; i++) {
+                int *pc = &pt_off[(size_t)win[i] * Np + pt_idx[i] + 1], *cc = &cam_off[(size_t)win[i] * Nc + cam_idx[i] + 1];
 #pragma omp atomic
-            (*pc)++;
+                (*pc)++;
 #pragma omp atomic
-            (*cc)++;
+                (*cc)++;
+            }
+            std::partial_sum(pt_off.begin(), pt_off.end(), pt_off.begin());
+            std::partial_sum(cam_off.begin(), cam_off.end(), cam_off.begin());
         }
-        std::partial_sum(pt_off.begin(), pt_off.end(), pt_off.begin());
-        std::partial_sum(cam_off.begin(), cam_off.end(), cam_off.begin());
     }
-    // device-order arrays: the caller's own when the list is in order (no copies: 4 GB at BASELINE config 4), else sorted copies
-    RawBuf<int> h_cam, h_pt, h_win, cam_obs;
-    RawBuf<double> h_obs;
     const int32_t *Hcam = cam_idx, *Hpt = pt_idx, *Hwin = win.data();
     const double *Hobs = obs;
-    if (!in_order) {
+    if (sorted_per_window) {
+        Hcam = h_cam.data(); Hpt = h_pt.data(); Hwin = h_win.data(); Hobs = h_obs.data();
+    } else if (!in_order) {
         h_cam.alloc(No); h_pt.alloc(No); h_win.alloc(No); h_obs.alloc(2 * (size_t)No);
         Hcam = h_cam.data(); Hpt = h_pt.data(); Hwin = h_win.data(); Hobs = h_obs.data();
         // scatter by (window, point): slots of a point are claimed atomically, then every point orders its
@@ -451,6 +520,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     // observations of every (window, camera) in increasing device order: only the general path's camera kernels read
     // this list (ba_cam_accumulate*), so it is built once the path is known
     auto build_cam_obs = [&]() {
+        fill_win();
         cam_obs.alloc(No);
         std::vector<int> cpos(cam_off.begin(), cam_off.end() - 1);
 #pragma omp parallel for schedule(static)
@@ -581,6 +651,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     }
     const bool use_runs = !run_off.empty();
     const bool need_cam_obs = !use_runs && !window_ok;
+    const bool need_pt_win = !use_runs && !window_ok;   // obs_pt / obs_win: ba_linearize_kernel and the pair lists
     if (need_cam_obs) build_cam_obs();
     lap("runs");
     pmv_ba_problem *p = new pmv_ba_problem();
@@ -599,7 +670,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     double *d_sys = nullptr;
     p->use_window = window_ok ? 1 : 0;
     auto alloc_all = [&]() {
-    rc |= dev_alloc(p, &d_cam, No); rc |= dev_alloc(p, &d_pt, No); rc |= dev_alloc(p, &d_win, No);
+    rc |= dev_alloc(p, &d_cam, No); rc |= dev_alloc(p, &d_pt, need_pt_win ? No : 1); rc |= dev_alloc(p, &d_win, need_pt_win ? No : 1);
     rc |= dev_alloc(p, &d_obs, 2 * (size_t)No); rc |= dev_alloc(p, &d_ptoff, wp + 1); rc |= dev_alloc(p, &d_camoff, wc + 1);
     rc |= dev_alloc(p, &d_camobs, need_cam_obs ? No : 1); rc |= dev_alloc(p, &d_camact, wc);
     rc |= dev_alloc(p, &D.poses, wc * 6); rc |= dev_alloc(p, &D.points, wp * 3);
@@ -680,7 +751,8 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
             stage_busy[b] = true;
         }
     };
-    up(d_cam, Hcam, sizeof(int) * No); up(d_pt, Hpt, sizeof(int) * No); up(d_win, Hwin, sizeof(int) * No);
+    up(d_cam, Hcam, sizeof(int) * No);
+    if (need_pt_win) { fill_win(); up(d_pt, Hpt, sizeof(int) * No); up(d_win, Hwin, sizeof(int) * No); }   // read by the general path's kernels only
     up(d_obs, Hobs, sizeof(double) * 2 * No); up(d_ptoff, pt_off.data(), sizeof(int) * (wp + 1));
     up(d_camoff, cam_off.data(), sizeof(int) * (wc + 1));
     if (need_cam_obs) up(d_camobs, cam_obs.data(), sizeof(int) * No);

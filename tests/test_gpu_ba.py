@@ -127,6 +127,34 @@ def test_batched_windows(ctx, synth):
         assert np.abs(P[i] - po).max() < 1e-5
 
 
+@pytest.mark.parametrize("order", ["camera_major", "point_major", "shuffled"])
+def test_many_windows_any_observation_order(ctx, synth, order):
+    """Problem creation sorts an unordered list of >= 64 windows window by window (stable counting sort by point; the
+    camera-major order CeresBundleAdjustment::apply produces needs no per-point sort), takes a (point, camera)-ordered
+    list in place, and insertion-sorts the points of an arbitrary order: every order gives the oracle's solve."""
+    nw = 70
+    ws = [synth.ba_window(200 + i, n_poses=5, n_points=90) for i in range(nw)]
+    rng = np.random.default_rng(11)
+    obs, cam, pt = [], [], []
+    for w in ws:
+        n = len(w["cam_idx"])
+        if order == "camera_major":
+            idx = np.lexsort((w["pt_idx"], w["cam_idx"]))
+        elif order == "point_major":
+            idx = np.lexsort((w["cam_idx"], w["pt_idx"]))
+        else:
+            idx = rng.permutation(n)
+        obs.append(w["obs"][idx]); cam.append(w["cam_idx"][idx]); pt.append(w["pt_idx"][idx])
+    off = np.cumsum([0] + [len(c) for c in cam])
+    P, X, S = ctx.ba_solve_batched(np.stack([w["poses"] for w in ws]), np.stack([w["points"] for w in ws]),
+                                   np.concatenate(obs), np.concatenate(cam), np.concatenate(pt), off, ws[0]["K"], 1.0, 5)
+    for i in (0, 1, 33, nw - 1):
+        po, xo, so = oracle.ba_solve(*_args(ws[i]), 1.0, 5)
+        assert abs(S[i]["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"], (order, i)
+        assert S[i]["iterations"] == so["iterations"]
+        assert np.abs(P[i] - po).max() < 1e-5
+
+
 def test_large_reduced_system_uses_blocked_cholesky(ctx, synth):
     """n = 6*40 = 240 > 160: the blocked HBM Cholesky (DMMA trailing update) instead of the smem one."""
     w = synth.ba_large(3, n_poses=40, n_points=3000, views=5, span=20)
