@@ -34,6 +34,18 @@ struct DevBuf {
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+struct HostBuf {  // grow-only pageable host scratch that outlives a call (fresh malloc blocks of tens of MB fault their
+                  // pages in again on every call: half of the run-construction time of a 1 M-point BA problem)
+    void *p = nullptr;
+    size_t cap = 0;
+    void *reserve(size_t bytes)
+    {
+        if (bytes > cap) { free(p); p = malloc(bytes + 64); cap = p ? bytes + 64 : 0; }
+        return p;
+    }
+    ~HostBuf() { free(p); }
+};
+
 struct PinBuf {  // grow-only pinned host staging buffer
     void *p = nullptr;
     size_t cap = 0;
@@ -132,6 +144,7 @@ struct pmv_ctx {
     DevBuf pts[4];    // prev_xy, next_xy, status, err
     DevBuf scratch[8];
     PinBuf pin[4];
+    HostBuf host[2];   // BA problem creation: tuple keys
 
     int last_code = 0;   // status of the last failure (entry points that return a handle report it through this)
     int fail(int code, const char *what, cudaError_t e = cudaSuccess)
