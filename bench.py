@@ -549,6 +549,24 @@ def run_extract(args, rank, world, local_rank):
         return ea.elapsed_time(eb) / reps
     ms_eig8 = timed8(lambda: ctx.min_eigen_val_batched_dev(d8.data_ptr(), NB8, Hh * pitch8, Hh, Ww, pitch8, eig8.data_ptr(), emax8.data_ptr()))
     ms_shi8 = timed8(lambda: ctx.shitomasi_response_batched_dev(d8.data_ptr(), NB8, Hh * pitch8, Hh, Ww, pitch8, R8.data_ptr(), rmax8.data_ptr()))
+    # the pyramid group on a batch that fills the GPU: 16 resident 4K pairs (16 prev images with Scharr planes + 16 next) per
+    # call, timed by the library's own CUDA events around the group and around its level-0 launch (64 features per pair: the
+    # tracking kernel that follows is not part of either figure)
+    NBP = 16
+    d16 = torch.cat([d8, torch.roll(d8, 3, 0)]).contiguous()
+    d16n = torch.roll(d16, 1, 0).contiguous()
+    p8 = (torch.rand(NBP, 64, 2, device="cuda") * torch.tensor([Ww - 40.0, Hh - 40.0], device="cuda") + 20.0).contiguous()
+    n8 = torch.zeros(NBP, 64, 2, dtype=torch.float32, device="cuda"); s8 = torch.zeros(NBP, 64, dtype=torch.uint8, device="cuda")
+    e8 = torch.zeros(NBP, 64, dtype=torch.float32, device="cuda")
+    ctx.profile(True)
+    for k in range(13):
+        if k == 3:
+            torch.cuda.synchronize(); ctx.profile_collect()
+        ctx.lk_track_batched_dev(d16.data_ptr(), d16n.data_ptr(), NBP, Hh * pitch8, Hh, Ww, pitch8, p8.data_ptr(), 64,
+                                 n8.data_ptr(), s8.data_ptr(), e8.data_ptr(), WIN, MAX_LEVEL)
+    torch.cuda.synchronize()
+    prof_p8 = ctx.profile_collect(); ctx.profile(False)
+    del d16, d16n
     dt_max = max_over_ranks(dt, world)
     dt_dev_max = max_over_ranks(dt_dev, world)
     value = world * steps / dt_dev_max
@@ -596,6 +614,9 @@ def run_extract(args, rank, world, local_rank):
                 "lk_track_kernel<14> (10k features)": frac(prof.get("lk", (0, 0)), 2 * 11016000 + NF * 21)}
         kern["mineig kernels, 8 resident 4K frames per launch (1 B/px in + 4 B/px out; inputs + outputs 332 MB > L2)"] = frac((ms_eig8, 1), NB8 * npx * 5)
         kern["shitomasi_response_kernel, 8 resident 4K frames per launch (1 B/px in + 8 B/px out; 597 MB > L2)"] = frac((ms_shi8, 1), NB8 * npx * 9)
+        pyr4k = 2073600 + 518400 + 129600      # levels 1-3 of a 3840 x 2160 frame
+        kern["pyramid group, 16 resident 4K pairs per call (SURVEY 8d bytes: 7 x 11.0 MB per pair; 1.23 GB > L2)"] = frac(prof_p8.get("pyramid", (0, 0)), NBP * 7 * (npx + pyr4k))
+        kern["pyr_fused_kernel level-0 launch of that call (reads W*H, writes level 1 + the prev images' Scharr planes)"] = frac(prof_p8.get("pyr_l0", (0, 0)), NBP * (2 * (npx + 2073600) + 5 * npx))
         main_k = kern["mineig kernels, 8 resident 4K frames per launch (1 B/px in + 4 B/px out; inputs + outputs 332 MB > L2)"]
         out = {"metric": "frames_per_s_extract_plus_lk", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps,
                "warmup": warmup, "ms_per_step": 1e3 * dt_dev_max / steps, "higher_is_better": True, "scaling": "weak",
