@@ -26,7 +26,8 @@ __host__ __device__ constexpr int fast_off(int k)
     return dy[k] * FS_P + dx[k];
 }
 
-__device__ __forceinline__ int fast_score_at(const uint8_t *p, int threshold)
+// segment test: >= 9 contiguous circle pixels brighter than v + t or darker than v - t
+__device__ __forceinline__ bool fast_segment_test(const uint8_t *p, int threshold)
 {
     // offsets relative to p in the staged tile (pitch FS_P)
     const int v = p[0];
@@ -36,19 +37,14 @@ __device__ __forceinline__ int fast_score_at(const uint8_t *p, int threshold)
         const int e0 = v - p[fast_off(0)], e8 = v - p[fast_off(8)], e4 = v - p[fast_off(4)], e12 = v - p[fast_off(12)];
         const bool bright = (e0 < -threshold || e8 < -threshold) && (e4 < -threshold || e12 < -threshold);
         const bool dark = (e0 > threshold || e8 > threshold) && (e4 > threshold || e12 > threshold);
-        if (!bright && !dark) return 0;
+        if (!bright && !dark) return false;
     }
-    int d[25];
-#pragma unroll
-    for (int k = 0; k < 16; k++) d[k] = v - p[fast_off(k)];
-#pragma unroll
-    for (int k = 16; k < 25; k++) d[k] = d[k - 16];
-    // segment test: >= 9 contiguous brighter (d < -t) or darker (d > t)
     unsigned mb = 0, md = 0;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        mb |= (unsigned)(d[k] < -threshold) << k;
-        md |= (unsigned)(d[k] > threshold) << k;
+        const int d = v - p[fast_off(k)];
+        mb |= (unsigned)(d < -threshold) << k;
+        md |= (unsigned)(d > threshold) << k;
     }
     auto run9 = [](unsigned m) {
         m |= m << 16;
@@ -57,8 +53,18 @@ __device__ __forceinline__ int fast_score_at(const uint8_t *p, int threshold)
         unsigned c = b & (b >> 4);
         return (c & (m >> 8)) != 0u;
     };
-    if (!run9(mb) && !run9(md)) return 0;
-    // cornerScore<16>
+    return run9(mb) || run9(md);
+}
+
+// cornerScore<16>: the largest threshold for which the pixel still passes the segment test
+__device__ __forceinline__ int fast_corner_score(const uint8_t *p, int threshold)
+{
+    const int v = p[0];
+    int d[25];
+#pragma unroll
+    for (int k = 0; k < 16; k++) d[k] = v - p[fast_off(k)];
+#pragma unroll
+    for (int k = 16; k < 25; k++) d[k] = d[k - 16];
     int a0 = threshold;
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
@@ -87,8 +93,9 @@ fast_kernel(const uint8_t *__restrict__ img, int rows, int cols, int pitch, int 
     __shared__ __align__(16) uint8_t s_px[FS_H][FS_P];
     __shared__ int s_sc[FC_H][FC_W + 1];
     __shared__ Rec128 s_rec[FT_H * FT_W];
-    __shared__ int s_n, s_base;
-    if (threadIdx.x == 0) s_n = 0;   // the barriers below order it before the first use
+    __shared__ unsigned short s_list[FC_H * FC_W];
+    __shared__ int s_n, s_base, s_nl;
+    if (threadIdx.x == 0) { s_n = 0; s_nl = 0; }   // the barriers below order it before the first use
     const int tid = threadIdx.x;
     const int tx0 = blockIdx.x * FT_W, ty0 = blockIdx.y * FT_H;
     if (tx0 >= 4 && tx0 + FT_W + 4 <= pitch && ty0 >= 4 && ty0 + FT_H + 4 <= rows) {
@@ -106,13 +113,20 @@ fast_kernel(const uint8_t *__restrict__ img, int rows, int cols, int pitch, int 
         }
     }
     __syncthreads();
-    // scores on the tile + 1 halo; pixels outside rows/cols 3..dim-4 are not corners
+    // Segment test on the tile + 1 halo (pixels outside rows/cols 3..dim-4 are not corners); the pixels that pass are
+    // LISTED, and the scores -- 10x the work of the test, needed by a few percent of the pixels -- are then computed by
+    // the whole CTA from that list instead of by the odd lane of a diverged warp.
     for (int i = tid; i < FC_H * FC_W; i += 256) {
         int r = i / FC_W, c = i - r * FC_W;
         int y = ty0 - 1 + r, x = tx0 - 1 + c;
-        int sc = 0;
-        if (y >= 3 && y < rows - 3 && x >= 3 && x < cols - 3) sc = fast_score_at(&s_px[r + 3][c + 3], threshold);
-        s_sc[r][c] = sc;
+        s_sc[r][c] = 0;
+        if (y >= 3 && y < rows - 3 && x >= 3 && x < cols - 3 && fast_segment_test(&s_px[r + 3][c + 3], threshold))
+            s_list[atomicAdd(&s_nl, 1)] = (unsigned short)i;
+    }
+    __syncthreads();
+    for (int k = tid; k < s_nl; k += 256) {
+        const int i = s_list[k], r = i / FC_W, c = i - r * FC_W;
+        s_sc[r][c] = fast_corner_score(&s_px[r + 3][c + 3], threshold);
     }
     __syncthreads();
     for (int i = tid; i < FT_H * FT_W; i += 256) {
