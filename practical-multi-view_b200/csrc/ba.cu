@@ -427,7 +427,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
             // order inside a point = ascending camera for camera-major input; a point whose cameras do not come out
             // ascending is insertion-sorted).  No atomics, no per-point std::sort: 0.4 -> 0.15 s at 143.7 M observations.
             sorted_per_window = true;
-            h_cam.alloc(No); h_pt.alloc(No); h_win.alloc(No); h_obs.alloc(2 * (size_t)No);
+            h_cam.alloc(No); h_obs.alloc(2 * (size_t)No);     // point / window of an observation: filled on demand (fill_pt_win_sorted)
 #pragma omp parallel
             {
                 std::vector<int> pos(Np + 1);
@@ -442,7 +442,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
                     for (int q = 0; q < Np; q++) po[q] = o0 + pos[q];
                     for (int i = o0; i < o1; i++) {
                         const int q = pt_idx[i], d = o0 + pos[q]++;
-                        h_cam[d] = cam_idx[i]; h_pt[d] = q; h_win[d] = w;
+                        h_cam[d] = cam_idx[i];
                         h_obs[2 * (size_t)d] = obs[2 * (size_t)i]; h_obs[2 * (size_t)d + 1] = obs[2 * (size_t)i + 1];
                     }
                     for (int q = 0; q < Np; q++) {          // cameras of a point ascending (stable): already so for camera-major input
@@ -480,8 +480,20 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     }
     const int32_t *Hcam = cam_idx, *Hpt = pt_idx, *Hwin = win.data();
     const double *Hobs = obs;
+    // point and window of every observation of a list sorted window by window: only the general path reads them
+    auto fill_pt_win_sorted = [&]() {
+        if (!sorted_per_window || h_pt.data()) return;
+        h_pt.alloc(No); h_win.alloc(No);
+        const long long nq = (long long)W * Np;
+#pragma omp parallel for schedule(static)
+        for (long long u = 0; u < nq; u++) {
+            const int wq = (int)(u / Np), pq = (int)(u - (long long)wq * Np);
+            for (int d = pt_off[u]; d < pt_off[u + 1]; d++) { h_pt[d] = pq; h_win[d] = wq; }
+        }
+        Hpt = h_pt.data(); Hwin = h_win.data();
+    };
     if (sorted_per_window) {
-        Hcam = h_cam.data(); Hpt = h_pt.data(); Hwin = h_win.data(); Hobs = h_obs.data();
+        Hcam = h_cam.data(); Hobs = h_obs.data(); Hpt = nullptr; Hwin = nullptr;
     } else if (!in_order) {
         h_cam.alloc(No); h_pt.alloc(No); h_win.alloc(No); h_obs.alloc(2 * (size_t)No);
         Hcam = h_cam.data(); Hpt = h_pt.data(); Hwin = h_win.data(); Hobs = h_obs.data();
@@ -520,7 +532,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
     // observations of every (window, camera) in increasing device order: only the general path's camera kernels read
     // this list (ba_cam_accumulate*), so it is built once the path is known
     auto build_cam_obs = [&]() {
-        fill_win();
+        fill_win(); fill_pt_win_sorted();
         cam_obs.alloc(No);
         std::vector<int> cpos(cam_off.begin(), cam_off.end() - 1);
 #pragma omp parallel for schedule(static)
@@ -771,7 +783,7 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
         }
     };
     up(d_cam, Hcam, sizeof(int) * No);
-    if (need_pt_win) { fill_win(); up(d_pt, Hpt, sizeof(int) * No); up(d_win, Hwin, sizeof(int) * No); }   // read by the general path's kernels only
+    if (need_pt_win) { fill_win(); fill_pt_win_sorted(); up(d_pt, Hpt, sizeof(int) * No); up(d_win, Hwin, sizeof(int) * No); }   // read by the general path's kernels only
     up(d_obs, Hobs, sizeof(double) * 2 * No); up(d_ptoff, pt_off.data(), sizeof(int) * (wp + 1));
     up(d_camoff, cam_off.data(), sizeof(int) * (wc + 1));
     if (need_cam_obs) up(d_camobs, cam_obs.data(), sizeof(int) * No);
@@ -1134,6 +1146,48 @@ PMV_API int pmv_ba_problem_solve(pmv_ba_problem *p, int max_iters)
     return PMV_OK;
 }
 
+// Device -> pageable host copy through the context's two pinned staging buffers: the next chunk travels while OpenMP
+// threads copy the previous one out (a cudaMemcpyAsync into pageable memory moves ~10 GB/s).  Synchronous on return.
+static int staged_download(pmv_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t s)
+{
+    constexpr size_t STAGE = (size_t)32 << 20;
+    if (bytes < ((size_t)4 << 20) || getenv("PMV_BA_NO_STAGING") || ctx->pin[2].reserve(STAGE) != cudaSuccess ||
+        ctx->pin[3].reserve(STAGE) != cudaSuccess) {
+        PMV_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+        PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+        return PMV_OK;
+    }
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming) != cudaSuccess) {
+        if (ev[0]) cudaEventDestroy(ev[0]);
+        return ctx->fail(PMV_ERR_CUDA, "staged download: events");
+    }
+    const size_t nchunks = (bytes + STAGE - 1) / STAGE;
+    auto issue = [&](size_t k) {
+        const size_t off = k * STAGE, nb = std::min(STAGE, bytes - off);
+        cudaMemcpyAsync(ctx->pin[2 + (k & 1)].p, static_cast<const char *>(src) + off, nb, cudaMemcpyDeviceToHost, s);
+        cudaEventRecord(ev[k & 1], s);
+    };
+    issue(0);
+    bool ok = true;
+    for (size_t k = 0; k < nchunks; k++) {
+        if (k + 1 < nchunks) issue(k + 1);
+        if (cudaEventSynchronize(ev[k & 1]) != cudaSuccess) ok = false;
+        const size_t off = k * STAGE, nb = std::min(STAGE, bytes - off);
+        const char *pin = ctx->pin[2 + (k & 1)].as<char>();
+        char *to = static_cast<char *>(dst) + off;
+        const long long pieces = (long long)((nb + ((size_t)1 << 20) - 1) >> 20);
+#pragma omp parallel for schedule(static)
+        for (long long q = 0; q < pieces; q++) {
+            const size_t a = (size_t)q << 20, len = std::min((size_t)1 << 20, nb - a);
+            memcpy(to + a, pin + a, len);
+        }
+    }
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    if (!ok || cudaStreamSynchronize(s) != cudaSuccess) return ctx->fail(PMV_ERR_CUDA, "staged download", cudaGetLastError());
+    return PMV_OK;
+}
+
 PMV_API int pmv_ba_problem_download(pmv_ba_problem *p, double *poses, double *points, pmv_ba_summary *sums)
 {
     if (!p) return PMV_ERR_INVALID;
@@ -1142,8 +1196,8 @@ PMV_API int pmv_ba_problem_download(pmv_ba_problem *p, double *poses, double *po
     const BADev &D = p->D;
     cudaStream_t s = ctx->stream;
     std::vector<BAState> st(D.W);
-    if (poses) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(poses, D.poses, (size_t)D.W * D.Nc * 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (points) PMV_CUDA_TRY(ctx, cudaMemcpyAsync(points, D.points, (size_t)D.W * D.Np * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (poses) { int rc = staged_download(ctx, poses, D.poses, (size_t)D.W * D.Nc * 6 * sizeof(double), s); if (rc) return rc; }
+    if (points) { int rc = staged_download(ctx, points, D.points, (size_t)D.W * D.Np * 3 * sizeof(double), s); if (rc) return rc; }
     PMV_CUDA_TRY(ctx, cudaMemcpyAsync(st.data(), D.st, sizeof(BAState) * D.W, cudaMemcpyDeviceToHost, s));
     PMV_CUDA_TRY(ctx, cudaStreamSynchronize(s));
     if (sums)
