@@ -99,7 +99,7 @@ struct PyrSet {  // all levels of one image batch
     int top = 0;  // effective max level
 };
 
-enum { PMV_ATTR_CHOL_SMALL = 0, PMV_ATTR_CHOL_BACKSUB, PMV_ATTR_CHOL_BAND, PMV_ATTR_WIN_SCHUR, PMV_ATTR_CHOL_SPIKE, PMV_ATTR_BS_SCAN, PMV_ATTR_LK_BASE /* + KPIX (<= 32) */ };
+enum { PMV_ATTR_CHOL_SMALL = 0, PMV_ATTR_CHOL_BACKSUB, PMV_ATTR_CHOL_BAND, PMV_ATTR_WIN_SCHUR, PMV_ATTR_CHOL_SPIKE, PMV_ATTR_BS_SCAN, PMV_ATTR_BS_SCAN_FAST, PMV_ATTR_LK_BASE /* + KPIX (<= 32) */ };
 
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 

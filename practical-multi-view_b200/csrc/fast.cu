@@ -203,7 +203,32 @@ PMV_API int pmv_fast(pmv_ctx *ctx, const uint8_t *img, int rows, int cols, int s
     const int n = total < max_feats ? total : max_feats;
     if (n > 0) {
         ProfScope ps(ctx, PMV_PHASE_SELECT, s);
-        int rc = sort_desc_128(ctx, d_rec, total, s);
+        int rc = PMV_OK;
+        // raster order = descending ~index.  Large lists: buckets of 2^shift consecutive pixel indices (at most that many
+        // keypoints each, so the quadratic last pass is bounded) -- five small launches instead of the bitonic network's
+        // 36 at 2^18 records (sort.cuh)
+        int shift = 9;
+        while (((npx - 1) >> shift) + 2 > (size_t)BS_BINS) shift++;    // bucket = (~0 >> shift) - (~index >> shift) <= (index >> shift) + 1
+        if (total >= 4 * SORT_CHUNK && shift <= 11) {
+            e = ctx->scratch[3].reserve((size_t)total * sizeof(Rec128));
+            if (e == cudaSuccess) e = ctx->scratch[4].reserve(3 * (size_t)BS_BINS * sizeof(int) + 16);
+            if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "fast sort workspace", e);
+            Rec128 *d_tmp = ctx->scratch[3].as<Rec128>();
+            int *d_hist = ctx->scratch[4].as<int>(), *d_start = d_hist + BS_BINS, *d_cursor = d_start + BS_BINS, *d_maxc = d_cursor + BS_BINS;
+            PMV_CUDA_TRY(ctx, cudaMemsetAsync(d_hist, 0, 3 * (size_t)BS_BINS * sizeof(int) + 16, s));
+            bs_hist_kernel<<<(total + 255) / 256, 256, 0, s>>>(d_rec, total, 0xffffffffu, shift, d_hist);
+            PMV_LAUNCH_CHECK(ctx, "bs_hist_kernel");
+            if (ctx->attr_first(PMV_ATTR_BS_SCAN_FAST)) cudaFuncSetAttribute(bs_scan_kernel,   // this translation unit's copy of the kernel
+                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SCAN_SMEM);
+            bs_scan_kernel<<<1, 1024, BS_SCAN_SMEM, s>>>(d_hist, d_start, d_maxc);
+            PMV_LAUNCH_CHECK(ctx, "bs_scan_kernel");
+            bs_scatter_kernel<<<(total + 255) / 256, 256, 0, s>>>(d_rec, total, nullptr, d_start, d_cursor, d_tmp, 0xffffffffu, shift);
+            PMV_LAUNCH_CHECK(ctx, "bs_scatter_kernel");
+            bs_rank_kernel<<<(total + 255) / 256, 256, 0, s>>>(d_tmp, total, nullptr, d_start, d_hist, d_rec, 0xffffffffu, shift);
+            PMV_LAUNCH_CHECK(ctx, "bs_rank_kernel");
+        } else {
+            rc = sort_desc_128(ctx, d_rec, total, s);
+        }
         if (rc) return rc;
         e = ctx->scratch[5].reserve((size_t)n * 12 + 16);
         if (e != cudaSuccess) return ctx->fail(PMV_ERR_NOMEM, "fast output", e);

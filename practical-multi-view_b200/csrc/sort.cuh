@@ -121,9 +121,17 @@ constexpr int BS_SHIFT = 14;          // bucket = (max_bits >> 14) - (bits >> 14
 constexpr int BS_BINS = 1 << 14;      // 32 octaves below the maximum; a wider range falls back to the bitonic network
 constexpr int BS_MAXBUCKET = 2048;    // above this the quadratic last pass is no longer cheap
 
-__device__ __forceinline__ int bs_bucket(unsigned bits, unsigned max_bits)
+// bucket of a 32-bit key (descending order): shift = BS_SHIFT for float responses, larger for index keys (FAST)
+__device__ __forceinline__ int bs_bucket(unsigned bits, unsigned max_bits, int shift = BS_SHIFT)
 {
-    return (int)(max_bits >> BS_SHIFT) - (int)(bits >> BS_SHIFT);
+    return (int)(max_bits >> shift) - (int)(bits >> shift);
+}
+
+// histogram of a record list whose producer did not build one (FAST: key = ~pixel index, max key = ~0)
+__global__ void __launch_bounds__(256) bs_hist_kernel(const Rec128 *__restrict__ in, int n, unsigned max_key, int shift, int *__restrict__ hist)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) atomicAdd(&hist[bs_bucket((unsigned)in[i].hi, max_key, shift)], 1);
 }
 
 // exclusive scan of the histogram (one CTA, the histogram staged in 64 KB of dynamic shared memory with coalesced
@@ -165,23 +173,27 @@ __global__ void __launch_bounds__(1024) bs_scan_kernel(const int *__restrict__ h
     }
 }
 
+// max_bits: device pointer to the largest key (GFTT: the response maximum found by the response kernel), or nullptr with
+// max_key given by value
 __global__ void __launch_bounds__(256) bs_scatter_kernel(const Rec128 *__restrict__ in, int n, const int *__restrict__ max_bits,
-                                                         const int *__restrict__ start, int *__restrict__ cursor, Rec128 *__restrict__ tmp)
+                                                         const int *__restrict__ start, int *__restrict__ cursor, Rec128 *__restrict__ tmp,
+                                                         unsigned max_key = 0u, int shift = BS_SHIFT)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const Rec128 r = in[i];
-    const int b = bs_bucket((unsigned)r.hi, (unsigned)*max_bits);
+    const int b = bs_bucket((unsigned)r.hi, max_bits ? (unsigned)*max_bits : max_key, shift);
     tmp[start[b] + atomicAdd(&cursor[b], 1)] = r;
 }
 
 __global__ void __launch_bounds__(256) bs_rank_kernel(const Rec128 *__restrict__ tmp, int n, const int *__restrict__ max_bits,
-                                                      const int *__restrict__ start, const int *__restrict__ hist, Rec128 *__restrict__ out)
+                                                      const int *__restrict__ start, const int *__restrict__ hist, Rec128 *__restrict__ out,
+                                                      unsigned max_key = 0u, int shift = BS_SHIFT)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const Rec128 r = tmp[i];
-    const int b = bs_bucket((unsigned)r.hi, (unsigned)*max_bits);
+    const int b = bs_bucket((unsigned)r.hi, max_bits ? (unsigned)*max_bits : max_key, shift);
     const int s0 = start[b], c = hist[b];
     int before = 0;
     for (int k = 0; k < c; k++) before += rec_greater(tmp[s0 + k], r) ? 1 : 0;
