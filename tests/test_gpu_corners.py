@@ -190,3 +190,31 @@ def test_gftt_on_resident_image_matches_host_call(ctx, synth, shape, roi, pitch_
     assert n == len(xy) and n > 50
     assert np.array_equal(d_xy[:n].cpu().numpy(), xy)
     assert np.array_equal(d_sc[:n].cpu().numpy(), sc)
+
+
+def test_fast_many_keypoints_bucket_sorted(ctx):
+    """More than 8192 keypoints: the raster-order sort goes through buckets of the pixel index (sort.cuh) instead of the
+    bitonic network.  Same list, scores included, as cv2 on a noisy 1280 x 1024 frame."""
+    import cv2
+    rng = np.random.default_rng(4)
+    img = cv2.GaussianBlur(rng.integers(0, 256, (1024, 1280), dtype=np.uint8), (0, 0), 1.2)
+    col, row, sc, tot = ctx.fast(img, 10, True)
+    kp = cv2.FastFeatureDetector_create(10, True).detect(img)
+    assert tot == len(kp) == len(col) and tot > 8192
+    assert np.array_equal(col, [int(k.pt[0]) for k in kp]) and np.array_equal(row, [int(k.pt[1]) for k in kp])
+    assert np.array_equal(sc, [k.response for k in kp])
+
+
+def test_gftt_plateaus_fall_back_to_the_bitonic_sort(ctx):
+    """A large periodic image has thousands of corners with EQUAL responses: the bucket sort of the candidate list would
+    degenerate, the selector falls back to the bitonic network, and ties still come out in OpenCV's order (higher address
+    first, greaterThanPtr)."""
+    import cv2
+    tile = np.zeros((16, 16), np.uint8)
+    tile[4:12, 4:12] = 200
+    tile[6:10, 6:10] = 90
+    img = np.tile(tile, (64, 80))          # 1024 x 1280, 5120 identical cells
+    xy, sc = ctx.gftt(img, 3000, 0.01, 5)
+    want = cv2.goodFeaturesToTrack(img, 3000, 0.01, 5).reshape(-1, 2)
+    assert len(xy) == len(want) == 3000
+    assert np.array_equal(xy, want)
