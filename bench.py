@@ -916,6 +916,17 @@ def run_lk(args, rank, world, local_rank):
 
 
 
+def restore_rank_threads():
+    """The CPU-baseline legs of rank 0 set the process-wide OpenMP thread count to all host cores (the oracle shares
+    libgomp with libpmv_cuda.so); before the next leg every rank goes back to its share, otherwise rank 0 indexes its BA
+    problems with N x too many threads on a box it shares with N - 1 other ranks."""
+    if "oracle" in sys.modules:
+        try:
+            sys.modules["oracle"].set_threads(int(os.environ.get("OMP_NUM_THREADS", "0")) or (os.cpu_count() or 1))
+        except Exception:
+            pass
+
+
 def sub_args(args, **kw):
     a = argparse.Namespace(**vars(args))
     for k, v in kw.items():
@@ -969,6 +980,7 @@ def main():
                             ("ba_large", run_ba_large, sub_args(args, steps=min(args.steps, 5)))):
             if os.environ.get("PMV_BENCH_SKIP", "").find(name) >= 0:
                 continue
+            restore_rank_threads()
             subs[name] = fn(a, rank, world, local_rank)
         if rank == 0:
             out["workloads"] = subs

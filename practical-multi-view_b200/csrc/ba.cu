@@ -1103,17 +1103,28 @@ PMV_API int pmv_ba_problem_solve(pmv_ba_problem *p, int max_iters)
     const bool want_graph = !(no_graph && no_graph[0] == '1') && !(p->transient && p->D.n <= 160);
     if (want_graph && (!p->graph_exec || p->graph_max_iters != max_iters)) {
         if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+        const char *trace = getenv("PMV_BA_TRACE");
+        auto t_last = std::chrono::steady_clock::now();
+        auto lap = [&](const char *what) {
+            if (!(trace && trace[0] == '1')) return;
+            const auto now = std::chrono::steady_clock::now();
+            fprintf(stderr, "ba_problem_solve: %-31s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+            t_last = now;
+        };
         // first iteration runs eagerly (sets function attributes, validates the launches) ...
         int rc = one_iteration();
         if (rc) return rc;
+        lap("first iteration enqueued");
         // ... then the same sequence is captured for replay
         cudaGraph_t graph = nullptr;
         const uint64_t l0 = ctx->launches;
         if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
             rc = one_iteration();
             cudaError_t e = cudaStreamEndCapture(s, &graph);
+            lap("iteration captured");
             if (rc == PMV_OK && e == cudaSuccess && graph &&
                 cudaGraphInstantiate(&p->graph_exec, graph, 0) == cudaSuccess) {
+                lap("graph instantiated");
                 p->graph_max_iters = max_iters;
                 p->graph_launches = ctx->launches - l0;
             } else {
