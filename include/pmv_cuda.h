@@ -297,6 +297,14 @@ PMV_API int pmv_ba_solve(pmv_ctx *ctx, double *poses, double *points, const doub
                          const int32_t *pt_idx, int Nc, int Np, int No, const double K[9], double huber_delta,
                          int max_iters, pmv_ba_summary *summary);
 
+/* Diagnostics / tests (no GPU needed): the host side of pmv_ba_problem_create -- the caller's observation list brought
+ * into device order, i.e. sorted by (window, point, camera, original index).  Outputs (any may be NULL): pt_off
+ * (W*Np + 1), cam_off (W*Nc + 1), cam / pt / win (No each), obs_sorted (2 No), cam_obs (No: device indices grouped by
+ * (window, camera), ascending), *route = 0 list taken in place (already ordered), 1 sorted window by window, 2 general. */
+PMV_API int pmv_ba_index_observations(const double *obs, const int32_t *cam_idx, const int32_t *pt_idx, const int32_t *obs_off, int W,
+                                      int Nc, int Np, int No, int32_t *pt_off, int32_t *cam_off, int32_t *cam, int32_t *pt, int32_t *win,
+                                      double *obs_sorted, int32_t *cam_obs, int *route);
+
 /* W independent windows in one call (BASELINE config 4): window w owns poses[w*Nc..], points[w*Np..]
  * and the observation slice [obs_off[w], obs_off[w+1]) whose cam_idx / pt_idx are window-local (obs_off[0] == 0,
  * obs_off[W] == No). */

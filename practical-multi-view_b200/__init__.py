@@ -75,6 +75,7 @@ _SIGS = {
     "pmv_min_eigen_val": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp]),
     "pmv_gftt": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _dbl, _dbl, _int, _int,
                         _vp, _vp, _i32p]),
+    "pmv_ba_index_observations": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32p]),
     "pmv_gftt_dev": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _dbl, _dbl, _vp, _vp, _i32p]),
     "pmv_shitomasi_response": (_int, [_vp, _vp, _int, _int, _int, _int, _vp]),
     "pmv_shitomasi": (_int, [_vp, _vp, _int, _int, _int, _int, _dbl, _int, _vp, _vp, _vp, _i32p]),
@@ -129,6 +130,26 @@ def _ptr(a):
     if isinstance(a, int):
         return C.c_void_p(a)
     return C.c_void_p(a.ctypes.data)
+
+
+def ba_index_observations(obs, cam_idx, pt_idx, Nc, Np, obs_off=None):
+    """Host side of BA problem creation (no GPU): the observation list in device order.  Returns a dict with pt_off, cam_off,
+    cam, pt, win, obs, cam_obs and route (0 taken in place, 1 sorted window by window, 2 general)."""
+    lib = load_library()
+    obs = np.ascontiguousarray(obs, np.float64); cam_idx = np.ascontiguousarray(cam_idx, np.int32); pt_idx = np.ascontiguousarray(pt_idx, np.int32)
+    No = len(cam_idx)
+    W = 1 if obs_off is None else len(obs_off) - 1
+    off = None if obs_off is None else np.ascontiguousarray(obs_off, np.int32)
+    out = {"pt_off": np.zeros(W * Np + 1, np.int32), "cam_off": np.zeros(W * Nc + 1, np.int32), "cam": np.zeros(No, np.int32),
+           "pt": np.zeros(No, np.int32), "win": np.zeros(No, np.int32), "obs": np.zeros((No, 2)), "cam_obs": np.zeros(No, np.int32)}
+    route = C.c_int(-1)
+    rc = lib.pmv_ba_index_observations(_ptr(obs), _ptr(cam_idx), _ptr(pt_idx), _ptr(off), W, Nc, Np, No, _ptr(out["pt_off"]),
+                                       _ptr(out["cam_off"]), _ptr(out["cam"]), _ptr(out["pt"]), _ptr(out["win"]), _ptr(out["obs"]),
+                                       _ptr(out["cam_obs"]), C.byref(route))
+    if rc != 0:
+        raise ValueError(f"pmv_ba_index_observations failed with status {rc}")
+    out["route"] = route.value
+    return out
 
 
 def kitti_parse_poses(path, stop=1 << 30):

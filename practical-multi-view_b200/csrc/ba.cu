@@ -304,6 +304,254 @@ int ba_iteration(pmv_ba_problem *p, cudaStream_t s)
     return PMV_OK;
 }
 
+// ---- host side of problem creation: the caller's observation list in DEVICE ORDER ---------------------------------
+// Device order = sorted by (window, point, camera, original index).  Three routes: the list is already in that order
+// (taken in place), an unordered list of many windows (every window sorted on its own), anything else (atomic
+// scatter + per-point sorts).  No CUDA in here: pmv_ba_index_observations exposes it to the CPU tests.
+// (OpenMP over windows / observations / points: 136 M observations at BASELINE config 4 took 5.5 s on one core)
+struct BAIndex {
+    // inputs (caller's arrays)
+    const double *obs = nullptr;
+    const int32_t *cam_idx = nullptr, *pt_idx = nullptr, *obs_off = nullptr;
+    int W = 0, Nc = 0, Np = 0, No = 0;
+    // results
+    std::vector<int> pt_off, cam_off;       // W*Np + 1, W*Nc + 1
+    int in_order = 0;                       // the caller's list was already in device order
+    bool sorted_per_window = false;         // unordered list of many windows: every window was sorted on its own
+    // device-order arrays: the caller's own when the list is in order (no copies: 4 GB at BASELINE config 4), else sorted copies
+    const int32_t *Hcam = nullptr, *Hpt = nullptr, *Hwin = nullptr;
+    const double *Hobs = nullptr;
+    RawBuf<int> win, h_cam, h_pt, h_win, cam_obs;
+    RawBuf<double> h_obs;
+    bool win_filled = false;
+
+    // window of every observation: only the unordered path and the general path's kernels need the array, so it is
+    // filled on demand (touching 572 MB of fresh pages cost more than the whole indexing pass at BASELINE config 4)
+    void fill_win()
+    {
+        if (win_filled) return;
+        win_filled = true;
+#pragma omp parallel for schedule(static)
+        for (int w = 0; w < W; w++) {
+            const int o0 = obs_off ? obs_off[w] : 0, o1 = obs_off ? obs_off[w + 1] : No;
+            for (int i = o0; i < o1; i++) win[i] = w;
+        }
+    }
+
+    // point and window of every observation of a list sorted window by window: only the general path reads them
+    void fill_pt_win_sorted()
+    {
+        if (!sorted_per_window || h_pt.data()) return;
+        h_pt.alloc(No); h_win.alloc(No);
+        const long long nq = (long long)W * Np;
+#pragma omp parallel for schedule(static)
+        for (long long u = 0; u < nq; u++) {
+            const int wq = (int)(u / Np), pq = (int)(u - (long long)wq * Np);
+            for (int d = pt_off[u]; d < pt_off[u + 1]; d++) { h_pt[d] = pq; h_win[d] = wq; }
+        }
+        Hpt = h_pt.data(); Hwin = h_win.data();
+    }
+
+    // observations of every (window, camera) in increasing device order: only the general path's camera kernels read
+    // this list (ba_cam_accumulate*), so it is built once the path is known
+    void build_cam_obs()
+    {
+        fill_win(); fill_pt_win_sorted();
+        cam_obs.alloc(No);
+        std::vector<int> cpos(cam_off.begin(), cam_off.end() - 1);
+#pragma omp parallel for schedule(static)
+        for (int d = 0; d < No; d++) {
+            int *cp = &cpos[(size_t)Hwin[d] * Nc + Hcam[d]];
+            int k;
+#pragma omp atomic capture
+            { k = *cp; (*cp)++; }
+            cam_obs[k] = d;
+        }
+        const long long nc = (long long)cam_off.size() - 1;
+#pragma omp parallel for schedule(dynamic, 64)
+        for (long long c = 0; c < nc; c++)
+            if (cam_off[c + 1] - cam_off[c] > 1) std::sort(cam_obs.data() + cam_off[c], cam_obs.data() + cam_off[c + 1]);
+    }
+
+    // returns PMV_OK or PMV_ERR_INVALID with *err set
+    int build(const char **err)
+    {
+        win.alloc(No);
+        for (int w = 0; w < W; w++) {
+            int o0 = obs_off ? obs_off[w] : 0, o1 = obs_off ? obs_off[w + 1] : No;
+            if (o0 < 0 || o1 < o0 || o1 > No) { *err = "pmv_ba_problem_create: bad obs_off"; return PMV_ERR_INVALID; }
+        }
+        if (obs_off && (obs_off[0] != 0 || obs_off[W] != No)) {
+            *err = "pmv_ba_problem_create: obs_off must cover the observation list (obs_off[0] == 0, obs_off[W] == No)";
+            return PMV_ERR_INVALID;
+        }
+        // ONE streaming pass over the caller's list (143.7 M observations at BASELINE config 4: five separate passes took 0.38 s):
+        // window of every observation, range check, "already in device order?" -- sorted by (window, point, camera), which is
+        // how structure-from-motion exports (and BAL files) come --, and, optimistically for that case, the point offsets
+        // (boundaries of the list) and thread-private per-camera histograms.  In order: the permutation is the identity and
+        // nothing has to be sorted or copied.  Otherwise the offsets are recounted below and the list is sorted.
+        pt_off.assign((size_t)W * Np + 1, 0); cam_off.assign((size_t)W * Nc + 1, 0);
+        int in_order_l = 1;
+        sorted_per_window = false;
+        {
+            const long long nq = (long long)W * Np;
+            const size_t bins = (size_t)W * Nc;
+            int T = 1;
+    #ifdef _OPENMP
+            T = std::max(1, omp_get_max_threads());
+    #endif
+            std::vector<int> hist((size_t)T * bins, 0);
+            int bad = 0, nthreads_used = 1;
+    #pragma omp parallel num_threads(T) reduction(| : bad) reduction(& : in_order_l)
+            {
+                int t = 0, nt = 1;
+    #ifdef _OPENMP
+                t = omp_get_thread_num(); nt = omp_get_num_threads();
+    #endif
+                if (t == 0) nthreads_used = nt;
+                int *hcnt = hist.data() + (size_t)t * bins;
+                const int i0 = (int)((long long)No * t / nt), i1 = (int)((long long)No * (t + 1) / nt);
+                int w = 0;
+                if (obs_off && i0 < i1) w = (int)(std::upper_bound(obs_off, obs_off + W + 1, i0) - obs_off) - 1;
+                long long kp = -1;          // key of the previous observation (the chunk's predecessor for its first one)
+                int cprev = -1;
+                if (i0 > 0 && i0 < i1) {
+                    int wq = 0;
+                    if (obs_off) wq = (int)(std::upper_bound(obs_off, obs_off + W + 1, i0 - 1) - obs_off) - 1;
+                    kp = (long long)wq * Np + pt_idx[i0 - 1]; cprev = cam_idx[i0 - 1];
+                }
+                for (int i = i0; i < i1; i++) {
+                    if (obs_off) while (i >= obs_off[w + 1]) w++;
+                    const int c = cam_idx[i], q = pt_idx[i];
+                    if (c < 0 || c >= Nc || q < 0 || q >= Np) { bad = 1; kp = nq; continue; }
+                    hcnt[(size_t)w * Nc + c]++;
+                    const long long k = (long long)w * Np + q;
+                    if (!(kp < k || (kp == k && cprev <= c))) in_order_l = 0;
+                    for (long long u = std::max(kp + 1, 0ll); u <= k; u++) pt_off[u] = i;    // pt_off[u] = first observation whose key is >= u
+                    kp = k; cprev = c;
+                }
+            }
+            if (bad) {
+                *err = "pmv_ba_problem_create: observation index out of range";
+                return PMV_ERR_INVALID;
+            }
+            in_order = in_order_l;
+            if (in_order) {
+                long long last = -1;
+                if (No) {
+                    const int wl = obs_off ? (int)(std::upper_bound(obs_off, obs_off + W + 1, No - 1) - obs_off) - 1 : 0;
+                    last = (long long)wl * Np + pt_idx[No - 1];
+                }
+    #pragma omp parallel for schedule(static)
+                for (long long u = last + 1; u <= nq; u++) pt_off[u] = No;
+    #pragma omp parallel for schedule(static)
+                for (long long b = 0; b < (long long)bins; b++) {
+                    int c = 0;
+                    for (int t = 0; t < nthreads_used; t++) c += hist[(size_t)t * bins + b];
+                    cam_off[b + 1] = c;
+                }
+                std::partial_sum(cam_off.begin(), cam_off.end(), cam_off.begin());
+            } else if (W >= 64) {
+                // Unordered list of many windows -- e.g. camera-major, the order CeresBundleAdjustment::apply adds its residual
+                // blocks in (frame by frame, CeresBundleAdjustment.cpp:27-52): a window's observations are contiguous in both
+                // orders, so every window is sorted on its own by one thread with a stable counting sort by point (original
+                // order inside a point = ascending camera for camera-major input; a point whose cameras do not come out
+                // ascending is insertion-sorted).  No atomics, no per-point std::sort: 0.4 -> 0.15 s at 143.7 M observations.
+                sorted_per_window = true;
+                h_cam.alloc(No); h_obs.alloc(2 * (size_t)No);     // point / window of an observation: filled on demand (fill_pt_win_sorted)
+    #pragma omp parallel
+                {
+                    std::vector<int> pos(Np + 1);
+    #pragma omp for schedule(dynamic, 4)
+                    for (int w = 0; w < W; w++) {
+                        const int o0 = obs_off[w], o1 = obs_off[w + 1];
+                        std::fill(pos.begin(), pos.end(), 0);
+                        int *ccnt = &cam_off[(size_t)w * Nc + 1];
+                        for (int i = o0; i < o1; i++) { pos[pt_idx[i] + 1]++; ccnt[cam_idx[i]]++; }
+                        for (int q = 0; q < Np; q++) pos[q + 1] += pos[q];
+                        int *po = &pt_off[(size_t)w * Np];
+                        for (int q = 0; q < Np; q++) po[q] = o0 + pos[q];
+                        for (int i = o0; i < o1; i++) {
+                            const int q = pt_idx[i], d = o0 + pos[q]++;
+                            h_cam[d] = cam_idx[i];
+                            h_obs[2 * (size_t)d] = obs[2 * (size_t)i]; h_obs[2 * (size_t)d + 1] = obs[2 * (size_t)i + 1];
+                        }
+                        for (int q = 0; q < Np; q++) {          // cameras of a point ascending (stable): already so for camera-major input
+                            const int a = po[q], b = o0 + pos[q];
+                            for (int d = a + 1; d < b; d++) {
+                                if (h_cam[d - 1] <= h_cam[d]) continue;
+                                const int c = h_cam[d];
+                                const double ox = h_obs[2 * (size_t)d], oy = h_obs[2 * (size_t)d + 1];
+                                int e = d;
+                                while (e > a && h_cam[e - 1] > c) {
+                                    h_cam[e] = h_cam[e - 1]; h_obs[2 * (size_t)e] = h_obs[2 * (size_t)e - 2]; h_obs[2 * (size_t)e + 1] = h_obs[2 * (size_t)e - 1];
+                                    e--;
+                                }
+                                h_cam[e] = c; h_obs[2 * (size_t)e] = ox; h_obs[2 * (size_t)e + 1] = oy;
+                            }
+                        }
+                    }
+                }
+                pt_off[(size_t)W * Np] = No;
+                std::partial_sum(cam_off.begin(), cam_off.end(), cam_off.begin());
+            } else {
+                std::fill(pt_off.begin(), pt_off.end(), 0);
+                fill_win();
+    #pragma omp parallel for schedule(static)
+                for (int i = 0; i < No; i++) {
+                    int *pc = &pt_off[(size_t)win[i] * Np + pt_idx[i] + 1], *cc = &cam_off[(size_t)win[i] * Nc + cam_idx[i] + 1];
+    #pragma omp atomic
+                    (*pc)++;
+    #pragma omp atomic
+                    (*cc)++;
+                }
+                std::partial_sum(pt_off.begin(), pt_off.end(), pt_off.begin());
+                std::partial_sum(cam_off.begin(), cam_off.end(), cam_off.begin());
+            }
+        }
+        Hcam = cam_idx; Hpt = pt_idx; Hwin = win.data();
+        Hobs = obs;
+        if (sorted_per_window) {
+            Hcam = h_cam.data(); Hobs = h_obs.data(); Hpt = nullptr; Hwin = nullptr;
+        } else if (!in_order) {
+            h_cam.alloc(No); h_pt.alloc(No); h_win.alloc(No); h_obs.alloc(2 * (size_t)No);
+            Hcam = h_cam.data(); Hpt = h_pt.data(); Hwin = h_win.data(); Hobs = h_obs.data();
+            // scatter by (window, point): slots of a point are claimed atomically, then every point orders its
+            // observations by (camera, original index) -- the result is the stable order a serial pass produces
+            std::vector<int> pos(pt_off.begin(), pt_off.end() - 1);
+            RawBuf<int> orig(No);
+    #pragma omp parallel for schedule(static)
+            for (int i = 0; i < No; i++) {
+                int *pp = &pos[(size_t)win[i] * Np + pt_idx[i]];
+                int d;
+    #pragma omp atomic capture
+                { d = *pp; (*pp)++; }
+                orig[d] = i;
+            }
+            const long long nq = (long long)pt_off.size() - 1;
+    #pragma omp parallel
+            {
+                std::vector<std::pair<int, int>> tmp;
+    #pragma omp for schedule(dynamic, 4096)
+                for (long long q = 0; q < nq; q++) {
+                    const int a = pt_off[q], b = pt_off[q + 1];
+                    if (b == a) continue;
+                    tmp.clear();
+                    for (int d = a; d < b; d++) tmp.push_back({cam_idx[orig[d]], orig[d]});
+                    if (b - a > 1) std::sort(tmp.begin(), tmp.end());
+                    const int wq = (int)(q / Np), pq = (int)(q - (long long)wq * Np);
+                    for (int d = a; d < b; d++) {
+                        const int src = tmp[d - a].second;
+                        h_cam[d] = tmp[d - a].first; h_pt[d] = pq; h_win[d] = wq;
+                        h_obs[2 * (size_t)d] = obs[2 * (size_t)src]; h_obs[2 * (size_t)d + 1] = obs[2 * (size_t)src + 1];
+                    }
+                }
+            }
+        }
+        return PMV_OK;
+    }
+};
+
 pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const double *points, const double *obs,
                                   const int32_t *cam_idx, const int32_t *pt_idx, const int32_t *obs_off, int W, int Nc,
                                   int Np, int No, const double K[9], double huber_delta, int sharded_rank,
@@ -329,225 +577,20 @@ pmv_ba_problem *ba_problem_create(pmv_ctx *ctx, const double *poses, const doubl
         fprintf(stderr, "ba_problem_create: %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
         t_last = now;
     };
-    // ---- host: order observations by (window, point), group them by (window, camera) ---------------
-    // (OpenMP over windows / observations / points: 136 M observations at BASELINE config 4 took 5.5 s on one core)
-    // window of every observation: only the unordered path and the general path's kernels need the array, so it is
-    // filled on demand (touching 572 MB of fresh pages cost more than the whole indexing pass at BASELINE config 4)
-    RawBuf<int> win(No);
-    bool win_filled = false;
-    auto fill_win = [&]() {
-        if (win_filled) return;
-        win_filled = true;
-#pragma omp parallel for schedule(static)
-        for (int w = 0; w < W; w++) {
-            const int o0 = obs_off ? obs_off[w] : 0, o1 = obs_off ? obs_off[w + 1] : No;
-            for (int i = o0; i < o1; i++) win[i] = w;
-        }
-    };
-    for (int w = 0; w < W; w++) {
-        int o0 = obs_off ? obs_off[w] : 0, o1 = obs_off ? obs_off[w + 1] : No;
-        if (o0 < 0 || o1 < o0 || o1 > No) { ctx->fail(PMV_ERR_INVALID, "pmv_ba_problem_create: bad obs_off"); return nullptr; }
-    }
-    if (obs_off && (obs_off[0] != 0 || obs_off[W] != No)) {
-        ctx->fail(PMV_ERR_INVALID, "pmv_ba_problem_create: obs_off must cover the observation list (obs_off[0] == 0, obs_off[W] == No)");
-        return nullptr;
-    }
-    // ONE streaming pass over the caller's list (143.7 M observations at BASELINE config 4: five separate passes took 0.38 s):
-    // window of every observation, range check, "already in device order?" -- sorted by (window, point, camera), which is
-    // how structure-from-motion exports (and BAL files) come --, and, optimistically for that case, the point offsets
-    // (boundaries of the list) and thread-private per-camera histograms.  In order: the permutation is the identity and
-    // nothing has to be sorted or copied.  Otherwise the offsets are recounted below and the list is sorted.
-    std::vector<int> pt_off((size_t)W * Np + 1, 0), cam_off((size_t)W * Nc + 1, 0);
-    int in_order = 1;
-    bool sorted_per_window = false;     // unordered list of many windows: every window was sorted on its own (below)
-    // device-order arrays: the caller's own when the list is in order (no copies: 4 GB at BASELINE config 4), else sorted copies
-    RawBuf<int> h_cam, h_pt, h_win, cam_obs;
-    RawBuf<double> h_obs;
+    // ---- host: order observations by (window, point), group them by (window, camera) (BAIndex above) ----
+    BAIndex X;
+    X.obs = obs; X.cam_idx = cam_idx; X.pt_idx = pt_idx; X.obs_off = obs_off; X.W = W; X.Nc = Nc; X.Np = Np; X.No = No;
     {
-        const long long nq = (long long)W * Np;
-        const size_t bins = (size_t)W * Nc;
-        int T = 1;
-#ifdef _OPENMP
-        T = std::max(1, omp_get_max_threads());
-#endif
-        std::vector<int> hist((size_t)T * bins, 0);
-        int bad = 0, nthreads_used = 1;
-#pragma omp parallel num_threads(T) reduction(| : bad) reduction(& : in_order)
-        {
-            int t = 0, nt = 1;
-#ifdef _OPENMP
-            t = omp_get_thread_num(); nt = omp_get_num_threads();
-#endif
-            if (t == 0) nthreads_used = nt;
-            int *hcnt = hist.data() + (size_t)t * bins;
-            const int i0 = (int)((long long)No * t / nt), i1 = (int)((long long)No * (t + 1) / nt);
-            int w = 0;
-            if (obs_off && i0 < i1) w = (int)(std::upper_bound(obs_off, obs_off + W + 1, i0) - obs_off) - 1;
-            long long kp = -1;          // key of the previous observation (the chunk's predecessor for its first one)
-            int cprev = -1;
-            if (i0 > 0 && i0 < i1) {
-                int wq = 0;
-                if (obs_off) wq = (int)(std::upper_bound(obs_off, obs_off + W + 1, i0 - 1) - obs_off) - 1;
-                kp = (long long)wq * Np + pt_idx[i0 - 1]; cprev = cam_idx[i0 - 1];
-            }
-            for (int i = i0; i < i1; i++) {
-                if (obs_off) while (i >= obs_off[w + 1]) w++;
-                const int c = cam_idx[i], q = pt_idx[i];
-                if (c < 0 || c >= Nc || q < 0 || q >= Np) { bad = 1; kp = nq; continue; }
-                hcnt[(size_t)w * Nc + c]++;
-                const long long k = (long long)w * Np + q;
-                if (!(kp < k || (kp == k && cprev <= c))) in_order = 0;
-                for (long long u = std::max(kp + 1, 0ll); u <= k; u++) pt_off[u] = i;    // pt_off[u] = first observation whose key is >= u
-                kp = k; cprev = c;
-            }
-        }
-        if (bad) {
-            ctx->fail(PMV_ERR_INVALID, "pmv_ba_problem_create: observation index out of range");
-            return nullptr;
-        }
-        if (in_order) {
-            long long last = -1;
-            if (No) {
-                const int wl = obs_off ? (int)(std::upper_bound(obs_off, obs_off + W + 1, No - 1) - obs_off) - 1 : 0;
-                last = (long long)wl * Np + pt_idx[No - 1];
-            }
-#pragma omp parallel for schedule(static)
-            for (long long u = last + 1; u <= nq; u++) pt_off[u] = No;
-#pragma omp parallel for schedule(static)
-            for (long long b = 0; b < (long long)bins; b++) {
-                int c = 0;
-                for (int t = 0; t < nthreads_used; t++) c += hist[(size_t)t * bins + b];
-                cam_off[b + 1] = c;
-            }
-            std::partial_sum(cam_off.begin(), cam_off.end(), cam_off.begin());
-        } else if (W >= 64) {
-            // Unordered list of many windows -- e.g. camera-major, the order CeresBundleAdjustment::apply adds its residual
-            // blocks in (frame by frame, CeresBundleAdjustment.cpp:27-52): a window's observations are contiguous in both
-            // orders, so every window is sorted on its own by one thread with a stable counting sort by point (original
-            // order inside a point = ascending camera for camera-major input; a point whose cameras do not come out
-            // ascending is insertion-sorted).  No atomics, no per-point std::sort: 0.4 -> 0.15 s at 143.7 M observations.
-            sorted_per_window = true;
-            h_cam.alloc(No); h_obs.alloc(2 * (size_t)No);     // point / window of an observation: filled on demand (fill_pt_win_sorted)
-#pragma omp parallel
-            {
-                std::vector<int> pos(Np + 1);
-#pragma omp for schedule(dynamic, 4)
-                for (int w = 0; w < W; w++) {
-                    const int o0 = obs_off[w], o1 = obs_off[w + 1];
-                    std::fill(pos.begin(), pos.end(), 0);
-                    int *ccnt = &cam_off[(size_t)w * Nc + 1];
-                    for (int i = o0; i < o1; i++) { pos[pt_idx[i] + 1]++; ccnt[cam_idx[i]]++; }
-                    for (int q = 0; q < Np; q++) pos[q + 1] += pos[q];
-                    int *po = &pt_off[(size_t)w * Np];
-                    for (int q = 0; q < Np; q++) po[q] = o0 + pos[q];
-                    for (int i = o0; i < o1; i++) {
-                        const int q = pt_idx[i], d = o0 + pos[q]++;
-                        h_cam[d] = cam_idx[i];
-                        h_obs[2 * (size_t)d] = obs[2 * (size_t)i]; h_obs[2 * (size_t)d + 1] = obs[2 * (size_t)i + 1];
-                    }
-                    for (int q = 0; q < Np; q++) {          // cameras of a point ascending (stable): already so for camera-major input
-                        const int a = po[q], b = o0 + pos[q];
-                        for (int d = a + 1; d < b; d++) {
-                            if (h_cam[d - 1] <= h_cam[d]) continue;
-                            const int c = h_cam[d];
-                            const double ox = h_obs[2 * (size_t)d], oy = h_obs[2 * (size_t)d + 1];
-                            int e = d;
-                            while (e > a && h_cam[e - 1] > c) {
-                                h_cam[e] = h_cam[e - 1]; h_obs[2 * (size_t)e] = h_obs[2 * (size_t)e - 2]; h_obs[2 * (size_t)e + 1] = h_obs[2 * (size_t)e - 1];
-                                e--;
-                            }
-                            h_cam[e] = c; h_obs[2 * (size_t)e] = ox; h_obs[2 * (size_t)e + 1] = oy;
-                        }
-                    }
-                }
-            }
-            pt_off[(size_t)W * Np] = No;
-            std::partial_sum(cam_off.begin(), cam_off.end(), cam_off.begin());
-        } else {
-            std::fill(pt_off.begin(), pt_off.end(), 0);
-            fill_win();
-#pragma omp parallel for schedule(static)
-            for (int i = 0; i < No; i++) {
-                int *pc = &pt_off[(size_t)win[i] * Np + pt_idx[i] + 1], *cc = &cam_off[(size_t)win[i] * Nc + cam_idx[i] + 1];
-#pragma omp atomic
-                (*pc)++;
-#pragma omp atomic
-                (*cc)++;
-            }
-            std::partial_sum(pt_off.begin(), pt_off.end(), pt_off.begin());
-            std::partial_sum(cam_off.begin(), cam_off.end(), cam_off.begin());
-        }
+        const char *err = nullptr;
+        if (X.build(&err) != PMV_OK) { ctx->fail(PMV_ERR_INVALID, err ? err : "pmv_ba_problem_create: bad observation list"); return nullptr; }
     }
-    const int32_t *Hcam = cam_idx, *Hpt = pt_idx, *Hwin = win.data();
-    const double *Hobs = obs;
-    // point and window of every observation of a list sorted window by window: only the general path reads them
-    auto fill_pt_win_sorted = [&]() {
-        if (!sorted_per_window || h_pt.data()) return;
-        h_pt.alloc(No); h_win.alloc(No);
-        const long long nq = (long long)W * Np;
-#pragma omp parallel for schedule(static)
-        for (long long u = 0; u < nq; u++) {
-            const int wq = (int)(u / Np), pq = (int)(u - (long long)wq * Np);
-            for (int d = pt_off[u]; d < pt_off[u + 1]; d++) { h_pt[d] = pq; h_win[d] = wq; }
-        }
-        Hpt = h_pt.data(); Hwin = h_win.data();
-    };
-    if (sorted_per_window) {
-        Hcam = h_cam.data(); Hobs = h_obs.data(); Hpt = nullptr; Hwin = nullptr;
-    } else if (!in_order) {
-        h_cam.alloc(No); h_pt.alloc(No); h_win.alloc(No); h_obs.alloc(2 * (size_t)No);
-        Hcam = h_cam.data(); Hpt = h_pt.data(); Hwin = h_win.data(); Hobs = h_obs.data();
-        // scatter by (window, point): slots of a point are claimed atomically, then every point orders its
-        // observations by (camera, original index) -- the result is the stable order a serial pass produces
-        std::vector<int> pos(pt_off.begin(), pt_off.end() - 1);
-        RawBuf<int> orig(No);
-#pragma omp parallel for schedule(static)
-        for (int i = 0; i < No; i++) {
-            int *pp = &pos[(size_t)win[i] * Np + pt_idx[i]];
-            int d;
-#pragma omp atomic capture
-            { d = *pp; (*pp)++; }
-            orig[d] = i;
-        }
-        const long long nq = (long long)pt_off.size() - 1;
-#pragma omp parallel
-        {
-            std::vector<std::pair<int, int>> tmp;
-#pragma omp for schedule(dynamic, 4096)
-            for (long long q = 0; q < nq; q++) {
-                const int a = pt_off[q], b = pt_off[q + 1];
-                if (b == a) continue;
-                tmp.clear();
-                for (int d = a; d < b; d++) tmp.push_back({cam_idx[orig[d]], orig[d]});
-                if (b - a > 1) std::sort(tmp.begin(), tmp.end());
-                const int wq = (int)(q / Np), pq = (int)(q - (long long)wq * Np);
-                for (int d = a; d < b; d++) {
-                    const int src = tmp[d - a].second;
-                    h_cam[d] = tmp[d - a].first; h_pt[d] = pq; h_win[d] = wq;
-                    h_obs[2 * (size_t)d] = obs[2 * (size_t)src]; h_obs[2 * (size_t)d + 1] = obs[2 * (size_t)src + 1];
-                }
-            }
-        }
-    }
-    // observations of every (window, camera) in increasing device order: only the general path's camera kernels read
-    // this list (ba_cam_accumulate*), so it is built once the path is known
-    auto build_cam_obs = [&]() {
-        fill_win(); fill_pt_win_sorted();
-        cam_obs.alloc(No);
-        std::vector<int> cpos(cam_off.begin(), cam_off.end() - 1);
-#pragma omp parallel for schedule(static)
-        for (int d = 0; d < No; d++) {
-            int *cp = &cpos[(size_t)Hwin[d] * Nc + Hcam[d]];
-            int k;
-#pragma omp atomic capture
-            { k = *cp; (*cp)++; }
-            cam_obs[k] = d;
-        }
-        const long long nc = (long long)cam_off.size() - 1;
-#pragma omp parallel for schedule(dynamic, 64)
-        for (long long c = 0; c < nc; c++)
-            if (cam_off[c + 1] - cam_off[c] > 1) std::sort(cam_obs.data() + cam_off[c], cam_obs.data() + cam_off[c + 1]);
-    };
+    std::vector<int> &pt_off = X.pt_off, &cam_off = X.cam_off;
+    const int32_t *&Hcam = X.Hcam, *&Hpt = X.Hpt, *&Hwin = X.Hwin;
+    const double *&Hobs = X.Hobs;
+    RawBuf<int> &cam_obs = X.cam_obs;
+    auto fill_win = [&]() { X.fill_win(); };
+    auto fill_pt_win_sorted = [&]() { X.fill_pt_win_sorted(); };
+    auto build_cam_obs = [&]() { X.build_cam_obs(); };
     lap("index observations");
     // PMV_BA_FORCE_GENERAL=1 (tests) keeps small problems on the general path so both are exercised
     const char *force_general = getenv("PMV_BA_FORCE_GENERAL");
@@ -1221,6 +1264,33 @@ PMV_API int pmv_ba_problem_download(pmv_ba_problem *p, double *poses, double *po
 }
 
 PMV_API size_t pmv_ba_problem_device_bytes(pmv_ba_problem *p) { return p ? p->bytes : 0; }
+
+PMV_API int pmv_ba_index_observations(const double *obs, const int32_t *cam_idx, const int32_t *pt_idx, const int32_t *obs_off, int W,
+                                      int Nc, int Np, int No, int32_t *pt_off, int32_t *cam_off, int32_t *cam, int32_t *pt, int32_t *win,
+                                      double *obs_sorted, int32_t *cam_obs, int *route)
+{
+    if (!obs || !cam_idx || !pt_idx || W <= 0 || Nc <= 0 || Np <= 0 || No < 0 || (W > 1 && !obs_off)) return PMV_ERR_INVALID;
+    BAIndex X;
+    X.obs = obs; X.cam_idx = cam_idx; X.pt_idx = pt_idx; X.obs_off = obs_off; X.W = W; X.Nc = Nc; X.Np = Np; X.No = No;
+    const char *err = nullptr;
+    const int rc = X.build(&err);
+    if (rc != PMV_OK) return rc;
+    X.fill_win(); X.fill_pt_win_sorted();
+    if (route) *route = X.in_order ? 0 : X.sorted_per_window ? 1 : 2;
+    if (pt_off) std::copy(X.pt_off.begin(), X.pt_off.end(), pt_off);
+    if (cam_off) std::copy(X.cam_off.begin(), X.cam_off.end(), cam_off);
+    for (int d = 0; d < No; d++) {
+        if (cam) cam[d] = X.Hcam[d];
+        if (pt) pt[d] = X.Hpt[d];
+        if (win) win[d] = X.Hwin[d];
+        if (obs_sorted) { obs_sorted[2 * (size_t)d] = X.Hobs[2 * (size_t)d]; obs_sorted[2 * (size_t)d + 1] = X.Hobs[2 * (size_t)d + 1]; }
+    }
+    if (cam_obs) {
+        X.build_cam_obs();
+        std::copy(X.cam_obs.data(), X.cam_obs.data() + No, cam_obs);
+    }
+    return PMV_OK;
+}
 
 PMV_API int pmv_ba_solve_batched(pmv_ctx *ctx, double *poses, double *points, const double *obs,
                                  const int32_t *cam_idx, const int32_t *pt_idx, const int32_t *obs_off, int W,
