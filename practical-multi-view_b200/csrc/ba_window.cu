@@ -195,7 +195,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) win_schur_kernel(const BADev D,
     const int nchunks = (D.Np + P - 1) / P;
     const bool is_producer = tid >= 256;
 
-    const int ntiles = Nc * (Nc + 1) / 2;
     const int ld = n + 1;
     // The two roles keep their accumulators in DISJOINT code paths so the register allocation is the
     // maximum of the two, not the sum.  cta_barrier() = one hand-off per chunk.
